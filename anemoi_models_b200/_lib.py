@@ -1,0 +1,91 @@
+"""ctypes binding of libanemoi_b200.so (the C ABI declared in include/anemoi_b200.h).
+
+There is no CPU path and no fallback: if the shared library is missing or a call fails, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+from ._build import LIBPATH
+
+AB2_F32, AB2_BF16 = 0, 1
+AB2_ERR_INVALID, AB2_ERR_UNSUPPORTED, AB2_ERR_CUDA = 1, 2, 3
+
+_vp, _i64, _i32, _sz, _f32 = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_float
+
+# name -> (restype, argtypes); must list every symbol of include/anemoi_b200.h (tests/test_abi.py checks it)
+SIGNATURES = {
+    "ab2_version": (_i32, []),
+    "ab2_last_error": (C.c_char_p, []),
+    "ab2_csr_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "ab2_csr_build": (_i32, [_vp, _i64, _i64, _i64] + [_vp] * 8 + [_vp, _sz, _vp]),
+    "ab2_edge_chunks_workspace_bytes": (_sz, [_i64]),
+    "ab2_edge_chunks": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "ab2_gtconv_fwd": (_i32, [_vp] * 4 + [_i32] + [_vp] * 3 + [_i64] * 3 + [_i32, _i32, _vp, _vp, _vp]),
+    "ab2_gtconv_bwd_workspace_bytes": (_sz, [_i64, _i32]),
+    "ab2_gtconv_bwd": (_i32, [_vp] * 4 + [_i32] + [_vp] * 6 + [_i64] * 3 + [_i32, _i32] + [_vp] * 7 + [_vp, _sz, _vp]),
+    "ab2_edge_gather_add_act": (_i32, [_vp] * 4 + [_i64] * 3 + [_i32] * 3 + [_vp] * 3),
+    "ab2_edge_gather_add_act_bwd": (_i32, [_vp] * 6 + [_i64] * 3 + [_i32] * 3 + [_vp] * 4),
+    "ab2_edge_ln_res_segsum": (_i32, [_vp] * 4 + [_f32] + [_vp] * 2 + [_i64] * 2 + [_i32] * 2 + [_vp] * 5),
+    "ab2_ln_bwd_parts": (_i32, []),
+    "ab2_edge_ln_res_segsum_bwd": (_i32, [_vp] * 7 + [_i64] * 2 + [_i32] * 2 + [_vp] * 3 + [_i32] + [_vp] * 3),
+    "ab2_gtconv_host_workspace_bytes": (_sz, [_i64] * 3 + [_i32] * 3),
+    "ab2_gtconv_fwd_bwd_host": (_i32, [_vp] * 5 + [_i32] + [_vp] * 6 + [_i64] * 3 + [_i32] * 2 + [_vp] * 5 + [_vp, _sz, _vp]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library.  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIBPATH):
+                    raise RuntimeError(
+                        f"{LIBPATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(anemoi_models_b200 has no CPU or PyTorch fallback)"
+                    )
+                handle = C.CDLL(LIBPATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(handle, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = handle
+    return _lib
+
+
+def check(rc: int) -> None:
+    """Translate a non-zero ab2_status into the Python exception the reference path would raise."""
+    if rc == 0:
+        return
+    msg = lib().ab2_last_error().decode("utf-8", "replace")
+    if rc in (AB2_ERR_INVALID, AB2_ERR_UNSUPPORTED):
+        raise ValueError(f"libanemoi_b200: {msg}")
+    raise RuntimeError(f"libanemoi_b200: {msg}")
+
+
+def ptr(t) -> int:
+    """Device (or pinned host) pointer of a tensor, 0 for None."""
+    return 0 if t is None else t.data_ptr()
+
+
+def dtype_code(dtype) -> int:
+    import torch
+
+    if dtype == torch.float32:
+        return AB2_F32
+    if dtype == torch.bfloat16:
+        return AB2_BF16
+    raise TypeError(f"anemoi_models_b200 supports float32 and bfloat16 tensors, got {dtype}")
+
+
+def current_stream(device) -> int:
+    """cudaStream_t of the calling thread's current stream (autograd worker threads have their own)."""
+    import torch
+
+    return torch.cuda.current_stream(device).cuda_stream

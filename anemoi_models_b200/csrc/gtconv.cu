@@ -1,0 +1,618 @@
+// Fused GraphTransformerConv forward / backward over a dst-sorted CSR (sm_100a).
+//
+// Replaces reference layers/conv.py:98-142 (+ PyG propagate / utils.softmax / scatter-add), where every
+// step materialises an [E,H,C] or [E,H] tensor in HBM.  Here a destination row is owned by a group of
+// threads (16 bytes of the row per thread, LPH consecutive lanes per head); the per-edge logit is reduced
+// with warp shuffles inside the head group, the segment softmax runs online (flash style, base-2) and the
+// weighted sum of (v_j + e_t) accumulates in registers: logits never touch HBM.
+//
+// HBM-bound: per edge one 16-B-per-lane read of e[t], k[src], v[src]; per dst one read of q and one write of out.
+// Backward = two passes, both deterministic (no atomics):
+//   bwd_dst (per dst segment):  recompute s, a; dq (registers), de (streamed), and the per-(edge,head) pair
+//                               (a, ds/sqrt(C)) to a small [E,H] float2 workspace;
+//   bwd_src (per src segment, CSC order): dk_j = sum ds*q_i, dv_j = sum a*g_i  (q, g rows are L2-resident).
+#include <cmath>
+
+#include "common.cuh"
+
+namespace ab2 {
+
+constexpr int kThreads = 128;  // CTA size of the vector kernels
+constexpr int kU = 4;          // edges in flight per thread (3 x 16 B loads each)
+
+struct RowMap {  // how a CTA's threads map onto (dst row, 16-byte chunk)
+  int tpd;       // threads per row handled by one CTA (= heads-per-slice * LPH)
+  int rpb;       // rows per CTA
+  int chunks;    // 16-byte chunks in a full row (= D*sizeof(T)/16)
+};
+
+template <int LPH>
+__device__ __forceinline__ unsigned group_mask() {
+  if constexpr (LPH == 32) {
+    return 0xffffffffu;
+  } else {
+    const unsigned lane = threadIdx.x & 31u;
+    return ((1u << LPH) - 1u) << (lane & ~(unsigned)(LPH - 1));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------
+template <typename T, int LPH>
+__global__ void __launch_bounds__(kThreads)
+gtconv_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ e,
+                  const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm, int Nd,
+                  RowMap rm, int H, float qscale, T* __restrict__ out, float* __restrict__ lse2) {
+  constexpr int VEC = Vec<T>::N;
+  const int lr = threadIdx.x / rm.tpd;
+  const int d = blockIdx.x * rm.rpb + lr;
+  if (lr >= rm.rpb || d >= Nd) return;
+  const int chunk = blockIdx.y * rm.tpd + (threadIdx.x - lr * rm.tpd);  // 16-byte chunk of the row
+  const size_t D = (size_t)rm.chunks * VEC;
+  const size_t off = (size_t)chunk * VEC;
+  const unsigned mask = group_mask<LPH>();
+
+  float qf[VEC];
+  unpack<T>(ldg16_keep(q + (size_t)d * D + off), qf);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) qf[i] *= qscale;  // log2(e)/sqrt(C): logits come out in base-2 units
+
+  const int beg = rowptr[d], end = rowptr[d + 1];
+  float m = -INFINITY, l = 0.f, acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+
+  int jn[kU], tn[kU];  // indices of the next chunk of edges, fetched one chunk ahead of the row loads
+#pragma unroll
+  for (int u = 0; u < kU; ++u) {
+    jn[u] = beg + u < end ? col[beg + u] : 0;
+    tn[u] = beg + u < end ? perm[beg + u] : 0;
+  }
+  for (int p = beg; p < end; p += kU) {
+    uint4 kr[kU], er[kU], vr[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (p + u < end) {
+        const size_t j = (size_t)jn[u], t = (size_t)tn[u];
+        kr[u] = ldg16_keep(k + j * D + off);
+        er[u] = ldg16(e + t * D + off);
+        vr[u] = ldg16_keep(v + j * D + off);
+      } else {
+        kr[u] = er[u] = vr[u] = make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int pn = p + kU + u;
+      jn[u] = pn < end ? col[pn] : 0;
+      tn[u] = pn < end ? perm[pn] : 0;
+    }
+    float s[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      float kf[VEC], ef[VEC];
+      unpack<T>(kr[u], kf);
+      unpack<T>(er[u], ef);
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) part = fmaf(qf[i], kf[i] + ef[i], part);
+      s[u] = part;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) s[u] = group_sum<LPH>(s[u], mask);
+    float mn = m;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (p + u >= end) s[u] = -INFINITY;
+      mn = fmaxf(mn, s[u]);
+    }
+    const float corr = fast_exp2(m - mn);  // first chunk: 2^(-inf) = 0
+    l *= corr;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] *= corr;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const float pw = fast_exp2(s[u] - mn);  // masked edges: 2^(-inf) = 0
+      l += pw;
+      float vf[VEC], ef[VEC];
+      unpack<T>(vr[u], vf);
+      unpack<T>(er[u], ef);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[i] = fmaf(pw, vf[i] + ef[i], acc[i]);
+    }
+    m = mn;
+  }
+  const float inv = 1.f / (l + 1e-16f);  // PyG: exp(s-max) / (sum + 1e-16); an empty segment keeps its zero row
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] *= inv;
+  stg16(out + (size_t)d * D + off, pack<T>(acc));
+  if ((chunk & (LPH - 1)) == 0) lse2[(size_t)d * H + chunk / LPH] = end > beg ? m + log2f(l + 1e-16f) : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// backward, dst pass
+// ------------------------------------------------------------------------------------------------------
+template <typename T, int LPH>
+__global__ void __launch_bounds__(kThreads)
+gtconv_bwd_dst_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ e,
+                      const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm, int Nd,
+                      RowMap rm, int H, float qscale, float scale, const T* __restrict__ out, const float* __restrict__ lse2,
+                      const T* __restrict__ g, T* __restrict__ dq, T* __restrict__ de, float2* __restrict__ ads) {
+  constexpr int VEC = Vec<T>::N;
+  const int lr = threadIdx.x / rm.tpd;
+  const int d = blockIdx.x * rm.rpb + lr;
+  if (lr >= rm.rpb || d >= Nd) return;
+  const int chunk = blockIdx.y * rm.tpd + (threadIdx.x - lr * rm.tpd);
+  const size_t D = (size_t)rm.chunks * VEC;
+  const size_t off = (size_t)chunk * VEC;
+  const unsigned mask = group_mask<LPH>();
+  const int h = chunk / LPH;
+  const bool leader = (chunk & (LPH - 1)) == 0;
+
+  float qf[VEC], gf[VEC], dqa[VEC];
+  unpack<T>(ldg16_keep(q + (size_t)d * D + off), qf);
+  unpack<T>(ldg16_keep(g + (size_t)d * D + off), gf);
+  float Dl;
+  {
+    float of[VEC];
+    unpack<T>(ldg16(out + (size_t)d * D + off), of);
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) part = fmaf(gf[i], of[i], part);
+    Dl = group_sum<LPH>(part, mask);
+  }
+  const float L = lse2[(size_t)d * H + h];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) dqa[i] = 0.f;
+
+  const int beg = rowptr[d], end = rowptr[d + 1];
+  int jn[kU], tn[kU];
+#pragma unroll
+  for (int u = 0; u < kU; ++u) {
+    jn[u] = beg + u < end ? col[beg + u] : 0;
+    tn[u] = beg + u < end ? perm[beg + u] : 0;
+  }
+  for (int p = beg; p < end; p += kU) {
+    uint4 kr[kU], er[kU], vr[kU];
+    size_t ts[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      ts[u] = (size_t)tn[u];
+      if (p + u < end) {
+        const size_t j = (size_t)jn[u];
+        kr[u] = ldg16_keep(k + j * D + off);
+        er[u] = ldg16(e + ts[u] * D + off);
+        vr[u] = ldg16_keep(v + j * D + off);
+      } else {
+        kr[u] = er[u] = vr[u] = make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int pn = p + kU + u;
+      jn[u] = pn < end ? col[pn] : 0;
+      tn[u] = pn < end ? perm[pn] : 0;
+    }
+    float s[kU], gv[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      float kf[VEC], ef[VEC], vf[VEC];
+      unpack<T>(kr[u], kf);
+      unpack<T>(er[u], ef);
+      unpack<T>(vr[u], vf);
+      float ps = 0.f, pg = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        ps = fmaf(qf[i], kf[i] + ef[i], ps);
+        pg = fmaf(gf[i], vf[i] + ef[i], pg);
+      }
+      s[u] = ps;
+      gv[u] = pg;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      s[u] = group_sum<LPH>(s[u], mask);
+      gv[u] = group_sum<LPH>(gv[u], mask);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (p + u < end) {
+        const float a = fast_exp2(fmaf(s[u], qscale, -L));
+        const float dss = a * (gv[u] - Dl) * scale;  // d(logit)/sqrt(C)
+        float kf[VEC], ef[VEC];
+        unpack<T>(kr[u], kf);
+        unpack<T>(er[u], ef);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) dqa[i] = fmaf(dss, kf[i] + ef[i], dqa[i]);
+        if (de) {
+          float o[VEC];
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) o[i] = fmaf(a, gf[i], dss * qf[i]);
+          stg16(de + ts[u] * D + off, pack<T>(o));
+        }
+        if (ads && leader) ads[(size_t)(p + u) * H + h] = make_float2(a, dss);
+      }
+    }
+  }
+  if (dq) stg16(dq + (size_t)d * D + off, pack<T>(dqa));
+}
+
+// ------------------------------------------------------------------------------------------------------
+// backward, src pass
+// ------------------------------------------------------------------------------------------------------
+template <typename T, int LPH>
+__global__ void __launch_bounds__(kThreads)
+gtconv_bwd_src_kernel(const T* __restrict__ q, const T* __restrict__ g, const int* __restrict__ colptr,
+                      const int* __restrict__ cpos, const int* __restrict__ crow, const float2* __restrict__ ads, int Ns,
+                      RowMap rm, int H, T* __restrict__ dk, T* __restrict__ dv) {
+  constexpr int VEC = Vec<T>::N;
+  const int lr = threadIdx.x / rm.tpd;
+  const int j = blockIdx.x * rm.rpb + lr;
+  if (lr >= rm.rpb || j >= Ns) return;
+  const int chunk = blockIdx.y * rm.tpd + (threadIdx.x - lr * rm.tpd);
+  const size_t D = (size_t)rm.chunks * VEC;
+  const size_t off = (size_t)chunk * VEC;
+  const int h = chunk / LPH;
+  float ka[VEC], va[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) ka[i] = va[i] = 0.f;
+  const int beg = colptr[j], end = colptr[j + 1];
+  for (int t = beg; t < end; t += kU) {
+    uint4 qr[kU], gr[kU];
+    float2 w[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (t + u < end) {
+        const size_t p = (size_t)cpos[t + u], i = (size_t)crow[t + u];
+        w[u] = __ldg(ads + p * H + h);
+        qr[u] = ldg16_keep(q + i * D + off);
+        gr[u] = ldg16_keep(g + i * D + off);
+      } else {
+        w[u] = make_float2(0.f, 0.f);
+        qr[u] = gr[u] = make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      float qf[VEC], gf[VEC];
+      unpack<T>(qr[u], qf);
+      unpack<T>(gr[u], gf);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        ka[i] = fmaf(w[u].y, qf[i], ka[i]);
+        va[i] = fmaf(w[u].x, gf[i], va[i]);
+      }
+    }
+  }
+  if (dk) stg16(dk + (size_t)j * D + off, pack<T>(ka));
+  if (dv) stg16(dv + (size_t)j * D + off, pack<T>(va));
+}
+
+// ------------------------------------------------------------------------------------------------------
+// generic kernels: any C (one warp per (row, head), lanes stride over channels).  Used when C*sizeof(T) is not
+// a power-of-two multiple of 16 bytes (e.g. C=5, C=24) -- small test shapes; not the tuned path.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kGenR = 8;  // channels per lane: C <= 256
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+gtconv_fwd_generic_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ e,
+                          const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm, int Nd, int H,
+                          int C, float qscale, T* __restrict__ out, float* __restrict__ lse2) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (w >= (long long)Nd * H) return;
+  const int d = (int)(w / H), h = (int)(w % H);
+  const size_t D = (size_t)H * C, ho = (size_t)h * C;
+  float qf[kGenR], acc[kGenR];
+#pragma unroll
+  for (int r = 0; r < kGenR; ++r) {
+    const int c = lane + 32 * r;
+    qf[r] = c < C ? to_f<T>(q[(size_t)d * D + ho + c]) * qscale : 0.f;
+    acc[r] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+  const int beg = rowptr[d], end = rowptr[d + 1];
+  for (int p = beg; p < end; ++p) {
+    const size_t j = (size_t)col[p], t = (size_t)perm[p];
+    float vv[kGenR], part = 0.f;
+#pragma unroll
+    for (int r = 0; r < kGenR; ++r) {
+      const int c = lane + 32 * r;
+      float kk = 0.f;
+      vv[r] = 0.f;
+      if (c < C) {
+        const float ef = to_f<T>(e[t * D + ho + c]);
+        kk = to_f<T>(k[j * D + ho + c]) + ef;
+        vv[r] = to_f<T>(v[j * D + ho + c]) + ef;
+      }
+      part = fmaf(qf[r], kk, part);
+    }
+    const float s = warp_sum(part);
+    const float mn = fmaxf(m, s);
+    const float corr = fast_exp2(m - mn), pw = fast_exp2(s - mn);
+    l = fmaf(l, corr, pw);
+#pragma unroll
+    for (int r = 0; r < kGenR; ++r) acc[r] = fmaf(acc[r], corr, pw * vv[r]);
+    m = mn;
+  }
+  const float inv = 1.f / (l + 1e-16f);
+#pragma unroll
+  for (int r = 0; r < kGenR; ++r) {
+    const int c = lane + 32 * r;
+    if (c < C) out[(size_t)d * D + ho + c] = from_f<T>(acc[r] * inv);
+  }
+  if (lane == 0) lse2[(size_t)d * H + h] = end > beg ? m + log2f(l + 1e-16f) : 0.f;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+gtconv_bwd_dst_generic_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ e,
+                              const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm, int Nd,
+                              int H, int C, float qscale, float scale, const T* __restrict__ out, const float* __restrict__ lse2,
+                              const T* __restrict__ g, T* __restrict__ dq, T* __restrict__ de, float2* __restrict__ ads) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (w >= (long long)Nd * H) return;
+  const int d = (int)(w / H), h = (int)(w % H);
+  const size_t D = (size_t)H * C, ho = (size_t)h * C;
+  float qf[kGenR], gf[kGenR], dqa[kGenR], part = 0.f;
+#pragma unroll
+  for (int r = 0; r < kGenR; ++r) {
+    const int c = lane + 32 * r;
+    qf[r] = gf[r] = dqa[r] = 0.f;
+    if (c < C) {
+      qf[r] = to_f<T>(q[(size_t)d * D + ho + c]);
+      gf[r] = to_f<T>(g[(size_t)d * D + ho + c]);
+      part = fmaf(gf[r], to_f<T>(out[(size_t)d * D + ho + c]), part);
+    }
+  }
+  const float Dl = warp_sum(part);
+  const float L = lse2[(size_t)d * H + h];
+  const int beg = rowptr[d], end = rowptr[d + 1];
+  for (int p = beg; p < end; ++p) {
+    const size_t j = (size_t)col[p], t = (size_t)perm[p];
+    float kk[kGenR], ps = 0.f, pg = 0.f;
+#pragma unroll
+    for (int r = 0; r < kGenR; ++r) {
+      const int c = lane + 32 * r;
+      kk[r] = 0.f;
+      float vv = 0.f;
+      if (c < C) {
+        const float ef = to_f<T>(e[t * D + ho + c]);
+        kk[r] = to_f<T>(k[j * D + ho + c]) + ef;
+        vv = to_f<T>(v[j * D + ho + c]) + ef;
+      }
+      ps = fmaf(qf[r], kk[r], ps);
+      pg = fmaf(gf[r], vv, pg);
+    }
+    const float s = warp_sum(ps), gv = warp_sum(pg);
+    const float a = fast_exp2(fmaf(s, qscale, -L));
+    const float dss = a * (gv - Dl) * scale;
+#pragma unroll
+    for (int r = 0; r < kGenR; ++r) {
+      const int c = lane + 32 * r;
+      dqa[r] = fmaf(dss, kk[r], dqa[r]);
+      if (de && c < C) de[t * D + ho + c] = from_f<T>(fmaf(a, gf[r], dss * qf[r]));
+    }
+    if (ads && lane == 0) ads[(size_t)p * H + h] = make_float2(a, dss);
+  }
+  if (dq) {
+#pragma unroll
+    for (int r = 0; r < kGenR; ++r) {
+      const int c = lane + 32 * r;
+      if (c < C) dq[(size_t)d * D + ho + c] = from_f<T>(dqa[r]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+gtconv_bwd_src_generic_kernel(const T* __restrict__ q, const T* __restrict__ g, const int* __restrict__ colptr,
+                              const int* __restrict__ cpos, const int* __restrict__ crow, const float2* __restrict__ ads, int Ns,
+                              int H, int C, T* __restrict__ dk, T* __restrict__ dv) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (w >= (long long)Ns * H) return;
+  const int j = (int)(w / H), h = (int)(w % H);
+  const size_t D = (size_t)H * C, ho = (size_t)h * C;
+  float ka[kGenR], va[kGenR];
+#pragma unroll
+  for (int r = 0; r < kGenR; ++r) ka[r] = va[r] = 0.f;
+  const int beg = colptr[j], end = colptr[j + 1];
+  for (int t = beg; t < end; ++t) {
+    const size_t p = (size_t)cpos[t], i = (size_t)crow[t];
+    const float2 w2 = ads[p * H + h];
+#pragma unroll
+    for (int r = 0; r < kGenR; ++r) {
+      const int c = lane + 32 * r;
+      if (c < C) {
+        ka[r] = fmaf(w2.y, to_f<T>(q[i * D + ho + c]), ka[r]);
+        va[r] = fmaf(w2.x, to_f<T>(g[i * D + ho + c]), va[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kGenR; ++r) {
+    const int c = lane + 32 * r;
+    if (c < C) {
+      if (dk) dk[(size_t)j * D + ho + c] = from_f<T>(ka[r]);
+      if (dv) dv[(size_t)j * D + ho + c] = from_f<T>(va[r]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host dispatch
+// ------------------------------------------------------------------------------------------------------
+struct Plan {
+  bool vector;  // 16-byte vector kernels applicable
+  int lph;
+  RowMap rm;
+  int slices;  // head slices per row (grid.y)
+};
+
+static Plan make_plan(int H, int C, int elt) {
+  Plan pl{};
+  const int head_bytes = C * elt;
+  pl.vector = false;
+  if (head_bytes % 16 == 0) {
+    const int lph = head_bytes / 16;
+    if (lph <= 32 && (lph & (lph - 1)) == 0) {
+      int hs = 1;  // heads per slice: largest divisor of H with hs*lph <= kThreads
+      for (int c = 1; c <= H; ++c)
+        if (H % c == 0 && c * lph <= kThreads) hs = c;
+      pl.vector = true;
+      pl.lph = lph;
+      pl.rm.tpd = hs * lph;
+      pl.rm.rpb = kThreads / pl.rm.tpd;
+      pl.rm.chunks = H * lph;
+      pl.slices = H / hs;
+    }
+  }
+  return pl;
+}
+
+template <typename T, int LPH>
+static void launch_fwd(const Plan& pl, const void* q, const void* k, const void* v, const void* e, const int* rowptr,
+                       const int* col, const int* perm, int Nd, int H, float qscale, void* out, float* lse2, cudaStream_t st) {
+  dim3 grid((Nd + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
+  gtconv_fwd_kernel<T, LPH><<<grid, kThreads, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (const T*)e, rowptr, col, perm,
+                                                      Nd, pl.rm, H, qscale, (T*)out, lse2);
+}
+template <typename T, int LPH>
+static void launch_bwd(const Plan& pl, const void* q, const void* k, const void* v, const void* e, const int* rowptr,
+                       const int* col, const int* perm, const int* colptr, const int* cpos, const int* crow, int Ns, int Nd,
+                       int H, float qscale, float scale, const void* out, const float* lse2, const void* g, void* dq, void* dk,
+                       void* dv, void* de, float2* ads, cudaStream_t st) {
+  if (Nd > 0) {
+    dim3 grid((Nd + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
+    gtconv_bwd_dst_kernel<T, LPH><<<grid, kThreads, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (const T*)e, rowptr, col,
+                                                            perm, Nd, pl.rm, H, qscale, scale, (const T*)out, lse2,
+                                                            (const T*)g, (T*)dq, (T*)de, (dk || dv) ? ads : nullptr);
+  }
+  if ((dk || dv) && Ns > 0) {
+    dim3 grid((Ns + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
+    gtconv_bwd_src_kernel<T, LPH><<<grid, kThreads, 0, st>>>((const T*)q, (const T*)g, colptr, cpos, crow, ads, Ns, pl.rm, H,
+                                                            (T*)dk, (T*)dv);
+  }
+}
+
+#define AB2_DISPATCH_LPH(T, lph, CALL)                                   \
+  switch (lph) {                                                         \
+    case 1: CALL(T, 1); break;                                           \
+    case 2: CALL(T, 2); break;                                           \
+    case 4: CALL(T, 4); break;                                           \
+    case 8: CALL(T, 8); break;                                           \
+    case 16: CALL(T, 16); break;                                         \
+    default: CALL(T, 32); break;                                         \
+  }
+
+static int check_common(const char* fn, int dtype, int64_t Ns, int64_t Nd, int64_t E, int H, int C) {
+  if (dtype != AB2_F32 && dtype != AB2_BF16) return fail(AB2_ERR_INVALID, "%s: dtype must be AB2_F32 or AB2_BF16", fn);
+  if (Ns < 0 || Nd < 0 || E < 0 || H <= 0 || C <= 0) return fail(AB2_ERR_INVALID, "%s: negative or zero dimension", fn);
+  if (Ns >= INT32_MAX || Nd >= INT32_MAX || E >= INT32_MAX) return fail(AB2_ERR_UNSUPPORTED, "%s: sizes must be < 2^31", fn);
+  if (C > 32 * kGenR && !make_plan(H, C, dtype == AB2_F32 ? 4 : 2).vector)
+    return fail(AB2_ERR_UNSUPPORTED, "%s: head width C=%d not supported (needs C*sizeof power-of-two multiple of 16 B, or C <= %d)", fn, C, 32 * kGenR);
+  return 0;
+}
+
+}  // namespace ab2
+
+using namespace ab2;
+
+extern "C" int ab2_gtconv_fwd(const void* q, const void* k, const void* v, const void* e, int dtype, const int32_t* rowptr,
+                              const int32_t* col, const int32_t* perm, int64_t Ns, int64_t Nd, int64_t E, int H, int C, void* out,
+                              float* lse2, void* stream) {
+  if (int rc = check_common("gtconv_fwd", dtype, Ns, Nd, E, H, C)) return rc;
+  if (Nd == 0) return AB2_OK;
+  if (!q || !out || !lse2 || !rowptr || (E > 0 && (!k || !v || !e || !col || !perm))) return fail(AB2_ERR_INVALID, "gtconv_fwd: null pointer argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float qscale = kLog2e / sqrtf((float)C);
+  const Plan pl = make_plan(H, C, dtype == AB2_F32 ? 4 : 2);
+  if (pl.vector) {
+#define CALL(T, L) launch_fwd<T, L>(pl, q, k, v, e, rowptr, col, perm, (int)Nd, H, qscale, out, lse2, st)
+    if (dtype == AB2_F32) {
+      AB2_DISPATCH_LPH(float, pl.lph, CALL)
+    } else {
+      AB2_DISPATCH_LPH(__nv_bfloat16, pl.lph, CALL)
+    }
+#undef CALL
+  } else {
+    const long long warps = (long long)Nd * H;
+    const unsigned grid = (unsigned)((warps + kThreads / 32 - 1) / (kThreads / 32));
+    if (dtype == AB2_F32)
+      gtconv_fwd_generic_kernel<float><<<grid, kThreads, 0, st>>>((const float*)q, (const float*)k, (const float*)v, (const float*)e,
+                                                                 rowptr, col, perm, (int)Nd, H, C, qscale, (float*)out, lse2);
+    else
+      gtconv_fwd_generic_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
+                                                                         (const __nv_bfloat16*)v, (const __nv_bfloat16*)e, rowptr, col,
+                                                                         perm, (int)Nd, H, C, qscale, (__nv_bfloat16*)out, lse2);
+  }
+  AB2_LAUNCH_OK("gtconv_fwd");
+  return AB2_OK;
+}
+
+extern "C" size_t ab2_gtconv_bwd_workspace_bytes(int64_t E, int H) { return (size_t)(E > 0 ? E : 1) * (size_t)H * sizeof(float2); }
+
+extern "C" int ab2_gtconv_bwd(const void* q, const void* k, const void* v, const void* e, int dtype, const int32_t* rowptr,
+                              const int32_t* col, const int32_t* perm, const int32_t* colptr, const int32_t* cpos,
+                              const int32_t* crow, int64_t Ns, int64_t Nd, int64_t E, int H, int C, const void* out,
+                              const float* lse2, const void* g, void* dq, void* dk, void* dv, void* de, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  if (int rc = check_common("gtconv_bwd", dtype, Ns, Nd, E, H, C)) return rc;
+  const bool need_src = dk || dv;
+  if (!rowptr || (Nd > 0 && (!q || !out || !lse2 || !g)) || (E > 0 && (!k || !v || !e || !col || !perm)))
+    return fail(AB2_ERR_INVALID, "gtconv_bwd: null pointer argument");
+  if (need_src && (!colptr || (E > 0 && (!cpos || !crow)))) return fail(AB2_ERR_INVALID, "gtconv_bwd: dk/dv requested without the CSC view");
+  if (need_src && (!workspace || workspace_bytes < ab2_gtconv_bwd_workspace_bytes(E, H)))
+    return fail(AB2_ERR_INVALID, "gtconv_bwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float scale = 1.f / sqrtf((float)C);
+  const float qscale = kLog2e * scale;
+  float2* ads = (float2*)workspace;
+  const Plan pl = make_plan(H, C, dtype == AB2_F32 ? 4 : 2);
+  if (pl.vector) {
+#define CALL(T, L) \
+  launch_bwd<T, L>(pl, q, k, v, e, rowptr, col, perm, colptr, cpos, crow, (int)Ns, (int)Nd, H, qscale, scale, out, lse2, g, dq, dk, dv, de, ads, st)
+    if (dtype == AB2_F32) {
+      AB2_DISPATCH_LPH(float, pl.lph, CALL)
+    } else {
+      AB2_DISPATCH_LPH(__nv_bfloat16, pl.lph, CALL)
+    }
+#undef CALL
+  } else {
+    const int wpb = kThreads / 32;
+    if (Nd > 0) {
+      const unsigned grid = (unsigned)(((long long)Nd * H + wpb - 1) / wpb);
+      if (dtype == AB2_F32)
+        gtconv_bwd_dst_generic_kernel<float><<<grid, kThreads, 0, st>>>(
+            (const float*)q, (const float*)k, (const float*)v, (const float*)e, rowptr, col, perm, (int)Nd, H, C, qscale, scale,
+            (const float*)out, lse2, (const float*)g, (float*)dq, (float*)de, need_src ? ads : nullptr);
+      else
+        gtconv_bwd_dst_generic_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>(
+            (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)e, rowptr, col, perm,
+            (int)Nd, H, C, qscale, scale, (const __nv_bfloat16*)out, lse2, (const __nv_bfloat16*)g, (__nv_bfloat16*)dq,
+            (__nv_bfloat16*)de, need_src ? ads : nullptr);
+    }
+    if (need_src && Ns > 0) {
+      const unsigned grid = (unsigned)(((long long)Ns * H + wpb - 1) / wpb);
+      if (dtype == AB2_F32)
+        gtconv_bwd_src_generic_kernel<float><<<grid, kThreads, 0, st>>>((const float*)q, (const float*)g, colptr, cpos, crow, ads,
+                                                                       (int)Ns, H, C, (float*)dk, (float*)dv);
+      else
+        gtconv_bwd_src_generic_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)g,
+                                                                               colptr, cpos, crow, ads, (int)Ns, H, C,
+                                                                               (__nv_bfloat16*)dk, (__nv_bfloat16*)dv);
+    }
+  }
+  AB2_LAUNCH_OK("gtconv_bwd");
+  return AB2_OK;
+}

@@ -1,0 +1,5 @@
+"""dst-node sharding with a halo exchange: replacement for `anemoi.models.distributed` on the graph path."""
+from .shapes import change_channels_in_shape, get_shape_shards  # noqa: F401
+from .khop_edges import sort_edges_1hop_chunks, sort_edges_1hop_sharding  # noqa: F401
+from .collectives import gather_tensor, reduce_shard_tensor, reduce_tensor, shard_tensor, sync_tensor  # noqa: F401
+from .halo import HaloPlan, build_bipartite_halo_plan, halo_gather, select_sharded_edges  # noqa: F401

@@ -1,0 +1,239 @@
+"""Drop-in graph blocks (reference layers/block.py:108-635): same class names, constructor arguments, parameter /
+state_dict names and `forward` signatures, with the edge path on the fused CUDA kernels.
+
+Single rank: LayerNorm + dense q/k/v/self/edge projections (tensor-core GEMMs through nn.Linear) -> fused conv ->
+projection + node MLP, as in the reference.
+
+Model-parallel group of P ranks: the reference shards heads (4+1 all-to-alls per GT block, every rank holding the whole
+edge list) or all-gathers node features (GraphConv blocks).  Here every rank keeps its dst rows and all edges
+pointing into them; only the halo of src rows is exchanged (see distributed/halo.py).  Inputs/outputs keep the
+reference's sharded layouts and `shapes` bookkeeping, so mappers/processors/models call these blocks unchanged.
+"""
+from __future__ import annotations
+
+import logging
+import os
+from abc import ABC, abstractmethod
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor, nn
+
+from ..distributed.collectives import shard_tensor, sync_tensor
+from ..distributed.halo import (HaloPlan, build_bipartite_halo_plan, build_local_halo_plan, halo_gather,
+                                select_sharded_edges)
+from ..distributed.shapes import bounds_from_shapes
+from ..graph import TensorKeyedCache, check_edge_index, get_csr, resolve_size
+from .conv import GraphConv, GraphTransformerConv
+from .mlp import MLP, activation_class
+
+LOGGER = logging.getLogger(__name__)
+
+# Number of mapper chunks used during inference -- read at import like the reference (block.py:39).  The fused conv
+# has no E x D temporaries, so chunking changes neither memory nor results; the variable stays accepted.
+NUM_CHUNKS_INFERENCE = int(os.environ.get("ANEMOI_INFERENCE_NUM_CHUNKS", "1"))
+
+_halo_cache = TensorKeyedCache()
+
+
+def _group_active(group) -> bool:
+    return group is not None and bool(group) and dist.get_world_size(group=group) > 1
+
+
+class BaseBlock(nn.Module, ABC):
+    """Base class for network blocks (reference block.py:42-58)."""
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+
+    @abstractmethod
+    def forward(self, x, edge_attr, edge_index, shapes, batch_size, size=None, model_comm_group=None): ...
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GraphConv blocks
+# ------------------------------------------------------------------------------------------------------------
+class GraphConvBaseBlock(BaseBlock):
+    """Message passing block with MLPs for node embeddings (reference block.py:108-167)."""
+
+    def __init__(self, in_channels: int, out_channels: int, mlp_extra_layers: int = 0, activation: str = "SiLU",
+                 update_src_nodes: bool = True, num_chunks: int = 1, **kwargs) -> None:
+        super().__init__(**kwargs)
+        self.update_src_nodes = update_src_nodes
+        self.num_chunks = num_chunks
+        self.node_mlp = MLP(2 * in_channels, out_channels, out_channels, n_extra_layers=mlp_extra_layers, activation=activation)
+        self.conv = GraphConv(in_channels=in_channels, out_channels=out_channels, mlp_extra_layers=mlp_extra_layers,
+                              activation=activation)
+
+    def _conv(self, x_src: Tensor, x_dst: Tensor, edge_attr: Tensor, edge_index: Tensor, shapes_src, shapes_dst,
+              model_comm_group, size):
+        """out rows of THIS rank's dst shard and the updated edge features of this rank's edges.
+        (The reference's `num_chunks` loop over edge slices, block.py:205-215, only bounds the size of its [E,3D]
+        temporaries; the fused path has none, so one call gives the same sums.)"""
+        if not _group_active(model_comm_group):
+            single = x_src is x_dst
+            return self.conv(x_src if single else (x_src, x_dst), edge_attr, edge_index, size=size)
+        # sharded: x_src / x_dst are this rank's rows; edge_index holds this rank's 1-hop edges with GLOBAL ids
+        check_edge_index(edge_index)
+        sb, db = bounds_from_shapes(shapes_src), bounds_from_shapes(shapes_dst)
+        rank = dist.get_rank(group=model_comm_group)
+        plan: HaloPlan = _halo_cache.get(edge_index, ("local", tuple(sb), tuple(db), rank),
+                                         lambda: build_local_halo_plan(edge_index, sb, db, model_comm_group))
+        x_need = halo_gather(x_src, plan, model_comm_group)  # replaces sync_tensor's full all-gather (block.py:203)
+        return self.conv((x_need, x_dst), edge_attr, plan.local_edge_index, size=(plan.n_needed, plan.num_dst_local))
+
+    @abstractmethod
+    def forward(self, x, edge_attr, edge_index, shapes, model_comm_group=None, size=None): ...
+
+
+class GraphConvProcessorBlock(GraphConvBaseBlock):
+    """reference block.py:170-223"""
+
+    def forward(self, x: Tensor, edge_attr: Tensor, edge_index: Tensor, shapes: tuple, model_comm_group=None,
+                size: Optional[Tuple[int, int]] = None):
+        out, edges_new = self._conv(x, x, edge_attr, edge_index, shapes[1], shapes[1], model_comm_group, size)
+        nodes_new = self.node_mlp(torch.cat([x, out], dim=1)) + x
+        return nodes_new, edges_new
+
+
+class GraphConvMapperBlock(GraphConvBaseBlock):
+    """reference block.py:226-286"""
+
+    def forward(self, x: Tuple[Tensor, Tensor], edge_attr: Tensor, edge_index: Tensor, shapes: tuple,
+                model_comm_group=None, size: Optional[Tuple[int, int]] = None):
+        out, edges_new = self._conv(x[0], x[1], edge_attr, edge_index, shapes[0], shapes[1], model_comm_group, size)
+        nodes_new_dst = self.node_mlp(torch.cat([x[1], out], dim=1)) + x[1]
+        # update only needed in forward mapper
+        nodes_new_src = x[0] if not self.update_src_nodes else self.node_mlp(torch.cat([x[0], x[0]], dim=1)) + x[0]
+        return (nodes_new_src, nodes_new_dst), edges_new
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GraphTransformer blocks
+# ------------------------------------------------------------------------------------------------------------
+class GraphTransformerBaseBlock(BaseBlock, ABC):
+    """Message passing block with MLPs for node embeddings (reference block.py:289-426)."""
+
+    def __init__(self, in_channels: int, hidden_dim: int, out_channels: int, edge_dim: int, num_heads: int = 16,
+                 bias: bool = True, activation: str = "GELU", num_chunks: int = 1, update_src_nodes: bool = False,
+                 **kwargs) -> None:
+        super().__init__(**kwargs)
+        self.update_src_nodes = update_src_nodes
+        self.out_channels_conv = out_channels // num_heads
+        self.num_heads = num_heads
+        self.num_chunks = num_chunks
+
+        self.lin_key = nn.Linear(in_channels, num_heads * self.out_channels_conv)
+        self.lin_query = nn.Linear(in_channels, num_heads * self.out_channels_conv)
+        self.lin_value = nn.Linear(in_channels, num_heads * self.out_channels_conv)
+        self.lin_self = nn.Linear(in_channels, num_heads * self.out_channels_conv, bias=bias)
+        self.lin_edge = nn.Linear(edge_dim, num_heads * self.out_channels_conv)
+
+        self.conv = GraphTransformerConv(out_channels=self.out_channels_conv)
+        self.projection = nn.Linear(out_channels, out_channels)
+
+        act_func = activation_class(activation)
+        self.node_dst_mlp = nn.Sequential(nn.LayerNorm(out_channels), nn.Linear(out_channels, hidden_dim), act_func(),
+                                          nn.Linear(hidden_dim, out_channels))
+        self.layer_norm1 = nn.LayerNorm(in_channels)
+        if self.update_src_nodes:
+            self.node_src_mlp = nn.Sequential(nn.LayerNorm(out_channels), nn.Linear(out_channels, hidden_dim), act_func(),
+                                              nn.Linear(hidden_dim, out_channels))
+
+    # -- kept for API compatibility (reference block.py:366-414).  On one rank they are pure reshapes; with a group
+    #    the reference's head all-to-all is not used by this implementation (forward() shards by dst rows instead).
+    def shard_qkve_heads(self, query, key, value, edges, shapes, batch_size, model_comm_group=None):
+        if _group_active(model_comm_group):
+            raise NotImplementedError("head sharding is replaced by dst-row sharding with a halo exchange; call forward()")
+        H, C = self.num_heads, self.out_channels_conv
+        return tuple(t.reshape(t.shape[0], H, C) for t in (query, key, value, edges))
+
+    def shard_output_seq(self, out, shapes, batch_size, model_comm_group=None):
+        if _group_active(model_comm_group):
+            raise NotImplementedError("sequence re-sharding is not needed: the conv output is already dst-row sharded")
+        return out.reshape(out.shape[0], -1)
+
+    def _attend(self, query: Tensor, key: Tensor, value: Tensor, edge_attr: Tensor, edge_index: Tensor, shapes: tuple,
+                batch_size: int, model_comm_group, size) -> Tensor:
+        """conv output rows [(own dst rows), H*C] for projected q [Nd_r,D], k/v [Ns_r,D] and RAW edge_attr."""
+        H, C = self.num_heads, self.out_channels_conv
+        if not _group_active(model_comm_group):
+            edges = self.lin_edge(edge_attr)
+            q, k, v, e = self.shard_qkve_heads(query, key, value, edges, shapes, batch_size, model_comm_group)
+            out = self.conv(query=q, key=k, value=v, edge_attr=e, edge_index=edge_index, size=size)
+            return self.shard_output_seq(out, shapes, batch_size, model_comm_group)
+        assert batch_size == 1, "Only batch size of 1 is supported when model is sharded across GPUs"
+        check_edge_index(edge_index)
+        shapes_src, shapes_dst, shapes_edge = shapes
+        sb, db = bounds_from_shapes(shapes_src), bounds_from_shapes(shapes_dst)
+        rank = dist.get_rank(group=model_comm_group)
+        plan: HaloPlan = _halo_cache.get(edge_index, ("bipartite", tuple(sb), tuple(db), rank),
+                                         lambda: build_bipartite_halo_plan(edge_index, sb, db, rank))
+        # raw attributes of the edges this rank owns (they arrive sharded by original edge order), then project locally
+        ea_local = select_sharded_edges(edge_attr, shapes_edge, plan.edge_ids, model_comm_group)
+        e = self.lin_edge(ea_local).view(-1, H, C)
+        k_need = halo_gather(key, plan, model_comm_group).view(-1, H, C)
+        v_need = halo_gather(value, plan, model_comm_group).view(-1, H, C)
+        out = self.conv(query=query.view(-1, H, C), key=k_need, value=v_need, edge_attr=e, edge_index=plan.local_edge_index,
+                        size=(plan.n_needed, plan.num_dst_local))
+        return out.reshape(out.shape[0], H * C)
+
+    @abstractmethod
+    def forward(self, x, edge_attr, edge_index, shapes, batch_size, model_comm_group=None, size=None): ...
+
+
+class GraphTransformerMapperBlock(GraphTransformerBaseBlock):
+    """Graph Transformer Block for node embeddings, bipartite (reference block.py:429-550)."""
+
+    def __init__(self, in_channels: int, hidden_dim: int, out_channels: int, edge_dim: int, num_heads: int = 16,
+                 bias: bool = True, activation: str = "GELU", num_chunks: int = 1, update_src_nodes: bool = False,
+                 **kwargs) -> None:
+        super().__init__(in_channels=in_channels, hidden_dim=hidden_dim, out_channels=out_channels, edge_dim=edge_dim,
+                         num_heads=num_heads, bias=bias, activation=activation, num_chunks=num_chunks,
+                         update_src_nodes=update_src_nodes, **kwargs)
+        self.layer_norm2 = nn.LayerNorm(in_channels)
+
+    def forward(self, x: Tuple[Tensor, Tensor], edge_attr: Tensor, edge_index: Tensor, shapes: tuple, batch_size: int,
+                model_comm_group=None, size: Optional[Tuple[int, int]] = None):
+        x_skip = x
+        x = (self.layer_norm1(x[0]), self.layer_norm2(x[1]))
+        x_r = self.lin_self(x[1])
+        query = self.lin_query(x[1])
+        key = self.lin_key(x[0])
+        value = self.lin_value(x[0])
+
+        if model_comm_group is not None:
+            assert (model_comm_group.size() == 1 or batch_size == 1), \
+                "Only batch size of 1 is supported when model is sharded across GPUs"
+
+        out = self._attend(query, key, value, edge_attr, edge_index, shapes, batch_size, model_comm_group, size)
+
+        out = self.projection(out + x_r)
+        out = out + x_skip[1]
+        nodes_new_dst = self.node_dst_mlp(out) + out
+        nodes_new_src = self.node_src_mlp(x_skip[0]) + x_skip[0] if self.update_src_nodes else x_skip[0]
+        return (nodes_new_src, nodes_new_dst), edge_attr
+
+
+class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
+    """Graph Transformer Block for node embeddings, one node set (reference block.py:553-635)."""
+
+    def forward(self, x: Tensor, edge_attr: Tensor, edge_index: Tensor, shapes: tuple, batch_size: int,
+                model_comm_group=None, size: Optional[Tuple[int, int]] = None):
+        x_skip = x
+        x = self.layer_norm1(x)
+        x_r = self.lin_self(x)
+        query = self.lin_query(x)
+        key = self.lin_key(x)
+        value = self.lin_value(x)
+
+        if model_comm_group is not None:
+            assert (model_comm_group.size() == 1 or batch_size == 1), \
+                "Only batch size of 1 is supported when model is sharded across GPUs"
+
+        out = self._attend(query, key, value, edge_attr, edge_index, shapes, batch_size, model_comm_group, size)
+        out = self.projection(out + x_r)
+        out = out + x_skip
+        nodes_new = self.node_dst_mlp(out) + out
+        return nodes_new, edge_attr

@@ -1,0 +1,107 @@
+"""Drop-in `GraphTransformerConv` and `GraphConv` (reference layers/conv.py:27-142).
+
+Same constructor arguments, `forward` signatures, attribute names and state_dict keys as the reference; the
+edge path underneath is the fused CUDA path of libanemoi_b200 instead of PyG's gather -> elementwise ->
+softmax -> scatter sequence.  CUDA tensors only.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple, Union
+
+import torch
+from torch import Tensor, nn
+
+from .. import ops
+from ..graph import GraphCSR, check_edge_index, get_csr, resolve_size
+from .mlp import MLP, AutocastLayerNorm
+
+Size = Optional[Tuple[int, int]]
+
+_MP_KWARGS = {"aggr", "flow", "node_dim", "decomposed_layers", "aggr_kwargs"}
+
+
+def _check_mp_kwargs(kwargs: dict, default_aggr: str) -> None:
+    """The reference forwards **kwargs to PyG MessagePassing; accept the same names, support what the path uses."""
+    unknown = set(kwargs) - _MP_KWARGS
+    if unknown:
+        raise TypeError(f"unexpected keyword argument(s) {sorted(unknown)}")
+    if kwargs.get("aggr", default_aggr) not in ("add", "sum"):
+        raise NotImplementedError("only aggr='add' is implemented (the reference never uses another one)")
+    if kwargs.get("flow", "source_to_target") != "source_to_target":
+        raise NotImplementedError("only flow='source_to_target' is implemented")
+
+
+class GraphTransformerConv(nn.Module):
+    """Message passing part of the graph transformer operator (reference conv.py:79-142).
+
+    out_i = sum_{t=(j->i)} softmax_i((q_i . (k_j + e_t)) / sqrt(C))_t * (v_j + e_t)
+    """
+
+    def __init__(self, out_channels: int, dropout: float = 0.0, **kwargs) -> None:
+        _check_mp_kwargs(kwargs, "add")
+        super().__init__()
+        self.out_channels = out_channels
+        self.dropout = dropout
+        self.aggr, self.flow, self.node_dim = "add", "source_to_target", 0
+
+    def forward(self, query: Tensor, key: Tensor, value: Tensor, edge_attr: Optional[Tensor], edge_index: Tensor,
+                size: Size = None, plan: Optional[GraphCSR] = None) -> Tensor:
+        if edge_attr is None:
+            # the reference adds edge_attr unconditionally (conv.py:142) and fails with a TypeError
+            raise TypeError("unsupported operand type(s) for +: 'Tensor' and 'NoneType' (edge_attr is required)")
+        if self.dropout > 0.0 and self.training:
+            raise NotImplementedError("attention dropout > 0 is not implemented (no reference caller sets it, block.py:339)")
+        check_edge_index(edge_index)
+        n_src, n_dst = resolve_size(size, key.shape[0], query.shape[0])
+        if value.shape[0] != n_src:
+            raise ValueError(f"Encountered tensor with size {value.shape[0]} in dimension 0, but expected size {n_src}.")
+        if query.shape[2] != self.out_channels:
+            # the reference scales by self.out_channels**0.5 whatever the tensor width is; keep them consistent
+            raise ValueError(f"query has {query.shape[2]} channels per head but out_channels={self.out_channels}")
+        if plan is None:
+            plan = get_csr(edge_index, n_src, n_dst)
+        return ops.gt_conv(query, key, value, edge_attr, plan)
+
+
+class GraphConv(nn.Module):
+    """Message passing module for convolutional node and edge interactions (reference conv.py:27-76).
+
+    edges_new = edge_mlp(cat[x_i, x_j, e]) + e ;  out = scatter_sum(edges_new, dst).  Returns (out, edges_new).
+    The first Linear(3D -> D) is evaluated as x_i Wi^T + x_j Wj^T + e We^T: the node terms are computed once per node
+    and gathered inside a fused kernel, so the [E, 3D] concat is never materialised.
+    """
+
+    def __init__(self, in_channels: int, out_channels: int, mlp_extra_layers: int = 0, activation: str = "SiLU",
+                 **kwargs) -> None:
+        _check_mp_kwargs(kwargs, "add")
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.activation = activation
+        self.edge_mlp = MLP(3 * in_channels, out_channels, out_channels, n_extra_layers=mlp_extra_layers, activation=activation)
+        self.aggr, self.flow, self.node_dim = "add", "source_to_target", -2
+
+    def forward(self, x: Union[Tensor, Tuple[Tensor, Tensor]], edge_attr: Tensor, edge_index: Tensor, size: Size = None,
+                plan: Optional[GraphCSR] = None):
+        x_src, x_dst = (x, x) if isinstance(x, Tensor) else (x[0], x[1])
+        check_edge_index(edge_index)
+        n_src, n_dst = resolve_size(size, x_src.shape[0], x_dst.shape[0])
+        if plan is None:
+            plan = get_csr(edge_index, n_src, n_dst)
+        layers = list(self.edge_mlp.model)
+        lin0 = layers[0]
+        Din = self.in_channels
+        if self.activation not in ops.ACT_CODES or edge_attr.shape[1] != lin0.in_features - 2 * Din or \
+                not isinstance(layers[-1], AutocastLayerNorm) or edge_attr.shape[1] != layers[-1].normalized_shape[0]:
+            raise NotImplementedError("GraphConv: unsupported edge_mlp configuration for the fused path")
+        F = torch.nn.functional
+        W0 = lin0.weight
+        # split first layer: cat order is [x_i (dst), x_j (src), edge_attr]  (reference conv.py:69)
+        pi = F.linear(x_dst, W0[:, :Din], lin0.bias)
+        pj = F.linear(x_src, W0[:, Din:2 * Din])
+        pe = F.linear(edge_attr, W0[:, 2 * Din:])
+        h = ops.edge_gather_add_act(pi, pj, pe, plan, self.activation)
+        for layer in layers[2:-1]:  # (Linear, act) x (n_extra+1), Linear -- tensor-core GEMMs
+            h = layer(h)
+        ln = layers[-1]
+        edges_new, out = ops.edge_ln_res_segsum(h, edge_attr, ln.weight, ln.bias, ln.eps, plan)
+        return out, edges_new

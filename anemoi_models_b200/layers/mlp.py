@@ -1,0 +1,63 @@
+"""MLP with the reference's structure and state_dict keys (reference layers/mlp.py:22-89, layers/utils.py:27-39).
+
+Dense node/edge-side contractions stay `nn.Linear` (cuBLASLt tensor-core GEMMs); the conv modules fuse what
+surrounds them.
+"""
+from __future__ import annotations
+
+import logging
+
+import torch
+from torch import Tensor, nn
+from torch.utils.checkpoint import checkpoint
+
+LOGGER = logging.getLogger(__name__)
+
+
+class CheckpointWrapper(nn.Module):
+    """reference layers/utils.py:16-24"""
+
+    def __init__(self, module: nn.Module) -> None:
+        super().__init__()
+        self.module = module
+
+    def forward(self, *args, **kwargs):
+        return checkpoint(self.module, *args, **kwargs, use_reentrant=False)
+
+
+class AutocastLayerNorm(nn.LayerNorm):
+    """LayerNorm whose output is cast back to the input dtype (reference layers/utils.py:27-39)."""
+
+    def forward(self, x: Tensor) -> Tensor:
+        return super().forward(x).type_as(x)
+
+
+def activation_class(activation: str):
+    try:
+        return getattr(nn, activation)
+    except AttributeError as ae:
+        LOGGER.error("Activation function %s not supported", activation)
+        raise RuntimeError from ae
+
+
+class MLP(nn.Module):
+    """Linear, act, (Linear, act) x (n_extra_layers + 1), Linear, [act], [AutocastLayerNorm] -- reference mlp.py:74-84."""
+
+    def __init__(self, in_features: int, hidden_dim: int, out_features: int, n_extra_layers: int = 0,
+                 activation: str = "SiLU", final_activation: bool = False, layer_norm: bool = True,
+                 checkpoints: bool = False) -> None:
+        super().__init__()
+        act_func = activation_class(activation)
+        mlp1 = nn.Sequential(nn.Linear(in_features, hidden_dim), act_func())
+        for _ in range(n_extra_layers + 1):
+            mlp1.append(nn.Linear(hidden_dim, hidden_dim))
+            mlp1.append(act_func())
+        mlp1.append(nn.Linear(hidden_dim, out_features))
+        if final_activation:
+            mlp1.append(act_func())
+        if layer_norm:
+            mlp1.append(AutocastLayerNorm(out_features))
+        self.model = CheckpointWrapper(mlp1) if checkpoints else mlp1
+
+    def forward(self, x: Tensor) -> Tensor:
+        return self.model(x)

@@ -1,0 +1,223 @@
+"""autograd wrappers over the C ABI (include/anemoi_b200.h).
+
+Every Function is stateless per call, saves only tensors with `ctx.save_for_backward` (so non-reentrant
+activation checkpointing -- reference processor.py:76, encoder_processor_decoder.py:159-166 -- works), takes the
+CUDA stream of the *calling* thread (backward runs on autograd's worker thread), and fails loudly on CPU tensors:
+there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from .graph import GraphCSR
+
+ACT_CODES = {"SiLU": 0, "GELU": 1, "ReLU": 2, "Identity": 3}
+
+
+def _require_cuda(*tensors: Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("anemoi_models_b200 runs on CUDA tensors only (no CPU fallback); got a CPU tensor")
+
+
+def _common_dtype(*tensors: Tensor) -> torch.dtype:
+    dt = tensors[0].dtype
+    for t in tensors[1:]:
+        dt = torch.promote_types(dt, t.dtype)
+    if dt not in (torch.float32, torch.bfloat16):
+        if dt in (torch.float16,):
+            return torch.float32
+        raise TypeError(f"unsupported dtype {dt}: anemoi_models_b200 computes in float32 or bfloat16")
+    return dt
+
+
+class _GTConvFn(torch.autograd.Function):
+    """Fused GraphTransformerConv (reference layers/conv.py:98-142 + PyG softmax/scatter)."""
+
+    @staticmethod
+    def forward(ctx, q: Tensor, k: Tensor, v: Tensor, e: Tensor, plan: GraphCSR) -> Tensor:
+        L = _lib.lib()
+        Nd, H, C = q.shape
+        Ns = k.shape[0]
+        E = plan.num_edges
+        dt = _lib.dtype_code(q.dtype)
+        out = torch.empty_like(q)
+        lse2 = torch.empty((Nd, H), dtype=torch.float32, device=q.device)
+        with torch.cuda.device(q.device):
+            _lib.check(L.ab2_gtconv_fwd(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(e), dt, _lib.ptr(plan.rowptr),
+                                        _lib.ptr(plan.col), _lib.ptr(plan.perm), Ns, Nd, E, H, C, _lib.ptr(out),
+                                        _lib.ptr(lse2), _lib.current_stream(q.device)))
+        ctx.save_for_backward(q, k, v, e, out, lse2)
+        ctx.plan = plan
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        q, k, v, e, out, lse2 = ctx.saved_tensors
+        plan: GraphCSR = ctx.plan
+        L = _lib.lib()
+        Nd, H, C = q.shape
+        Ns = k.shape[0]
+        E = plan.num_edges
+        dt = _lib.dtype_code(q.dtype)
+        g = g.contiguous()
+        if g.dtype != q.dtype:
+            g = g.to(q.dtype)
+        need = ctx.needs_input_grad
+        dq = torch.empty_like(q) if need[0] else None
+        dk = torch.empty_like(k) if need[1] else None
+        dv = torch.empty_like(v) if need[2] else None
+        de = torch.empty_like(e) if need[3] else None
+        ws_bytes = L.ab2_gtconv_bwd_workspace_bytes(E, H)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device) if (need[1] or need[2]) else None
+        with torch.cuda.device(q.device):
+            _lib.check(L.ab2_gtconv_bwd(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(e), dt, _lib.ptr(plan.rowptr),
+                                        _lib.ptr(plan.col), _lib.ptr(plan.perm), _lib.ptr(plan.colptr), _lib.ptr(plan.cpos),
+                                        _lib.ptr(plan.crow), Ns, Nd, E, H, C, _lib.ptr(out), _lib.ptr(lse2), _lib.ptr(g),
+                                        _lib.ptr(dq), _lib.ptr(dk), _lib.ptr(dv), _lib.ptr(de), _lib.ptr(ws),
+                                        ws_bytes if ws is not None else 0, _lib.current_stream(q.device)))
+        return dq, dk, dv, de, None
+
+
+def gt_conv(query: Tensor, key: Tensor, value: Tensor, edge_attr: Tensor, plan: GraphCSR) -> Tensor:
+    """out[Nd,H,C] of the fused graph-transformer convolution; q [Nd,H,C], k/v [Ns,H,C], e [E,H,C] (original edge order)."""
+    _require_cuda(query, key, value, edge_attr)
+    if query.dim() != 3 or key.dim() != 3 or value.dim() != 3 or edge_attr.dim() != 3:
+        raise ValueError("query/key/value/edge_attr must be [N, heads, channels]")
+    if key.shape != value.shape or key.shape[1:] != query.shape[1:] or edge_attr.shape[1:] != query.shape[1:]:
+        raise ValueError(f"inconsistent shapes q{tuple(query.shape)} k{tuple(key.shape)} v{tuple(value.shape)} e{tuple(edge_attr.shape)}")
+    if edge_attr.shape[0] != plan.num_edges:
+        raise ValueError(f"edge_attr has {edge_attr.shape[0]} rows but edge_index has {plan.num_edges} edges")
+    if query.shape[0] != plan.num_dst or key.shape[0] != plan.num_src:
+        raise ValueError("node counts do not match the graph plan")
+    dt = _common_dtype(query, key, value, edge_attr)
+    q, k, v, e = (t.to(dt).contiguous() for t in (query, key, value, edge_attr))
+    return _GTConvFn.apply(q, k, v, e, plan)
+
+
+class _EdgeGatherAddActFn(torch.autograd.Function):
+    """h0[t] = act(pi[dst_t] + pj[src_t] + pe[t]) -- the first edge-MLP layer of GraphConv after splitting
+    Linear(3D->D) over cat[x_i, x_j, e] (reference conv.py:69, mlp.py:74) into node-side and edge-side terms."""
+
+    @staticmethod
+    def forward(ctx, pi: Tensor, pj: Tensor, pe: Tensor, plan: GraphCSR, act: int) -> Tensor:
+        L = _lib.lib()
+        E, D = pe.shape
+        dt = _lib.dtype_code(pe.dtype)
+        h0 = torch.empty_like(pe)
+        pre = torch.empty_like(pe)
+        with torch.cuda.device(pe.device):
+            _lib.check(L.ab2_edge_gather_add_act(_lib.ptr(pi), _lib.ptr(pj), _lib.ptr(pe), _lib.ptr(plan.edge_index), E,
+                                                 plan.num_src, plan.num_dst, D, dt, act, _lib.ptr(h0), _lib.ptr(pre),
+                                                 _lib.current_stream(pe.device)))
+        ctx.save_for_backward(pre)
+        ctx.plan, ctx.act = plan, act
+        return h0
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        (pre,) = ctx.saved_tensors
+        plan: GraphCSR = ctx.plan
+        L = _lib.lib()
+        E, D = pre.shape
+        dt = _lib.dtype_code(pre.dtype)
+        g = g.contiguous().to(pre.dtype)
+        gpe = torch.empty_like(pre)
+        dpi = torch.empty((plan.num_dst, D), dtype=pre.dtype, device=pre.device)
+        dpj = torch.empty((plan.num_src, D), dtype=pre.dtype, device=pre.device)
+        with torch.cuda.device(pre.device):
+            _lib.check(L.ab2_edge_gather_add_act_bwd(_lib.ptr(g), _lib.ptr(pre), _lib.ptr(plan.rowptr), _lib.ptr(plan.perm),
+                                                     _lib.ptr(plan.colptr), _lib.ptr(plan.cpos), E, plan.num_src, plan.num_dst,
+                                                     D, dt, ctx.act, _lib.ptr(gpe), _lib.ptr(dpi), _lib.ptr(dpj),
+                                                     _lib.current_stream(pre.device)))
+        return dpi, dpj, gpe, None, None
+
+
+def edge_gather_add_act(pi: Tensor, pj: Tensor, pe: Tensor, plan: GraphCSR, activation: str) -> Tensor:
+    _require_cuda(pi, pj, pe)
+    dt = _common_dtype(pi, pj, pe)
+    return _EdgeGatherAddActFn.apply(pi.to(dt).contiguous(), pj.to(dt).contiguous(), pe.to(dt).contiguous(), plan,
+                                     ACT_CODES[activation])
+
+
+class _EdgeLnResSegsumFn(torch.autograd.Function):
+    """edges_new = LayerNorm(y) + e ; out = segment-sum of edges_new over dst  (reference mlp.py:84 AutocastLayerNorm,
+    conv.py:69 residual, conv.py:74 scatter-sum) in one pass over the CSR."""
+
+    @staticmethod
+    def forward(ctx, y: Tensor, e: Tensor, gamma: Tensor, beta: Tensor, eps: float, plan: GraphCSR):
+        L = _lib.lib()
+        E, D = y.shape
+        dt = _lib.dtype_code(y.dtype)
+        edges_new = torch.empty_like(y)
+        out = torch.empty((plan.num_dst, D), dtype=y.dtype, device=y.device)
+        mean = torch.empty(E, dtype=torch.float32, device=y.device)
+        rstd = torch.empty(E, dtype=torch.float32, device=y.device)
+        with torch.cuda.device(y.device):
+            _lib.check(L.ab2_edge_ln_res_segsum(_lib.ptr(y), _lib.ptr(e), _lib.ptr(gamma), _lib.ptr(beta), eps,
+                                                _lib.ptr(plan.rowptr), _lib.ptr(plan.perm), E, plan.num_dst, D, dt,
+                                                _lib.ptr(edges_new), _lib.ptr(out), _lib.ptr(mean), _lib.ptr(rstd),
+                                                _lib.current_stream(y.device)))
+        ctx.save_for_backward(y, gamma, mean, rstd)
+        ctx.plan = plan
+        ctx.param_dtypes = (gamma.dtype, beta.dtype)
+        return edges_new, out
+
+    @staticmethod
+    def backward(ctx, g_edges: Optional[Tensor], g_out: Optional[Tensor]):
+        y, gamma, mean, rstd = ctx.saved_tensors
+        plan: GraphCSR = ctx.plan
+        L = _lib.lib()
+        E, D = y.shape
+        dt = _lib.dtype_code(y.dtype)
+        if g_out is None:
+            g_out = torch.zeros((plan.num_dst, D), dtype=y.dtype, device=y.device)
+        g_out = g_out.contiguous().to(y.dtype)
+        if g_edges is not None:
+            g_edges = g_edges.contiguous().to(y.dtype)
+        dy = torch.empty_like(y)
+        de = torch.empty_like(y)
+        nparts = L.ab2_ln_bwd_parts()
+        partial = torch.empty((nparts, 2, D), dtype=torch.float32, device=y.device)
+        dgamma = torch.empty(D, dtype=torch.float32, device=y.device)
+        dbeta = torch.empty(D, dtype=torch.float32, device=y.device)
+        with torch.cuda.device(y.device):
+            _lib.check(L.ab2_edge_ln_res_segsum_bwd(_lib.ptr(g_edges), _lib.ptr(g_out), _lib.ptr(y), _lib.ptr(gamma),
+                                                    _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(plan.edge_index), E, plan.num_dst,
+                                                    D, dt, _lib.ptr(dy), _lib.ptr(de), _lib.ptr(partial), nparts,
+                                                    _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.current_stream(y.device)))
+        return dy, de, dgamma.to(ctx.param_dtypes[0]), dbeta.to(ctx.param_dtypes[1]), None, None
+
+
+def edge_ln_res_segsum(y: Tensor, e: Tensor, gamma: Tensor, beta: Tensor, eps: float, plan: GraphCSR) -> Tuple[Tensor, Tensor]:
+    _require_cuda(y, e, gamma, beta)
+    dt = _common_dtype(y, e)
+    return _EdgeLnResSegsumFn.apply(y.to(dt).contiguous(), e.to(dt).contiguous(), gamma.to(dt).contiguous(),
+                                    beta.to(dt).contiguous(), float(eps), plan)
+
+
+def gt_conv_host(q: Tensor, k: Tensor, v: Tensor, e: Tensor, g: Tensor, plan: GraphCSR, dev_ws: Optional[Tensor] = None):
+    """GraphTransformerConv forward+backward on PINNED HOST tensors through `ab2_gtconv_fwd_bwd_host`
+    (the host-buffer C-ABI call).  Returns pinned host tensors (out, dq, dk, dv, de)."""
+    for t in (q, k, v, e, g):
+        if t.is_cuda or not t.is_pinned():
+            raise ValueError("gt_conv_host expects pinned host tensors")
+    L = _lib.lib()
+    Nd, H, C = q.shape
+    Ns, E = k.shape[0], e.shape[0]
+    dt = _lib.dtype_code(q.dtype)
+    need = L.ab2_gtconv_host_workspace_bytes(Ns, Nd, E, H, C, dt)
+    if dev_ws is None or dev_ws.numel() < need:
+        dev_ws = torch.empty(need, dtype=torch.uint8, device=plan.device)
+    outs = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (q, q, k, v, e)]
+    with torch.cuda.device(plan.device):
+        _lib.check(L.ab2_gtconv_fwd_bwd_host(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(e), _lib.ptr(g), dt,
+                                             _lib.ptr(plan.rowptr), _lib.ptr(plan.col), _lib.ptr(plan.perm),
+                                             _lib.ptr(plan.colptr), _lib.ptr(plan.cpos), _lib.ptr(plan.crow), Ns, Nd, E, H, C,
+                                             *[_lib.ptr(o) for o in outs], _lib.ptr(dev_ws), dev_ws.numel(),
+                                             _lib.current_stream(plan.device)))
+    return tuple(outs)

@@ -1,0 +1,146 @@
+/*
+ * anemoi_b200.h -- C ABI of libanemoi_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the graph message-passing hot path of ecmwf/anemoi-models.  The reference is pure
+ * Python (no FFI of its own); each entry point below names the reference interface it replaces
+ * (paths relative to src/anemoi/models/ of the reference tree).  The Python host side
+ * (anemoi_models_b200/) binds these with ctypes; INTEGRATION.md shows the stub a reference maintainer adds.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer on the current CUDA device unless the name ends in `_host`.
+ *   - The caller allocates every input, output and workspace; the library never allocates, frees or
+ *     retains device memory across calls.  (`*_host` entry points own a small internal staging pool.)
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden synchronisation,
+ *     except where a function's comment says it synchronises.
+ *   - Return value 0 = success; non-zero = ab2_status.  ab2_last_error() returns a thread-local message.
+ *   - Row-major, contiguous tensors.  dtype: AB2_F32 (fp32 in, fp32 out) or AB2_BF16 (bf16 in/out, fp32 math).
+ */
+#ifndef ANEMOI_B200_H
+#define ANEMOI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { AB2_F32 = 0, AB2_BF16 = 1 } ab2_dtype;
+
+typedef enum {
+  AB2_OK = 0,
+  AB2_ERR_INVALID = 1,     /* bad argument (shape, dtype, null pointer, workspace too small) */
+  AB2_ERR_UNSUPPORTED = 2, /* shape outside what the kernels cover */
+  AB2_ERR_CUDA = 3         /* a CUDA runtime call / launch failed */
+} ab2_status;
+
+/* Library version (major*10000 + minor*100 + patch). */
+int ab2_version(void);
+/* Thread-local description of the last non-zero status returned on this thread. */
+const char* ab2_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * dst-sorted CSR (+ src-sorted CSC view) of edge_index.
+ * Replaces: PyG MessagePassing._collect/_lift index_select by edge_index[0|1] and the scatter-by-index
+ * aggregate (called from layers/conv.py:64,110), i.e. the gather/scatter plan of every conv call.
+ * One-off per graph (edge_index is a constant buffer, layers/mapper.py:144-148).
+ *
+ * edge_index : int64 [2,E], row 0 = src (j), row 1 = dst (i)  (flow source_to_target)
+ * rowptr     : int32 [Nd+1]   segment offsets of each dst in the sorted order
+ * col        : int32 [E]      src id of sorted position p
+ * perm       : int32 [E]      original edge id of sorted position p  (STABLE: ascending within a dst)
+ * rowidx     : int32 [E]      dst id of sorted position p
+ * colptr     : int32 [Ns+1]   segment offsets of each src in the src-sorted order
+ * cpos       : int32 [E]      CSR position p of src-sorted position t (ascending within a src)
+ * crow       : int32 [E]      dst id of src-sorted position t
+ * flags      : int32 [4]      [0] = 1 if perm is the identity; [1] = number of edges with src/dst out of range
+ * Requires E, Ns, Nd < 2^31.  Result is bit-exact equal to torch.sort(edge_index[1], stable=True).
+ * ------------------------------------------------------------------------------------------------- */
+size_t ab2_csr_workspace_bytes(int64_t E, int64_t Ns, int64_t Nd);
+int ab2_csr_build(const int64_t* edge_index, int64_t E, int64_t Ns, int64_t Nd, int32_t* rowptr, int32_t* col,
+                  int32_t* perm, int32_t* rowidx, int32_t* colptr, int32_t* cpos, int32_t* crow, int32_t* flags,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stable partition of edges by dst chunk.
+ * Replaces: distributed/khop_edges.py:88-130 sort_edges_1hop_chunks / :50-85 sort_edges_1hop_sharding
+ * (PyG bipartite_subgraph / k_hop_subgraph masks).  chunk c owns dst rows [bounds_host[c], bounds_host[c+1]).
+ * bounds_host : HOST int64 [num_chunks+1]
+ * order       : int64 [E]  original edge ids, grouped by chunk, original order inside a chunk
+ * counts      : int64 [num_chunks] (device)
+ * Edges whose dst lies in no chunk are dropped (their slots at the tail of `order` stay untouched). */
+size_t ab2_edge_chunks_workspace_bytes(int64_t E);
+int ab2_edge_chunks(const int64_t* edge_index, int64_t E, const int64_t* bounds_host, int num_chunks, int64_t* order,
+                    int64_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * GraphTransformerConv forward.
+ * Replaces: layers/conv.py:98-142 GraphTransformerConv.forward/message + PyG propagate, utils.softmax and
+ * the "add" aggregate:  out_i = sum_t softmax_i(q_i.(k_j+e_t)/sqrt(C))_t * (v_j+e_t)  over edges t=(j->i).
+ *
+ * q [Nd,H,C]; k,v [Ns,H,C]; e [E,H,C] in ORIGINAL edge order (row perm[p] belongs to sorted position p);
+ * out [Nd,H,C]; lse2 [Nd,H] fp32 = log2(sum_t 2^(s_t*log2e) + 1e-16) (base-2 log-sum-exp, kept for backward).
+ * dst without incoming edges -> zero row (PyG scatter into zeros).
+ * ------------------------------------------------------------------------------------------------- */
+int ab2_gtconv_fwd(const void* q, const void* k, const void* v, const void* e, int dtype, const int32_t* rowptr,
+                   const int32_t* col, const int32_t* perm, int64_t Ns, int64_t Nd, int64_t E, int H, int C,
+                   void* out, float* lse2, void* stream);
+
+/* GraphTransformerConv backward (the autograd graph of the ops above in the reference).
+ * g = d(out) [Nd,H,C].  Writes dq [Nd,H,C], dk,dv [Ns,H,C], de [E,H,C] (original edge order); any of the four
+ * may be NULL to skip it.  workspace: ab2_gtconv_bwd_workspace_bytes(E,H) bytes (per-edge, per-head softmax
+ * weight and logit gradient, 8 B each).  Deterministic: no atomics. */
+size_t ab2_gtconv_bwd_workspace_bytes(int64_t E, int H);
+int ab2_gtconv_bwd(const void* q, const void* k, const void* v, const void* e, int dtype, const int32_t* rowptr,
+                   const int32_t* col, const int32_t* perm, const int32_t* colptr, const int32_t* cpos,
+                   const int32_t* crow, int64_t Ns, int64_t Nd, int64_t E, int H, int C, const void* out,
+                   const float* lse2, const void* g, void* dq, void* dk, void* dv, void* de, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * GraphConv edge path (layers/conv.py:61-76): the parts of
+ *   edges_new = edge_mlp(cat[x_i, x_j, e]) + e ;  out = scatter_sum(edges_new, dst)
+ * that are not plain GEMMs.  The first Linear(3D->D) is split as x_i Wi^T + x_j Wj^T + e We^T so the node
+ * terms are computed once per node (pi = x_dst Wi^T + b0 [Nd,D], pj = x_src Wj^T [Ns,D]).
+ * ------------------------------------------------------------------------------------------------- */
+/* h0[t] = act(pi[dst_t] + pj[src_t] + pe[t]) for every edge t (original order); pre[t] optionally keeps the
+ * pre-activation for backward.  act: 0 = SiLU, 1 = GELU(erf), 2 = ReLU, 3 = identity. */
+int ab2_edge_gather_add_act(const void* pi, const void* pj, const void* pe, const int64_t* edge_index, int64_t E,
+                            int64_t Ns, int64_t Nd, int D, int dtype, int act, void* h0, void* pre, void* stream);
+/* Backward of the above: gpre[t] = g[t]*act'(pre[t]) (written to gpe, original order);
+ * dpi[i] = sum over edges into i, dpj[j] = sum over edges out of j (CSR / CSC segment sums, deterministic). */
+int ab2_edge_gather_add_act_bwd(const void* g, const void* pre, const int32_t* rowptr, const int32_t* perm,
+                                const int32_t* colptr, const int32_t* cpos, int64_t E, int64_t Ns, int64_t Nd, int D,
+                                int dtype, int act, void* gpe, void* dpi, void* dpj, void* stream);
+/* edges_new[t] = LayerNorm(y[t]; gamma, beta, eps) + e[t];  out[i] = sum of edges_new over incoming edges.
+ * Also writes mean/rstd [E] fp32 for backward. */
+int ab2_edge_ln_res_segsum(const void* y, const void* e, const void* gamma, const void* beta, float eps,
+                           const int32_t* rowptr, const int32_t* perm, int64_t E, int64_t Nd, int D, int dtype,
+                           void* edges_new, void* out, float* mean, float* rstd, void* stream);
+/* Backward: gt[t] = g_edges[t] + g_out[dst_t];  de[t] = gt[t];  dy[t] = LN-backward(gt[t]);
+ * dgamma/dbeta [D] fp32 = column sums, reduced deterministically through `partial` ([nparts,2,D] fp32,
+ * nparts = ab2_ln_bwd_parts() CTAs each own a fixed slice of the edges). */
+int ab2_ln_bwd_parts(void);
+int ab2_edge_ln_res_segsum_bwd(const void* g_edges /* may be NULL */, const void* g_out, const void* y,
+                               const void* gamma, const float* mean, const float* rstd, const int64_t* edge_index,
+                               int64_t E, int64_t Nd, int D, int dtype, void* dy, void* de, float* partial,
+                               int nparts, float* dgamma, float* dbeta, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Host-buffer entry point (what a reference-side plugin with CPU tensors calls): one GraphTransformerConv
+ * forward+backward with q,k,v,e,g in PINNED HOST memory and out,dq,dk,dv,de written back to host memory.
+ * Device staging buffers are supplied by the caller (dev_ws, >= ab2_gtconv_host_workspace_bytes()).
+ * Copies are chunked and overlapped with the kernels on internal streams; the call returns after everything
+ * has landed in host memory (it synchronises).
+ * ------------------------------------------------------------------------------------------------- */
+size_t ab2_gtconv_host_workspace_bytes(int64_t Ns, int64_t Nd, int64_t E, int H, int C, int dtype);
+int ab2_gtconv_fwd_bwd_host(const void* q_host, const void* k_host, const void* v_host, const void* e_host,
+                            const void* g_host, int dtype, const int32_t* rowptr, const int32_t* col,
+                            const int32_t* perm, const int32_t* colptr, const int32_t* cpos, const int32_t* crow,
+                            int64_t Ns, int64_t Nd, int64_t E, int H, int C, void* out_host, void* dq_host,
+                            void* dk_host, void* dv_host, void* de_host, void* dev_ws, size_t dev_ws_bytes,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANEMOI_B200_H */

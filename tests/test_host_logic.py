@@ -1,0 +1,149 @@
+"""Host-side mirror of the reference interface: constructors, attribute / state_dict names, argument checking,
+shape bookkeeping, plan caching -- everything that does not need a GPU.  CPU tensors must be refused loudly."""
+import numpy as np
+import pytest
+import torch
+
+import anemoi_models_b200 as b2
+from anemoi_models_b200.distributed import shapes as b2shapes
+from anemoi_models_b200.graph import TensorKeyedCache, check_edge_index, resolve_size
+from conftest import load_golden, t
+
+
+def test_conv_constructor_and_attributes():
+    conv = b2.GraphTransformerConv(out_channels=16)
+    assert conv.out_channels == 16 and conv.dropout == 0.0
+    assert list(conv.state_dict()) == []
+    gc = b2.GraphConv(in_channels=8, out_channels=8, mlp_extra_layers=1)
+    keys = list(gc.state_dict())
+    assert keys[0] == "edge_mlp.model.0.weight" and gc.edge_mlp.model[0].in_features == 24
+    assert "edge_mlp.model.7.weight" in keys  # Linear,act,(Linear,act)x2,Linear,LayerNorm -> LN is index 7
+    with pytest.raises(TypeError):
+        b2.GraphTransformerConv(out_channels=4, bogus=1)
+    with pytest.raises(RuntimeError):
+        b2.GraphConv(4, 4, activation="NotAnActivation")
+
+
+@pytest.mark.parametrize("name,cls", [("block_gt_mapper.npz", "GraphTransformerMapperBlock"),
+                                      ("block_gt_processor.npz", "GraphTransformerProcessorBlock")])
+def test_gt_block_state_dict_names_match_reference(name, cls):
+    z = load_golden(name)
+    _, _, D, H, ed, hid = (int(x) for x in z["meta"])
+    blk = getattr(b2, cls)(in_channels=D, hidden_dim=hid, out_channels=D, edge_dim=ed, num_heads=H)
+    ref_keys = sorted(k[2:] for k in z if k.startswith("p."))
+    assert sorted(blk.state_dict()) == ref_keys
+    blk.load_state_dict({k[2:]: t(v) for k, v in z.items() if k.startswith("p.")})
+    # attributes the reference's tests assert on (tests/layers/block/test_block_graphtransformer.py:84-101)
+    assert blk.out_channels_conv == D // H and blk.num_heads == H and blk.num_chunks == 1
+    assert isinstance(blk.conv, b2.GraphTransformerConv) and isinstance(blk.lin_key, torch.nn.Linear)
+    q = torch.zeros(7, D)
+    qs, ks, vs, es = blk.shard_qkve_heads(q, q, q, q, None, 1)
+    assert qs.shape == (7, H, D // H)
+    assert blk.shard_output_seq(qs, None, 1).shape == (7, D)
+
+
+@pytest.mark.parametrize("name,cls", [("block_graphconv_processor.npz", "GraphConvProcessorBlock"),
+                                      ("block_graphconv_mapper.npz", "GraphConvMapperBlock")])
+def test_graphconv_block_state_dict_names_match_reference(name, cls):
+    z = load_golden(name)
+    D = int(z["meta"][-1])
+    blk = getattr(b2, cls)(in_channels=D, out_channels=D)
+    assert sorted(blk.state_dict()) == sorted(k[2:] for k in z if k.startswith("p."))
+    assert blk.update_src_nodes is True and blk.num_chunks == 1
+
+
+def test_unknown_activation_raises_runtime_error():
+    with pytest.raises(RuntimeError):
+        b2.GraphTransformerProcessorBlock(8, 16, 8, edge_dim=3, num_heads=2, activation="Nope")
+
+
+def test_edge_index_and_size_checks_like_pyg():
+    with pytest.raises(ValueError):
+        check_edge_index(torch.zeros(2, 3))  # float
+    with pytest.raises(ValueError):
+        check_edge_index(torch.zeros(3, 3, dtype=torch.long))
+    with pytest.raises(ValueError):
+        check_edge_index(torch.zeros(6, dtype=torch.long))
+    with pytest.raises(ValueError):
+        check_edge_index([[0], [1]])
+    assert resolve_size(None, 5, 3) == (5, 3)
+    assert resolve_size((None, 3), 5, 3) == (5, 3)
+    with pytest.raises(ValueError):
+        resolve_size((4, 3), 5, 3)
+    with pytest.raises(ValueError):
+        resolve_size((5, 2), 5, 3)
+
+
+def test_cpu_tensors_are_refused_loudly():
+    z = load_golden("gtconv_kat3.npz")
+    conv = b2.GraphTransformerConv(out_channels=2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        conv(t(z["q"]), t(z["k"]), t(z["v"]), t(z["e"]), t(z["edge_index"]), (2, 3))
+    with pytest.raises(TypeError):
+        conv(t(z["q"]), t(z["k"]), t(z["v"]), None, t(z["edge_index"]), (2, 3))
+    with pytest.raises(ValueError):
+        conv(t(z["q"]), t(z["k"]), t(z["v"]), t(z["e"]), t(z["edge_index"]), (7, 3))
+    gc = b2.GraphConv(4, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        gc(torch.zeros(3, 4), torch.zeros(2, 4), torch.tensor([[0, 1], [1, 2]]))
+
+
+def test_shape_shards_bit_exact():
+    z = load_golden("sharding.npz")
+    for key, (rows, P) in {"shards_10_3": (10, 3), "shards_40320_8": (40320, 8), "shards_7_8": (7, 8)}.items():
+        sizes = b2shapes.tensor_split_sizes(rows, P)
+        assert sizes == [int(s[0]) for s in z[key]]
+        assert sizes == [x.shape[0] for x in torch.tensor_split(torch.empty(rows), P)]
+    assert b2shapes.get_shape_shards(torch.empty(9, 4), 0, None) == [[9, 4]]
+    assert b2shapes.change_channels_in_shape([[5, 3], [4, 3]], 7) == [[5, 7], [4, 7]]
+    assert b2shapes.change_channels_in_shape([], 7) == []
+    assert b2shapes.bounds_from_shapes([[5, 3], [4, 3], [4, 3]]) == [0, 5, 9, 13]
+
+
+def test_tensor_keyed_cache_identity_content_and_version():
+    cache = TensorKeyedCache(maxsize=2)
+    built = []
+
+    def builder(tag):
+        def f():
+            built.append(tag)
+            return tag
+        return f
+
+    a = torch.tensor([[0, 1], [1, 0]])
+    assert cache.get(a, (2, 2), builder("A")) == "A"
+    assert cache.get(a, (2, 2), builder("A2")) == "A" and built == ["A"]          # identity hit
+    assert cache.get(a.clone(), (2, 2), builder("A3")) == "A" and built == ["A"]  # content hit
+    assert cache.get(a, (3, 2), builder("B")) == "B"                             # other sizes -> new plan
+    a[0, 0] = 1                                                                   # in-place edit bumps _version
+    assert cache.get(a, (2, 2), builder("C")) == "C"
+    assert built == ["A", "B", "C"]
+
+
+def test_install_rebinds_and_restores_reference_symbols():
+    import sys
+    import types
+
+    # a stand-in for the reference package layout (the real one is only present in the build container)
+    made = []
+    for name in ("anemoi", "anemoi.models", "anemoi.models.layers", "anemoi.models.layers.block",
+                 "anemoi.models.layers.conv", "anemoi.models.layers.mapper", "anemoi.models.layers.chunk"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+            made.append(name)
+    blockmod = sys.modules["anemoi.models.layers.block"]
+    sentinel = object()
+    old = getattr(blockmod, "GraphTransformerConv", None)
+    blockmod.GraphTransformerConv = sentinel
+    try:
+        b2.install()
+        assert blockmod.GraphTransformerConv is b2.GraphTransformerConv
+        b2.uninstall()
+        assert blockmod.GraphTransformerConv is sentinel
+    finally:
+        if old is None:
+            del blockmod.GraphTransformerConv
+        else:
+            blockmod.GraphTransformerConv = old
+        for name in made:
+            sys.modules.pop(name, None)
