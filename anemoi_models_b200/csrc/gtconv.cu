@@ -488,21 +488,20 @@ static void launch_fwd(const Plan& pl, const void* q, const void* k, const void*
                                                       Nd, pl.rm, H, qscale, (T*)out, lse2);
 }
 template <typename T, int LPH>
-static void launch_bwd(const Plan& pl, const void* q, const void* k, const void* v, const void* e, const int* rowptr,
-                       const int* col, const int* perm, const int* colptr, const int* cpos, const int* crow, int Ns, int Nd,
-                       int H, float qscale, float scale, const void* out, const float* lse2, const void* g, void* dq, void* dk,
-                       void* dv, void* de, float2* ads, cudaStream_t st) {
-  if (Nd > 0) {
-    dim3 grid((Nd + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
-    gtconv_bwd_dst_kernel<T, LPH><<<grid, kThreads, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (const T*)e, rowptr, col,
-                                                            perm, Nd, pl.rm, H, qscale, scale, (const T*)out, lse2,
-                                                            (const T*)g, (T*)dq, (T*)de, (dk || dv) ? ads : nullptr);
-  }
-  if ((dk || dv) && Ns > 0) {
-    dim3 grid((Ns + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
-    gtconv_bwd_src_kernel<T, LPH><<<grid, kThreads, 0, st>>>((const T*)q, (const T*)g, colptr, cpos, crow, ads, Ns, pl.rm, H,
-                                                            (T*)dk, (T*)dv);
-  }
+static void launch_bwd_dst(const Plan& pl, const void* q, const void* k, const void* v, const void* e, const int* rowptr,
+                           const int* col, const int* perm, int Nd, int H, float qscale, float scale, const void* out,
+                           const float* lse2, const void* g, void* dq, void* de, float2* ads, cudaStream_t st) {
+  dim3 grid((Nd + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
+  gtconv_bwd_dst_kernel<T, LPH><<<grid, kThreads, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (const T*)e, rowptr, col, perm,
+                                                          Nd, pl.rm, H, qscale, scale, (const T*)out, lse2, (const T*)g, (T*)dq,
+                                                          (T*)de, ads);
+}
+template <typename T, int LPH>
+static void launch_bwd_src(const Plan& pl, const void* q, const void* g, const int* colptr, const int* cpos, const int* crow,
+                           const float2* ads, int Ns, int H, void* dk, void* dv, cudaStream_t st) {
+  dim3 grid((Ns + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
+  gtconv_bwd_src_kernel<T, LPH><<<grid, kThreads, 0, st>>>((const T*)q, (const T*)g, colptr, cpos, crow, ads, Ns, pl.rm, H,
+                                                          (T*)dk, (T*)dv);
 }
 
 #define AB2_DISPATCH_LPH(T, lph, CALL)                                   \
@@ -562,26 +561,22 @@ extern "C" int ab2_gtconv_fwd(const void* q, const void* k, const void* v, const
 
 extern "C" size_t ab2_gtconv_bwd_workspace_bytes(int64_t E, int H) { return (size_t)(E > 0 ? E : 1) * (size_t)H * sizeof(float2); }
 
-extern "C" int ab2_gtconv_bwd(const void* q, const void* k, const void* v, const void* e, int dtype, const int32_t* rowptr,
-                              const int32_t* col, const int32_t* perm, const int32_t* colptr, const int32_t* cpos,
-                              const int32_t* crow, int64_t Ns, int64_t Nd, int64_t E, int H, int C, const void* out,
-                              const float* lse2, const void* g, void* dq, void* dk, void* dv, void* de, void* workspace,
-                              size_t workspace_bytes, void* stream) {
-  if (int rc = check_common("gtconv_bwd", dtype, Ns, Nd, E, H, C)) return rc;
-  const bool need_src = dk || dv;
-  if (!rowptr || (Nd > 0 && (!q || !out || !lse2 || !g)) || (E > 0 && (!k || !v || !e || !col || !perm)))
-    return fail(AB2_ERR_INVALID, "gtconv_bwd: null pointer argument");
-  if (need_src && (!colptr || (E > 0 && (!cpos || !crow)))) return fail(AB2_ERR_INVALID, "gtconv_bwd: dk/dv requested without the CSC view");
-  if (need_src && (!workspace || workspace_bytes < ab2_gtconv_bwd_workspace_bytes(E, H)))
-    return fail(AB2_ERR_INVALID, "gtconv_bwd: workspace too small");
+extern "C" int ab2_gtconv_bwd_dst(const void* q, const void* k, const void* v, const void* e, int dtype, const int32_t* rowptr,
+                                  const int32_t* col, const int32_t* perm, int64_t Ns, int64_t Nd, int64_t E, int H, int C,
+                                  const void* out, const float* lse2, const void* g, void* dq, void* de, void* ads_ws,
+                                  size_t ads_ws_bytes, void* stream) {
+  if (int rc = check_common("gtconv_bwd_dst", dtype, Ns, Nd, E, H, C)) return rc;
+  if (Nd == 0) return AB2_OK;
+  if (!rowptr || !q || !out || !lse2 || !g || (E > 0 && (!k || !v || !e || !col || !perm)))
+    return fail(AB2_ERR_INVALID, "gtconv_bwd_dst: null pointer argument");
+  if (ads_ws && ads_ws_bytes < ab2_gtconv_bwd_workspace_bytes(E, H)) return fail(AB2_ERR_INVALID, "gtconv_bwd_dst: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   const float scale = 1.f / sqrtf((float)C);
   const float qscale = kLog2e * scale;
-  float2* ads = (float2*)workspace;
+  float2* ads = (float2*)ads_ws;
   const Plan pl = make_plan(H, C, dtype == AB2_F32 ? 4 : 2);
   if (pl.vector) {
-#define CALL(T, L) \
-  launch_bwd<T, L>(pl, q, k, v, e, rowptr, col, perm, colptr, cpos, crow, (int)Ns, (int)Nd, H, qscale, scale, out, lse2, g, dq, dk, dv, de, ads, st)
+#define CALL(T, L) launch_bwd_dst<T, L>(pl, q, k, v, e, rowptr, col, perm, (int)Nd, H, qscale, scale, out, lse2, g, dq, de, ads, st)
     if (dtype == AB2_F32) {
       AB2_DISPATCH_LPH(float, pl.lph, CALL)
     } else {
@@ -590,29 +585,65 @@ extern "C" int ab2_gtconv_bwd(const void* q, const void* k, const void* v, const
 #undef CALL
   } else {
     const int wpb = kThreads / 32;
-    if (Nd > 0) {
-      const unsigned grid = (unsigned)(((long long)Nd * H + wpb - 1) / wpb);
-      if (dtype == AB2_F32)
-        gtconv_bwd_dst_generic_kernel<float><<<grid, kThreads, 0, st>>>(
-            (const float*)q, (const float*)k, (const float*)v, (const float*)e, rowptr, col, perm, (int)Nd, H, C, qscale, scale,
-            (const float*)out, lse2, (const float*)g, (float*)dq, (float*)de, need_src ? ads : nullptr);
-      else
-        gtconv_bwd_dst_generic_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>(
-            (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)e, rowptr, col, perm,
-            (int)Nd, H, C, qscale, scale, (const __nv_bfloat16*)out, lse2, (const __nv_bfloat16*)g, (__nv_bfloat16*)dq,
-            (__nv_bfloat16*)de, need_src ? ads : nullptr);
-    }
-    if (need_src && Ns > 0) {
-      const unsigned grid = (unsigned)(((long long)Ns * H + wpb - 1) / wpb);
-      if (dtype == AB2_F32)
-        gtconv_bwd_src_generic_kernel<float><<<grid, kThreads, 0, st>>>((const float*)q, (const float*)g, colptr, cpos, crow, ads,
-                                                                       (int)Ns, H, C, (float*)dk, (float*)dv);
-      else
-        gtconv_bwd_src_generic_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)g,
-                                                                               colptr, cpos, crow, ads, (int)Ns, H, C,
-                                                                               (__nv_bfloat16*)dk, (__nv_bfloat16*)dv);
-    }
+    const unsigned grid = (unsigned)(((long long)Nd * H + wpb - 1) / wpb);
+    if (dtype == AB2_F32)
+      gtconv_bwd_dst_generic_kernel<float><<<grid, kThreads, 0, st>>>(
+          (const float*)q, (const float*)k, (const float*)v, (const float*)e, rowptr, col, perm, (int)Nd, H, C, qscale, scale,
+          (const float*)out, lse2, (const float*)g, (float*)dq, (float*)de, ads);
+    else
+      gtconv_bwd_dst_generic_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>(
+          (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)e, rowptr, col, perm,
+          (int)Nd, H, C, qscale, scale, (const __nv_bfloat16*)out, lse2, (const __nv_bfloat16*)g, (__nv_bfloat16*)dq,
+          (__nv_bfloat16*)de, ads);
   }
-  AB2_LAUNCH_OK("gtconv_bwd");
+  AB2_LAUNCH_OK("gtconv_bwd_dst");
   return AB2_OK;
+}
+
+extern "C" int ab2_gtconv_bwd_src(const void* q, const void* g, int dtype, const int32_t* colptr, const int32_t* cpos,
+                                  const int32_t* crow, int64_t Ns, int64_t Nd, int64_t E, int H, int C, const void* ads_ws,
+                                  void* dk, void* dv, void* stream) {
+  if (int rc = check_common("gtconv_bwd_src", dtype, Ns, Nd, E, H, C)) return rc;
+  if (Ns == 0 || (!dk && !dv)) return AB2_OK;
+  if (!colptr || !ads_ws || (E > 0 && (!q || !g || !cpos || !crow))) return fail(AB2_ERR_INVALID, "gtconv_bwd_src: null pointer argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float2* ads = (const float2*)ads_ws;
+  const Plan pl = make_plan(H, C, dtype == AB2_F32 ? 4 : 2);
+  if (pl.vector) {
+#define CALL(T, L) launch_bwd_src<T, L>(pl, q, g, colptr, cpos, crow, ads, (int)Ns, H, dk, dv, st)
+    if (dtype == AB2_F32) {
+      AB2_DISPATCH_LPH(float, pl.lph, CALL)
+    } else {
+      AB2_DISPATCH_LPH(__nv_bfloat16, pl.lph, CALL)
+    }
+#undef CALL
+  } else {
+    const int wpb = kThreads / 32;
+    const unsigned grid = (unsigned)(((long long)Ns * H + wpb - 1) / wpb);
+    if (dtype == AB2_F32)
+      gtconv_bwd_src_generic_kernel<float><<<grid, kThreads, 0, st>>>((const float*)q, (const float*)g, colptr, cpos, crow, ads,
+                                                                     (int)Ns, H, C, (float*)dk, (float*)dv);
+    else
+      gtconv_bwd_src_generic_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)g,
+                                                                             colptr, cpos, crow, ads, (int)Ns, H, C,
+                                                                             (__nv_bfloat16*)dk, (__nv_bfloat16*)dv);
+  }
+  AB2_LAUNCH_OK("gtconv_bwd_src");
+  return AB2_OK;
+}
+
+extern "C" int ab2_gtconv_bwd(const void* q, const void* k, const void* v, const void* e, int dtype, const int32_t* rowptr,
+                              const int32_t* col, const int32_t* perm, const int32_t* colptr, const int32_t* cpos,
+                              const int32_t* crow, int64_t Ns, int64_t Nd, int64_t E, int H, int C, const void* out,
+                              const float* lse2, const void* g, void* dq, void* dk, void* dv, void* de, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  const bool need_src = dk || dv;
+  if (need_src && (!workspace || workspace_bytes < ab2_gtconv_bwd_workspace_bytes(E, H)))
+    return fail(AB2_ERR_INVALID, "gtconv_bwd: workspace too small");
+  if (need_src && (!colptr || (E > 0 && (!cpos || !crow)))) return fail(AB2_ERR_INVALID, "gtconv_bwd: dk/dv requested without the CSC view");
+  if (int rc = ab2_gtconv_bwd_dst(q, k, v, e, dtype, rowptr, col, perm, Ns, Nd, E, H, C, out, lse2, g, dq, de,
+                                  need_src ? workspace : nullptr, workspace_bytes, stream))
+    return rc;
+  if (!need_src) return AB2_OK;
+  return ab2_gtconv_bwd_src(q, g, dtype, colptr, cpos, crow, Ns, Nd, E, H, C, workspace, dk, dv, stream);
 }

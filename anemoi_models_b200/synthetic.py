@@ -1,0 +1,111 @@
+"""Deterministic synthetic grids and edge sets for benchmarks and full-size tests (SURVEY.md 8d recipes).
+
+The reference ships no graph builder (graphs come from anemoi-graphs as `sub_graph`), so the named shapes are
+re-created by closed-form recipes: octahedral reduced Gaussian grids `oN`, a Fibonacci sphere standing in for
+`n320`, encoder edges by cut-off radius (0.6 x the largest nearest-neighbour distance of the dst grid, the
+anemoi-graphs default), k-nearest-neighbour edges for decoders / processors.  Host-side numpy/scipy, one-off.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+
+
+def octahedral_rows(N: int):
+    """(latitudes[2N] north->south in radians, points per row[2N]) of the octahedral reduced Gaussian grid oN."""
+    x, _ = np.polynomial.legendre.leggauss(2 * N)
+    lat = np.arcsin(x)[::-1]  # north -> south
+    r = np.arange(2 * N)
+    r = np.minimum(r, 2 * N - 1 - r)  # row index counted from the nearer pole
+    return lat, 20 + 4 * r
+
+
+def octahedral_grid(N: int, row_lo: int = 0, row_hi: Optional[int] = None) -> Tuple[np.ndarray, int]:
+    """xyz of rows [row_lo, row_hi) of oN (points ordered north->south, west->east) and the global index of the
+    first returned point.  o48: 10,944 points, o96: 40,320, o1280: 6,599,680."""
+    lat, npts = octahedral_rows(N)
+    row_hi = 2 * N if row_hi is None else row_hi
+    first = int(npts[:row_lo].sum())
+    lats = np.repeat(lat[row_lo:row_hi], npts[row_lo:row_hi])
+    lons = np.concatenate([np.arange(n) * (2 * np.pi / n) for n in npts[row_lo:row_hi]]) if row_hi > row_lo else np.zeros(0)
+    return latlon_to_xyz(lats, lons), first
+
+
+def octahedral_size(N: int) -> int:
+    return 4 * N * N + 36 * N
+
+
+def fibonacci_sphere(M: int, lo: int = 0, hi: Optional[int] = None) -> np.ndarray:
+    """xyz of points [lo, hi) of an M-point Fibonacci sphere, ordered north->south (index order = latitude order)."""
+    hi = M if hi is None else hi
+    i = np.arange(lo, hi, dtype=np.float64)
+    z = 1.0 - (2.0 * i + 1.0) / M
+    phi = i * (np.pi * (3.0 - np.sqrt(5.0)))
+    rxy = np.sqrt(np.maximum(0.0, 1.0 - z * z))
+    return np.stack([rxy * np.cos(phi), rxy * np.sin(phi), z], axis=1)
+
+
+def latlon_to_xyz(lat: np.ndarray, lon: np.ndarray) -> np.ndarray:
+    return np.stack([np.cos(lat) * np.cos(lon), np.cos(lat) * np.sin(lon), np.sin(lat)], axis=1)
+
+
+def max_nn_distance(xyz: np.ndarray) -> float:
+    from scipy.spatial import cKDTree
+
+    d, _ = cKDTree(xyz).query(xyz, k=2, workers=-1)
+    return float(d[:, 1].max())
+
+
+def cutoff_edges(src_xyz: np.ndarray, dst_xyz: np.ndarray, radius: float, src_offset: int = 0, dst_offset: int = 0) -> np.ndarray:
+    """edge_index [2,E] int64: every src within chord distance `radius` of a dst; grouped by dst ascending,
+    src ascending inside a dst."""
+    from scipy.spatial import cKDTree
+
+    tree = cKDTree(src_xyz)
+    nbrs = tree.query_ball_point(dst_xyz, radius, return_sorted=True, workers=-1)
+    counts = np.fromiter((len(n) for n in nbrs), dtype=np.int64, count=len(nbrs))
+    src = np.concatenate([np.asarray(n, dtype=np.int64) for n in nbrs]) if counts.sum() else np.zeros(0, np.int64)
+    dst = np.repeat(np.arange(len(nbrs), dtype=np.int64), counts)
+    return np.stack([src + src_offset, dst + dst_offset])
+
+
+def knn_edges(src_xyz: np.ndarray, dst_xyz: np.ndarray, k: int, exclude_self: bool = False) -> np.ndarray:
+    """edge_index [2,E]: the k nearest src of every dst (decoder: k=3; processor: k=8 without self loops)."""
+    from scipy.spatial import cKDTree
+
+    kk = k + 1 if exclude_self else k
+    _, idx = cKDTree(src_xyz).query(dst_xyz, k=kk, workers=-1)
+    idx = idx.reshape(len(dst_xyz), kk)
+    if exclude_self:
+        idx = idx[:, 1:]
+    dst = np.repeat(np.arange(len(dst_xyz), dtype=np.int64), k)
+    return np.stack([idx.reshape(-1).astype(np.int64), dst])
+
+
+def encoder_graph(src_points: int, dst_N: int, cutoff: float = 0.6):
+    """Whole `fibonacci(src_points) -> o<dst_N>` cut-off encoder graph (headline: 542,080 -> o96)."""
+    dst_xyz, _ = octahedral_grid(dst_N)
+    radius = cutoff * max_nn_distance(dst_xyz)
+    ei = cutoff_edges(fibonacci_sphere(src_points), dst_xyz, radius)
+    return ei, src_points, len(dst_xyz), radius
+
+
+def encoder_graph_band(src_points: int, dst_N: int, parts: int, part: int, cutoff: float = 0.6):
+    """Edges (GLOBAL node ids) whose dst lies in shard `part` of `tensor_split(arange(Nd), parts)` -- what one rank
+    of a dst-sharded run owns.  Only the src points of the matching latitude band are generated."""
+    from .distributed.shapes import tensor_split_sizes
+
+    dst_xyz, _ = octahedral_grid(dst_N)
+    nd = len(dst_xyz)
+    radius = cutoff * max_nn_distance(dst_xyz)
+    sizes = tensor_split_sizes(nd, parts)
+    lo = sum(sizes[:part])
+    hi = lo + sizes[part]
+    band = dst_xyz[lo:hi]
+    # Fibonacci index range covering the band's z range plus the cut-off radius
+    zmax, zmin = band[:, 2].max() + radius, band[:, 2].min() - radius
+    i_lo = max(0, int(np.floor((1.0 - zmax) * src_points / 2.0)) - 1)
+    i_hi = min(src_points, int(np.ceil((1.0 - zmin) * src_points / 2.0)) + 1)
+    ei = cutoff_edges(fibonacci_sphere(src_points, i_lo, i_hi), band, radius, src_offset=i_lo, dst_offset=lo)
+    return ei, src_points, nd, radius

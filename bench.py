@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- GT-conv edges/s, forward+backward, on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU op sequence (oracle port) on host cores
+
+A "step" = one GraphTransformerConv forward + backward (conv boundary, reference layers/conv.py:98) over one
+synthetic graph.  N=1: BASELINE configs[1] -- GT mapper encoder n320 (542,080 pts, Fibonacci sphere) -> o96 (40,320),
+hidden 1024, 16 heads, bf16, cut-off-0.6 edges (E = 748,256).  N>1 (weak scaling, one process per GPU): the same graph
+family at N x the node counts (Fibonacci N*542,080 -> o<N'> with ~N*40,320 points), dst rows sharded by tensor_split
+like the model's shard shapes, each rank owning the edges into its rows; every step exchanges the halo of k/v rows
+(NCCL all-to-all over NVLink) before the forward and returns the halo gradients after the backward.
+
+One JSON line on stdout (rank 0).  `value` = edges/s with inputs resident in HBM; `e2e` = the same step through the
+host-buffer C-ABI entry point (pinned host tensors in, H2D/D2H copies inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, C = 16, 64
+D = H * C
+SRC_POINTS, DST_N = 542080, 96
+METRIC, UNIT = "gt_conv_fwd_bwd_edges_per_s", "edges/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def dst_N_for(parts: int) -> int:
+    """octahedral resolution whose point count is closest to parts * 40,320 (o96 for parts = 1)."""
+    target = parts * (4 * DST_N * DST_N + 36 * DST_N)
+    n = int(round((-36 + (36 * 36 + 16 * target) ** 0.5) / 8))
+    return n
+
+
+def workload_name(parts: int) -> str:
+    if parts == 1:
+        return "GT mapper encoder conv n320(542080, Fibonacci) -> o96(40320), cut-off 0.6, D=1024, H=16, bf16 fwd+bwd"
+    return (f"same graph family at {parts}x area: Fibonacci({parts * SRC_POINTS}) -> o{dst_N_for(parts)}, dst-row sharded over "
+            f"{parts} ranks with k/v halo exchange, D=1024, H=16, bf16 fwd+bwd")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed regions run."""
+
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+               0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, device_index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.nv = pynvml
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:  # NVML missing: report that instead of inventing numbers
+            self.nv, self.err = None, repr(exc)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join()
+            self._thread = None
+
+    def summary(self):
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": self.err}
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------------------------------------------
+def build_shard(parts: int, part: int):
+    """edge_index (GLOBAL ids) of the edges into shard `part`, plus global sizes and shard bounds."""
+    from anemoi_models_b200 import synthetic as S
+    from anemoi_models_b200.distributed.shapes import tensor_split_sizes
+
+    ns = parts * SRC_POINTS
+    ei, ns, nd, radius = S.encoder_graph_band(ns, dst_N_for(parts), parts, part)
+    sb = np.concatenate([[0], np.cumsum(tensor_split_sizes(ns, parts))]).tolist()
+    db = np.concatenate([[0], np.cumsum(tensor_split_sizes(nd, parts))]).tolist()
+    return ei, ns, nd, sb, db
+
+
+def algorithmic_bytes(E, Ns, Nd, b=2):
+    """Compulsory HBM traffic, each tensor touched once per kernel (DESIGN.md 'roofline accounting')."""
+    idx_fwd = 4 * (2 * E + Nd + 1)  # col + perm + rowptr
+    fwd = b * (E * D + 2 * Ns * D + 2 * Nd * D) + idx_fwd + 4 * Nd * H
+    bwd_dst = b * (2 * E * D + 2 * Ns * D + 4 * Nd * D) + idx_fwd + 4 * Nd * H + 8 * E * H
+    bwd_src = b * (2 * Ns * D + 2 * Nd * D) + 8 * E * H + 4 * (2 * E + Ns + 1)
+    # SURVEY 8d / BASELINE.md step figure (the north_star target is quoted on this one; it does not count the small
+    # [E,H] softmax-weight workspace or the second read of q and g by the src pass)
+    step = b * (3 * E * D + 6 * Ns * D + 6 * Nd * D) + 8 * (E + Nd + 1) + 8 * Nd * H
+    return {"fwd": fwd, "bwd_dst": bwd_dst, "bwd_src": bwd_src, "step_survey": step}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    import anemoi_models_b200 as b2
+    from anemoi_models_b200 import _lib, ops
+    from anemoi_models_b200.distributed.halo import build_local_halo_plan, halo_gather
+    from anemoi_models_b200.graph import GraphCSR
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    L = _lib.lib()
+    ei_np, Ns_g, Nd_g, sb, db = build_shard(world, rank)
+    ei_glob = torch.from_numpy(ei_np).to(dev)
+    E = ei_glob.shape[1]
+    torch.manual_seed(1234 + rank)
+    bf = torch.bfloat16
+    nd_loc, ns_loc = db[rank + 1] - db[rank], sb[rank + 1] - sb[rank]
+    q = torch.randn(nd_loc, H, C, device=dev, dtype=bf)
+    g = torch.randn(nd_loc, H, C, device=dev, dtype=bf)
+    e = torch.randn(E, H, C, device=dev, dtype=bf)
+    k_own = torch.randn(ns_loc, H, C, device=dev, dtype=bf)
+    v_own = torch.randn(ns_loc, H, C, device=dev, dtype=bf)
+
+    if world > 1:
+        hplan = build_local_halo_plan(ei_glob, sb, db, group)
+        ei_loc = hplan.local_edge_index
+        n_src = hplan.n_needed
+    else:
+        hplan, ei_loc, n_src = None, ei_glob, Ns_g
+    plan = GraphCSR(ei_loc, n_src, nd_loc)
+    conv = b2.GraphTransformerConv(out_channels=C)
+
+    def step():
+        """one forward + backward of the conv boundary; returns nothing (grads land in .grad buffers)"""
+        qq, ee = q.detach().requires_grad_(True), e.detach().requires_grad_(True)
+        kk, vv = k_own.detach().requires_grad_(True), v_own.detach().requires_grad_(True)
+        if world > 1:
+            kn, vn = halo_gather(kk, hplan, group), halo_gather(vv, hplan, group)
+        else:
+            kn, vn = kk, vv
+        out = conv(qq, kn, vn, ee, ei_loc, (n_src, nd_loc), plan=plan)
+        out.backward(g)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with sampler:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            step()
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    tmax = torch.tensor([ms], device=dev, dtype=torch.float64)
+    etot = torch.tensor([float(E)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(etot, op=dist.ReduceOp.SUM)
+    ms_per_step = float(tmax) / args.steps
+    value = float(etot) / (ms_per_step * 1e-3)
+
+    # ---- per-kernel durations (CUDA events on the launching stream, rank 0's shard) -> roofline of the dominant kernel
+    st = torch.cuda.current_stream(dev).cuda_stream
+    out = torch.empty_like(q)
+    lse2 = torch.empty(nd_loc, H, device=dev, dtype=torch.float32)
+    kn = torch.randn(n_src, H, C, device=dev, dtype=bf) if world > 1 else k_own
+    vn = torch.randn(n_src, H, C, device=dev, dtype=bf) if world > 1 else v_own
+    dq, de, dk, dv = torch.empty_like(q), torch.empty_like(e), torch.empty_like(kn), torch.empty_like(vn)
+    ws_bytes = L.ab2_gtconv_bwd_workspace_bytes(E, H)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    P = _lib.ptr
+    kreps = 20
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(kreps)]
+
+    def kernels(ev=None):
+        if ev: ev[0].record()
+        _lib.check(L.ab2_gtconv_fwd(P(q), P(kn), P(vn), P(e), 1, P(plan.rowptr), P(plan.col), P(plan.perm), n_src, nd_loc, E, H, C,
+                                    P(out), P(lse2), st))
+        if ev: ev[1].record()
+        _lib.check(L.ab2_gtconv_bwd_dst(P(q), P(kn), P(vn), P(e), 1, P(plan.rowptr), P(plan.col), P(plan.perm), n_src, nd_loc, E,
+                                        H, C, P(out), P(lse2), P(g), P(dq), P(de), P(ws), ws_bytes, st))
+        if ev: ev[2].record()
+        _lib.check(L.ab2_gtconv_bwd_src(P(q), P(g), 1, P(plan.colptr), P(plan.cpos), P(plan.crow), n_src, nd_loc, E, H, C, P(ws),
+                                        P(dk), P(dv), st))
+        if ev: ev[3].record()
+
+    for _ in range(3):
+        kernels()
+    torch.cuda.synchronize()
+    with sampler:
+        for r in range(kreps):
+            kernels(evs[r])
+        torch.cuda.synchronize()
+    kt = {name: float(np.mean([evs[r][i].elapsed_time(evs[r][i + 1]) for r in range(kreps)]))
+          for i, name in enumerate(("fwd", "bwd_dst", "bwd_src"))}
+    ab = algorithmic_bytes(E, n_src, nd_loc)
+    peak, peak_src = peaks()
+    dom = max(kt, key=kt.get)
+    achieved = ab[dom] / (kt[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": f"gtconv_{dom}_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ab[dom], "launch_ms": round(kt[dom], 4)}
+    kern = {n: {"ms": round(kt[n], 4), "algorithmic_GB": round(ab[n] / 1e9, 3), "GBps": round(ab[n] / (kt[n] * 1e-3) / 1e9, 1),
+                "frac_of_peak": round(ab[n] / (kt[n] * 1e-3) / 1e9 / peak, 4)} for n in kt}
+    t_kernels = sum(kt.values())
+    step_gbps = ab["step_survey"] / (t_kernels * 1e-3) / 1e9
+
+    # ---- e2e: the same step through the host-buffer C-ABI call (pinned host tensors in and out), rank-local
+    e2e = None
+    if world == 1:
+        host = [x.cpu().pin_memory() for x in (q, k_own, v_own, e, g)]
+        need = L.ab2_gtconv_host_workspace_bytes(n_src, nd_loc, E, H, C, 1)
+        dev_ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        outs = [torch.empty(x.shape, dtype=x.dtype, pin_memory=True) for x in (q, q, k_own, v_own, e)]
+
+        def host_step():
+            _lib.check(L.ab2_gtconv_fwd_bwd_host(*[P(x) for x in host], 1, P(plan.rowptr), P(plan.col), P(plan.perm),
+                                                 P(plan.colptr), P(plan.cpos), P(plan.crow), n_src, nd_loc, E, H, C,
+                                                 *[P(o) for o in outs], P(dev_ws), need, st))
+
+        host_step()
+        torch.cuda.synchronize()
+        n_e2e = max(1, min(args.steps, args.e2e_steps))
+        with sampler:
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                host_step()  # synchronises internally: results are in host memory when it returns
+            t1 = time.perf_counter()
+        e2e_ms = (t1 - t0) * 1e3 / n_e2e
+        e2e = {"value": E / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": round(e2e_ms, 3), "steps": n_e2e,
+               "h2d_bytes_per_step": int(sum(x.numel() * x.element_size() for x in host)),
+               "d2h_bytes_per_step": int(sum(x.numel() * x.element_size() for x in outs)),
+               "api": "ab2_gtconv_fwd_bwd_host (pinned host q,k,v,e,g in; out,dq,dk,dv,de back to host)"}
+        del host, outs, dev_ws
+
+    # ---- CPU baseline: the reference's op sequence (oracle port) on this box's host cores, bounded sample
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_reference_sample(ei_np, Ns_g, Nd_g, steps=2, warmup=1)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": workload_name(world), "edges_total": int(float(etot)), "edges_rank0": int(E),
+                       "src_rows_rank0": int(n_src), "dst_rows_rank0": int(nd_loc), "hidden": D, "heads": H,
+                       "l2": "inputs (>5 GB per step) exceed the 126 MB L2; no flush between steps",
+                       "timed_region": "conv forward + backward (+ halo all-to-all of k,v and its backward when n_gpus>1); CSR build excluded (one-off, cached)"},
+            "clocks": sampler.summary(),
+            "e2e": e2e if e2e is not None else {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                                                 "note": "host-buffer arm is measured at n_gpus=1"},
+            "gpu_launches": 3 * args.steps,
+            "roofline": roofline,
+            "roofline_step": {"achieved": round(step_gbps, 1), "peak": peak, "unit": "GB/s", "frac": round(step_gbps / peak, 4),
+                              "bytes": ab["step_survey"], "kernel_ms_sum": round(t_kernels, 4),
+                              "note": "SURVEY 8d algorithmic bytes of fwd+bwd over the sum of the three kernel durations"},
+            "kernels": kern,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's unfused op sequence (oracle port of conv.py + PyG) on host cores
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(ei_np, Ns, Nd, steps, warmup, frac=8):
+    """fp32, all host threads, on a contiguous 1/`frac` dst subset of the same graph (src rows compacted)."""
+    from oracle import gtconv as og
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    nd_s = Nd // frac
+    keep = ei_np[1] < nd_s
+    sub = ei_np[:, keep]
+    needed, inv = np.unique(sub[0], return_inverse=True)
+    ei = torch.from_numpy(np.stack([inv.astype(np.int64), sub[1]]))
+    ns_s, E = len(needed), ei.shape[1]
+    gen = torch.Generator().manual_seed(0)
+    q = torch.randn(nd_s, H, C, generator=gen)
+    k = torch.randn(ns_s, H, C, generator=gen)
+    v = torch.randn(ns_s, H, C, generator=gen)
+    e = torch.randn(E, H, C, generator=gen)
+    g = torch.randn(nd_s, H, C, generator=gen)
+    for _ in range(warmup):
+        og.gt_conv_unfused_fwd_bwd(q, k, v, e, ei, g, (ns_s, nd_s))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        og.gt_conv_unfused_fwd_bwd(q, k, v, e, ei, g, (ns_s, nd_s))
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": E / dt, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": round(dt * 1e3, 2),
+            "sample": f"contiguous 1/{frac} dst subset of the headline graph ({E} edges, {ns_s} src, {nd_s} dst), fp32, "
+                      f"{steps} timed fwd+bwd after {warmup} warm-up; oracle/gtconv.py gt_conv_unfused = reference conv.py:98-142 + PyG op sequence on torch CPU"}
+
+
+def run_reference(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from anemoi_models_b200 import synthetic as S
+
+    ei_np, Ns, Nd, _ = S.encoder_graph(SRC_POINTS, DST_N)
+    res = cpu_reference_sample(ei_np, Ns, Nd, steps=max(1, min(args.steps, 5)), warmup=max(1, min(args.warmup, 2)))
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": max(1, min(args.steps, 5)), "warmup": max(1, min(args.warmup, 2)), "ms_per_step": res["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(1), "note": "each step = bounded sample: 1/8 dst subset on host cores"},
+            "cpu_baseline": res,
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -90,6 +90,16 @@ int ab2_gtconv_fwd(const void* q, const void* k, const void* v, const void* e, i
  * may be NULL to skip it.  workspace: ab2_gtconv_bwd_workspace_bytes(E,H) bytes (per-edge, per-head softmax
  * weight and logit gradient, 8 B each).  Deterministic: no atomics. */
 size_t ab2_gtconv_bwd_workspace_bytes(int64_t E, int H);
+/* The two passes of the backward, callable on their own (ab2_gtconv_bwd = dst pass, then src pass):
+ *   dst pass (per dst segment): dq, de and the per-(edge, head) pair (softmax weight, logit gradient / sqrt(C)) -> ads_ws;
+ *   src pass (per src segment of the CSC view): dk_j = sum ds * q_i, dv_j = sum a * g_i  read from ads_ws. */
+int ab2_gtconv_bwd_dst(const void* q, const void* k, const void* v, const void* e, int dtype, const int32_t* rowptr,
+                       const int32_t* col, const int32_t* perm, int64_t Ns, int64_t Nd, int64_t E, int H, int C,
+                       const void* out, const float* lse2, const void* g, void* dq, void* de, void* ads_ws,
+                       size_t ads_ws_bytes, void* stream);
+int ab2_gtconv_bwd_src(const void* q, const void* g, int dtype, const int32_t* colptr, const int32_t* cpos,
+                       const int32_t* crow, int64_t Ns, int64_t Nd, int64_t E, int H, int C, const void* ads_ws, void* dk,
+                       void* dv, void* stream);
 int ab2_gtconv_bwd(const void* q, const void* k, const void* v, const void* e, int dtype, const int32_t* rowptr,
                    const int32_t* col, const int32_t* perm, const int32_t* colptr, const int32_t* cpos,
                    const int32_t* crow, int64_t Ns, int64_t Nd, int64_t E, int H, int C, const void* out,
