@@ -1,0 +1,312 @@
+"""world_size-2 (and 3) CPU tests over gloo of the multi-GPU host logic: shard/gather/sync duals, the halo plan and
+exchange, the edge-attribute selection, and the dst-row-sharded blocks end to end.
+
+The CUDA conv cannot run here, so the sharded-block tests swap the conv call for the CPU oracle (test
+infrastructure) -- what is under test is the partitioning, the exchange and the gradient routing.  Parity contract
+(SURVEY.md 8c): (1) concatenated per-rank outputs == single-rank output; (2) sum over ranks of weight grads ==
+single-rank weight grads; (3) grads of sharded inputs == the matching slices of the single-rank grads;
+(4) integer partition == the reference's sort_edges_1hop_chunks.
+"""
+import os
+import socket
+import sys
+import traceback
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, load_golden, t
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, fn_name, q):
+    try:
+        for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle", "pyg_shim")):
+            if p not in sys.path:
+                sys.path.insert(0, p)
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        torch.set_num_threads(1)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        globals()[fn_name](rank, world)
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, None))
+    except Exception:  # pragma: no cover - surfaced in the parent
+        q.put((rank, traceback.format_exc()))
+
+
+def run_distributed(fn_name, world=2):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, fn_name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    errs = [f"rank {r}:\n{e}" for r, e in results if e]
+    assert not errs, "\n".join(errs)
+
+
+# ------------------------------------------------------------------------------------------------------------
+def _collectives(rank, world):
+    from anemoi_models_b200.distributed import (gather_tensor, get_shape_shards, reduce_shard_tensor, reduce_tensor,
+                                                shard_tensor, sync_tensor)
+
+    group = dist.group.WORLD
+    torch.manual_seed(0)
+    full = torch.randn(7, 3)  # uneven shards: 4 + 3 (world 2) / 3 + 2 + 2 (world 3)
+    shapes = get_shape_shards(full, 0, group)
+    assert shapes == [list(x.shape) for x in torch.tensor_split(full, world, dim=0)]
+    bounds = np.cumsum([0] + [s[0] for s in shapes])
+    mine = slice(bounds[rank], bounds[rank + 1])
+
+    x = full.clone().requires_grad_(True)
+    y = shard_tensor(x, 0, shapes, group)
+    assert torch.equal(y, full[mine])
+    (y * (rank + 1)).sum().backward()  # backward all-gathers: every rank sees the complete gradient
+    expect = torch.cat([torch.full((s[0], 3), float(r + 1)) for r, s in enumerate(shapes)])
+    assert torch.equal(x.grad, expect)
+
+    x = full.clone().requires_grad_(True)
+    y = shard_tensor(x, 0, shapes, group, gather_in_backward=False)
+    y.sum().backward()
+    assert torch.equal(x.grad[mine], torch.ones_like(full[mine])) and float(x.grad.sum()) == full[mine].numel()
+
+    xs = full[mine].clone().requires_grad_(True)
+    y = gather_tensor(xs, 0, shapes, group)
+    assert torch.equal(y, full)
+    (y * torch.arange(7.0).view(-1, 1)).sum().backward()
+    assert torch.equal(xs.grad, torch.arange(7.0).view(-1, 1).expand(7, 3)[mine])
+
+    xs = full[mine].clone().requires_grad_(True)
+    y = sync_tensor(xs, 0, shapes, group)
+    assert torch.equal(y, full)
+    (y * (rank + 1)).sum().backward()  # backward: sum over ranks, own slice
+    assert torch.allclose(xs.grad, torch.full_like(xs, float(sum(range(1, world + 1)))))
+
+    x = (full * (rank + 1)).requires_grad_(True)
+    y = reduce_tensor(x, group)
+    assert torch.allclose(y, full * sum(range(1, world + 1)))
+    y.sum().backward()
+    assert torch.equal(x.grad, torch.ones_like(full))
+
+    x = (full * (rank + 1)).requires_grad_(True)
+    y = reduce_shard_tensor(x, 0, shapes, group)
+    assert torch.allclose(y, full[mine] * sum(range(1, world + 1)))
+    (y * (rank + 1)).sum().backward()
+    assert torch.equal(x.grad, expect)
+    # along another dim and bf16 payloads
+    fb = torch.randn(3, 5).bfloat16()
+    sh = get_shape_shards(fb, 1, group)
+    b1 = np.cumsum([0] + [s[1] for s in sh])
+    part = fb[:, b1[rank]:b1[rank + 1]].contiguous()
+    assert torch.equal(gather_tensor(part, 1, sh, group), fb)
+    # identity without a group
+    assert shard_tensor(full, 0, shapes, None) is full and sync_tensor(full, 0, shapes, None) is full
+
+
+def test_collectives_world2():
+    run_distributed("_collectives", 2)
+
+
+def test_collectives_world3():
+    run_distributed("_collectives", 3)
+
+
+# ------------------------------------------------------------------------------------------------------------
+def _halo(rank, world):
+    from anemoi_models_b200.distributed.halo import (build_bipartite_halo_plan, build_local_halo_plan, halo_gather,
+                                                     select_sharded_edges)
+    from anemoi_models_b200.distributed.shapes import bounds_from_shapes, get_shape_shards
+    from oracle import sharding as osh
+
+    group = dist.group.WORLD
+    z = load_golden("sharding.npz")
+    ns, nd, _ = (int(x) for x in z["meta"])
+    ei_np = z["bip_edge_index"]
+    ei = t(ei_np)
+    E = ei.shape[1]
+    sb = bounds_from_shapes(get_shape_shards(torch.empty(ns, 1), 0, group))
+    db = bounds_from_shapes(get_shape_shards(torch.empty(nd, 1), 0, group))
+    plan = build_bipartite_halo_plan(ei, sb, db, rank)
+    ref = osh.halo_plan(ei_np, ns, nd, world)[rank]
+    # (4) integer contract: own edges == chunk `rank` of the reference partition (golden from the reference itself)
+    counts = z[f"bip_counts_P{world}"] if f"bip_counts_P{world}" in z else None
+    assert np.array_equal(plan.edge_ids.numpy(), ref["edge_ids"])
+    if counts is not None:
+        off = int(counts[:rank].sum())
+        assert np.array_equal(plan.edge_ids.numpy(), z[f"bip_ids_P{world}"][off:off + int(counts[rank])])
+    assert plan.n_needed == len(ref["needed_src"])
+    assert plan.recv_counts == [len(ref["recv_from"][p]) for p in range(world)]
+    needed = torch.from_numpy(ref["needed_src"])
+    assert torch.equal(needed[plan.local_edge_index[0]], ei[0, plan.edge_ids])
+    assert torch.equal(plan.local_edge_index[1] + db[rank], ei[1, plan.edge_ids])
+
+    # exchange: forward picks exactly the needed rows of the (virtual) full tensor
+    torch.manual_seed(1)
+    x_full = torch.randn(ns, 6)
+    xs = x_full[sb[rank]:sb[rank + 1]].clone().requires_grad_(True)
+    got = halo_gather(xs, plan, group)
+    assert torch.equal(got, x_full[needed])
+    # backward: d x_full[j] = sum over ranks of the cotangents of row j
+    w = torch.randn(plan.n_needed, 6, generator=torch.Generator().manual_seed(10 + rank))
+    (got * w).sum().backward()
+    dense = torch.zeros(ns, 6)
+    dense[needed] = w
+    dist.all_reduce(dense)
+    assert torch.allclose(xs.grad, dense[sb[rank]:sb[rank + 1]], atol=1e-6)
+
+    # the plan built from LOCAL edges only (GraphConv path) gives the same exchange
+    plan2 = build_local_halo_plan(ei[:, plan.edge_ids], sb, db, group)
+    assert plan2.n_needed == plan.n_needed and plan2.recv_counts == plan.recv_counts and plan2.send_counts == plan.send_counts
+    assert torch.equal(plan2.send_idx, plan.send_idx) and torch.equal(plan2.local_edge_index, plan.local_edge_index)
+
+    # raw edge attributes sharded by original order -> rows of own edges; backward returns the shard's gradient
+    ea_full = torch.randn(E, 4, generator=torch.Generator().manual_seed(5))
+    shapes_e = get_shape_shards(ea_full, 0, group)
+    eb = bounds_from_shapes(shapes_e)
+    ea = ea_full[eb[rank]:eb[rank + 1]].clone().requires_grad_(True)
+    sel = select_sharded_edges(ea, shapes_e, plan.edge_ids, group)
+    assert torch.equal(sel, ea_full[plan.edge_ids])
+    (sel * (rank + 2.0)).sum().backward()
+    owner_of_edge = torch.from_numpy(np.searchsorted(np.array(db), ei_np[1], side="right") - 1)
+    expect = (owner_of_edge.float() + 2.0).view(-1, 1).expand(E, 4)
+    assert torch.allclose(ea.grad, expect[eb[rank]:eb[rank + 1]])
+
+
+def test_halo_world2():
+    run_distributed("_halo", 2)
+
+
+def test_halo_world3():
+    run_distributed("_halo", 3)
+
+
+# ------------------------------------------------------------------------------------------------------------
+class _CpuPlan:
+    def __init__(self, edge_index, ns, nd):
+        self.edge_index, self.num_src, self.num_dst, self.num_edges = edge_index, ns, nd, edge_index.shape[1]
+
+
+def _patch_conv_with_oracle():
+    """CPU stand-in for the CUDA conv entry points (tests only)."""
+    import anemoi_models_b200.layers.conv as convmod
+    from anemoi_models_b200 import ops
+    from oracle import gtconv as og
+
+    convmod.get_csr = lambda ei, ns, nd: _CpuPlan(ei, ns, nd)
+    ops.gt_conv = lambda q, k, v, e, plan: og.gt_conv_unfused(q, k, v, e, plan.edge_index, (plan.num_src, plan.num_dst))
+
+    def graphconv_forward(self, x, edge_attr, edge_index, size=None, plan=None):
+        p = dict(self.named_parameters())
+        return og.graph_conv_unfused(x, edge_attr, edge_index, {"edge_mlp." + k[len("edge_mlp."):]: v for k, v in p.items()},
+                                     "edge_mlp.", size=size)
+
+    convmod.GraphConv.forward = graphconv_forward
+
+
+def _sharded_gt_blocks(rank, world):
+    import anemoi_models_b200 as b2
+    from anemoi_models_b200.distributed.shapes import bounds_from_shapes, get_shape_shards
+    from oracle import blocks as oblocks
+
+    _patch_conv_with_oracle()
+    group = dist.group.WORLD
+    for fixture, kind in (("block_gt_mapper.npz", "mapper"), ("block_gt_processor.npz", "processor")):
+        z = load_golden(fixture)
+        ns, nd, D, H, ed, hid = (int(x) for x in z["meta"])
+        params = {k[2:]: t(v) for k, v in z.items() if k.startswith("p.")}
+        ei = t(z["edge_index"])
+        E = ei.shape[1]
+        ea_full = t(z["ea"])
+        gd = t(z["gd"])
+        cls = b2.GraphTransformerMapperBlock if kind == "mapper" else b2.GraphTransformerProcessorBlock
+        blk = cls(D, hid, D, edge_dim=ed, num_heads=H)
+        blk.load_state_dict(params)
+        sh_src = get_shape_shards(torch.empty(ns, D), 0, group)
+        sh_dst = get_shape_shards(torch.empty(nd, D), 0, group)
+        sh_e = get_shape_shards(ea_full, 0, group)
+        sb, db, eb = bounds_from_shapes(sh_src), bounds_from_shapes(sh_dst), bounds_from_shapes(sh_e)
+        ea = ea_full[eb[rank]:eb[rank + 1]].clone().requires_grad_(True)
+        if kind == "mapper":
+            xs = t(z["xs"])[sb[rank]:sb[rank + 1]].clone().requires_grad_(True)
+            xd = t(z["xd"])[db[rank]:db[rank + 1]].clone().requires_grad_(True)
+            (src_new, dst_new), ea_out = blk((xs, xd), ea, ei, (sh_src, sh_dst, sh_e), 1, group, size=(ns, nd))
+            ref_out, ref_dx = t(z["dst_new"]), {"xs": t(z["dxs"]), "xd": t(z["dxd"])}
+            assert src_new is xs
+        else:
+            xd = t(z["x"])[db[rank]:db[rank + 1]].clone().requires_grad_(True)
+            dst_new, ea_out = blk(xd, ea, ei, (sh_dst, sh_dst, sh_e), 1, group)
+            ref_out, ref_dx = t(z["nodes_new"]), {"xd": t(z["dx"])}
+        assert ea_out is ea
+        # (1) outputs: own dst rows of the single-rank reference result
+        assert torch.allclose(dst_new, ref_out[db[rank]:db[rank + 1]], atol=2e-6), float((dst_new - ref_out[db[rank]:db[rank + 1]]).abs().max())
+        (dst_new * gd[db[rank]:db[rank + 1]]).sum().backward()
+        # (3) input grads: slices of the single-rank grads
+        assert torch.allclose(xd.grad, ref_dx["xd"][db[rank]:db[rank + 1]], atol=5e-6)
+        if kind == "mapper":
+            assert torch.allclose(xs.grad, ref_dx["xs"][sb[rank]:sb[rank + 1]], atol=5e-6)
+        assert torch.allclose(ea.grad, t(z["dea"])[eb[rank]:eb[rank + 1]], atol=5e-6)
+        # (2) weight grads are per-rank partial sums (the trainer reduces them): their sum is the single-rank grad
+        for name, p in blk.named_parameters():
+            gsum = p.grad.clone() if p.grad is not None else torch.zeros_like(p)
+            dist.all_reduce(gsum)
+            ref = t(z["gp." + name])
+            assert torch.allclose(gsum, ref, atol=2e-5 * max(1.0, float(ref.abs().max()))), name
+
+
+def test_sharded_gt_blocks_world2():
+    run_distributed("_sharded_gt_blocks", 2)
+
+
+def test_sharded_gt_blocks_world3():
+    run_distributed("_sharded_gt_blocks", 3)
+
+
+def _sharded_graphconv_block(rank, world):
+    import anemoi_models_b200 as b2
+    from anemoi_models_b200.distributed.shapes import bounds_from_shapes, get_shape_shards
+    from oracle import sharding as osh
+
+    _patch_conv_with_oracle()
+    group = dist.group.WORLD
+    z = load_golden("block_graphconv_processor.npz")
+    n, D = (int(x) for x in z["meta"])
+    params = {k[2:]: t(v) for k, v in z.items() if k.startswith("p.")}
+    ei = t(z["edge_index"])
+    blk = b2.GraphConvProcessorBlock(D, D)
+    blk.load_state_dict(params)
+    sh = get_shape_shards(torch.empty(n, D), 0, group)
+    nb = bounds_from_shapes(sh)
+    # what the reference's GNNProcessor does before the blocks (processor.py:239-246): partition edges by dst owner
+    ids = torch.from_numpy(osh.edges_1hop_chunks(n, ei.numpy(), world)[rank])
+    x = t(z["x"])[nb[rank]:nb[rank + 1]].clone().requires_grad_(True)
+    e = t(z["e"])[ids].clone().requires_grad_(True)
+    nodes_new, edges_new = blk(x, e, ei[:, ids], (sh, sh, None), group)
+    assert torch.allclose(nodes_new, t(z["nodes_new"])[nb[rank]:nb[rank + 1]], atol=2e-6)
+    assert torch.allclose(edges_new, t(z["edges_new"])[ids], atol=2e-6)
+    ((nodes_new * t(z["gd"])[nb[rank]:nb[rank + 1]]).sum() + (edges_new * t(z["ge"])[ids]).sum()).backward()
+    assert torch.allclose(x.grad, t(z["dx"])[nb[rank]:nb[rank + 1]], atol=5e-6)
+    assert torch.allclose(e.grad, t(z["de"])[ids], atol=5e-6)
+    for name, p in blk.named_parameters():
+        gsum = p.grad.clone()
+        dist.all_reduce(gsum)
+        ref = t(z["gp." + name])
+        assert torch.allclose(gsum, ref, atol=2e-5 * max(1.0, float(ref.abs().max()))), name
+
+
+def test_sharded_graphconv_block_world2():
+    run_distributed("_sharded_graphconv_block", 2)
