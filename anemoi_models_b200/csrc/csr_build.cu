@@ -259,8 +259,13 @@ __global__ void finalize_csr_kernel(const int64_t* __restrict__ src_row, const i
   }
 }
 
-__global__ void finalize_csc_kernel(const int* __restrict__ cpos, const int* __restrict__ rowidx, int n, int* __restrict__ crow) {
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) crow[t] = rowidx[cpos[t]];
+__global__ void finalize_csc_kernel(const int* __restrict__ cpos, const int* __restrict__ rowidx, int n, int* __restrict__ crow,
+                                    int* __restrict__ csr2csc) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int p = cpos[t];
+    crow[t] = rowidx[p];
+    if (csr2csc) csr2csc[p] = t;  // inverse permutation of cpos
+  }
 }
 
 __global__ void init_flags_kernel(int* flags) {
@@ -357,8 +362,8 @@ extern "C" size_t ab2_csr_workspace_bytes(int64_t E, int64_t Ns, int64_t Nd) {
 }
 
 extern "C" int ab2_csr_build(const int64_t* edge_index, int64_t E, int64_t Ns, int64_t Nd, int32_t* rowptr, int32_t* col,
-                             int32_t* perm, int32_t* rowidx, int32_t* colptr, int32_t* cpos, int32_t* crow, int32_t* flags,
-                             void* workspace, size_t workspace_bytes, void* stream) {
+                             int32_t* perm, int32_t* rowidx, int32_t* colptr, int32_t* cpos, int32_t* crow, int32_t* csr2csc,
+                             int32_t* flags, void* workspace, size_t workspace_bytes, void* stream) {
   if (E < 0 || Ns < 0 || Nd < 0 || E >= INT_MAX || Ns >= INT_MAX || Nd >= INT_MAX)
     return fail(AB2_ERR_UNSUPPORTED, "csr_build: E, Ns, Nd must be in [0, 2^31-1) (got %lld, %lld, %lld)", (long long)E, (long long)Ns, (long long)Nd);
   if (!rowptr || !flags || !workspace || (E > 0 && (!edge_index || !col || !perm || !rowidx)))
@@ -388,7 +393,7 @@ extern "C" int ab2_csr_build(const int64_t* edge_index, int64_t E, int64_t Ns, i
     if (int rc = stable_sort_by_key<int32_t>(col, E, (int)Ns, nullptr, 0, colptr, cpos, flags + 2, w, st)) return rc;
     if (E > 0) {
       const int grid = (int)std::min<int64_t>((E + 255) / 256, (int64_t)sms * 16);
-      finalize_csc_kernel<<<grid, 256, 0, st>>>(cpos, rowidx, (int)E, crow);
+      finalize_csc_kernel<<<grid, 256, 0, st>>>(cpos, rowidx, (int)E, crow, csr2csc);
       AB2_LAUNCH_OK("finalize_csc_kernel");
     }
   }

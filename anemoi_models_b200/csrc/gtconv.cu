@@ -136,9 +136,10 @@ gtconv_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __r
 template <typename T, int LPH>
 __global__ void __launch_bounds__(kThreads)
 gtconv_bwd_dst_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ e,
-                      const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm, int Nd,
-                      RowMap rm, int H, float qscale, float scale, const T* __restrict__ out, const float* __restrict__ lse2,
-                      const T* __restrict__ g, T* __restrict__ dq, T* __restrict__ de, float2* __restrict__ ads) {
+                      const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm,
+                      const int* __restrict__ csr2csc, int Nd, RowMap rm, int H, float qscale, float scale,
+                      const T* __restrict__ out, const float* __restrict__ lse2, const T* __restrict__ g, T* __restrict__ dq,
+                      T* __restrict__ de, float2* __restrict__ ads) {
   constexpr int VEC = Vec<T>::N;
   const int lr = threadIdx.x / rm.tpd;
   const int d = blockIdx.x * rm.rpb + lr;
@@ -167,18 +168,20 @@ gtconv_bwd_dst_kernel(const T* __restrict__ q, const T* __restrict__ k, const T*
   for (int i = 0; i < VEC; ++i) dqa[i] = 0.f;
 
   const int beg = rowptr[d], end = rowptr[d + 1];
-  int jn[kU], tn[kU];
+  int jn[kU], tn[kU], cn[kU];
 #pragma unroll
   for (int u = 0; u < kU; ++u) {
     jn[u] = beg + u < end ? col[beg + u] : 0;
     tn[u] = beg + u < end ? perm[beg + u] : 0;
+    cn[u] = (ads && beg + u < end) ? csr2csc[beg + u] : 0;
   }
   for (int p = beg; p < end; p += kU) {
     uint4 kr[kU], er[kU], vr[kU];
-    size_t ts[kU];
+    size_t ts[kU], cs[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       ts[u] = (size_t)tn[u];
+      cs[u] = (size_t)cn[u];
       if (p + u < end) {
         const size_t j = (size_t)jn[u];
         kr[u] = ldg16_keep(k + j * D + off);
@@ -193,6 +196,7 @@ gtconv_bwd_dst_kernel(const T* __restrict__ q, const T* __restrict__ k, const T*
       const int pn = p + kU + u;
       jn[u] = pn < end ? col[pn] : 0;
       tn[u] = pn < end ? perm[pn] : 0;
+      cn[u] = (ads && pn < end) ? csr2csc[pn] : 0;
     }
     float s[kU], gv[kU];
 #pragma unroll
@@ -231,7 +235,7 @@ gtconv_bwd_dst_kernel(const T* __restrict__ q, const T* __restrict__ k, const T*
           for (int i = 0; i < VEC; ++i) o[i] = fmaf(a, gf[i], dss * qf[i]);
           stg16(de + ts[u] * D + off, pack<T>(o));
         }
-        if (ads && leader) ads[(size_t)(p + u) * H + h] = make_float2(a, dss);
+        if (ads && leader) ads[cs[u] * H + h] = make_float2(a, dss);  // stored at the edge's src-sorted position
       }
     }
   }
@@ -241,52 +245,86 @@ gtconv_bwd_dst_kernel(const T* __restrict__ q, const T* __restrict__ k, const T*
 // ------------------------------------------------------------------------------------------------------
 // backward, src pass
 // ------------------------------------------------------------------------------------------------------
+// A thread group owns kSrcRows CONSECUTIVE src rows: their outgoing edges are one contiguous range of the CSC order,
+// so the group streams that range in chunks of kU edges (all loads of a chunk in flight together) with a single
+// accumulator pair that is flushed whenever the row changes.  (One row per group left the kernel latency-bound:
+// the mean out-degree of an encoder graph is 1.4, i.e. one dependent index->row->store chain per CTA.)
+constexpr int kSrcRows = 8;
+
 template <typename T, int LPH>
 __global__ void __launch_bounds__(kThreads)
 gtconv_bwd_src_kernel(const T* __restrict__ q, const T* __restrict__ g, const int* __restrict__ colptr,
-                      const int* __restrict__ cpos, const int* __restrict__ crow, const float2* __restrict__ ads, int Ns,
-                      RowMap rm, int H, T* __restrict__ dk, T* __restrict__ dv) {
+                      const int* __restrict__ crow, const float2* __restrict__ ads, int Ns, RowMap rm, int H,
+                      T* __restrict__ dk, T* __restrict__ dv) {
   constexpr int VEC = Vec<T>::N;
   const int lr = threadIdx.x / rm.tpd;
-  const int j = blockIdx.x * rm.rpb + lr;
-  if (lr >= rm.rpb || j >= Ns) return;
+  const long long j0 = ((long long)blockIdx.x * rm.rpb + lr) * kSrcRows;
+  if (lr >= rm.rpb || j0 >= Ns) return;
   const int chunk = blockIdx.y * rm.tpd + (threadIdx.x - lr * rm.tpd);
   const size_t D = (size_t)rm.chunks * VEC;
   const size_t off = (size_t)chunk * VEC;
   const int h = chunk / LPH;
+  int c[kSrcRows + 1];  // CSC offsets of the group's rows (rows past Ns are empty)
+#pragma unroll
+  for (int i = 0; i <= kSrcRows; ++i) c[i] = colptr[min(j0 + i, (long long)Ns)];
   float ka[VEC], va[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) ka[i] = va[i] = 0.f;
-  const int beg = colptr[j], end = colptr[j + 1];
-  for (int t = beg; t < end; t += kU) {
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  int cur = 0;  // row (relative to j0) the accumulators belong to
+
+  auto flush_to = [&](int r) {  // store row `cur`, zero-fill the edge-less rows between, move on to row r
+    if (dk) stg16(dk + (size_t)(j0 + cur) * D + off, pack<T>(ka));
+    if (dv) stg16(dv + (size_t)(j0 + cur) * D + off, pack<T>(va));
+    for (int z = cur + 1; z < r; ++z) {
+      if (j0 + z < Ns) {
+        if (dk) stg16(dk + (size_t)(j0 + z) * D + off, zero4);
+        if (dv) stg16(dv + (size_t)(j0 + z) * D + off, zero4);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) ka[i] = va[i] = 0.f;
+    cur = r;
+  };
+
+  const int tend = c[kSrcRows];
+  for (int tb = c[0]; tb < tend; tb += kU) {
     uint4 qr[kU], gr[kU];
     float2 w[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      if (t + u < end) {
-        const size_t p = (size_t)cpos[t + u], i = (size_t)crow[t + u];
-        w[u] = __ldg(ads + p * H + h);
+      if (tb + u < tend) {
+        const size_t i = (size_t)crow[tb + u];
+        w[u] = __ldg(ads + (size_t)(tb + u) * H + h);
         qr[u] = ldg16_keep(q + i * D + off);
         gr[u] = ldg16_keep(g + i * D + off);
       } else {
         w[u] = make_float2(0.f, 0.f);
-        qr[u] = gr[u] = make_uint4(0, 0, 0, 0);
+        qr[u] = gr[u] = zero4;
       }
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      float qf[VEC], gf[VEC];
-      unpack<T>(qr[u], qf);
-      unpack<T>(gr[u], gf);
+      const int t = tb + u;
+      if (t < tend) {
+        int r = 0;
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        ka[i] = fmaf(w[u].y, qf[i], ka[i]);
-        va[i] = fmaf(w[u].x, gf[i], va[i]);
+        for (int i = 1; i < kSrcRows; ++i) r += (t >= c[i]) ? 1 : 0;
+        if (r != cur) flush_to(r);
+        float qf[VEC], gf[VEC];
+        unpack<T>(qr[u], qf);
+        unpack<T>(gr[u], gf);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          ka[i] = fmaf(w[u].y, qf[i], ka[i]);
+          va[i] = fmaf(w[u].x, gf[i], va[i]);
+        }
       }
     }
   }
-  if (dk) stg16(dk + (size_t)j * D + off, pack<T>(ka));
-  if (dv) stg16(dv + (size_t)j * D + off, pack<T>(va));
+  // last row with edges, then the trailing edge-less rows of the group
+  const int last = (int)min((long long)kSrcRows, (long long)Ns - j0);
+  flush_to(last);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -355,8 +393,8 @@ gtconv_fwd_generic_kernel(const T* __restrict__ q, const T* __restrict__ k, cons
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 gtconv_bwd_dst_generic_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ e,
-                              const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm, int Nd,
-                              int H, int C, float qscale, float scale, const T* __restrict__ out, const float* __restrict__ lse2,
+                              const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm,
+                              const int* __restrict__ csr2csc, int Nd, int H, int C, float qscale, float scale, const T* __restrict__ out, const float* __restrict__ lse2,
                               const T* __restrict__ g, T* __restrict__ dq, T* __restrict__ de, float2* __restrict__ ads) {
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -402,7 +440,7 @@ gtconv_bwd_dst_generic_kernel(const T* __restrict__ q, const T* __restrict__ k, 
       dqa[r] = fmaf(dss, kk[r], dqa[r]);
       if (de && c < C) de[t * D + ho + c] = from_f<T>(fmaf(a, gf[r], dss * qf[r]));
     }
-    if (ads && lane == 0) ads[(size_t)p * H + h] = make_float2(a, dss);
+    if (ads && lane == 0) ads[(size_t)csr2csc[p] * H + h] = make_float2(a, dss);
   }
   if (dq) {
 #pragma unroll
@@ -416,8 +454,8 @@ gtconv_bwd_dst_generic_kernel(const T* __restrict__ q, const T* __restrict__ k, 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 gtconv_bwd_src_generic_kernel(const T* __restrict__ q, const T* __restrict__ g, const int* __restrict__ colptr,
-                              const int* __restrict__ cpos, const int* __restrict__ crow, const float2* __restrict__ ads, int Ns,
-                              int H, int C, T* __restrict__ dk, T* __restrict__ dv) {
+                              const int* __restrict__ crow, const float2* __restrict__ ads, int Ns, int H, int C,
+                              T* __restrict__ dk, T* __restrict__ dv) {
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   if (w >= (long long)Ns * H) return;
@@ -428,8 +466,8 @@ gtconv_bwd_src_generic_kernel(const T* __restrict__ q, const T* __restrict__ g, 
   for (int r = 0; r < kGenR; ++r) ka[r] = va[r] = 0.f;
   const int beg = colptr[j], end = colptr[j + 1];
   for (int t = beg; t < end; ++t) {
-    const size_t p = (size_t)cpos[t], i = (size_t)crow[t];
-    const float2 w2 = ads[p * H + h];
+    const size_t i = (size_t)crow[t];
+    const float2 w2 = ads[(size_t)t * H + h];
 #pragma unroll
     for (int r = 0; r < kGenR; ++r) {
       const int c = lane + 32 * r;
@@ -489,19 +527,20 @@ static void launch_fwd(const Plan& pl, const void* q, const void* k, const void*
 }
 template <typename T, int LPH>
 static void launch_bwd_dst(const Plan& pl, const void* q, const void* k, const void* v, const void* e, const int* rowptr,
-                           const int* col, const int* perm, int Nd, int H, float qscale, float scale, const void* out,
-                           const float* lse2, const void* g, void* dq, void* de, float2* ads, cudaStream_t st) {
+                           const int* col, const int* perm, const int* csr2csc, int Nd, int H, float qscale, float scale,
+                           const void* out, const float* lse2, const void* g, void* dq, void* de, float2* ads, cudaStream_t st) {
   dim3 grid((Nd + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
   gtconv_bwd_dst_kernel<T, LPH><<<grid, kThreads, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (const T*)e, rowptr, col, perm,
-                                                          Nd, pl.rm, H, qscale, scale, (const T*)out, lse2, (const T*)g, (T*)dq,
-                                                          (T*)de, ads);
+                                                          csr2csc, Nd, pl.rm, H, qscale, scale, (const T*)out, lse2,
+                                                          (const T*)g, (T*)dq, (T*)de, ads);
 }
 template <typename T, int LPH>
-static void launch_bwd_src(const Plan& pl, const void* q, const void* g, const int* colptr, const int* cpos, const int* crow,
+static void launch_bwd_src(const Plan& pl, const void* q, const void* g, const int* colptr, const int* crow,
                            const float2* ads, int Ns, int H, void* dk, void* dv, cudaStream_t st) {
-  dim3 grid((Ns + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
-  gtconv_bwd_src_kernel<T, LPH><<<grid, kThreads, 0, st>>>((const T*)q, (const T*)g, colptr, cpos, crow, ads, Ns, pl.rm, H,
-                                                          (T*)dk, (T*)dv);
+  const int groups = (Ns + kSrcRows - 1) / kSrcRows;
+  dim3 grid((groups + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
+  gtconv_bwd_src_kernel<T, LPH><<<grid, kThreads, 0, st>>>((const T*)q, (const T*)g, colptr, crow, ads, Ns, pl.rm, H, (T*)dk,
+                                                          (T*)dv);
 }
 
 #define AB2_DISPATCH_LPH(T, lph, CALL)                                   \
@@ -562,21 +601,22 @@ extern "C" int ab2_gtconv_fwd(const void* q, const void* k, const void* v, const
 extern "C" size_t ab2_gtconv_bwd_workspace_bytes(int64_t E, int H) { return (size_t)(E > 0 ? E : 1) * (size_t)H * sizeof(float2); }
 
 extern "C" int ab2_gtconv_bwd_dst(const void* q, const void* k, const void* v, const void* e, int dtype, const int32_t* rowptr,
-                                  const int32_t* col, const int32_t* perm, int64_t Ns, int64_t Nd, int64_t E, int H, int C,
-                                  const void* out, const float* lse2, const void* g, void* dq, void* de, void* ads_ws,
-                                  size_t ads_ws_bytes, void* stream) {
+                                  const int32_t* col, const int32_t* perm, const int32_t* csr2csc, int64_t Ns, int64_t Nd,
+                                  int64_t E, int H, int C, const void* out, const float* lse2, const void* g, void* dq, void* de,
+                                  void* ads_ws, size_t ads_ws_bytes, void* stream) {
   if (int rc = check_common("gtconv_bwd_dst", dtype, Ns, Nd, E, H, C)) return rc;
   if (Nd == 0) return AB2_OK;
   if (!rowptr || !q || !out || !lse2 || !g || (E > 0 && (!k || !v || !e || !col || !perm)))
     return fail(AB2_ERR_INVALID, "gtconv_bwd_dst: null pointer argument");
   if (ads_ws && ads_ws_bytes < ab2_gtconv_bwd_workspace_bytes(E, H)) return fail(AB2_ERR_INVALID, "gtconv_bwd_dst: workspace too small");
+  if (ads_ws && E > 0 && !csr2csc) return fail(AB2_ERR_INVALID, "gtconv_bwd_dst: ads_ws given without csr2csc");
   cudaStream_t st = (cudaStream_t)stream;
   const float scale = 1.f / sqrtf((float)C);
   const float qscale = kLog2e * scale;
   float2* ads = (float2*)ads_ws;
   const Plan pl = make_plan(H, C, dtype == AB2_F32 ? 4 : 2);
   if (pl.vector) {
-#define CALL(T, L) launch_bwd_dst<T, L>(pl, q, k, v, e, rowptr, col, perm, (int)Nd, H, qscale, scale, out, lse2, g, dq, de, ads, st)
+#define CALL(T, L) launch_bwd_dst<T, L>(pl, q, k, v, e, rowptr, col, perm, csr2csc, (int)Nd, H, qscale, scale, out, lse2, g, dq, de, ads, st)
     if (dtype == AB2_F32) {
       AB2_DISPATCH_LPH(float, pl.lph, CALL)
     } else {
@@ -588,29 +628,29 @@ extern "C" int ab2_gtconv_bwd_dst(const void* q, const void* k, const void* v, c
     const unsigned grid = (unsigned)(((long long)Nd * H + wpb - 1) / wpb);
     if (dtype == AB2_F32)
       gtconv_bwd_dst_generic_kernel<float><<<grid, kThreads, 0, st>>>(
-          (const float*)q, (const float*)k, (const float*)v, (const float*)e, rowptr, col, perm, (int)Nd, H, C, qscale, scale,
-          (const float*)out, lse2, (const float*)g, (float*)dq, (float*)de, ads);
+          (const float*)q, (const float*)k, (const float*)v, (const float*)e, rowptr, col, perm, csr2csc, (int)Nd, H, C, qscale,
+          scale, (const float*)out, lse2, (const float*)g, (float*)dq, (float*)de, ads);
     else
       gtconv_bwd_dst_generic_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>(
           (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)e, rowptr, col, perm,
-          (int)Nd, H, C, qscale, scale, (const __nv_bfloat16*)out, lse2, (const __nv_bfloat16*)g, (__nv_bfloat16*)dq,
+          csr2csc, (int)Nd, H, C, qscale, scale, (const __nv_bfloat16*)out, lse2, (const __nv_bfloat16*)g, (__nv_bfloat16*)dq,
           (__nv_bfloat16*)de, ads);
   }
   AB2_LAUNCH_OK("gtconv_bwd_dst");
   return AB2_OK;
 }
 
-extern "C" int ab2_gtconv_bwd_src(const void* q, const void* g, int dtype, const int32_t* colptr, const int32_t* cpos,
-                                  const int32_t* crow, int64_t Ns, int64_t Nd, int64_t E, int H, int C, const void* ads_ws,
-                                  void* dk, void* dv, void* stream) {
+extern "C" int ab2_gtconv_bwd_src(const void* q, const void* g, int dtype, const int32_t* colptr, const int32_t* crow,
+                                  int64_t Ns, int64_t Nd, int64_t E, int H, int C, const void* ads_ws, void* dk, void* dv,
+                                  void* stream) {
   if (int rc = check_common("gtconv_bwd_src", dtype, Ns, Nd, E, H, C)) return rc;
   if (Ns == 0 || (!dk && !dv)) return AB2_OK;
-  if (!colptr || !ads_ws || (E > 0 && (!q || !g || !cpos || !crow))) return fail(AB2_ERR_INVALID, "gtconv_bwd_src: null pointer argument");
+  if (!colptr || !ads_ws || (E > 0 && (!q || !g || !crow))) return fail(AB2_ERR_INVALID, "gtconv_bwd_src: null pointer argument");
   cudaStream_t st = (cudaStream_t)stream;
   const float2* ads = (const float2*)ads_ws;
   const Plan pl = make_plan(H, C, dtype == AB2_F32 ? 4 : 2);
   if (pl.vector) {
-#define CALL(T, L) launch_bwd_src<T, L>(pl, q, g, colptr, cpos, crow, ads, (int)Ns, H, dk, dv, st)
+#define CALL(T, L) launch_bwd_src<T, L>(pl, q, g, colptr, crow, ads, (int)Ns, H, dk, dv, st)
     if (dtype == AB2_F32) {
       AB2_DISPATCH_LPH(float, pl.lph, CALL)
     } else {
@@ -621,11 +661,11 @@ extern "C" int ab2_gtconv_bwd_src(const void* q, const void* g, int dtype, const
     const int wpb = kThreads / 32;
     const unsigned grid = (unsigned)(((long long)Ns * H + wpb - 1) / wpb);
     if (dtype == AB2_F32)
-      gtconv_bwd_src_generic_kernel<float><<<grid, kThreads, 0, st>>>((const float*)q, (const float*)g, colptr, cpos, crow, ads,
-                                                                     (int)Ns, H, C, (float*)dk, (float*)dv);
+      gtconv_bwd_src_generic_kernel<float><<<grid, kThreads, 0, st>>>((const float*)q, (const float*)g, colptr, crow, ads, (int)Ns,
+                                                                     H, C, (float*)dk, (float*)dv);
     else
       gtconv_bwd_src_generic_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)g,
-                                                                             colptr, cpos, crow, ads, (int)Ns, H, C,
+                                                                             colptr, crow, ads, (int)Ns, H, C,
                                                                              (__nv_bfloat16*)dk, (__nv_bfloat16*)dv);
   }
   AB2_LAUNCH_OK("gtconv_bwd_src");
@@ -633,17 +673,17 @@ extern "C" int ab2_gtconv_bwd_src(const void* q, const void* g, int dtype, const
 }
 
 extern "C" int ab2_gtconv_bwd(const void* q, const void* k, const void* v, const void* e, int dtype, const int32_t* rowptr,
-                              const int32_t* col, const int32_t* perm, const int32_t* colptr, const int32_t* cpos,
+                              const int32_t* col, const int32_t* perm, const int32_t* colptr, const int32_t* csr2csc,
                               const int32_t* crow, int64_t Ns, int64_t Nd, int64_t E, int H, int C, const void* out,
                               const float* lse2, const void* g, void* dq, void* dk, void* dv, void* de, void* workspace,
                               size_t workspace_bytes, void* stream) {
   const bool need_src = dk || dv;
   if (need_src && (!workspace || workspace_bytes < ab2_gtconv_bwd_workspace_bytes(E, H)))
     return fail(AB2_ERR_INVALID, "gtconv_bwd: workspace too small");
-  if (need_src && (!colptr || (E > 0 && (!cpos || !crow)))) return fail(AB2_ERR_INVALID, "gtconv_bwd: dk/dv requested without the CSC view");
-  if (int rc = ab2_gtconv_bwd_dst(q, k, v, e, dtype, rowptr, col, perm, Ns, Nd, E, H, C, out, lse2, g, dq, de,
+  if (need_src && (!colptr || (E > 0 && (!csr2csc || !crow)))) return fail(AB2_ERR_INVALID, "gtconv_bwd: dk/dv requested without the CSC view");
+  if (int rc = ab2_gtconv_bwd_dst(q, k, v, e, dtype, rowptr, col, perm, csr2csc, Ns, Nd, E, H, C, out, lse2, g, dq, de,
                                   need_src ? workspace : nullptr, workspace_bytes, stream))
     return rc;
   if (!need_src) return AB2_OK;
-  return ab2_gtconv_bwd_src(q, g, dtype, colptr, cpos, crow, Ns, Nd, E, H, C, workspace, dk, dv, stream);
+  return ab2_gtconv_bwd_src(q, g, dtype, colptr, crow, Ns, Nd, E, H, C, workspace, dk, dv, stream);
 }

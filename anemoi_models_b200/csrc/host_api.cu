@@ -39,7 +39,7 @@ extern "C" size_t ab2_gtconv_host_workspace_bytes(int64_t Ns, int64_t Nd, int64_
 
 extern "C" int ab2_gtconv_fwd_bwd_host(const void* q_host, const void* k_host, const void* v_host, const void* e_host,
                                        const void* g_host, int dtype, const int32_t* rowptr, const int32_t* col,
-                                       const int32_t* perm, const int32_t* colptr, const int32_t* cpos, const int32_t* crow,
+                                       const int32_t* perm, const int32_t* colptr, const int32_t* csr2csc, const int32_t* crow,
                                        int64_t Ns, int64_t Nd, int64_t E, int H, int C, void* out_host, void* dq_host,
                                        void* dk_host, void* dv_host, void* de_host, void* dev_ws, size_t dev_ws_bytes,
                                        void* stream) {
@@ -85,7 +85,7 @@ extern "C" int ab2_gtconv_fwd_bwd_host(const void* q_host, const void* k_host, c
     TRY(cudaStreamWaitEvent(comp, ev_g, 0));
   }
   if (rc == AB2_OK)
-    rc = ab2_gtconv_bwd(w.q, w.k, w.v, w.e, dtype, rowptr, col, perm, colptr, cpos, crow, Ns, Nd, E, H, C, w.out,
+    rc = ab2_gtconv_bwd(w.q, w.k, w.v, w.e, dtype, rowptr, col, perm, colptr, csr2csc, crow, Ns, Nd, E, H, C, w.out,
                         (const float*)w.lse2, w.g, dq_host ? w.dq : nullptr, dk_host ? w.dk : nullptr,
                         dv_host ? w.dv : nullptr, de_host ? w.de : nullptr, w.ads, ab2_gtconv_bwd_workspace_bytes(E, H), comp);
   if (rc == AB2_OK) {

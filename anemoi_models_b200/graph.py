@@ -45,9 +45,9 @@ def resolve_size(size, n_src: int, n_dst: int) -> Tuple[int, int]:
 
 
 class GraphCSR:
-    """Device-resident plan: rowptr/col/perm/rowidx (dst-sorted) and colptr/cpos/crow (src-sorted view)."""
+    """Device-resident plan: rowptr/col/perm/rowidx (dst-sorted) and colptr/cpos/crow/csr2csc (src-sorted view)."""
 
-    __slots__ = ("num_src", "num_dst", "num_edges", "rowptr", "col", "perm", "rowidx", "colptr", "cpos", "crow",
+    __slots__ = ("num_src", "num_dst", "num_edges", "rowptr", "col", "perm", "rowidx", "colptr", "cpos", "crow", "csr2csc",
                  "perm_is_identity", "edge_index", "device")
 
     def __init__(self, edge_index: Tensor, num_src: int, num_dst: int):
@@ -68,13 +68,15 @@ class GraphCSR:
         self.colptr = torch.empty(num_src + 1, **i32)
         self.cpos = torch.empty(E, **i32)
         self.crow = torch.empty(E, **i32)
+        self.csr2csc = torch.empty(E, **i32)
         flags = torch.empty(4, **i32)
         ws_bytes = L.ab2_csr_workspace_bytes(E, num_src, num_dst)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.check(L.ab2_csr_build(_lib.ptr(ei), E, num_src, num_dst, _lib.ptr(self.rowptr), _lib.ptr(self.col),
                                        _lib.ptr(self.perm), _lib.ptr(self.rowidx), _lib.ptr(self.colptr),
-                                       _lib.ptr(self.cpos), _lib.ptr(self.crow), _lib.ptr(flags), _lib.ptr(ws), ws_bytes,
+                                       _lib.ptr(self.cpos), _lib.ptr(self.crow), _lib.ptr(self.csr2csc), _lib.ptr(flags),
+                                       _lib.ptr(ws), ws_bytes,
                                        _lib.current_stream(dev)))
         f = flags.tolist()  # one-off sync: the plan is cached
         if f[1] != 0:

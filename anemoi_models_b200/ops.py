@@ -76,7 +76,7 @@ class _GTConvFn(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device) if (need[1] or need[2]) else None
         with torch.cuda.device(q.device):
             _lib.check(L.ab2_gtconv_bwd(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(e), dt, _lib.ptr(plan.rowptr),
-                                        _lib.ptr(plan.col), _lib.ptr(plan.perm), _lib.ptr(plan.colptr), _lib.ptr(plan.cpos),
+                                        _lib.ptr(plan.col), _lib.ptr(plan.perm), _lib.ptr(plan.colptr), _lib.ptr(plan.csr2csc),
                                         _lib.ptr(plan.crow), Ns, Nd, E, H, C, _lib.ptr(out), _lib.ptr(lse2), _lib.ptr(g),
                                         _lib.ptr(dq), _lib.ptr(dk), _lib.ptr(dv), _lib.ptr(de), _lib.ptr(ws),
                                         ws_bytes if ws is not None else 0, _lib.current_stream(q.device)))
@@ -217,7 +217,7 @@ def gt_conv_host(q: Tensor, k: Tensor, v: Tensor, e: Tensor, g: Tensor, plan: Gr
     with torch.cuda.device(plan.device):
         _lib.check(L.ab2_gtconv_fwd_bwd_host(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(e), _lib.ptr(g), dt,
                                              _lib.ptr(plan.rowptr), _lib.ptr(plan.col), _lib.ptr(plan.perm),
-                                             _lib.ptr(plan.colptr), _lib.ptr(plan.cpos), _lib.ptr(plan.crow), Ns, Nd, E, H, C,
+                                             _lib.ptr(plan.colptr), _lib.ptr(plan.csr2csc), _lib.ptr(plan.crow), Ns, Nd, E, H, C,
                                              *[_lib.ptr(o) for o in outs], _lib.ptr(dev_ws), dev_ws.numel(),
                                              _lib.current_stream(plan.device)))
     return tuple(outs)

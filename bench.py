@@ -51,7 +51,11 @@ def dst_N_for(parts: int) -> int:
     return n
 
 
-def workload_name(parts: int) -> str:
+def workload_name(parts: int, workload: str = "encoder") -> str:
+    if workload == "decoder":
+        return "GT mapper decoder conv o96(40320) -> n320(542080, Fibonacci), 3-NN, D=1024, H=16, bf16 fwd+bwd (report line, not the headline)"
+    if workload == "processor":
+        return "GT processor conv on o96(40320), 8-NN, D=1024, H=16, bf16 fwd+bwd (report line, not the headline)"
     if parts == 1:
         return "GT mapper encoder conv n320(542080, Fibonacci) -> o96(40320), cut-off 0.6, D=1024, H=16, bf16 fwd+bwd"
     return (f"same graph family at {parts}x area: Fibonacci({parts * SRC_POINTS}) -> o{dst_N_for(parts)}, dst-row sharded over "
@@ -122,13 +126,21 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # workload
 # ----------------------------------------------------------------------------------------------------------------
-def build_shard(parts: int, part: int):
+def build_shard(parts: int, part: int, workload: str = "encoder"):
     """edge_index (GLOBAL ids) of the edges into shard `part`, plus global sizes and shard bounds."""
     from anemoi_models_b200 import synthetic as S
     from anemoi_models_b200.distributed.shapes import tensor_split_sizes
 
     ns = parts * SRC_POINTS
-    ei, ns, nd, radius = S.encoder_graph_band(ns, dst_N_for(parts), parts, part)
+    if workload == "encoder":
+        ei, ns, nd, radius = S.encoder_graph_band(ns, dst_N_for(parts), parts, part)
+    else:
+        assert parts == 1, "decoder / processor workloads are single-GPU report lines"
+        hidden, _ = S.octahedral_grid(DST_N)
+        if workload == "decoder":  # o96 -> n320, 3 nearest hidden nodes per data node
+            ei, ns, nd = S.knn_edges(hidden, S.fibonacci_sphere(SRC_POINTS), 3), len(hidden), SRC_POINTS
+        else:  # processor on o96: 8 nearest neighbours, no self loops
+            ei, ns, nd = S.knn_edges(hidden, hidden, 8, exclude_self=True), len(hidden), len(hidden)
     sb = np.concatenate([[0], np.cumsum(tensor_split_sizes(ns, parts))]).tolist()
     db = np.concatenate([[0], np.cumsum(tensor_split_sizes(nd, parts))]).tolist()
     return ei, ns, nd, sb, db
@@ -168,7 +180,7 @@ def run_ours(args):
         group = dist.group.WORLD
 
     L = _lib.lib()
-    ei_np, Ns_g, Nd_g, sb, db = build_shard(world, rank)
+    ei_np, Ns_g, Nd_g, sb, db = build_shard(world, rank, args.workload)
     ei_glob = torch.from_numpy(ei_np).to(dev)
     E = ei_glob.shape[1]
     torch.manual_seed(1234 + rank)
@@ -245,11 +257,10 @@ def run_ours(args):
         _lib.check(L.ab2_gtconv_fwd(P(q), P(kn), P(vn), P(e), 1, P(plan.rowptr), P(plan.col), P(plan.perm), n_src, nd_loc, E, H, C,
                                     P(out), P(lse2), st))
         if ev: ev[1].record()
-        _lib.check(L.ab2_gtconv_bwd_dst(P(q), P(kn), P(vn), P(e), 1, P(plan.rowptr), P(plan.col), P(plan.perm), n_src, nd_loc, E,
-                                        H, C, P(out), P(lse2), P(g), P(dq), P(de), P(ws), ws_bytes, st))
+        _lib.check(L.ab2_gtconv_bwd_dst(P(q), P(kn), P(vn), P(e), 1, P(plan.rowptr), P(plan.col), P(plan.perm), P(plan.csr2csc),
+                                        n_src, nd_loc, E, H, C, P(out), P(lse2), P(g), P(dq), P(de), P(ws), ws_bytes, st))
         if ev: ev[2].record()
-        _lib.check(L.ab2_gtconv_bwd_src(P(q), P(g), 1, P(plan.colptr), P(plan.cpos), P(plan.crow), n_src, nd_loc, E, H, C, P(ws),
-                                        P(dk), P(dv), st))
+        _lib.check(L.ab2_gtconv_bwd_src(P(q), P(g), 1, P(plan.colptr), P(plan.crow), n_src, nd_loc, E, H, C, P(ws), P(dk), P(dv), st))
         if ev: ev[3].record()
 
     for _ in range(3):
@@ -283,7 +294,7 @@ def run_ours(args):
 
         def host_step():
             _lib.check(L.ab2_gtconv_fwd_bwd_host(*[P(x) for x in host], 1, P(plan.rowptr), P(plan.col), P(plan.perm),
-                                                 P(plan.colptr), P(plan.cpos), P(plan.crow), n_src, nd_loc, E, H, C,
+                                                 P(plan.colptr), P(plan.csr2csc), P(plan.crow), n_src, nd_loc, E, H, C,
                                                  *[P(o) for o in outs], P(dev_ws), need, st))
 
         host_step()
@@ -303,7 +314,7 @@ def run_ours(args):
 
     # ---- CPU baseline: the reference's op sequence (oracle port) on this box's host cores, bounded sample
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "encoder":
         cpu_baseline = cpu_reference_sample(ei_np, Ns_g, Nd_g, steps=2, warmup=1)
 
     if rank == 0:
@@ -311,7 +322,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": workload_name(world), "edges_total": int(float(etot)), "edges_rank0": int(E),
+            "config": {"workload": workload_name(world, args.workload), "edges_total": int(float(etot)), "edges_rank0": int(E),
                        "src_rows_rank0": int(n_src), "dst_rows_rank0": int(nd_loc), "hidden": D, "heads": H,
                        "l2": "inputs (>5 GB per step) exceed the 126 MB L2; no flush between steps",
                        "timed_region": "conv forward + backward (+ halo all-to-all of k,v and its backward when n_gpus>1); CSR build excluded (one-off, cached)"},
@@ -391,6 +402,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="encoder", choices=["encoder", "decoder", "processor"],
+                    help="encoder = BASELINE configs[1] (the headline); the others are extra report lines")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

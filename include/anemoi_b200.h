@@ -53,13 +53,14 @@ const char* ab2_last_error(void);
  * colptr     : int32 [Ns+1]   segment offsets of each src in the src-sorted order
  * cpos       : int32 [E]      CSR position p of src-sorted position t (ascending within a src)
  * crow       : int32 [E]      dst id of src-sorted position t
+ * csr2csc    : int32 [E]      src-sorted position t of CSR position p (inverse of cpos); may be NULL
  * flags      : int32 [4]      [0] = 1 if perm is the identity; [1] = number of edges with src/dst out of range
  * Requires E, Ns, Nd < 2^31.  Result is bit-exact equal to torch.sort(edge_index[1], stable=True).
  * ------------------------------------------------------------------------------------------------- */
 size_t ab2_csr_workspace_bytes(int64_t E, int64_t Ns, int64_t Nd);
 int ab2_csr_build(const int64_t* edge_index, int64_t E, int64_t Ns, int64_t Nd, int32_t* rowptr, int32_t* col,
-                  int32_t* perm, int32_t* rowidx, int32_t* colptr, int32_t* cpos, int32_t* crow, int32_t* flags,
-                  void* workspace, size_t workspace_bytes, void* stream);
+                  int32_t* perm, int32_t* rowidx, int32_t* colptr, int32_t* cpos, int32_t* crow, int32_t* csr2csc,
+                  int32_t* flags, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Stable partition of edges by dst chunk.
  * Replaces: distributed/khop_edges.py:88-130 sort_edges_1hop_chunks / :50-85 sort_edges_1hop_sharding
@@ -91,17 +92,17 @@ int ab2_gtconv_fwd(const void* q, const void* k, const void* v, const void* e, i
  * weight and logit gradient, 8 B each).  Deterministic: no atomics. */
 size_t ab2_gtconv_bwd_workspace_bytes(int64_t E, int H);
 /* The two passes of the backward, callable on their own (ab2_gtconv_bwd = dst pass, then src pass):
- *   dst pass (per dst segment): dq, de and the per-(edge, head) pair (softmax weight, logit gradient / sqrt(C)) -> ads_ws;
- *   src pass (per src segment of the CSC view): dk_j = sum ds * q_i, dv_j = sum a * g_i  read from ads_ws. */
+ *   dst pass (per dst segment): dq, de and the per-(edge, head) pair (softmax weight, logit gradient / sqrt(C)),
+ *            stored at the edge's SRC-SORTED position csr2csc[p] of ads_ws so that the src pass reads it contiguously;
+ *   src pass (per block of consecutive src rows, CSC order): dk_j = sum ds * q_i, dv_j = sum a * g_i. */
 int ab2_gtconv_bwd_dst(const void* q, const void* k, const void* v, const void* e, int dtype, const int32_t* rowptr,
-                       const int32_t* col, const int32_t* perm, int64_t Ns, int64_t Nd, int64_t E, int H, int C,
-                       const void* out, const float* lse2, const void* g, void* dq, void* de, void* ads_ws,
+                       const int32_t* col, const int32_t* perm, const int32_t* csr2csc, int64_t Ns, int64_t Nd, int64_t E,
+                       int H, int C, const void* out, const float* lse2, const void* g, void* dq, void* de, void* ads_ws,
                        size_t ads_ws_bytes, void* stream);
-int ab2_gtconv_bwd_src(const void* q, const void* g, int dtype, const int32_t* colptr, const int32_t* cpos,
-                       const int32_t* crow, int64_t Ns, int64_t Nd, int64_t E, int H, int C, const void* ads_ws, void* dk,
-                       void* dv, void* stream);
+int ab2_gtconv_bwd_src(const void* q, const void* g, int dtype, const int32_t* colptr, const int32_t* crow, int64_t Ns,
+                       int64_t Nd, int64_t E, int H, int C, const void* ads_ws, void* dk, void* dv, void* stream);
 int ab2_gtconv_bwd(const void* q, const void* k, const void* v, const void* e, int dtype, const int32_t* rowptr,
-                   const int32_t* col, const int32_t* perm, const int32_t* colptr, const int32_t* cpos,
+                   const int32_t* col, const int32_t* perm, const int32_t* colptr, const int32_t* csr2csc,
                    const int32_t* crow, int64_t Ns, int64_t Nd, int64_t E, int H, int C, const void* out,
                    const float* lse2, const void* g, void* dq, void* dk, void* dv, void* de, void* workspace,
                    size_t workspace_bytes, void* stream);
@@ -145,7 +146,7 @@ int ab2_edge_ln_res_segsum_bwd(const void* g_edges /* may be NULL */, const void
 size_t ab2_gtconv_host_workspace_bytes(int64_t Ns, int64_t Nd, int64_t E, int H, int C, int dtype);
 int ab2_gtconv_fwd_bwd_host(const void* q_host, const void* k_host, const void* v_host, const void* e_host,
                             const void* g_host, int dtype, const int32_t* rowptr, const int32_t* col,
-                            const int32_t* perm, const int32_t* colptr, const int32_t* cpos, const int32_t* crow,
+                            const int32_t* perm, const int32_t* colptr, const int32_t* csr2csc, const int32_t* crow,
                             int64_t Ns, int64_t Nd, int64_t E, int H, int C, void* out_host, void* dq_host,
                             void* dk_host, void* dv_host, void* de_host, void* dev_ws, size_t dev_ws_bytes,
                             void* stream);

@@ -55,5 +55,5 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert b"dtype" in L.ab2_last_error()
     with pytest.raises(ValueError):
         _lib.check(rc)
-    rc = L.ab2_csr_build(0, 2**31, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)  # E too large for int32 indices
+    rc = L.ab2_csr_build(0, 2**31, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)  # E too large for int32 indices
     assert rc == _lib.AB2_ERR_UNSUPPORTED

@@ -24,6 +24,9 @@ def _check_plan(ei_np, ns, nd):
     assert np.array_equal(plan.colptr.cpu().numpy(), colptr)
     assert np.array_equal(plan.cpos.cpu().numpy(), pos)
     assert np.array_equal(plan.crow.cpu().numpy(), row)
+    inv = np.empty_like(pos)
+    inv[pos] = np.arange(len(pos), dtype=pos.dtype)
+    assert np.array_equal(plan.csr2csc.cpu().numpy(), inv)
     assert plan.perm_is_identity == bool(np.array_equal(perm, np.arange(ei_np.shape[1])))
     return plan
 

@@ -91,6 +91,42 @@ def test_skewed_degrees_and_f64_oracle():
         assert rel_err(r[key], torch.from_numpy(o[key])) < FP32_TOL, key
 
 
+def test_decoder_like_graph_high_out_degree():
+    """3 incoming edges per dst from nearby src (decoder shape): src out-degree ~36, many consecutive CSC segments,
+    plus a block of src rows without any edge (zero dk/dv rows written by the src pass)."""
+    gen = torch.Generator().manual_seed(23)
+    ns, nd, H, C = 500, 6000, 4, 16
+    base = (torch.arange(nd) * (ns - 100) // nd)
+    src = (base.view(-1, 1) + torch.randint(0, 3, (nd, 3), generator=gen)).clamp_(max=ns - 101).view(-1)  # rows >= 400 unused
+    dst = torch.arange(nd).repeat_interleave(3)
+    ei = torch.stack([src, dst])
+    E = ei.shape[1]
+    q, k, v, e, g = (torch.randn(n, H, C, generator=gen) for n in (nd, ns, ns, E, nd))
+    ref = og.gt_conv_unfused_fwd_bwd(q, k, v, e, ei, g, (ns, nd))
+    r = run_b2(q, k, v, e, ei, g, (ns, nd))
+    for key in ("out", "dq", "dk", "dv", "de"):
+        assert rel_err(r[key], ref[key]) < FP32_TOL, (key, rel_err(r[key], ref[key]))
+    assert float(r["dk"][400:].abs().max()) == 0.0 and float(r["dv"][400:].abs().max()) == 0.0
+    rb = run_b2(q, k, v, e, ei, g, (ns, nd), torch.bfloat16)
+    cast = lambda x: x.bfloat16().float()
+    refb = og.gt_conv_unfused_fwd_bwd(cast(q), cast(k), cast(v), cast(e), ei, cast(g), (ns, nd))
+    for key in ("out", "dq", "dk", "dv", "de"):
+        assert rel_err(rb[key].float(), refb[key]) < BF16_TOL, (key, rel_err(rb[key].float(), refb[key]))
+
+
+@pytest.mark.parametrize("ns", [1, 7, 8, 9, 17])
+def test_src_row_block_boundaries(ns):
+    """The src pass owns blocks of 8 consecutive src rows: exercise row counts around the block size."""
+    gen = torch.Generator().manual_seed(ns)
+    nd, E, H, C = 11, 60, 2, 8
+    ei = torch.stack([torch.randint(0, ns, (E,), generator=gen), torch.randint(0, nd, (E,), generator=gen)])
+    q, k, v, e, g = (torch.randn(n, H, C, generator=gen) for n in (nd, ns, ns, E, nd))
+    ref = og.gt_conv_unfused_fwd_bwd(q, k, v, e, ei, g, (ns, nd))
+    r = run_b2(q, k, v, e, ei, g, (ns, nd))
+    for key in ("out", "dq", "dk", "dv", "de"):
+        assert rel_err(r[key], ref[key]) < FP32_TOL, (key, rel_err(r[key], ref[key]))
+
+
 def test_empty_edge_set_and_size_errors():
     import anemoi_models_b200 as b2
 
