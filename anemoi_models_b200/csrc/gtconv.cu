@@ -12,6 +12,7 @@
 //                               (a, ds/sqrt(C)) to a small [E,H] float2 workspace;
 //   bwd_src (per src segment, CSC order): dk_j = sum ds*q_i, dv_j = sum a*g_i  (q, g rows are L2-resident).
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -245,6 +246,284 @@ gtconv_bwd_dst_kernel(const T* __restrict__ q, const T* __restrict__ k, const T*
 // ------------------------------------------------------------------------------------------------------
 // backward, src pass
 // ------------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------------
+// low in-degree variants (decoder: 3 edges per dst, processor: 8): a thread group owns kDstRows CONSECUTIVE dst rows,
+// whose incoming edges are one contiguous CSR range.  It streams that range in chunks of U edges with a single
+// softmax / gradient state that is flushed when the row changes.  With one row per group these graphs are
+// latency-bound: a CTA lives for one dependent rowptr -> index -> row -> store chain and moves only a few KB.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kDstRows = 4;
+
+template <int R>
+__device__ __forceinline__ int row_of(int t, const int (&c)[R + 1]) {
+  int r = 0;
+#pragma unroll
+  for (int i = 1; i < R; ++i) r += (t >= c[i]) ? 1 : 0;
+  return r;
+}
+template <int R>
+__device__ __forceinline__ uint4 select_row(const uint4 (&x)[R], int r) {
+  uint4 y = x[0];
+#pragma unroll
+  for (int i = 1; i < R; ++i)
+    if (r == i) y = x[i];
+  return y;
+}
+template <int R>
+__device__ __forceinline__ float select_row(const float (&x)[R], int r) {
+  float y = x[0];
+#pragma unroll
+  for (int i = 1; i < R; ++i)
+    if (r == i) y = x[i];
+  return y;
+}
+
+template <typename T, int LPH>
+__global__ void __launch_bounds__(kThreads)
+gtconv_fwd_rows_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ e,
+                       const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm, int Nd,
+                       RowMap rm, int H, float qscale, T* __restrict__ out, float* __restrict__ lse2) {
+  constexpr int VEC = Vec<T>::N;
+  constexpr int R = kDstRows;
+  const int lr = threadIdx.x / rm.tpd;
+  const long long d0 = ((long long)blockIdx.x * rm.rpb + lr) * R;
+  if (lr >= rm.rpb || d0 >= Nd) return;
+  const int chunk = blockIdx.y * rm.tpd + (threadIdx.x - lr * rm.tpd);
+  const size_t D = (size_t)rm.chunks * VEC;
+  const size_t off = (size_t)chunk * VEC;
+  const unsigned mask = group_mask<LPH>();
+  const bool leader = (chunk & (LPH - 1)) == 0;
+  const int h = chunk / LPH;
+  const int nrows = (int)min((long long)R, (long long)Nd - d0);
+
+  int c[R + 1];
+  uint4 qraw[R];
+#pragma unroll
+  for (int i = 0; i <= R; ++i) c[i] = rowptr[min(d0 + i, (long long)Nd)];
+#pragma unroll
+  for (int i = 0; i < R; ++i) qraw[i] = ldg16_keep(q + (size_t)min(d0 + i, (long long)Nd - 1) * D + off);
+
+  float m = -INFINITY, l = 0.f, acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+  int cur = 0;
+
+  auto flush_to = [&](int r) {  // finish row `cur` (PyG: divide by sum + 1e-16), zero the edge-less rows up to r
+    const float inv = 1.f / (l + 1e-16f);
+    float o[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o[i] = acc[i] * inv;
+    stg16(out + (size_t)(d0 + cur) * D + off, pack<T>(o));
+    if (leader) lse2[(size_t)(d0 + cur) * H + h] = l > 0.f ? m + log2f(l + 1e-16f) : 0.f;
+    for (int z = cur + 1; z < r && z < nrows; ++z) {
+      stg16(out + (size_t)(d0 + z) * D + off, make_uint4(0, 0, 0, 0));
+      if (leader) lse2[(size_t)(d0 + z) * H + h] = 0.f;
+    }
+    m = -INFINITY;
+    l = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+    cur = r;
+  };
+
+  const int beg = c[0], end = c[R];
+  int jn[kU], tn[kU];
+#pragma unroll
+  for (int u = 0; u < kU; ++u) {
+    jn[u] = beg + u < end ? col[beg + u] : 0;
+    tn[u] = beg + u < end ? perm[beg + u] : 0;
+  }
+  for (int p = beg; p < end; p += kU) {
+    uint4 kr[kU], er[kU], vr[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (p + u < end) {
+        const size_t j = (size_t)jn[u], t = (size_t)tn[u];
+        kr[u] = ldg16_keep(k + j * D + off);
+        er[u] = ldg16(e + t * D + off);
+        vr[u] = ldg16_keep(v + j * D + off);
+      } else {
+        kr[u] = er[u] = vr[u] = make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int pn = p + kU + u;
+      jn[u] = pn < end ? col[pn] : 0;
+      tn[u] = pn < end ? perm[pn] : 0;
+    }
+    float s[kU];
+    int rr[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      rr[u] = row_of<R>(p + u, c);
+      float qf[VEC], kf[VEC], ef[VEC];
+      unpack<T>(select_row<R>(qraw, rr[u]), qf);
+      unpack<T>(kr[u], kf);
+      unpack<T>(er[u], ef);
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) part = fmaf(qf[i], kf[i] + ef[i], part);
+      s[u] = part;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) s[u] = group_sum<LPH>(s[u], mask) * qscale;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (p + u < end) {
+        if (rr[u] != cur) flush_to(rr[u]);
+        const float mn = fmaxf(m, s[u]);
+        const float corr = fast_exp2(m - mn), pw = fast_exp2(s[u] - mn);
+        l = fmaf(l, corr, pw);
+        float vf[VEC], ef[VEC];
+        unpack<T>(vr[u], vf);
+        unpack<T>(er[u], ef);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = fmaf(acc[i], corr, pw * (vf[i] + ef[i]));
+        m = mn;
+      }
+    }
+  }
+  flush_to(nrows);
+}
+
+constexpr int kUB = 2;  // edges in flight per thread in the multi-row backward (per-row q, g state costs registers)
+
+template <typename T, int LPH>
+__global__ void __launch_bounds__(kThreads, 4)
+gtconv_bwd_dst_rows_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ e,
+                           const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm,
+                           const int* __restrict__ csr2csc, int Nd, RowMap rm, int H, float qscale, float scale,
+                           const T* __restrict__ out, const float* __restrict__ lse2, const T* __restrict__ g,
+                           T* __restrict__ dq, T* __restrict__ de, float2* __restrict__ ads) {
+  constexpr int VEC = Vec<T>::N;
+  constexpr int R = kDstRows;
+  const int lr = threadIdx.x / rm.tpd;
+  const long long d0 = ((long long)blockIdx.x * rm.rpb + lr) * R;
+  if (lr >= rm.rpb || d0 >= Nd) return;
+  const int chunk = blockIdx.y * rm.tpd + (threadIdx.x - lr * rm.tpd);
+  const size_t D = (size_t)rm.chunks * VEC;
+  const size_t off = (size_t)chunk * VEC;
+  const unsigned mask = group_mask<LPH>();
+  const bool leader = (chunk & (LPH - 1)) == 0;
+  const int h = chunk / LPH;
+  const int nrows = (int)min((long long)R, (long long)Nd - d0);
+
+  int c[R + 1];
+  uint4 qraw[R], graw[R];
+  float Dl[R], Ls[R];
+#pragma unroll
+  for (int i = 0; i <= R; ++i) c[i] = rowptr[min(d0 + i, (long long)Nd)];
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const size_t row = (size_t)min(d0 + i, (long long)Nd - 1);
+    qraw[i] = ldg16_keep(q + row * D + off);
+    graw[i] = ldg16_keep(g + row * D + off);
+    float gf[VEC], of[VEC];
+    unpack<T>(graw[i], gf);
+    unpack<T>(ldg16(out + row * D + off), of);
+    float part = 0.f;
+#pragma unroll
+    for (int x = 0; x < VEC; ++x) part = fmaf(gf[x], of[x], part);
+    Dl[i] = group_sum<LPH>(part, mask);
+    Ls[i] = lse2[row * H + h];
+  }
+  float dqa[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) dqa[i] = 0.f;
+  int cur = 0;
+  auto flush_to = [&](int r) {
+    if (dq) {
+      stg16(dq + (size_t)(d0 + cur) * D + off, pack<T>(dqa));
+      for (int z = cur + 1; z < r && z < nrows; ++z) stg16(dq + (size_t)(d0 + z) * D + off, make_uint4(0, 0, 0, 0));
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) dqa[i] = 0.f;
+    cur = r;
+  };
+
+  const int beg = c[0], end = c[R];
+  int jn[kUB], tn[kUB], cn[kUB];
+#pragma unroll
+  for (int u = 0; u < kUB; ++u) {
+    jn[u] = beg + u < end ? col[beg + u] : 0;
+    tn[u] = beg + u < end ? perm[beg + u] : 0;
+    cn[u] = (ads && beg + u < end) ? csr2csc[beg + u] : 0;
+  }
+  for (int p = beg; p < end; p += kUB) {
+    uint4 kr[kUB], er[kUB], vr[kUB];
+    size_t ts[kUB], cs[kUB];
+#pragma unroll
+    for (int u = 0; u < kUB; ++u) {
+      ts[u] = (size_t)tn[u];
+      cs[u] = (size_t)cn[u];
+      if (p + u < end) {
+        const size_t j = (size_t)jn[u];
+        kr[u] = ldg16_keep(k + j * D + off);
+        er[u] = ldg16(e + ts[u] * D + off);
+        vr[u] = ldg16_keep(v + j * D + off);
+      } else {
+        kr[u] = er[u] = vr[u] = make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUB; ++u) {
+      const int pn = p + kUB + u;
+      jn[u] = pn < end ? col[pn] : 0;
+      tn[u] = pn < end ? perm[pn] : 0;
+      cn[u] = (ads && pn < end) ? csr2csc[pn] : 0;
+    }
+    float s[kUB], gv[kUB];
+    int rr[kUB];
+#pragma unroll
+    for (int u = 0; u < kUB; ++u) {
+      rr[u] = row_of<R>(p + u, c);
+      float qf[VEC], gf[VEC], kf[VEC], ef[VEC], vf[VEC];
+      unpack<T>(select_row<R>(qraw, rr[u]), qf);
+      unpack<T>(select_row<R>(graw, rr[u]), gf);
+      unpack<T>(kr[u], kf);
+      unpack<T>(er[u], ef);
+      unpack<T>(vr[u], vf);
+      float ps = 0.f, pg = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        ps = fmaf(qf[i], kf[i] + ef[i], ps);
+        pg = fmaf(gf[i], vf[i] + ef[i], pg);
+      }
+      s[u] = ps;
+      gv[u] = pg;
+    }
+#pragma unroll
+    for (int u = 0; u < kUB; ++u) {
+      s[u] = group_sum<LPH>(s[u], mask);
+      gv[u] = group_sum<LPH>(gv[u], mask);
+    }
+#pragma unroll
+    for (int u = 0; u < kUB; ++u) {
+      if (p + u < end) {
+        if (rr[u] != cur) flush_to(rr[u]);
+        const float a = fast_exp2(fmaf(s[u], qscale, -select_row<R>(Ls, rr[u])));
+        const float dss = a * (gv[u] - select_row<R>(Dl, rr[u])) * scale;
+        float kf[VEC], ef[VEC];
+        unpack<T>(kr[u], kf);
+        unpack<T>(er[u], ef);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) dqa[i] = fmaf(dss, kf[i] + ef[i], dqa[i]);
+        if (de) {
+          float qf[VEC], gf[VEC], o[VEC];
+          unpack<T>(select_row<R>(qraw, rr[u]), qf);
+          unpack<T>(select_row<R>(graw, rr[u]), gf);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) o[i] = fmaf(a, gf[i], dss * qf[i]);
+          stg16(de + ts[u] * D + off, pack<T>(o));
+        }
+        if (ads && leader) ads[cs[u] * H + h] = make_float2(a, dss);
+      }
+    }
+  }
+  flush_to(nrows);
+}
+
 // A thread group owns kSrcRows CONSECUTIVE src rows: their outgoing edges are one contiguous range of the CSC order,
 // so the group streams that range in chunks of kU edges (all loads of a chunk in flight together) with a single
 // accumulator pair that is flushed whenever the row changes.  (One row per group left the kernel latency-bound:
@@ -519,16 +798,33 @@ static Plan make_plan(int H, int C, int elt) {
 }
 
 template <typename T, int LPH>
-static void launch_fwd(const Plan& pl, const void* q, const void* k, const void* v, const void* e, const int* rowptr,
-                       const int* col, const int* perm, int Nd, int H, float qscale, void* out, float* lse2, cudaStream_t st) {
-  dim3 grid((Nd + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
-  gtconv_fwd_kernel<T, LPH><<<grid, kThreads, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (const T*)e, rowptr, col, perm,
-                                                      Nd, pl.rm, H, qscale, (T*)out, lse2);
+static void launch_fwd(const Plan& pl, bool low_degree, const void* q, const void* k, const void* v, const void* e,
+                       const int* rowptr, const int* col, const int* perm, int Nd, int H, float qscale, void* out,
+                       float* lse2, cudaStream_t st) {
+  if (low_degree) {
+    const int groups = (Nd + kDstRows - 1) / kDstRows;
+    dim3 grid((groups + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
+    gtconv_fwd_rows_kernel<T, LPH><<<grid, kThreads, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (const T*)e, rowptr, col,
+                                                             perm, Nd, pl.rm, H, qscale, (T*)out, lse2);
+  } else {
+    dim3 grid((Nd + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
+    gtconv_fwd_kernel<T, LPH><<<grid, kThreads, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (const T*)e, rowptr, col, perm,
+                                                        Nd, pl.rm, H, qscale, (T*)out, lse2);
+  }
 }
 template <typename T, int LPH>
-static void launch_bwd_dst(const Plan& pl, const void* q, const void* k, const void* v, const void* e, const int* rowptr,
-                           const int* col, const int* perm, const int* csr2csc, int Nd, int H, float qscale, float scale,
-                           const void* out, const float* lse2, const void* g, void* dq, void* de, float2* ads, cudaStream_t st) {
+static void launch_bwd_dst(const Plan& pl, bool low_degree, const void* q, const void* k, const void* v, const void* e,
+                           const int* rowptr, const int* col, const int* perm, const int* csr2csc, int Nd, int H, float qscale,
+                           float scale, const void* out, const float* lse2, const void* g, void* dq, void* de, float2* ads,
+                           cudaStream_t st) {
+  if (low_degree) {
+    const int groups = (Nd + kDstRows - 1) / kDstRows;
+    dim3 grid((groups + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
+    gtconv_bwd_dst_rows_kernel<T, LPH><<<grid, kThreads, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (const T*)e, rowptr, col,
+                                                                 perm, csr2csc, Nd, pl.rm, H, qscale, scale, (const T*)out,
+                                                                 lse2, (const T*)g, (T*)dq, (T*)de, ads);
+    return;
+  }
   dim3 grid((Nd + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
   gtconv_bwd_dst_kernel<T, LPH><<<grid, kThreads, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (const T*)e, rowptr, col, perm,
                                                           csr2csc, Nd, pl.rm, H, qscale, scale, (const T*)out, lse2,
@@ -553,6 +849,16 @@ static void launch_bwd_src(const Plan& pl, const void* q, const void* g, const i
     default: CALL(T, 32); break;                                         \
   }
 
+// mean in-degree below which a thread group takes kDstRows consecutive dst rows instead of one (env AB2_ROW_BLOCKS=0/1 forces it)
+static bool use_row_blocks(int64_t E, int64_t Nd) {
+  static const int forced = [] {
+    const char* s = getenv("AB2_ROW_BLOCKS");
+    return s ? atoi(s) : -1;
+  }();
+  if (forced >= 0) return forced != 0;
+  return Nd > 0 && E < 12 * Nd;
+}
+
 static int check_common(const char* fn, int dtype, int64_t Ns, int64_t Nd, int64_t E, int H, int C) {
   if (dtype != AB2_F32 && dtype != AB2_BF16) return fail(AB2_ERR_INVALID, "%s: dtype must be AB2_F32 or AB2_BF16", fn);
   if (Ns < 0 || Nd < 0 || E < 0 || H <= 0 || C <= 0) return fail(AB2_ERR_INVALID, "%s: negative or zero dimension", fn);
@@ -575,8 +881,9 @@ extern "C" int ab2_gtconv_fwd(const void* q, const void* k, const void* v, const
   cudaStream_t st = (cudaStream_t)stream;
   const float qscale = kLog2e / sqrtf((float)C);
   const Plan pl = make_plan(H, C, dtype == AB2_F32 ? 4 : 2);
+  const bool low_degree = use_row_blocks(E, Nd);
   if (pl.vector) {
-#define CALL(T, L) launch_fwd<T, L>(pl, q, k, v, e, rowptr, col, perm, (int)Nd, H, qscale, out, lse2, st)
+#define CALL(T, L) launch_fwd<T, L>(pl, low_degree, q, k, v, e, rowptr, col, perm, (int)Nd, H, qscale, out, lse2, st)
     if (dtype == AB2_F32) {
       AB2_DISPATCH_LPH(float, pl.lph, CALL)
     } else {
@@ -615,8 +922,9 @@ extern "C" int ab2_gtconv_bwd_dst(const void* q, const void* k, const void* v, c
   const float qscale = kLog2e * scale;
   float2* ads = (float2*)ads_ws;
   const Plan pl = make_plan(H, C, dtype == AB2_F32 ? 4 : 2);
+  const bool low_degree = use_row_blocks(E, Nd);
   if (pl.vector) {
-#define CALL(T, L) launch_bwd_dst<T, L>(pl, q, k, v, e, rowptr, col, perm, csr2csc, (int)Nd, H, qscale, scale, out, lse2, g, dq, de, ads, st)
+#define CALL(T, L) launch_bwd_dst<T, L>(pl, low_degree, q, k, v, e, rowptr, col, perm, csr2csc, (int)Nd, H, qscale, scale, out, lse2, g, dq, de, ads, st)
     if (dtype == AB2_F32) {
       AB2_DISPATCH_LPH(float, pl.lph, CALL)
     } else {

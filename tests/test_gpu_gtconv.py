@@ -73,8 +73,9 @@ SHAPES = [(16, 64), (16, 16), (4, 8), (2, 4), (8, 32), (4, 128), (2, 256), (16, 
 
 @pytest.mark.parametrize("H,C", SHAPES)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_random_graphs_all_shapes(H, C, dtype):
-    q, k, v, e, ei, g = _random_case(H * 1000 + C, ns=300, nd=150, E=2500, H=H, C=C)
+@pytest.mark.parametrize("E", [2500, 700])  # mean in-degree 16.7 (one dst row per thread group) and 4.7 (row-block kernels)
+def test_random_graphs_all_shapes(H, C, dtype, E):
+    q, k, v, e, ei, g = _random_case(H * 1000 + C + E, ns=300, nd=150, E=E, H=H, C=C)
     cast = (lambda x: x) if dtype == torch.float32 else (lambda x: x.bfloat16().float())
     ref = og.gt_conv_unfused_fwd_bwd(cast(q), cast(k), cast(v), cast(e), ei, cast(g), (300, 150))
     r = run_b2(q, k, v, e, ei, g, (300, 150), dtype)
@@ -112,6 +113,25 @@ def test_decoder_like_graph_high_out_degree():
     refb = og.gt_conv_unfused_fwd_bwd(cast(q), cast(k), cast(v), cast(e), ei, cast(g), (ns, nd))
     for key in ("out", "dq", "dk", "dv", "de"):
         assert rel_err(rb[key].float(), refb[key]) < BF16_TOL, (key, rel_err(rb[key].float(), refb[key]))
+
+
+@pytest.mark.parametrize("nd", [1, 3, 4, 5, 9])
+def test_dst_row_block_boundaries(nd):
+    """Low in-degree graphs: a thread group owns 4 consecutive dst rows; row counts around the block size, rows
+    without edges at the start, in the middle and at the end of a block."""
+    gen = torch.Generator().manual_seed(100 + nd)
+    ns, H, C = 13, 2, 8
+    E = 3 * nd
+    dst = torch.randint(0, nd, (E,), generator=gen)
+    if nd >= 4:
+        dst[dst == 0] = nd - 2  # row 0 and the last row stay empty
+        dst[dst == nd - 1] = 1
+    ei = torch.stack([torch.randint(0, ns, (E,), generator=gen), dst])
+    q, k, v, e, g = (torch.randn(n, H, C, generator=gen) for n in (nd, ns, ns, E, nd))
+    ref = og.gt_conv_unfused_fwd_bwd(q, k, v, e, ei, g, (ns, nd))
+    r = run_b2(q, k, v, e, ei, g, (ns, nd))
+    for key in ("out", "dq", "dk", "dv", "de"):
+        assert rel_err(r[key], ref[key]) < FP32_TOL, (key, rel_err(r[key], ref[key]))
 
 
 @pytest.mark.parametrize("ns", [1, 7, 8, 9, 17])
