@@ -34,6 +34,7 @@ SIGNATURES = {
     "ab2_ln_bwd_parts": (_i32, []),
     "ab2_edge_ln_res_segsum_bwd": (_i32, [_vp] * 7 + [_i64] * 2 + [_i32] * 2 + [_vp] * 3 + [_i32] + [_vp] * 3),
     "ab2_gtconv_host_workspace_bytes": (_sz, [_i64] * 3 + [_i32] * 3),
+    "ab2_gtconv_fwd_bwd_host_streamed": (_i32, [_vp] * 5 + [_i32] + [_vp] * 6 + [_i64] * 3 + [_i32] * 2 + [_vp] * 5 + [_vp, _i32, _vp, _sz, _vp]),
     "ab2_gtconv_fwd_bwd_host": (_i32, [_vp] * 5 + [_i32] + [_vp] * 6 + [_i64] * 3 + [_i32] * 2 + [_vp] * 5 + [_vp, _sz, _vp]),
 }
 

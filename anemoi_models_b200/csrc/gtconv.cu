@@ -247,7 +247,7 @@ gtconv_bwd_dst_kernel(const T* __restrict__ q, const T* __restrict__ k, const T*
 // backward, src pass
 // ------------------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------------------
-// low in-degree variants (decoder: 3 edges per dst, processor: 8): a thread group owns kDstRows CONSECUTIVE dst rows,
+// low in-degree forward variant (decoder: 3 edges per dst): a thread group owns kDstRows CONSECUTIVE dst rows,
 // whose incoming edges are one contiguous CSR range.  It streams that range in chunks of U edges with a single
 // softmax / gradient state that is flushed when the row changes.  With one row per group these graphs are
 // latency-bound: a CTA lives for one dependent rowptr -> index -> row -> store chain and moves only a few KB.
@@ -381,143 +381,6 @@ gtconv_fwd_rows_kernel(const T* __restrict__ q, const T* __restrict__ k, const T
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[i] = fmaf(acc[i], corr, pw * (vf[i] + ef[i]));
         m = mn;
-      }
-    }
-  }
-  flush_to(nrows);
-}
-
-constexpr int kUB = 2;  // edges in flight per thread in the multi-row backward (per-row q, g state costs registers)
-
-template <typename T, int LPH>
-__global__ void __launch_bounds__(kThreads, 4)
-gtconv_bwd_dst_rows_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ e,
-                           const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm,
-                           const int* __restrict__ csr2csc, int Nd, RowMap rm, int H, float qscale, float scale,
-                           const T* __restrict__ out, const float* __restrict__ lse2, const T* __restrict__ g,
-                           T* __restrict__ dq, T* __restrict__ de, float2* __restrict__ ads) {
-  constexpr int VEC = Vec<T>::N;
-  constexpr int R = kDstRows;
-  const int lr = threadIdx.x / rm.tpd;
-  const long long d0 = ((long long)blockIdx.x * rm.rpb + lr) * R;
-  if (lr >= rm.rpb || d0 >= Nd) return;
-  const int chunk = blockIdx.y * rm.tpd + (threadIdx.x - lr * rm.tpd);
-  const size_t D = (size_t)rm.chunks * VEC;
-  const size_t off = (size_t)chunk * VEC;
-  const unsigned mask = group_mask<LPH>();
-  const bool leader = (chunk & (LPH - 1)) == 0;
-  const int h = chunk / LPH;
-  const int nrows = (int)min((long long)R, (long long)Nd - d0);
-
-  int c[R + 1];
-  uint4 qraw[R], graw[R];
-  float Dl[R], Ls[R];
-#pragma unroll
-  for (int i = 0; i <= R; ++i) c[i] = rowptr[min(d0 + i, (long long)Nd)];
-#pragma unroll
-  for (int i = 0; i < R; ++i) {
-    const size_t row = (size_t)min(d0 + i, (long long)Nd - 1);
-    qraw[i] = ldg16_keep(q + row * D + off);
-    graw[i] = ldg16_keep(g + row * D + off);
-    float gf[VEC], of[VEC];
-    unpack<T>(graw[i], gf);
-    unpack<T>(ldg16(out + row * D + off), of);
-    float part = 0.f;
-#pragma unroll
-    for (int x = 0; x < VEC; ++x) part = fmaf(gf[x], of[x], part);
-    Dl[i] = group_sum<LPH>(part, mask);
-    Ls[i] = lse2[row * H + h];
-  }
-  float dqa[VEC];
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) dqa[i] = 0.f;
-  int cur = 0;
-  auto flush_to = [&](int r) {
-    if (dq) {
-      stg16(dq + (size_t)(d0 + cur) * D + off, pack<T>(dqa));
-      for (int z = cur + 1; z < r && z < nrows; ++z) stg16(dq + (size_t)(d0 + z) * D + off, make_uint4(0, 0, 0, 0));
-    }
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) dqa[i] = 0.f;
-    cur = r;
-  };
-
-  const int beg = c[0], end = c[R];
-  int jn[kUB], tn[kUB], cn[kUB];
-#pragma unroll
-  for (int u = 0; u < kUB; ++u) {
-    jn[u] = beg + u < end ? col[beg + u] : 0;
-    tn[u] = beg + u < end ? perm[beg + u] : 0;
-    cn[u] = (ads && beg + u < end) ? csr2csc[beg + u] : 0;
-  }
-  for (int p = beg; p < end; p += kUB) {
-    uint4 kr[kUB], er[kUB], vr[kUB];
-    size_t ts[kUB], cs[kUB];
-#pragma unroll
-    for (int u = 0; u < kUB; ++u) {
-      ts[u] = (size_t)tn[u];
-      cs[u] = (size_t)cn[u];
-      if (p + u < end) {
-        const size_t j = (size_t)jn[u];
-        kr[u] = ldg16_keep(k + j * D + off);
-        er[u] = ldg16(e + ts[u] * D + off);
-        vr[u] = ldg16_keep(v + j * D + off);
-      } else {
-        kr[u] = er[u] = vr[u] = make_uint4(0, 0, 0, 0);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kUB; ++u) {
-      const int pn = p + kUB + u;
-      jn[u] = pn < end ? col[pn] : 0;
-      tn[u] = pn < end ? perm[pn] : 0;
-      cn[u] = (ads && pn < end) ? csr2csc[pn] : 0;
-    }
-    float s[kUB], gv[kUB];
-    int rr[kUB];
-#pragma unroll
-    for (int u = 0; u < kUB; ++u) {
-      rr[u] = row_of<R>(p + u, c);
-      float qf[VEC], gf[VEC], kf[VEC], ef[VEC], vf[VEC];
-      unpack<T>(select_row<R>(qraw, rr[u]), qf);
-      unpack<T>(select_row<R>(graw, rr[u]), gf);
-      unpack<T>(kr[u], kf);
-      unpack<T>(er[u], ef);
-      unpack<T>(vr[u], vf);
-      float ps = 0.f, pg = 0.f;
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        ps = fmaf(qf[i], kf[i] + ef[i], ps);
-        pg = fmaf(gf[i], vf[i] + ef[i], pg);
-      }
-      s[u] = ps;
-      gv[u] = pg;
-    }
-#pragma unroll
-    for (int u = 0; u < kUB; ++u) {
-      s[u] = group_sum<LPH>(s[u], mask);
-      gv[u] = group_sum<LPH>(gv[u], mask);
-    }
-#pragma unroll
-    for (int u = 0; u < kUB; ++u) {
-      if (p + u < end) {
-        if (rr[u] != cur) flush_to(rr[u]);
-        const float a = fast_exp2(fmaf(s[u], qscale, -select_row<R>(Ls, rr[u])));
-        const float dss = a * (gv[u] - select_row<R>(Dl, rr[u])) * scale;
-        float kf[VEC], ef[VEC];
-        unpack<T>(kr[u], kf);
-        unpack<T>(er[u], ef);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) dqa[i] = fmaf(dss, kf[i] + ef[i], dqa[i]);
-        if (de) {
-          float qf[VEC], gf[VEC], o[VEC];
-          unpack<T>(select_row<R>(qraw, rr[u]), qf);
-          unpack<T>(select_row<R>(graw, rr[u]), gf);
-#pragma unroll
-          for (int i = 0; i < VEC; ++i) o[i] = fmaf(a, gf[i], dss * qf[i]);
-          stg16(de + ts[u] * D + off, pack<T>(o));
-        }
-        if (ads && leader) ads[cs[u] * H + h] = make_float2(a, dss);
       }
     }
   }
@@ -817,14 +680,7 @@ static void launch_bwd_dst(const Plan& pl, bool low_degree, const void* q, const
                            const int* rowptr, const int* col, const int* perm, const int* csr2csc, int Nd, int H, float qscale,
                            float scale, const void* out, const float* lse2, const void* g, void* dq, void* de, float2* ads,
                            cudaStream_t st) {
-  if (low_degree) {
-    const int groups = (Nd + kDstRows - 1) / kDstRows;
-    dim3 grid((groups + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
-    gtconv_bwd_dst_rows_kernel<T, LPH><<<grid, kThreads, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (const T*)e, rowptr, col,
-                                                                 perm, csr2csc, Nd, pl.rm, H, qscale, scale, (const T*)out,
-                                                                 lse2, (const T*)g, (T*)dq, (T*)de, ads);
-    return;
-  }
+  (void)low_degree;  // a multi-row dst pass was measured on B200: no gain at in-degree 3, slower at in-degree 8
   dim3 grid((Nd + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
   gtconv_bwd_dst_kernel<T, LPH><<<grid, kThreads, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (const T*)e, rowptr, col, perm,
                                                           csr2csc, Nd, pl.rm, H, qscale, scale, (const T*)out, lse2,
@@ -849,14 +705,15 @@ static void launch_bwd_src(const Plan& pl, const void* q, const void* g, const i
     default: CALL(T, 32); break;                                         \
   }
 
-// mean in-degree below which a thread group takes kDstRows consecutive dst rows instead of one (env AB2_ROW_BLOCKS=0/1 forces it)
+// mean in-degree below which a forward thread group takes kDstRows consecutive dst rows instead of one
+// (measured on B200: decoder graph, in-degree 3: 2.42 -> 1.85 ms; processor graph, in-degree 8: no gain).  AB2_ROW_BLOCKS=0/1 forces it.
 static bool use_row_blocks(int64_t E, int64_t Nd) {
   static const int forced = [] {
     const char* s = getenv("AB2_ROW_BLOCKS");
     return s ? atoi(s) : -1;
   }();
   if (forced >= 0) return forced != 0;
-  return Nd > 0 && E < 12 * Nd;
+  return Nd > 0 && E < 6 * Nd;
 }
 
 static int check_common(const char* fn, int dtype, int64_t Ns, int64_t Nd, int64_t E, int H, int C) {

@@ -48,7 +48,7 @@ class GraphCSR:
     """Device-resident plan: rowptr/col/perm/rowidx (dst-sorted) and colptr/cpos/crow/csr2csc (src-sorted view)."""
 
     __slots__ = ("num_src", "num_dst", "num_edges", "rowptr", "col", "perm", "rowidx", "colptr", "cpos", "crow", "csr2csc",
-                 "perm_is_identity", "edge_index", "device")
+                 "perm_is_identity", "edge_index", "device", "_host_meta")
 
     def __init__(self, edge_index: Tensor, num_src: int, num_dst: int):
         check_edge_index(edge_index)
@@ -82,6 +82,7 @@ class GraphCSR:
         if f[1] != 0:
             raise IndexError(f"edge_index has {f[1]} edge(s) with a node id outside size=({num_src}, {num_dst})")
         self.perm_is_identity = bool(f[0])
+        self._host_meta = {}
 
 
 class TensorKeyedCache:

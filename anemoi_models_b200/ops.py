@@ -200,9 +200,47 @@ def edge_ln_res_segsum(y: Tensor, e: Tensor, gamma: Tensor, beta: Tensor, eps: f
                                     beta.to(dt).contiguous(), float(eps), plan)
 
 
-def gt_conv_host(q: Tensor, k: Tensor, v: Tensor, e: Tensor, g: Tensor, plan: GraphCSR, dev_ws: Optional[Tensor] = None):
-    """GraphTransformerConv forward+backward on PINNED HOST tensors through `ab2_gtconv_fwd_bwd_host`
-    (the host-buffer C-ABI call).  Returns pinned host tensors (out, dq, dk, dv, de)."""
+def host_stream_meta(plan: GraphCSR, nchunks: int = 16) -> Tensor:
+    """Chunk table for `ab2_gtconv_fwd_bwd_host_streamed` (host int64 [nchunks, 8], see include/anemoi_b200.h).
+    One-off per plan (cached): chunk bounds by dst rows, the edge range of each chunk, the running maximum of the src ids
+    referenced so far and the first src id that still has an edge in a later chunk."""
+    key = int(nchunks)
+    if key in plan._host_meta:
+        return plan._host_meta[key]
+    from .distributed.shapes import tensor_split_sizes
+
+    Nd, Ns = plan.num_dst, plan.num_src
+    nchunks = max(1, min(int(nchunks), max(Nd, 1)))
+    bounds = [0]
+    for s_ in tensor_split_sizes(Nd, nchunks):
+        bounds.append(bounds[-1] + s_)
+    rp = plan.rowptr[torch.tensor(bounds, device=plan.device)].tolist()
+    smin, smax = [], []
+    for c in range(nchunks):
+        if rp[c + 1] > rp[c]:
+            seg = plan.col[rp[c]:rp[c + 1]]
+            smin.append(int(seg.min()))
+            smax.append(int(seg.max()))
+        else:
+            smin.append(Ns)
+            smax.append(-1)
+    meta = torch.zeros((nchunks, 8), dtype=torch.int64)
+    run_max, suffix_min = -1, [Ns] * (nchunks + 1)
+    for c in range(nchunks - 1, -1, -1):
+        suffix_min[c] = min(suffix_min[c + 1], smin[c])
+    for c in range(nchunks):
+        run_max = max(run_max, smax[c])
+        meta[c, 0], meta[c, 1], meta[c, 2], meta[c, 3] = bounds[c], bounds[c + 1], rp[c], rp[c + 1]
+        meta[c, 4], meta[c, 5] = run_max, suffix_min[c + 1]
+    plan._host_meta[key] = meta
+    return meta
+
+
+def gt_conv_host(q: Tensor, k: Tensor, v: Tensor, e: Tensor, g: Tensor, plan: GraphCSR, dev_ws: Optional[Tensor] = None,
+                 outs=None, nchunks: int = 16):
+    """GraphTransformerConv forward+backward on PINNED HOST tensors through the host-buffer C-ABI calls.
+    Dst-sorted edge lists take the streamed entry point (uploads, kernels and downloads overlap); any other edge order
+    takes `ab2_gtconv_fwd_bwd_host`.  Returns pinned host tensors (out, dq, dk, dv, de)."""
     for t in (q, k, v, e, g):
         if t.is_cuda or not t.is_pinned():
             raise ValueError("gt_conv_host expects pinned host tensors")
@@ -213,11 +251,16 @@ def gt_conv_host(q: Tensor, k: Tensor, v: Tensor, e: Tensor, g: Tensor, plan: Gr
     need = L.ab2_gtconv_host_workspace_bytes(Ns, Nd, E, H, C, dt)
     if dev_ws is None or dev_ws.numel() < need:
         dev_ws = torch.empty(need, dtype=torch.uint8, device=plan.device)
-    outs = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (q, q, k, v, e)]
+    if outs is None:
+        outs = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (q, q, k, v, e)]
+    common = [_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(e), _lib.ptr(g), dt, _lib.ptr(plan.rowptr), _lib.ptr(plan.col),
+              _lib.ptr(plan.perm), _lib.ptr(plan.colptr), _lib.ptr(plan.csr2csc), _lib.ptr(plan.crow), Ns, Nd, E, H, C,
+              *[_lib.ptr(o) for o in outs]]
     with torch.cuda.device(plan.device):
-        _lib.check(L.ab2_gtconv_fwd_bwd_host(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(e), _lib.ptr(g), dt,
-                                             _lib.ptr(plan.rowptr), _lib.ptr(plan.col), _lib.ptr(plan.perm),
-                                             _lib.ptr(plan.colptr), _lib.ptr(plan.csr2csc), _lib.ptr(plan.crow), Ns, Nd, E, H, C,
-                                             *[_lib.ptr(o) for o in outs], _lib.ptr(dev_ws), dev_ws.numel(),
-                                             _lib.current_stream(plan.device)))
+        if plan.perm_is_identity and nchunks > 1 and E > 0:
+            meta = host_stream_meta(plan, nchunks)
+            _lib.check(L.ab2_gtconv_fwd_bwd_host_streamed(*common, meta.data_ptr(), meta.shape[0], _lib.ptr(dev_ws),
+                                                          dev_ws.numel(), _lib.current_stream(plan.device)))
+        else:
+            _lib.check(L.ab2_gtconv_fwd_bwd_host(*common, _lib.ptr(dev_ws), dev_ws.numel(), _lib.current_stream(plan.device)))
     return tuple(outs)

@@ -293,9 +293,7 @@ def run_ours(args):
         outs = [torch.empty(x.shape, dtype=x.dtype, pin_memory=True) for x in (q, q, k_own, v_own, e)]
 
         def host_step():
-            _lib.check(L.ab2_gtconv_fwd_bwd_host(*[P(x) for x in host], 1, P(plan.rowptr), P(plan.col), P(plan.perm),
-                                                 P(plan.colptr), P(plan.csr2csc), P(plan.crow), n_src, nd_loc, E, H, C,
-                                                 *[P(o) for o in outs], P(dev_ws), need, st))
+            ops.gt_conv_host(*host, plan, dev_ws=dev_ws, outs=outs, nchunks=args.e2e_chunks)
 
         host_step()
         torch.cuda.synchronize()
@@ -309,7 +307,9 @@ def run_ours(args):
         e2e = {"value": E / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": round(e2e_ms, 3), "steps": n_e2e,
                "h2d_bytes_per_step": int(sum(x.numel() * x.element_size() for x in host)),
                "d2h_bytes_per_step": int(sum(x.numel() * x.element_size() for x in outs)),
-               "api": "ab2_gtconv_fwd_bwd_host (pinned host q,k,v,e,g in; out,dq,dk,dv,de back to host)"}
+               "api": ("ab2_gtconv_fwd_bwd_host_streamed" if plan.perm_is_identity and args.e2e_chunks > 1 else "ab2_gtconv_fwd_bwd_host")
+                      + " (pinned host q,k,v,e,g in; out,dq,dk,dv,de back to pinned host; copies inside the call)",
+               "chunks": args.e2e_chunks}
         del host, outs, dev_ws
 
     # ---- CPU baseline: the reference's op sequence (oracle port) on this box's host cores, bounded sample
@@ -401,6 +401,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-chunks", type=int, default=16, help="dst-row chunks of the streamed host-buffer call (1 = unstreamed)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="encoder", choices=["encoder", "decoder", "processor"],
                     help="encoder = BASELINE configs[1] (the headline); the others are extra report lines")

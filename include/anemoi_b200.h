@@ -151,6 +151,19 @@ int ab2_gtconv_fwd_bwd_host(const void* q_host, const void* k_host, const void* 
                             void* dk_host, void* dv_host, void* de_host, void* dev_ws, size_t dev_ws_bytes,
                             void* stream);
 
+/* Streamed variant of the call above for dst-sorted edge lists (perm == identity): the dst rows are cut into
+ * `nchunks` pieces; chunk c+1 uploads while chunk c computes and chunk c-1 downloads, so the two PCIe directions overlap.
+ * meta_host : HOST int64 [nchunks][8] = {d0, d1, p0, p1, smax, src_final, 0, 0} with [d0,d1) the dst rows of the chunk,
+ *             [p0,p1) = [rowptr[d0], rowptr[d1]) its edges, smax the largest src id referenced by chunks <= c (-1: none),
+ *             src_final the first src id that still has an edge in a later chunk (Ns for the last chunk).
+ * All five gradients/outputs are written.  Results are bit-identical to ab2_gtconv_fwd_bwd_host. */
+int ab2_gtconv_fwd_bwd_host_streamed(const void* q_host, const void* k_host, const void* v_host, const void* e_host,
+                                     const void* g_host, int dtype, const int32_t* rowptr, const int32_t* col,
+                                     const int32_t* perm, const int32_t* colptr, const int32_t* csr2csc,
+                                     const int32_t* crow, int64_t Ns, int64_t Nd, int64_t E, int H, int C, void* out_host,
+                                     void* dq_host, void* dk_host, void* dv_host, void* de_host, const int64_t* meta_host,
+                                     int nchunks, void* dev_ws, size_t dev_ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -154,21 +154,48 @@ def test_graphconv_blocks_golden():
     _check_param_grads(blk, z, 2e-5)
 
 
-def test_host_buffer_entry_point_matches_device_path():
-    """ab2_gtconv_fwd_bwd_host (pinned host in/out, copies inside the call) == the device-resident path, bit for bit."""
+def test_host_buffer_entry_points_match_device_path():
+    """ab2_gtconv_fwd_bwd_host and its streamed variant (pinned host in/out, copies inside the call) == the
+    device-resident path, bit for bit; dst-sorted and shuffled edge lists."""
     import anemoi_models_b200 as b2
     from anemoi_models_b200 import ops
     from anemoi_models_b200.graph import get_csr
 
     torch.manual_seed(3)
     ns, nd, E, H, C = 500, 200, 4000, 4, 16
-    ei = torch.stack([torch.randint(0, ns, (E,)), torch.randint(0, nd, (E,))]).cuda()
-    for dtype in (torch.float32, torch.bfloat16):
-        q, k, v, e, g = (torch.randn(s, H, C).to(dtype).pin_memory() for s in (nd, ns, ns, E, nd))
-        plan = get_csr(ei, ns, nd)
-        out, dq, dk, dv, de = ops.gt_conv_host(q, k, v, e, g, plan)
-        qd, kd, vd, ed = (x.cuda().requires_grad_(True) for x in (q, k, v, e))
-        o = b2.GraphTransformerConv(C)(qd, kd, vd, ed, ei, (ns, nd))
-        o.backward(g.cuda())
-        for a, b_ in ((out, o), (dq, qd.grad), (dk, kd.grad), (dv, vd.grad), (de, ed.grad)):
-            assert torch.equal(a, b_.detach().cpu())
+    ei = torch.stack([torch.randint(0, ns, (E,)), torch.randint(0, nd, (E,))])
+    ei_sorted = ei[:, torch.sort(ei[1], stable=True).indices]
+    for edges, chunks in ((ei, 16), (ei_sorted, 1), (ei_sorted, 7), (ei_sorted, 16), (ei_sorted, 500)):
+        edges = edges.cuda()
+        for dtype in (torch.float32, torch.bfloat16):
+            q, k, v, e, g = (torch.randn(s, H, C).to(dtype).pin_memory() for s in (nd, ns, ns, E, nd))
+            plan = get_csr(edges, ns, nd)
+            assert plan.perm_is_identity == (edges is not ei.cuda() and bool(torch.equal(edges.cpu(), ei_sorted)))
+            out, dq, dk, dv, de = ops.gt_conv_host(q, k, v, e, g, plan, nchunks=chunks)
+            qd, kd, vd, ed = (x.cuda().requires_grad_(True) for x in (q, k, v, e))
+            o = b2.GraphTransformerConv(C)(qd, kd, vd, ed, edges, (ns, nd))
+            o.backward(g.cuda())
+            for a, b_ in ((out, o), (dq, qd.grad), (dk, kd.grad), (dv, vd.grad), (de, ed.grad)):
+                assert torch.equal(a, b_.detach().cpu())
+
+
+def test_host_stream_meta_covers_every_row_once():
+    from anemoi_models_b200 import ops
+    from anemoi_models_b200.graph import GraphCSR
+
+    torch.manual_seed(4)
+    ns, nd = 300, 90
+    dst = torch.sort(torch.randint(0, nd, (1000,))).values
+    src = (dst * 3 + torch.randint(0, 30, (1000,))).clamp_(max=ns - 1)
+    plan = GraphCSR(torch.stack([src, dst]).cuda(), ns, nd)
+    meta = ops.host_stream_meta(plan, 8)
+    assert meta[0, 0] == 0 and meta[-1, 1] == nd and meta[0, 2] == 0 and meta[-1, 3] == 1000
+    assert torch.equal(meta[1:, 0], meta[:-1, 1]) and torch.equal(meta[1:, 2], meta[:-1, 3])
+    assert bool((meta[1:, 4] >= meta[:-1, 4]).all()) and bool((meta[1:, 5] >= meta[:-1, 5]).all())
+    rowptr = plan.rowptr.cpu()
+    for c in range(8):
+        d0, d1, p0, p1, smax, fin = (int(x) for x in meta[c, :6])
+        assert p0 == int(rowptr[d0]) and p1 == int(rowptr[d1])
+        assert int(src[:p1].max()) == smax if p1 > 0 else smax == -1
+        later = src[p1:]
+        assert fin == (int(later.min()) if later.numel() else ns)
