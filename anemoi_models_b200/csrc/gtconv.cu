@@ -27,6 +27,17 @@ struct RowMap {  // how a CTA's threads map onto (dst row, 16-byte chunk)
   int chunks;    // 16-byte chunks in a full row (= D*sizeof(T)/16)
 };
 
+// src rows live in two pieces when the graph is dst-row sharded: rows [0, nsplit) in the rank's own k / v shard, rows
+// [nsplit, Ns) in the halo buffer received from the peers (k2 / v2).  Single GPU: nsplit = Ns and k2, v2 are never read.
+template <typename T>
+__device__ __forceinline__ const T* src_row(const T* own, const T* halo, int nsplit, size_t j, size_t D) {
+  return j < (size_t)nsplit ? own + j * D : halo + (j - (size_t)nsplit) * D;
+}
+template <typename T>
+__device__ __forceinline__ T* src_row(T* own, T* halo, int nsplit, size_t j, size_t D) {
+  return j < (size_t)nsplit ? own + j * D : halo + (j - (size_t)nsplit) * D;
+}
+
 template <int LPH>
 __device__ __forceinline__ unsigned group_mask() {
   if constexpr (LPH == 32) {
@@ -44,7 +55,8 @@ template <typename T, int LPH>
 __global__ void __launch_bounds__(kThreads)
 gtconv_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ e,
                   const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm, int Nd,
-                  RowMap rm, int H, float qscale, T* __restrict__ out, float* __restrict__ lse2) {
+                  RowMap rm, int H, float qscale, T* __restrict__ out, float* __restrict__ lse2, const T* __restrict__ k2,
+                  const T* __restrict__ v2, int nsplit) {
   constexpr int VEC = Vec<T>::N;
   const int lr = threadIdx.x / rm.tpd;
   const int d = blockIdx.x * rm.rpb + lr;
@@ -76,9 +88,9 @@ gtconv_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __r
     for (int u = 0; u < kU; ++u) {
       if (p + u < end) {
         const size_t j = (size_t)jn[u], t = (size_t)tn[u];
-        kr[u] = ldg16_keep(k + j * D + off);
+        kr[u] = ldg16_keep(src_row(k, k2, nsplit, j, D) + off);
         er[u] = ldg16(e + t * D + off);
-        vr[u] = ldg16_keep(v + j * D + off);
+        vr[u] = ldg16_keep(src_row(v, v2, nsplit, j, D) + off);
       } else {
         kr[u] = er[u] = vr[u] = make_uint4(0, 0, 0, 0);
       }
@@ -140,7 +152,8 @@ gtconv_bwd_dst_kernel(const T* __restrict__ q, const T* __restrict__ k, const T*
                       const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm,
                       const int* __restrict__ csr2csc, int Nd, RowMap rm, int H, float qscale, float scale,
                       const T* __restrict__ out, const float* __restrict__ lse2, const T* __restrict__ g, T* __restrict__ dq,
-                      T* __restrict__ de, float2* __restrict__ ads) {
+                      T* __restrict__ de, float2* __restrict__ ads, const T* __restrict__ k2, const T* __restrict__ v2,
+                      int nsplit) {
   constexpr int VEC = Vec<T>::N;
   const int lr = threadIdx.x / rm.tpd;
   const int d = blockIdx.x * rm.rpb + lr;
@@ -185,9 +198,9 @@ gtconv_bwd_dst_kernel(const T* __restrict__ q, const T* __restrict__ k, const T*
       cs[u] = (size_t)cn[u];
       if (p + u < end) {
         const size_t j = (size_t)jn[u];
-        kr[u] = ldg16_keep(k + j * D + off);
+        kr[u] = ldg16_keep(src_row(k, k2, nsplit, j, D) + off);
         er[u] = ldg16(e + ts[u] * D + off);
-        vr[u] = ldg16_keep(v + j * D + off);
+        vr[u] = ldg16_keep(src_row(v, v2, nsplit, j, D) + off);
       } else {
         kr[u] = er[u] = vr[u] = make_uint4(0, 0, 0, 0);
       }
@@ -282,7 +295,8 @@ template <typename T, int LPH>
 __global__ void __launch_bounds__(kThreads)
 gtconv_fwd_rows_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ e,
                        const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm, int Nd,
-                       RowMap rm, int H, float qscale, T* __restrict__ out, float* __restrict__ lse2) {
+                       RowMap rm, int H, float qscale, T* __restrict__ out, float* __restrict__ lse2,
+                       const T* __restrict__ k2, const T* __restrict__ v2, int nsplit) {
   constexpr int VEC = Vec<T>::N;
   constexpr int R = kDstRows;
   const int lr = threadIdx.x / rm.tpd;
@@ -339,9 +353,9 @@ gtconv_fwd_rows_kernel(const T* __restrict__ q, const T* __restrict__ k, const T
     for (int u = 0; u < kU; ++u) {
       if (p + u < end) {
         const size_t j = (size_t)jn[u], t = (size_t)tn[u];
-        kr[u] = ldg16_keep(k + j * D + off);
+        kr[u] = ldg16_keep(src_row(k, k2, nsplit, j, D) + off);
         er[u] = ldg16(e + t * D + off);
-        vr[u] = ldg16_keep(v + j * D + off);
+        vr[u] = ldg16_keep(src_row(v, v2, nsplit, j, D) + off);
       } else {
         kr[u] = er[u] = vr[u] = make_uint4(0, 0, 0, 0);
       }
@@ -397,7 +411,7 @@ template <typename T, int LPH>
 __global__ void __launch_bounds__(kThreads)
 gtconv_bwd_src_kernel(const T* __restrict__ q, const T* __restrict__ g, const int* __restrict__ colptr,
                       const int* __restrict__ crow, const float2* __restrict__ ads, int Ns, RowMap rm, int H,
-                      T* __restrict__ dk, T* __restrict__ dv) {
+                      T* __restrict__ dk, T* __restrict__ dv, T* __restrict__ dk2, T* __restrict__ dv2, int nsplit) {
   constexpr int VEC = Vec<T>::N;
   const int lr = threadIdx.x / rm.tpd;
   const long long j0 = ((long long)blockIdx.x * rm.rpb + lr) * kSrcRows;
@@ -416,12 +430,12 @@ gtconv_bwd_src_kernel(const T* __restrict__ q, const T* __restrict__ g, const in
   int cur = 0;  // row (relative to j0) the accumulators belong to
 
   auto flush_to = [&](int r) {  // store row `cur`, zero-fill the edge-less rows between, move on to row r
-    if (dk) stg16(dk + (size_t)(j0 + cur) * D + off, pack<T>(ka));
-    if (dv) stg16(dv + (size_t)(j0 + cur) * D + off, pack<T>(va));
+    if (dk) stg16(src_row(dk, dk2, nsplit, (size_t)(j0 + cur), D) + off, pack<T>(ka));
+    if (dv) stg16(src_row(dv, dv2, nsplit, (size_t)(j0 + cur), D) + off, pack<T>(va));
     for (int z = cur + 1; z < r; ++z) {
       if (j0 + z < Ns) {
-        if (dk) stg16(dk + (size_t)(j0 + z) * D + off, zero4);
-        if (dv) stg16(dv + (size_t)(j0 + z) * D + off, zero4);
+        if (dk) stg16(src_row(dk, dk2, nsplit, (size_t)(j0 + z), D) + off, zero4);
+        if (dv) stg16(src_row(dv, dv2, nsplit, (size_t)(j0 + z), D) + off, zero4);
       }
     }
 #pragma unroll
@@ -485,7 +499,8 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 gtconv_fwd_generic_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ e,
                           const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm, int Nd, int H,
-                          int C, float qscale, T* __restrict__ out, float* __restrict__ lse2) {
+                          int C, float qscale, T* __restrict__ out, float* __restrict__ lse2, const T* __restrict__ k2,
+                          const T* __restrict__ v2, int nsplit) {
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   if (w >= (long long)Nd * H) return;
@@ -510,8 +525,8 @@ gtconv_fwd_generic_kernel(const T* __restrict__ q, const T* __restrict__ k, cons
       vv[r] = 0.f;
       if (c < C) {
         const float ef = to_f<T>(e[t * D + ho + c]);
-        kk = to_f<T>(k[j * D + ho + c]) + ef;
-        vv[r] = to_f<T>(v[j * D + ho + c]) + ef;
+        kk = to_f<T>(src_row(k, k2, nsplit, j, D)[ho + c]) + ef;
+        vv[r] = to_f<T>(src_row(v, v2, nsplit, j, D)[ho + c]) + ef;
       }
       part = fmaf(qf[r], kk, part);
     }
@@ -537,7 +552,8 @@ __global__ void __launch_bounds__(kThreads)
 gtconv_bwd_dst_generic_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ e,
                               const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm,
                               const int* __restrict__ csr2csc, int Nd, int H, int C, float qscale, float scale, const T* __restrict__ out, const float* __restrict__ lse2,
-                              const T* __restrict__ g, T* __restrict__ dq, T* __restrict__ de, float2* __restrict__ ads) {
+                              const T* __restrict__ g, T* __restrict__ dq, T* __restrict__ de, float2* __restrict__ ads,
+                              const T* __restrict__ k2, const T* __restrict__ v2, int nsplit) {
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   if (w >= (long long)Nd * H) return;
@@ -567,8 +583,8 @@ gtconv_bwd_dst_generic_kernel(const T* __restrict__ q, const T* __restrict__ k, 
       float vv = 0.f;
       if (c < C) {
         const float ef = to_f<T>(e[t * D + ho + c]);
-        kk[r] = to_f<T>(k[j * D + ho + c]) + ef;
-        vv = to_f<T>(v[j * D + ho + c]) + ef;
+        kk[r] = to_f<T>(src_row(k, k2, nsplit, j, D)[ho + c]) + ef;
+        vv = to_f<T>(src_row(v, v2, nsplit, j, D)[ho + c]) + ef;
       }
       ps = fmaf(qf[r], kk[r], ps);
       pg = fmaf(gf[r], vv, pg);
@@ -597,7 +613,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 gtconv_bwd_src_generic_kernel(const T* __restrict__ q, const T* __restrict__ g, const int* __restrict__ colptr,
                               const int* __restrict__ crow, const float2* __restrict__ ads, int Ns, int H, int C,
-                              T* __restrict__ dk, T* __restrict__ dv) {
+                              T* __restrict__ dk, T* __restrict__ dv, T* __restrict__ dk2, T* __restrict__ dv2, int nsplit) {
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   if (w >= (long long)Ns * H) return;
@@ -623,8 +639,8 @@ gtconv_bwd_src_generic_kernel(const T* __restrict__ q, const T* __restrict__ g, 
   for (int r = 0; r < kGenR; ++r) {
     const int c = lane + 32 * r;
     if (c < C) {
-      if (dk) dk[(size_t)j * D + ho + c] = from_f<T>(ka[r]);
-      if (dv) dv[(size_t)j * D + ho + c] = from_f<T>(va[r]);
+      if (dk) src_row(dk, dk2, nsplit, (size_t)j, D)[ho + c] = from_f<T>(ka[r]);
+      if (dv) src_row(dv, dv2, nsplit, (size_t)j, D)[ho + c] = from_f<T>(va[r]);
     }
   }
 }
@@ -660,39 +676,73 @@ static Plan make_plan(int H, int C, int elt) {
   return pl;
 }
 
+// everything a conv launch needs (host side)
+struct ConvArgs {
+  const void *q, *k, *v, *e;        // k, v: the rank's own src rows [0, n_own)
+  const void *k_halo, *v_halo;      // src rows [n_own, Ns) (NULL on one GPU)
+  const int *rowptr, *col, *perm, *colptr, *csr2csc, *crow;
+  int Ns, Nd, n_own, H, C;
+  int64_t E;
+  float qscale, scale;
+  const void *out, *g;
+  const float* lse2_in;
+  void *out_w, *dq, *dk, *dv, *dk_halo, *dv_halo, *de;
+  float* lse2_w;
+  float2* ads;
+  bool low_degree;
+  cudaStream_t st;
+};
+
 template <typename T, int LPH>
-static void launch_fwd(const Plan& pl, bool low_degree, const void* q, const void* k, const void* v, const void* e,
-                       const int* rowptr, const int* col, const int* perm, int Nd, int H, float qscale, void* out,
-                       float* lse2, cudaStream_t st) {
-  if (low_degree) {
-    const int groups = (Nd + kDstRows - 1) / kDstRows;
+static void launch_fwd(const Plan& pl, const ConvArgs& a) {
+  if (a.low_degree) {
+    const int groups = (a.Nd + kDstRows - 1) / kDstRows;
     dim3 grid((groups + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
-    gtconv_fwd_rows_kernel<T, LPH><<<grid, kThreads, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (const T*)e, rowptr, col,
-                                                             perm, Nd, pl.rm, H, qscale, (T*)out, lse2);
+    gtconv_fwd_rows_kernel<T, LPH><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.k, (const T*)a.v, (const T*)a.e,
+                                                               a.rowptr, a.col, a.perm, a.Nd, pl.rm, a.H, a.qscale, (T*)a.out_w,
+                                                               a.lse2_w, (const T*)a.k_halo, (const T*)a.v_halo, a.n_own);
   } else {
-    dim3 grid((Nd + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
-    gtconv_fwd_kernel<T, LPH><<<grid, kThreads, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (const T*)e, rowptr, col, perm,
-                                                        Nd, pl.rm, H, qscale, (T*)out, lse2);
+    dim3 grid((a.Nd + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
+    gtconv_fwd_kernel<T, LPH><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.k, (const T*)a.v, (const T*)a.e, a.rowptr,
+                                                          a.col, a.perm, a.Nd, pl.rm, a.H, a.qscale, (T*)a.out_w, a.lse2_w,
+                                                          (const T*)a.k_halo, (const T*)a.v_halo, a.n_own);
   }
 }
 template <typename T, int LPH>
-static void launch_bwd_dst(const Plan& pl, bool low_degree, const void* q, const void* k, const void* v, const void* e,
-                           const int* rowptr, const int* col, const int* perm, const int* csr2csc, int Nd, int H, float qscale,
-                           float scale, const void* out, const float* lse2, const void* g, void* dq, void* de, float2* ads,
-                           cudaStream_t st) {
-  (void)low_degree;  // a multi-row dst pass was measured on B200: no gain at in-degree 3, slower at in-degree 8
-  dim3 grid((Nd + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
-  gtconv_bwd_dst_kernel<T, LPH><<<grid, kThreads, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (const T*)e, rowptr, col, perm,
-                                                          csr2csc, Nd, pl.rm, H, qscale, scale, (const T*)out, lse2,
-                                                          (const T*)g, (T*)dq, (T*)de, ads);
+static void launch_bwd_dst(const Plan& pl, const ConvArgs& a) {
+  // (a multi-row dst pass was measured on B200: no gain at in-degree 3, slower at in-degree 8 -- one row per group here)
+  dim3 grid((a.Nd + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
+  gtconv_bwd_dst_kernel<T, LPH><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.k, (const T*)a.v, (const T*)a.e, a.rowptr,
+                                                            a.col, a.perm, a.csr2csc, a.Nd, pl.rm, a.H, a.qscale, a.scale,
+                                                            (const T*)a.out, a.lse2_in, (const T*)a.g, (T*)a.dq, (T*)a.de, a.ads,
+                                                            (const T*)a.k_halo, (const T*)a.v_halo, a.n_own);
 }
 template <typename T, int LPH>
-static void launch_bwd_src(const Plan& pl, const void* q, const void* g, const int* colptr, const int* crow,
-                           const float2* ads, int Ns, int H, void* dk, void* dv, cudaStream_t st) {
-  const int groups = (Ns + kSrcRows - 1) / kSrcRows;
+static void launch_bwd_src(const Plan& pl, const ConvArgs& a) {
+  const int groups = (a.Ns + kSrcRows - 1) / kSrcRows;
   dim3 grid((groups + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
-  gtconv_bwd_src_kernel<T, LPH><<<grid, kThreads, 0, st>>>((const T*)q, (const T*)g, colptr, crow, ads, Ns, pl.rm, H, (T*)dk,
-                                                          (T*)dv);
+  gtconv_bwd_src_kernel<T, LPH><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.g, a.colptr, a.crow, a.ads, a.Ns, pl.rm,
+                                                            a.H, (T*)a.dk, (T*)a.dv, (T*)a.dk_halo, (T*)a.dv_halo, a.n_own);
+}
+template <typename T>
+static void launch_generic(int which, const ConvArgs& a) {
+  const int wpb = kThreads / 32;
+  if (which == 0) {
+    const unsigned grid = (unsigned)(((long long)a.Nd * a.H + wpb - 1) / wpb);
+    gtconv_fwd_generic_kernel<T><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.k, (const T*)a.v, (const T*)a.e, a.rowptr,
+                                                             a.col, a.perm, a.Nd, a.H, a.C, a.qscale, (T*)a.out_w, a.lse2_w,
+                                                             (const T*)a.k_halo, (const T*)a.v_halo, a.n_own);
+  } else if (which == 1) {
+    const unsigned grid = (unsigned)(((long long)a.Nd * a.H + wpb - 1) / wpb);
+    gtconv_bwd_dst_generic_kernel<T><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.k, (const T*)a.v, (const T*)a.e,
+                                                                 a.rowptr, a.col, a.perm, a.csr2csc, a.Nd, a.H, a.C, a.qscale,
+                                                                 a.scale, (const T*)a.out, a.lse2_in, (const T*)a.g, (T*)a.dq,
+                                                                 (T*)a.de, a.ads, (const T*)a.k_halo, (const T*)a.v_halo, a.n_own);
+  } else {
+    const unsigned grid = (unsigned)(((long long)a.Ns * a.H + wpb - 1) / wpb);
+    gtconv_bwd_src_generic_kernel<T><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.g, a.colptr, a.crow, a.ads, a.Ns, a.H,
+                                                                 a.C, (T*)a.dk, (T*)a.dv, (T*)a.dk_halo, (T*)a.dv_halo, a.n_own);
+  }
 }
 
 #define AB2_DISPATCH_LPH(T, lph, CALL)                                   \
@@ -704,6 +754,31 @@ static void launch_bwd_src(const Plan& pl, const void* q, const void* g, const i
     case 16: CALL(T, 16); break;                                         \
     default: CALL(T, 32); break;                                         \
   }
+
+// which: 0 = forward, 1 = backward dst pass, 2 = backward src pass
+static int run_conv(int which, int dtype, const ConvArgs& a, const char* name) {
+  const Plan pl = make_plan(a.H, a.C, dtype == AB2_F32 ? 4 : 2);
+  if (pl.vector) {
+#define CALL(T, L)                                \
+  do {                                            \
+    if (which == 0) launch_fwd<T, L>(pl, a);      \
+    else if (which == 1) launch_bwd_dst<T, L>(pl, a); \
+    else launch_bwd_src<T, L>(pl, a);             \
+  } while (0)
+    if (dtype == AB2_F32) {
+      AB2_DISPATCH_LPH(float, pl.lph, CALL)
+    } else {
+      AB2_DISPATCH_LPH(__nv_bfloat16, pl.lph, CALL)
+    }
+#undef CALL
+  } else if (dtype == AB2_F32) {
+    launch_generic<float>(which, a);
+  } else {
+    launch_generic<__nv_bfloat16>(which, a);
+  }
+  AB2_LAUNCH_OK(name);
+  return AB2_OK;
+}
 
 // mean in-degree below which a forward thread group takes kDstRows consecutive dst rows instead of one
 // (measured on B200: decoder graph, in-degree 3: 2.42 -> 1.85 ms; processor graph, in-degree 8: no gain).  AB2_ROW_BLOCKS=0/1 forces it.
@@ -725,116 +800,115 @@ static int check_common(const char* fn, int dtype, int64_t Ns, int64_t Nd, int64
   return 0;
 }
 
+static ConvArgs base_args(const void* q, const void* k, const void* v, const void* k_halo, const void* v_halo, int64_t n_own,
+                          const void* e, const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t Ns, int64_t Nd,
+                          int64_t E, int H, int C, void* stream) {
+  ConvArgs a{};
+  a.q = q; a.k = k; a.v = v; a.e = e;
+  a.k_halo = k_halo; a.v_halo = v_halo;
+  a.n_own = (int)((k_halo || v_halo) ? n_own : Ns);
+  a.rowptr = rowptr; a.col = col; a.perm = perm;
+  a.Ns = (int)Ns; a.Nd = (int)Nd; a.E = E; a.H = H; a.C = C;
+  a.scale = 1.f / sqrtf((float)C);
+  a.qscale = kLog2e * a.scale;
+  a.low_degree = use_row_blocks(E, Nd);
+  a.st = (cudaStream_t)stream;
+  return a;
+}
+
+static int check_halo(const char* fn, const void* k_halo, const void* v_halo, int64_t n_own, int64_t Ns) {
+  if ((k_halo == nullptr) != (v_halo == nullptr)) return fail(AB2_ERR_INVALID, "%s: k_halo and v_halo must be given together", fn);
+  if (k_halo && (n_own < 0 || n_own > Ns)) return fail(AB2_ERR_INVALID, "%s: n_own must be in [0, Ns]", fn);
+  return 0;
+}
+
 }  // namespace ab2
 
 using namespace ab2;
 
+extern "C" int ab2_gtconv_fwd_halo(const void* q, const void* k, const void* v, const void* k_halo, const void* v_halo,
+                                   int64_t n_own, const void* e, int dtype, const int32_t* rowptr, const int32_t* col,
+                                   const int32_t* perm, int64_t Ns, int64_t Nd, int64_t E, int H, int C, void* out, float* lse2,
+                                   void* stream) {
+  if (int rc = check_common("gtconv_fwd", dtype, Ns, Nd, E, H, C)) return rc;
+  if (int rc = check_halo("gtconv_fwd", k_halo, v_halo, n_own, Ns)) return rc;
+  if (Nd == 0) return AB2_OK;
+  if (!q || !out || !lse2 || !rowptr || (E > 0 && (!e || !col || !perm)) || (E > 0 && !k_halo && (!k || !v)))
+    return fail(AB2_ERR_INVALID, "gtconv_fwd: null pointer argument");
+  ConvArgs a = base_args(q, k, v, k_halo, v_halo, n_own, e, rowptr, col, perm, Ns, Nd, E, H, C, stream);
+  a.qscale = kLog2e / sqrtf((float)C);
+  a.out_w = out;
+  a.lse2_w = lse2;
+  return run_conv(0, dtype, a, "gtconv_fwd");
+}
+
 extern "C" int ab2_gtconv_fwd(const void* q, const void* k, const void* v, const void* e, int dtype, const int32_t* rowptr,
                               const int32_t* col, const int32_t* perm, int64_t Ns, int64_t Nd, int64_t E, int H, int C, void* out,
                               float* lse2, void* stream) {
-  if (int rc = check_common("gtconv_fwd", dtype, Ns, Nd, E, H, C)) return rc;
-  if (Nd == 0) return AB2_OK;
-  if (!q || !out || !lse2 || !rowptr || (E > 0 && (!k || !v || !e || !col || !perm))) return fail(AB2_ERR_INVALID, "gtconv_fwd: null pointer argument");
-  cudaStream_t st = (cudaStream_t)stream;
-  const float qscale = kLog2e / sqrtf((float)C);
-  const Plan pl = make_plan(H, C, dtype == AB2_F32 ? 4 : 2);
-  const bool low_degree = use_row_blocks(E, Nd);
-  if (pl.vector) {
-#define CALL(T, L) launch_fwd<T, L>(pl, low_degree, q, k, v, e, rowptr, col, perm, (int)Nd, H, qscale, out, lse2, st)
-    if (dtype == AB2_F32) {
-      AB2_DISPATCH_LPH(float, pl.lph, CALL)
-    } else {
-      AB2_DISPATCH_LPH(__nv_bfloat16, pl.lph, CALL)
-    }
-#undef CALL
-  } else {
-    const long long warps = (long long)Nd * H;
-    const unsigned grid = (unsigned)((warps + kThreads / 32 - 1) / (kThreads / 32));
-    if (dtype == AB2_F32)
-      gtconv_fwd_generic_kernel<float><<<grid, kThreads, 0, st>>>((const float*)q, (const float*)k, (const float*)v, (const float*)e,
-                                                                 rowptr, col, perm, (int)Nd, H, C, qscale, (float*)out, lse2);
-    else
-      gtconv_fwd_generic_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
-                                                                         (const __nv_bfloat16*)v, (const __nv_bfloat16*)e, rowptr, col,
-                                                                         perm, (int)Nd, H, C, qscale, (__nv_bfloat16*)out, lse2);
-  }
-  AB2_LAUNCH_OK("gtconv_fwd");
-  return AB2_OK;
+  return ab2_gtconv_fwd_halo(q, k, v, nullptr, nullptr, Ns, e, dtype, rowptr, col, perm, Ns, Nd, E, H, C, out, lse2, stream);
 }
 
 extern "C" size_t ab2_gtconv_bwd_workspace_bytes(int64_t E, int H) { return (size_t)(E > 0 ? E : 1) * (size_t)H * sizeof(float2); }
+
+static int bwd_dst_impl(ConvArgs a, int dtype, const int32_t* csr2csc, const void* out, const float* lse2, const void* g, void* dq,
+                        void* de, void* ads_ws, size_t ads_ws_bytes) {
+  if (a.Nd == 0) return AB2_OK;
+  if (!a.rowptr || !a.q || !out || !lse2 || !g || (a.E > 0 && (!a.e || !a.col || !a.perm)) || (a.E > 0 && !a.k_halo && (!a.k || !a.v)))
+    return fail(AB2_ERR_INVALID, "gtconv_bwd_dst: null pointer argument");
+  if (ads_ws && ads_ws_bytes < ab2_gtconv_bwd_workspace_bytes(a.E, a.H)) return fail(AB2_ERR_INVALID, "gtconv_bwd_dst: workspace too small");
+  if (ads_ws && a.E > 0 && !csr2csc) return fail(AB2_ERR_INVALID, "gtconv_bwd_dst: ads_ws given without csr2csc");
+  a.csr2csc = csr2csc;
+  a.out = out; a.lse2_in = lse2; a.g = g;
+  a.dq = dq; a.de = de;
+  a.ads = (float2*)ads_ws;
+  return run_conv(1, dtype, a, "gtconv_bwd_dst");
+}
+
+static int bwd_src_impl(ConvArgs a, int dtype, const int32_t* colptr, const int32_t* crow, const void* g, const void* ads_ws, void* dk,
+                        void* dv, void* dk_halo, void* dv_halo) {
+  if (a.Ns == 0 || (!dk && !dv && !dk_halo && !dv_halo)) return AB2_OK;
+  if (!colptr || !ads_ws || (a.E > 0 && (!a.q || !g || !crow))) return fail(AB2_ERR_INVALID, "gtconv_bwd_src: null pointer argument");
+  if (a.n_own < a.Ns && ((dk && !dk_halo) || (dv && !dv_halo)))
+    return fail(AB2_ERR_INVALID, "gtconv_bwd_src: halo rows present but dk_halo / dv_halo missing");
+  a.colptr = colptr; a.crow = crow; a.g = g;
+  a.ads = (float2*)ads_ws;
+  a.dk = dk; a.dv = dv; a.dk_halo = dk_halo; a.dv_halo = dv_halo;
+  return run_conv(2, dtype, a, "gtconv_bwd_src");
+}
 
 extern "C" int ab2_gtconv_bwd_dst(const void* q, const void* k, const void* v, const void* e, int dtype, const int32_t* rowptr,
                                   const int32_t* col, const int32_t* perm, const int32_t* csr2csc, int64_t Ns, int64_t Nd,
                                   int64_t E, int H, int C, const void* out, const float* lse2, const void* g, void* dq, void* de,
                                   void* ads_ws, size_t ads_ws_bytes, void* stream) {
   if (int rc = check_common("gtconv_bwd_dst", dtype, Ns, Nd, E, H, C)) return rc;
-  if (Nd == 0) return AB2_OK;
-  if (!rowptr || !q || !out || !lse2 || !g || (E > 0 && (!k || !v || !e || !col || !perm)))
-    return fail(AB2_ERR_INVALID, "gtconv_bwd_dst: null pointer argument");
-  if (ads_ws && ads_ws_bytes < ab2_gtconv_bwd_workspace_bytes(E, H)) return fail(AB2_ERR_INVALID, "gtconv_bwd_dst: workspace too small");
-  if (ads_ws && E > 0 && !csr2csc) return fail(AB2_ERR_INVALID, "gtconv_bwd_dst: ads_ws given without csr2csc");
-  cudaStream_t st = (cudaStream_t)stream;
-  const float scale = 1.f / sqrtf((float)C);
-  const float qscale = kLog2e * scale;
-  float2* ads = (float2*)ads_ws;
-  const Plan pl = make_plan(H, C, dtype == AB2_F32 ? 4 : 2);
-  const bool low_degree = use_row_blocks(E, Nd);
-  if (pl.vector) {
-#define CALL(T, L) launch_bwd_dst<T, L>(pl, low_degree, q, k, v, e, rowptr, col, perm, csr2csc, (int)Nd, H, qscale, scale, out, lse2, g, dq, de, ads, st)
-    if (dtype == AB2_F32) {
-      AB2_DISPATCH_LPH(float, pl.lph, CALL)
-    } else {
-      AB2_DISPATCH_LPH(__nv_bfloat16, pl.lph, CALL)
-    }
-#undef CALL
-  } else {
-    const int wpb = kThreads / 32;
-    const unsigned grid = (unsigned)(((long long)Nd * H + wpb - 1) / wpb);
-    if (dtype == AB2_F32)
-      gtconv_bwd_dst_generic_kernel<float><<<grid, kThreads, 0, st>>>(
-          (const float*)q, (const float*)k, (const float*)v, (const float*)e, rowptr, col, perm, csr2csc, (int)Nd, H, C, qscale,
-          scale, (const float*)out, lse2, (const float*)g, (float*)dq, (float*)de, ads);
-    else
-      gtconv_bwd_dst_generic_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>(
-          (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)e, rowptr, col, perm,
-          csr2csc, (int)Nd, H, C, qscale, scale, (const __nv_bfloat16*)out, lse2, (const __nv_bfloat16*)g, (__nv_bfloat16*)dq,
-          (__nv_bfloat16*)de, ads);
-  }
-  AB2_LAUNCH_OK("gtconv_bwd_dst");
-  return AB2_OK;
+  return bwd_dst_impl(base_args(q, k, v, nullptr, nullptr, Ns, e, rowptr, col, perm, Ns, Nd, E, H, C, stream), dtype, csr2csc, out,
+                      lse2, g, dq, de, ads_ws, ads_ws_bytes);
 }
 
 extern "C" int ab2_gtconv_bwd_src(const void* q, const void* g, int dtype, const int32_t* colptr, const int32_t* crow,
                                   int64_t Ns, int64_t Nd, int64_t E, int H, int C, const void* ads_ws, void* dk, void* dv,
                                   void* stream) {
   if (int rc = check_common("gtconv_bwd_src", dtype, Ns, Nd, E, H, C)) return rc;
-  if (Ns == 0 || (!dk && !dv)) return AB2_OK;
-  if (!colptr || !ads_ws || (E > 0 && (!q || !g || !crow))) return fail(AB2_ERR_INVALID, "gtconv_bwd_src: null pointer argument");
-  cudaStream_t st = (cudaStream_t)stream;
-  const float2* ads = (const float2*)ads_ws;
-  const Plan pl = make_plan(H, C, dtype == AB2_F32 ? 4 : 2);
-  if (pl.vector) {
-#define CALL(T, L) launch_bwd_src<T, L>(pl, q, g, colptr, crow, ads, (int)Ns, H, dk, dv, st)
-    if (dtype == AB2_F32) {
-      AB2_DISPATCH_LPH(float, pl.lph, CALL)
-    } else {
-      AB2_DISPATCH_LPH(__nv_bfloat16, pl.lph, CALL)
-    }
-#undef CALL
-  } else {
-    const int wpb = kThreads / 32;
-    const unsigned grid = (unsigned)(((long long)Ns * H + wpb - 1) / wpb);
-    if (dtype == AB2_F32)
-      gtconv_bwd_src_generic_kernel<float><<<grid, kThreads, 0, st>>>((const float*)q, (const float*)g, colptr, crow, ads, (int)Ns,
-                                                                     H, C, (float*)dk, (float*)dv);
-    else
-      gtconv_bwd_src_generic_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)g,
-                                                                             colptr, crow, ads, (int)Ns, H, C,
-                                                                             (__nv_bfloat16*)dk, (__nv_bfloat16*)dv);
-  }
-  AB2_LAUNCH_OK("gtconv_bwd_src");
-  return AB2_OK;
+  return bwd_src_impl(base_args(q, nullptr, nullptr, nullptr, nullptr, Ns, nullptr, nullptr, nullptr, nullptr, Ns, Nd, E, H, C, stream),
+                      dtype, colptr, crow, g, ads_ws, dk, dv, nullptr, nullptr);
+}
+
+extern "C" int ab2_gtconv_bwd_halo(const void* q, const void* k, const void* v, const void* k_halo, const void* v_halo,
+                                   int64_t n_own, const void* e, int dtype, const int32_t* rowptr, const int32_t* col,
+                                   const int32_t* perm, const int32_t* colptr, const int32_t* csr2csc, const int32_t* crow,
+                                   int64_t Ns, int64_t Nd, int64_t E, int H, int C, const void* out, const float* lse2,
+                                   const void* g, void* dq, void* dk, void* dv, void* dk_halo, void* dv_halo, void* de,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_common("gtconv_bwd", dtype, Ns, Nd, E, H, C)) return rc;
+  if (int rc = check_halo("gtconv_bwd", k_halo, v_halo, n_own, Ns)) return rc;
+  const bool need_src = dk || dv || dk_halo || dv_halo;
+  if (need_src && (!workspace || workspace_bytes < ab2_gtconv_bwd_workspace_bytes(E, H)))
+    return fail(AB2_ERR_INVALID, "gtconv_bwd: workspace too small");
+  if (need_src && (!colptr || (E > 0 && (!csr2csc || !crow)))) return fail(AB2_ERR_INVALID, "gtconv_bwd: dk/dv requested without the CSC view");
+  const ConvArgs a = base_args(q, k, v, k_halo, v_halo, n_own, e, rowptr, col, perm, Ns, Nd, E, H, C, stream);
+  if (int rc = bwd_dst_impl(a, dtype, csr2csc, out, lse2, g, dq, de, need_src ? workspace : nullptr, workspace_bytes)) return rc;
+  if (!need_src) return AB2_OK;
+  return bwd_src_impl(a, dtype, colptr, crow, g, workspace, dk, dv, dk_halo, dv_halo);
 }
 
 extern "C" int ab2_gtconv_bwd(const void* q, const void* k, const void* v, const void* e, int dtype, const int32_t* rowptr,
@@ -842,13 +916,6 @@ extern "C" int ab2_gtconv_bwd(const void* q, const void* k, const void* v, const
                               const int32_t* crow, int64_t Ns, int64_t Nd, int64_t E, int H, int C, const void* out,
                               const float* lse2, const void* g, void* dq, void* dk, void* dv, void* de, void* workspace,
                               size_t workspace_bytes, void* stream) {
-  const bool need_src = dk || dv;
-  if (need_src && (!workspace || workspace_bytes < ab2_gtconv_bwd_workspace_bytes(E, H)))
-    return fail(AB2_ERR_INVALID, "gtconv_bwd: workspace too small");
-  if (need_src && (!colptr || (E > 0 && (!csr2csc || !crow)))) return fail(AB2_ERR_INVALID, "gtconv_bwd: dk/dv requested without the CSC view");
-  if (int rc = ab2_gtconv_bwd_dst(q, k, v, e, dtype, rowptr, col, perm, csr2csc, Ns, Nd, E, H, C, out, lse2, g, dq, de,
-                                  need_src ? workspace : nullptr, workspace_bytes, stream))
-    return rc;
-  if (!need_src) return AB2_OK;
-  return ab2_gtconv_bwd_src(q, g, dtype, colptr, crow, Ns, Nd, E, H, C, workspace, dk, dv, stream);
+  return ab2_gtconv_bwd_halo(q, k, v, nullptr, nullptr, Ns, e, dtype, rowptr, col, perm, colptr, csr2csc, crow, Ns, Nd, E, H, C, out,
+                             lse2, g, dq, dk, dv, nullptr, nullptr, de, workspace, workspace_bytes, stream);
 }

@@ -2,4 +2,5 @@
 from .shapes import change_channels_in_shape, get_shape_shards  # noqa: F401
 from .khop_edges import sort_edges_1hop_chunks, sort_edges_1hop_sharding  # noqa: F401
 from .collectives import gather_tensor, reduce_shard_tensor, reduce_tensor, shard_tensor, sync_tensor  # noqa: F401
-from .halo import HaloPlan, build_bipartite_halo_plan, halo_gather, select_sharded_edges  # noqa: F401
+from .halo import (HaloPlan, build_bipartite_halo_plan, build_local_halo_plan, exchange_rows, halo_exchange,  # noqa: F401
+                   halo_gather, return_rows, select_sharded_edges)

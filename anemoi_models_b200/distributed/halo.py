@@ -24,20 +24,32 @@ class HaloPlan:
     rank: int
     world: int
     edge_ids: Tensor           # [E_r] original ids of the edges this rank owns (original order = reference chunk r)
-    local_edge_index: Tensor   # [2, E_r] row 0 = index into the compact src buffer, row 1 = dst - dst_lo
-    n_needed: int              # rows of the compact src buffer (= sum(recv_counts))
-    send_idx: Tensor           # [sum(send_counts)] rows of the OWN src shard to send, grouped by peer
-    send_counts: List[int]
-    recv_counts: List[int]
+    local_edge_index: Tensor   # [2, E_r] row 0 = COMPACT src index, row 1 = dst - dst_lo
+    n_own: int                 # src rows of the own shard: compact indices [0, n_own) = global id - src_lo
+    n_halo: int                # src rows owned by peers: compact indices [n_own, n_own + n_halo), ascending global id
+    send_idx: Tensor           # [sum(send_counts)] rows of the OWN src shard the peers need, grouped by peer
+    send_counts: List[int]     # per peer (0 for self)
+    recv_counts: List[int]     # per peer (0 for self); sum = n_halo
     num_dst_local: int
     dst_lo: int
-    num_src_local: int
     src_lo: int
-    csr: object = field(default=None, repr=False)  # GraphCSR of the local graph, built lazily on CUDA
+    halo_ids: Tensor = field(default=None, repr=False)  # [n_halo] global ids of the halo rows
+
+    @property
+    def n_src(self) -> int:
+        return self.n_own + self.n_halo
 
 
-def _unique_sorted(x: Tensor) -> Tensor:
-    return torch.unique(x, sorted=True)
+def _compact_sources(src: Tensor, src_bounds: List[int], rank: int):
+    """compact index of every edge's src: own rows keep (id - src_lo), the others are numbered n_own + position in the
+    sorted list of distinct non-owned ids.  Returns (compact src, halo ids sorted, owner rank of each halo id)."""
+    lo, hi = src_bounds[rank], src_bounds[rank + 1]
+    own = (src >= lo) & (src < hi)
+    halo_ids = torch.unique(src[~own], sorted=True)
+    compact = torch.where(own, src - lo, (hi - lo) + torch.searchsorted(halo_ids, src))
+    sb = torch.tensor(src_bounds, device=src.device, dtype=torch.long)
+    owner = torch.searchsorted(sb, halo_ids, right=True) - 1
+    return compact, halo_ids, owner
 
 
 def build_bipartite_halo_plan(edge_index: Tensor, src_bounds: List[int], dst_bounds: List[int], rank: int) -> HaloPlan:
@@ -50,82 +62,97 @@ def build_bipartite_halo_plan(edge_index: Tensor, src_bounds: List[int], dst_bou
     src, dst = edge_index[0].long(), edge_index[1].long()
     src_lo, src_hi = src_bounds[rank], src_bounds[rank + 1]
     send_lists, send_counts = [], []
-    needed_mine = None
     mask_mine = None
     for p in range(P):
         mask = (dst >= dst_bounds[p]) & (dst < dst_bounds[p + 1])
-        needed = _unique_sorted(src[mask])
         if p == rank:
-            needed_mine, mask_mine = needed, mask
-        own = needed[(needed >= src_lo) & (needed < src_hi)] - src_lo
-        send_lists.append(own)
-        send_counts.append(int(own.numel()))
-    sb = torch.tensor(src_bounds, device=edge_index.device, dtype=torch.long)
-    owner = torch.searchsorted(sb, needed_mine, right=True) - 1
-    recv_counts = torch.bincount(owner, minlength=P)[:P].tolist()
+            mask_mine = mask
+            send_lists.append(src.new_zeros(0))
+            send_counts.append(0)
+            continue
+        needed = torch.unique(src[mask], sorted=True)  # what peer p's edges reference ...
+        mine = needed[(needed >= src_lo) & (needed < src_hi)] - src_lo  # ... of my rows
+        send_lists.append(mine)
+        send_counts.append(int(mine.numel()))
     edge_ids = mask_mine.nonzero(as_tuple=False).view(-1)
-    local_src = torch.searchsorted(needed_mine, src[edge_ids])
+    compact, halo_ids, owner = _compact_sources(src[edge_ids], src_bounds, rank)
+    recv_counts = torch.bincount(owner, minlength=P)[:P].tolist()
     local_dst = dst[edge_ids] - dst_bounds[rank]
-    return HaloPlan(rank=rank, world=P, edge_ids=edge_ids, local_edge_index=torch.stack([local_src, local_dst]).contiguous(),
-                    n_needed=int(needed_mine.numel()), send_idx=torch.cat(send_lists) if send_lists else src.new_zeros(0),
+    return HaloPlan(rank=rank, world=P, edge_ids=edge_ids, local_edge_index=torch.stack([compact, local_dst]).contiguous(),
+                    n_own=src_hi - src_lo, n_halo=int(halo_ids.numel()), send_idx=torch.cat(send_lists),
                     send_counts=send_counts, recv_counts=[int(c) for c in recv_counts],
-                    num_dst_local=dst_bounds[rank + 1] - dst_bounds[rank], dst_lo=dst_bounds[rank],
-                    num_src_local=src_hi - src_lo, src_lo=src_lo)
+                    num_dst_local=dst_bounds[rank + 1] - dst_bounds[rank], dst_lo=dst_bounds[rank], src_lo=src_lo,
+                    halo_ids=halo_ids)
 
 
 def build_local_halo_plan(edge_index_local: Tensor, src_bounds: List[int], dst_bounds: List[int], group) -> HaloPlan:
     """Plan when each rank only holds ITS edges (global node ids) -- the GraphConv path, where the processor has
-    already partitioned the edges with sort_edges_1hop_sharding (reference processor.py:239-246).  The lists of
-    needed rows are exchanged once (two small all-to-alls) and the plan is cached by the caller."""
+    already partitioned the edges with sort_edges_1hop_sharding (reference processor.py:239-246), and the weak-scaling
+    bench.  The lists of needed rows are exchanged once (two small all-to-alls); the caller caches the plan."""
     rank, P = dist.get_rank(group=group), dist.get_world_size(group=group)
     dev = edge_index_local.device
     src, dst = edge_index_local[0].long(), edge_index_local[1].long()
-    needed = _unique_sorted(src)
-    sb = torch.tensor(src_bounds, device=dev, dtype=torch.long)
-    owner = torch.searchsorted(sb, needed, right=True) - 1
+    compact, halo_ids, owner = _compact_sources(src, src_bounds, rank)
     recv_counts = torch.bincount(owner, minlength=P)[:P]
     send_counts = torch.empty_like(recv_counts)
     dist.all_to_all_single(send_counts, recv_counts, group=group)
     send_counts_l, recv_counts_l = send_counts.tolist(), recv_counts.tolist()
     send_idx = torch.empty(sum(send_counts_l), dtype=torch.long, device=dev)
-    dist.all_to_all_single(send_idx, needed.contiguous(), send_counts_l, recv_counts_l, group=group)
+    dist.all_to_all_single(send_idx, halo_ids.contiguous(), send_counts_l, recv_counts_l, group=group)
     send_idx = send_idx - src_bounds[rank]
-    local_src = torch.searchsorted(needed, src)
     local_dst = dst - dst_bounds[rank]
     return HaloPlan(rank=rank, world=P, edge_ids=torch.arange(src.numel(), device=dev),
-                    local_edge_index=torch.stack([local_src, local_dst]).contiguous(), n_needed=int(needed.numel()),
-                    send_idx=send_idx, send_counts=[int(c) for c in send_counts_l], recv_counts=[int(c) for c in recv_counts_l],
-                    num_dst_local=dst_bounds[rank + 1] - dst_bounds[rank], dst_lo=dst_bounds[rank],
-                    num_src_local=src_bounds[rank + 1] - src_bounds[rank], src_lo=src_bounds[rank])
+                    local_edge_index=torch.stack([compact, local_dst]).contiguous(),
+                    n_own=src_bounds[rank + 1] - src_bounds[rank], n_halo=int(halo_ids.numel()), send_idx=send_idx,
+                    send_counts=[int(c) for c in send_counts_l], recv_counts=[int(c) for c in recv_counts_l],
+                    num_dst_local=dst_bounds[rank + 1] - dst_bounds[rank], dst_lo=dst_bounds[rank], src_lo=src_bounds[rank],
+                    halo_ids=halo_ids)
 
 
-class _HaloGather(torch.autograd.Function):
-    """fwd: compact buffer of the src rows this rank's edges need ([own rows | halo rows], ascending global id);
-    bwd: gradients of those rows travel back to their owners and are summed there (fp32 accumulation)."""
+def exchange_rows(x: Tensor, plan: HaloPlan, group) -> Tensor:
+    """[n_halo, ...] rows of peers' shards this rank's edges reference (one all-to-all; no autograd)."""
+    send = x.index_select(0, plan.send_idx).contiguous()
+    recv = torch.empty((plan.n_halo,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_to_all_single(recv, send, plan.recv_counts, plan.send_counts, group=group)
+    return recv
+
+
+def return_rows(g_halo: Tensor, plan: HaloPlan, group, into: Tensor) -> Tensor:
+    """Send the gradients of halo rows back to their owners and add them into `into` ([n_own, ...], in place).
+    Peers are added one after the other; the ids inside one peer's list are distinct, so the sum order is fixed."""
+    back = torch.empty((sum(plan.send_counts),) + tuple(g_halo.shape[1:]), dtype=g_halo.dtype, device=g_halo.device)
+    dist.all_to_all_single(back, g_halo.contiguous(), plan.send_counts, plan.recv_counts, group=group)
+    off = 0
+    for cnt in plan.send_counts:
+        if cnt:
+            into.index_add_(0, plan.send_idx[off:off + cnt], back[off:off + cnt].to(into.dtype))
+        off += cnt
+    return into
+
+
+class _HaloExchange(torch.autograd.Function):
+    """Differentiable exchange_rows (used for the small node tensors of the GraphConv path and by the CPU tests);
+    the GT conv uses the fused `ops.gt_conv_sharded`, which adds the returned gradients in place."""
 
     @staticmethod
     def forward(ctx, x: Tensor, plan: HaloPlan, group) -> Tensor:
-        ctx.plan, ctx.group = plan, group
-        ctx.rows = x.shape[0]
-        send = x.index_select(0, plan.send_idx).contiguous()
-        recv = torch.empty((plan.n_needed,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-        dist.all_to_all_single(recv, send, plan.recv_counts, plan.send_counts, group=group)
-        return recv
+        ctx.plan, ctx.group, ctx.shape = plan, group, tuple(x.shape)
+        return exchange_rows(x, plan, group)
 
     @staticmethod
     def backward(ctx, g: Tensor):
-        plan: HaloPlan = ctx.plan
-        g = g.contiguous()
-        back = torch.empty((sum(plan.send_counts),) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
-        dist.all_to_all_single(back, g, plan.send_counts, plan.recv_counts, group=ctx.group)
-        dx = torch.zeros((ctx.rows,) + tuple(g.shape[1:]), dtype=torch.float32, device=g.device)
-        dx.index_add_(0, plan.send_idx, back.float())
+        dx = torch.zeros(ctx.shape, dtype=torch.float32, device=g.device)
+        return_rows(g.float(), ctx.plan, ctx.group, dx)
         return dx.to(g.dtype), None, None
 
 
+def halo_exchange(x: Tensor, plan: HaloPlan, group) -> Tensor:
+    return _HaloExchange.apply(x, plan, group)
+
+
 def halo_gather(x: Tensor, plan: HaloPlan, group) -> Tensor:
-    """[n_needed, ...] rows of the (row-sharded) tensor x referenced by this rank's edges."""
-    return _HaloGather.apply(x, plan, group)
+    """[n_own + n_halo, ...] = own rows followed by the halo rows (the compact src space of plan.local_edge_index)."""
+    return torch.cat([x, halo_exchange(x, plan, group)], dim=0)
 
 
 class _SelectShardedEdges(torch.autograd.Function):

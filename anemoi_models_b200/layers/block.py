@@ -21,7 +21,7 @@ import torch.distributed as dist
 from torch import Tensor, nn
 
 from ..distributed.collectives import shard_tensor, sync_tensor
-from ..distributed.halo import (HaloPlan, build_bipartite_halo_plan, build_local_halo_plan, halo_gather,
+from ..distributed.halo import (HaloPlan, build_bipartite_halo_plan, build_local_halo_plan, halo_exchange, halo_gather,
                                 select_sharded_edges)
 from ..distributed.shapes import bounds_from_shapes
 from ..graph import TensorKeyedCache, check_edge_index, get_csr, resolve_size
@@ -81,7 +81,7 @@ class GraphConvBaseBlock(BaseBlock):
         plan: HaloPlan = _halo_cache.get(edge_index, ("local", tuple(sb), tuple(db), rank),
                                          lambda: build_local_halo_plan(edge_index, sb, db, model_comm_group))
         x_need = halo_gather(x_src, plan, model_comm_group)  # replaces sync_tensor's full all-gather (block.py:203)
-        return self.conv((x_need, x_dst), edge_attr, plan.local_edge_index, size=(plan.n_needed, plan.num_dst_local))
+        return self.conv((x_need, x_dst), edge_attr, plan.local_edge_index, size=(plan.n_src, plan.num_dst_local))
 
     @abstractmethod
     def forward(self, x, edge_attr, edge_index, shapes, model_comm_group=None, size=None): ...
@@ -173,10 +173,16 @@ class GraphTransformerBaseBlock(BaseBlock, ABC):
         # raw attributes of the edges this rank owns (they arrive sharded by original edge order), then project locally
         ea_local = select_sharded_edges(edge_attr, shapes_edge, plan.edge_ids, model_comm_group)
         e = self.lin_edge(ea_local).view(-1, H, C)
-        k_need = halo_gather(key, plan, model_comm_group).view(-1, H, C)
-        v_need = halo_gather(value, plan, model_comm_group).view(-1, H, C)
-        out = self.conv(query=query.view(-1, H, C), key=k_need, value=v_need, edge_attr=e, edge_index=plan.local_edge_index,
-                        size=(plan.n_needed, plan.num_dst_local))
+        q, k, v = query.view(-1, H, C), key.view(-1, H, C), value.view(-1, H, C)
+        size = (plan.n_src, plan.num_dst_local)
+        if q.is_cuda:
+            from .. import ops
+
+            csr = get_csr(plan.local_edge_index, *size)
+            out = ops.gt_conv_sharded(q, k, v, e, csr, plan, model_comm_group)
+        else:  # generic composition (differentiable exchange + conv on [own | halo] rows)
+            halo = (halo_exchange(k, plan, model_comm_group), halo_exchange(v, plan, model_comm_group))
+            out = self.conv(query=q, key=k, value=v, edge_attr=e, edge_index=plan.local_edge_index, size=size, halo=halo)
         return out.reshape(out.shape[0], H * C)
 
     @abstractmethod

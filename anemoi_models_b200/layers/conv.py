@@ -45,22 +45,25 @@ class GraphTransformerConv(nn.Module):
         self.aggr, self.flow, self.node_dim = "add", "source_to_target", 0
 
     def forward(self, query: Tensor, key: Tensor, value: Tensor, edge_attr: Optional[Tensor], edge_index: Tensor,
-                size: Size = None, plan: Optional[GraphCSR] = None) -> Tensor:
+                size: Size = None, plan: Optional[GraphCSR] = None, halo=None) -> Tensor:
+        """`halo=(key_halo, value_halo)`: extra src rows appended after `key`/`value` (dst-row sharding; the src ids of
+        `edge_index` are then indices into [key | key_halo])."""
         if edge_attr is None:
             # the reference adds edge_attr unconditionally (conv.py:142) and fails with a TypeError
             raise TypeError("unsupported operand type(s) for +: 'Tensor' and 'NoneType' (edge_attr is required)")
         if self.dropout > 0.0 and self.training:
             raise NotImplementedError("attention dropout > 0 is not implemented (no reference caller sets it, block.py:339)")
         check_edge_index(edge_index)
-        n_src, n_dst = resolve_size(size, key.shape[0], query.shape[0])
-        if value.shape[0] != n_src:
-            raise ValueError(f"Encountered tensor with size {value.shape[0]} in dimension 0, but expected size {n_src}.")
+        n_halo = 0 if halo is None else halo[0].shape[0]
+        n_src, n_dst = resolve_size(size, key.shape[0] + n_halo, query.shape[0])
+        if value.shape[0] + n_halo != n_src:
+            raise ValueError(f"Encountered tensor with size {value.shape[0] + n_halo} in dimension 0, but expected size {n_src}.")
         if query.shape[2] != self.out_channels:
             # the reference scales by self.out_channels**0.5 whatever the tensor width is; keep them consistent
             raise ValueError(f"query has {query.shape[2]} channels per head but out_channels={self.out_channels}")
         if plan is None:
             plan = get_csr(edge_index, n_src, n_dst)
-        return ops.gt_conv(query, key, value, edge_attr, plan)
+        return ops.gt_conv(query, key, value, edge_attr, plan, halo=halo)
 
 
 class GraphConv(nn.Module):

@@ -35,68 +35,137 @@ def _common_dtype(*tensors: Tensor) -> torch.dtype:
     return dt
 
 
+def _conv_forward(q, k, v, k_halo, v_halo, e, plan):
+    L = _lib.lib()
+    Nd, H, C = q.shape
+    n_own = k.shape[0]
+    Ns = n_own + (k_halo.shape[0] if k_halo is not None else 0)
+    out = torch.empty_like(q)
+    lse2 = torch.empty((Nd, H), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(L.ab2_gtconv_fwd_halo(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(k_halo), _lib.ptr(v_halo), n_own,
+                                         _lib.ptr(e), _lib.dtype_code(q.dtype), _lib.ptr(plan.rowptr), _lib.ptr(plan.col),
+                                         _lib.ptr(plan.perm), Ns, Nd, plan.num_edges, H, C, _lib.ptr(out), _lib.ptr(lse2),
+                                         _lib.current_stream(q.device)))
+    return out, lse2
+
+
+def _conv_backward(q, k, v, k_halo, v_halo, e, out, lse2, g, plan, need):
+    """need = (dq, dk, dv, de) flags; returns (dq, dk, dv, de, dk_halo, dv_halo)."""
+    L = _lib.lib()
+    Nd, H, C = q.shape
+    n_own = k.shape[0]
+    Ns = n_own + (k_halo.shape[0] if k_halo is not None else 0)
+    E = plan.num_edges
+    g = g.contiguous()
+    if g.dtype != q.dtype:
+        g = g.to(q.dtype)
+    dq = torch.empty_like(q) if need[0] else None
+    dk = torch.empty_like(k) if need[1] else None
+    dv = torch.empty_like(v) if need[2] else None
+    de = torch.empty_like(e) if need[3] else None
+    dkh = torch.empty_like(k_halo) if (need[1] and k_halo is not None) else None
+    dvh = torch.empty_like(v_halo) if (need[2] and v_halo is not None) else None
+    ws_bytes = L.ab2_gtconv_bwd_workspace_bytes(E, H)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device) if (need[1] or need[2]) else None
+    with torch.cuda.device(q.device):
+        _lib.check(L.ab2_gtconv_bwd_halo(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(k_halo), _lib.ptr(v_halo), n_own,
+                                         _lib.ptr(e), _lib.dtype_code(q.dtype), _lib.ptr(plan.rowptr), _lib.ptr(plan.col),
+                                         _lib.ptr(plan.perm), _lib.ptr(plan.colptr), _lib.ptr(plan.csr2csc), _lib.ptr(plan.crow),
+                                         Ns, Nd, E, H, C, _lib.ptr(out), _lib.ptr(lse2), _lib.ptr(g), _lib.ptr(dq), _lib.ptr(dk),
+                                         _lib.ptr(dv), _lib.ptr(dkh), _lib.ptr(dvh), _lib.ptr(de), _lib.ptr(ws),
+                                         ws_bytes if ws is not None else 0, _lib.current_stream(q.device)))
+    return dq, dk, dv, de, dkh, dvh
+
+
 class _GTConvFn(torch.autograd.Function):
-    """Fused GraphTransformerConv (reference layers/conv.py:98-142 + PyG softmax/scatter)."""
+    """Fused GraphTransformerConv (reference layers/conv.py:98-142 + PyG softmax/scatter).  The src rows may come in two
+    pieces (own shard + halo buffer); gradients are returned for each piece."""
 
     @staticmethod
-    def forward(ctx, q: Tensor, k: Tensor, v: Tensor, e: Tensor, plan: GraphCSR) -> Tensor:
-        L = _lib.lib()
-        Nd, H, C = q.shape
-        Ns = k.shape[0]
-        E = plan.num_edges
-        dt = _lib.dtype_code(q.dtype)
-        out = torch.empty_like(q)
-        lse2 = torch.empty((Nd, H), dtype=torch.float32, device=q.device)
-        with torch.cuda.device(q.device):
-            _lib.check(L.ab2_gtconv_fwd(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(e), dt, _lib.ptr(plan.rowptr),
-                                        _lib.ptr(plan.col), _lib.ptr(plan.perm), Ns, Nd, E, H, C, _lib.ptr(out),
-                                        _lib.ptr(lse2), _lib.current_stream(q.device)))
-        ctx.save_for_backward(q, k, v, e, out, lse2)
+    def forward(ctx, q: Tensor, k: Tensor, v: Tensor, e: Tensor, k_halo, v_halo, plan: GraphCSR) -> Tensor:
+        out, lse2 = _conv_forward(q, k, v, k_halo, v_halo, e, plan)
+        ctx.has_halo = k_halo is not None
+        if ctx.has_halo:
+            ctx.save_for_backward(q, k, v, e, out, lse2, k_halo, v_halo)
+        else:
+            ctx.save_for_backward(q, k, v, e, out, lse2)
         ctx.plan = plan
         return out
 
     @staticmethod
     def backward(ctx, g: Tensor):
-        q, k, v, e, out, lse2 = ctx.saved_tensors
-        plan: GraphCSR = ctx.plan
-        L = _lib.lib()
-        Nd, H, C = q.shape
-        Ns = k.shape[0]
-        E = plan.num_edges
-        dt = _lib.dtype_code(q.dtype)
-        g = g.contiguous()
-        if g.dtype != q.dtype:
-            g = g.to(q.dtype)
-        need = ctx.needs_input_grad
-        dq = torch.empty_like(q) if need[0] else None
-        dk = torch.empty_like(k) if need[1] else None
-        dv = torch.empty_like(v) if need[2] else None
-        de = torch.empty_like(e) if need[3] else None
-        ws_bytes = L.ab2_gtconv_bwd_workspace_bytes(E, H)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device) if (need[1] or need[2]) else None
-        with torch.cuda.device(q.device):
-            _lib.check(L.ab2_gtconv_bwd(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(e), dt, _lib.ptr(plan.rowptr),
-                                        _lib.ptr(plan.col), _lib.ptr(plan.perm), _lib.ptr(plan.colptr), _lib.ptr(plan.csr2csc),
-                                        _lib.ptr(plan.crow), Ns, Nd, E, H, C, _lib.ptr(out), _lib.ptr(lse2), _lib.ptr(g),
-                                        _lib.ptr(dq), _lib.ptr(dk), _lib.ptr(dv), _lib.ptr(de), _lib.ptr(ws),
-                                        ws_bytes if ws is not None else 0, _lib.current_stream(q.device)))
-        return dq, dk, dv, de, None
+        if ctx.has_halo:
+            q, k, v, e, out, lse2, k_halo, v_halo = ctx.saved_tensors
+        else:
+            (q, k, v, e, out, lse2), k_halo, v_halo = ctx.saved_tensors, None, None
+        n = ctx.needs_input_grad
+        need = (n[0], n[1] or n[4], n[2] or n[5], n[3])
+        dq, dk, dv, de, dkh, dvh = _conv_backward(q, k, v, k_halo, v_halo, e, out, lse2, g, ctx.plan, need)
+        return dq, dk, dv, de, dkh, dvh, None
 
 
-def gt_conv(query: Tensor, key: Tensor, value: Tensor, edge_attr: Tensor, plan: GraphCSR) -> Tensor:
-    """out[Nd,H,C] of the fused graph-transformer convolution; q [Nd,H,C], k/v [Ns,H,C], e [E,H,C] (original edge order)."""
-    _require_cuda(query, key, value, edge_attr)
+def _check_conv_args(query, key, value, edge_attr, plan, n_halo):
     if query.dim() != 3 or key.dim() != 3 or value.dim() != 3 or edge_attr.dim() != 3:
         raise ValueError("query/key/value/edge_attr must be [N, heads, channels]")
     if key.shape != value.shape or key.shape[1:] != query.shape[1:] or edge_attr.shape[1:] != query.shape[1:]:
         raise ValueError(f"inconsistent shapes q{tuple(query.shape)} k{tuple(key.shape)} v{tuple(value.shape)} e{tuple(edge_attr.shape)}")
     if edge_attr.shape[0] != plan.num_edges:
         raise ValueError(f"edge_attr has {edge_attr.shape[0]} rows but edge_index has {plan.num_edges} edges")
-    if query.shape[0] != plan.num_dst or key.shape[0] != plan.num_src:
+    if query.shape[0] != plan.num_dst or key.shape[0] + n_halo != plan.num_src:
         raise ValueError("node counts do not match the graph plan")
+
+
+def gt_conv(query: Tensor, key: Tensor, value: Tensor, edge_attr: Tensor, plan: GraphCSR, halo=None) -> Tensor:
+    """out[Nd,H,C] of the fused graph-transformer convolution; q [Nd,H,C], k/v [n_own,H,C], e [E,H,C] (original edge
+    order).  `halo=(k_halo, v_halo)` appends src rows [n_own, n_own+n_halo) held in separate buffers (dst-row sharding)."""
+    k_halo, v_halo = halo if halo is not None else (None, None)
+    _require_cuda(query, key, value, edge_attr, k_halo, v_halo)
+    _check_conv_args(query, key, value, edge_attr, plan, 0 if k_halo is None else k_halo.shape[0])
     dt = _common_dtype(query, key, value, edge_attr)
     q, k, v, e = (t.to(dt).contiguous() for t in (query, key, value, edge_attr))
-    return _GTConvFn.apply(q, k, v, e, plan)
+    if k_halo is not None:
+        k_halo, v_halo = k_halo.to(dt).contiguous(), v_halo.to(dt).contiguous()
+    return _GTConvFn.apply(q, k, v, e, k_halo, v_halo, plan)
+
+
+class _GTConvShardedFn(torch.autograd.Function):
+    """dst-row-sharded conv with the halo exchange inside: forward pulls the k / v rows of peers this rank's edges
+    reference (NCCL all-to-all over NVLink) straight into the halo buffers the kernels read; backward sends the
+    gradients of those rows home and adds them into dk / dv in place (no full-size temporaries)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, e, plan: GraphCSR, hplan, group):
+        from .distributed.halo import exchange_rows
+
+        k_halo = exchange_rows(k, hplan, group)
+        v_halo = exchange_rows(v, hplan, group)
+        out, lse2 = _conv_forward(q, k, v, k_halo, v_halo, e, plan)
+        ctx.save_for_backward(q, k, v, e, out, lse2, k_halo, v_halo)
+        ctx.plan, ctx.hplan, ctx.group = plan, hplan, group
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from .distributed.halo import return_rows
+
+        q, k, v, e, out, lse2, k_halo, v_halo = ctx.saved_tensors
+        n = ctx.needs_input_grad
+        dq, dk, dv, de, dkh, dvh = _conv_backward(q, k, v, k_halo, v_halo, e, out, lse2, g, ctx.plan, (n[0], n[1], n[2], n[3]))
+        if n[1]:
+            return_rows(dkh, ctx.hplan, ctx.group, dk)
+        if n[2]:
+            return_rows(dvh, ctx.hplan, ctx.group, dv)
+        return dq, dk, dv, de, None, None, None
+
+
+def gt_conv_sharded(query: Tensor, key: Tensor, value: Tensor, edge_attr: Tensor, plan: GraphCSR, hplan, group) -> Tensor:
+    """Fused conv on this rank's dst rows; key/value are the rank's own src rows, the halo is exchanged inside."""
+    _require_cuda(query, key, value, edge_attr)
+    _check_conv_args(query, key, value, edge_attr, plan, hplan.n_halo)
+    dt = _common_dtype(query, key, value, edge_attr)
+    q, k, v, e = (t.to(dt).contiguous() for t in (query, key, value, edge_attr))
+    return _GTConvShardedFn.apply(q, k, v, e, plan, hplan, group)
 
 
 class _EdgeGatherAddActFn(torch.autograd.Function):

@@ -109,3 +109,52 @@ def encoder_graph_band(src_points: int, dst_N: int, parts: int, part: int, cutof
     i_hi = min(src_points, int(np.ceil((1.0 - zmin) * src_points / 2.0)) + 1)
     ei = cutoff_edges(fibonacci_sphere(src_points, i_lo, i_hi), band, radius, src_offset=i_lo, dst_offset=lo)
     return ei, src_points, nd, radius
+
+
+def icosahedron():
+    """12 vertices / 20 faces of the unit icosahedron."""
+    phi = (1.0 + np.sqrt(5.0)) / 2.0
+    v = np.array([[-1, phi, 0], [1, phi, 0], [-1, -phi, 0], [1, -phi, 0], [0, -1, phi], [0, 1, phi], [0, -1, -phi],
+                  [0, 1, -phi], [phi, 0, -1], [phi, 0, 1], [-phi, 0, -1], [-phi, 0, 1]], dtype=np.float64)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    f = np.array([[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4], [11, 10, 2], [10, 7, 6],
+                  [7, 1, 8], [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9], [4, 9, 5], [2, 4, 11], [6, 2, 10],
+                  [8, 6, 7], [9, 8, 1]], dtype=np.int64)
+    return v, f
+
+
+def multiscale_icosahedral_mesh(refinement: int = 6):
+    """Multi-scale icosahedral mesh: nodes of the finest level (refinement 6 -> 40,962), edge set = union of the edges of
+    every level 0..refinement, both directions (E = 2 * 30 * (4**(refinement+1) - 1) / 3 = 327,660 for refinement 6).
+    Returns (xyz[N,3], edge_index[2,E] int64 sorted by dst then src)."""
+    verts, faces = icosahedron()
+    verts = [tuple(x) for x in verts]
+    edges = set()
+
+    def add_face_edges(fs):
+        for a, b, c in fs:
+            for x, y in ((a, b), (b, c), (c, a)):
+                edges.add((int(x), int(y)))
+                edges.add((int(y), int(x)))
+
+    add_face_edges(faces)
+    for _ in range(refinement):
+        mid = {}
+        new_faces = []
+
+        def midpoint(a, b):
+            key = (a, b) if a < b else (b, a)
+            if key not in mid:
+                m = np.asarray(verts[a]) + np.asarray(verts[b])
+                m /= np.linalg.norm(m)
+                verts.append(tuple(m))
+                mid[key] = len(verts) - 1
+            return mid[key]
+
+        for a, b, c in faces:
+            ab, bc, ca = midpoint(a, b), midpoint(b, c), midpoint(c, a)
+            new_faces += [[a, ab, ca], [b, bc, ab], [c, ca, bc], [ab, bc, ca]]
+        faces = np.asarray(new_faces, dtype=np.int64)
+        add_face_edges(faces)
+    e = np.asarray(sorted(edges, key=lambda t: (t[1], t[0])), dtype=np.int64).T
+    return np.asarray(verts), np.ascontiguousarray(e)

@@ -163,7 +163,7 @@ def run_ours(args):
 
     import anemoi_models_b200 as b2
     from anemoi_models_b200 import _lib, ops
-    from anemoi_models_b200.distributed.halo import build_local_halo_plan, halo_gather
+    from anemoi_models_b200.distributed.halo import build_local_halo_plan
     from anemoi_models_b200.graph import GraphCSR
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -195,7 +195,7 @@ def run_ours(args):
     if world > 1:
         hplan = build_local_halo_plan(ei_glob, sb, db, group)
         ei_loc = hplan.local_edge_index
-        n_src = hplan.n_needed
+        n_src = hplan.n_src
     else:
         hplan, ei_loc, n_src = None, ei_glob, Ns_g
     plan = GraphCSR(ei_loc, n_src, nd_loc)
@@ -206,10 +206,9 @@ def run_ours(args):
         qq, ee = q.detach().requires_grad_(True), e.detach().requires_grad_(True)
         kk, vv = k_own.detach().requires_grad_(True), v_own.detach().requires_grad_(True)
         if world > 1:
-            kn, vn = halo_gather(kk, hplan, group), halo_gather(vv, hplan, group)
+            out = ops.gt_conv_sharded(qq, kk, vv, ee, plan, hplan, group)
         else:
-            kn, vn = kk, vv
-        out = conv(qq, kn, vn, ee, ei_loc, (n_src, nd_loc), plan=plan)
+            out = conv(qq, kk, vv, ee, ei_loc, (n_src, nd_loc), plan=plan)
         out.backward(g)
         return out
 
@@ -323,7 +322,7 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": workload_name(world, args.workload), "edges_total": int(float(etot)), "edges_rank0": int(E),
-                       "src_rows_rank0": int(n_src), "dst_rows_rank0": int(nd_loc), "hidden": D, "heads": H,
+                       "src_rows_rank0": int(n_src), "halo_rows_rank0": int(hplan.n_halo) if hplan is not None else 0, "dst_rows_rank0": int(nd_loc), "hidden": D, "heads": H,
                        "l2": "inputs (>5 GB per step) exceed the 126 MB L2; no flush between steps",
                        "timed_region": "conv forward + backward (+ halo all-to-all of k,v and its backward when n_gpus>1); CSR build excluded (one-off, cached)"},
             "clocks": sampler.summary(),
@@ -375,6 +374,59 @@ def cpu_reference_sample(ei_np, Ns, Nd, steps, warmup, frac=8):
                       f"{steps} timed fwd+bwd after {warmup} warm-up; oracle/gtconv.py gt_conv_unfused = reference conv.py:98-142 + PyG op sequence on torch CPU"}
 
 
+def run_graphconv(args):
+    """Report line (not the headline): one GraphConvProcessorBlock layer (reference block.py:170-223), fwd+bwd, bf16, on the
+    multi-scale icosahedral mesh of BASELINE configs[2] (refinement 6: 40,962 nodes, 327,660 edges), hidden D=512.
+    The edge MLP is GEMM work (tensor roofline); the kernels of this repo cover the gather/activation/LayerNorm/scatter."""
+    import anemoi_models_b200 as b2
+    from anemoi_models_b200 import synthetic as S
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    Dg = args.graphconv_dim
+    xyz, ei_np = S.multiscale_icosahedral_mesh(6)
+    N, E = xyz.shape[0], ei_np.shape[1]
+    ei = torch.from_numpy(ei_np).to(dev)
+    torch.manual_seed(0)
+    blk = b2.GraphConvProcessorBlock(Dg, Dg).to(dev).to(torch.bfloat16)
+    x = torch.randn(N, Dg, device=dev, dtype=torch.bfloat16)
+    e = torch.randn(E, Dg, device=dev, dtype=torch.bfloat16)
+    gx, ge = torch.randn_like(x), torch.randn_like(e)
+    shapes = ([[N, Dg]], [[N, Dg]], None)
+
+    def step():
+        xx, ee = x.detach().requires_grad_(True), e.detach().requires_grad_(True)
+        nodes, edges = blk(xx, ee, ei, shapes)
+        torch.autograd.backward([nodes, edges], [gx, ge])
+
+    sampler = ClockSampler(0)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with sampler:
+        ev0.record()
+        for _ in range(args.steps):
+            step()
+        ev1.record()
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    # executed GEMM FLOPs with the split first layer: edge GEMMs pe, W1, W2 (3 x 2*E*D^2), node GEMMs pi, pj (2 x 2*N*D^2),
+    # node MLP 2*N*(2D*D + D*D + D*D); backward = 2x forward
+    flops_fwd = 6 * E * Dg * Dg + 4 * N * Dg * Dg + 8 * N * Dg * Dg
+    tfs = 3 * flops_fwd / (ms * 1e-3) / 1e12
+    with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+        tpeak = float(json.load(f)["bf16_tflops"])
+    line = {"metric": "graphconv_block_fwd_bwd_edges_per_s", "value": E / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"GraphConvProcessorBlock layer, multi-scale icosahedral mesh r6 (N={N}, E={E}), D={Dg}, bf16 fwd+bwd (report line)"},
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "tensor", "achieved": round(tfs, 1), "peak": tpeak, "unit": "TFLOP/s", "frac": round(tfs / tpeak, 4),
+                         "traffic": None, "note": "executed GEMM FLOPs (split first layer) of the whole block over the block time; GEMMs run on cuBLASLt"}}
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -403,11 +455,14 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-chunks", type=int, default=16, help="dst-row chunks of the streamed host-buffer call (1 = unstreamed)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="encoder", choices=["encoder", "decoder", "processor"],
+    ap.add_argument("--graphconv-dim", type=int, default=512)
+    ap.add_argument("--workload", default="encoder", choices=["encoder", "decoder", "processor", "graphconv"],
                     help="encoder = BASELINE configs[1] (the headline); the others are extra report lines")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "graphconv":
+        run_graphconv(args)
     else:
         run_ours(args)
 

@@ -107,6 +107,21 @@ int ab2_gtconv_bwd(const void* q, const void* k, const void* v, const void* e, i
                    const float* lse2, const void* g, void* dq, void* dk, void* dv, void* de, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* dst-row-sharded variants (one process per GPU).  The rank's edges index a COMPACT src space of Ns = n_own + n_halo
+ * rows: [0, n_own) are the rank's own k / v rows (k, v), [n_own, Ns) the halo rows received from the peers (k_halo,
+ * v_halo -- e.g. the receive buffer of an NCCL all-to-all, or peer memory mapped through NVLink).  No concatenation
+ * copy is needed.  Backward writes the gradients of own rows to dk / dv and those of halo rows to dk_halo / dv_halo
+ * (to be sent back to their owners).  Replaces the reference's head all-to-all (layers/block.py:366-414). */
+int ab2_gtconv_fwd_halo(const void* q, const void* k, const void* v, const void* k_halo, const void* v_halo, int64_t n_own,
+                        const void* e, int dtype, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
+                        int64_t Ns, int64_t Nd, int64_t E, int H, int C, void* out, float* lse2, void* stream);
+int ab2_gtconv_bwd_halo(const void* q, const void* k, const void* v, const void* k_halo, const void* v_halo, int64_t n_own,
+                        const void* e, int dtype, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
+                        const int32_t* colptr, const int32_t* csr2csc, const int32_t* crow, int64_t Ns, int64_t Nd,
+                        int64_t E, int H, int C, const void* out, const float* lse2, const void* g, void* dq, void* dk,
+                        void* dv, void* dk_halo, void* dv_halo, void* de, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * GraphConv edge path (layers/conv.py:61-76): the parts of
  *   edges_new = edge_mlp(cat[x_i, x_j, e]) + e ;  out = scatter_sum(edges_new, dst)

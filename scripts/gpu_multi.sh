@@ -6,7 +6,7 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 python -c "import __graft_entry__ as g; g.build()" > $OUT/build.log 2>&1
 nvidia-smi topo -m > $OUT/topo.txt 2>&1
-timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_graphconv_blocks.py -x -q -m gpu > $OUT/pytest_multi.log 2>&1; echo "pytest exit $?" | tee -a $OUT/pytest_multi.log
+timeout 900 python -m pytest tests -x -q -m gpu > $OUT/pytest_multi.log 2>&1; echo "pytest exit $?" | tee -a $OUT/pytest_multi.log
 tail -12 $OUT/pytest_multi.log
 for n in 1 $N; do
   if [ $n == 1 ]; then

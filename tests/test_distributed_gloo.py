@@ -149,29 +149,35 @@ def _halo(rank, world):
     if counts is not None:
         off = int(counts[:rank].sum())
         assert np.array_equal(plan.edge_ids.numpy(), z[f"bip_ids_P{world}"][off:off + int(counts[rank])])
-    assert plan.n_needed == len(ref["needed_src"])
-    assert plan.recv_counts == [len(ref["recv_from"][p]) for p in range(world)]
+    # compact src space = [own shard | halo rows (ascending global id)]
     needed = torch.from_numpy(ref["needed_src"])
-    assert torch.equal(needed[plan.local_edge_index[0]], ei[0, plan.edge_ids])
+    own_mask = (needed >= sb[rank]) & (needed < sb[rank + 1])
+    assert plan.n_own == sb[rank + 1] - sb[rank] and plan.n_halo == int((~own_mask).sum())
+    assert torch.equal(plan.halo_ids, needed[~own_mask])
+    assert plan.recv_counts == [0 if p == rank else len(ref["recv_from"][p]) for p in range(world)]
+    assert plan.send_counts[rank] == 0
+    glob_of_compact = torch.cat([torch.arange(sb[rank], sb[rank + 1]), plan.halo_ids])
+    assert torch.equal(glob_of_compact[plan.local_edge_index[0]], ei[0, plan.edge_ids])
     assert torch.equal(plan.local_edge_index[1] + db[rank], ei[1, plan.edge_ids])
 
-    # exchange: forward picks exactly the needed rows of the (virtual) full tensor
+    # exchange: forward = own rows followed by exactly the halo rows of the (virtual) full tensor
     torch.manual_seed(1)
     x_full = torch.randn(ns, 6)
     xs = x_full[sb[rank]:sb[rank + 1]].clone().requires_grad_(True)
     got = halo_gather(xs, plan, group)
-    assert torch.equal(got, x_full[needed])
+    assert torch.equal(got, x_full[glob_of_compact])
     # backward: d x_full[j] = sum over ranks of the cotangents of row j
-    w = torch.randn(plan.n_needed, 6, generator=torch.Generator().manual_seed(10 + rank))
+    w = torch.randn(plan.n_src, 6, generator=torch.Generator().manual_seed(10 + rank))
     (got * w).sum().backward()
     dense = torch.zeros(ns, 6)
-    dense[needed] = w
+    dense[glob_of_compact] = w
     dist.all_reduce(dense)
     assert torch.allclose(xs.grad, dense[sb[rank]:sb[rank + 1]], atol=1e-6)
 
-    # the plan built from LOCAL edges only (GraphConv path) gives the same exchange
+    # the plan built from LOCAL edges only (GraphConv path, bench) gives the same exchange
     plan2 = build_local_halo_plan(ei[:, plan.edge_ids], sb, db, group)
-    assert plan2.n_needed == plan.n_needed and plan2.recv_counts == plan.recv_counts and plan2.send_counts == plan.send_counts
+    assert (plan2.n_own, plan2.n_halo) == (plan.n_own, plan.n_halo)
+    assert plan2.recv_counts == plan.recv_counts and plan2.send_counts == plan.send_counts
     assert torch.equal(plan2.send_idx, plan.send_idx) and torch.equal(plan2.local_edge_index, plan.local_edge_index)
 
     # raw edge attributes sharded by original order -> rows of own edges; backward returns the shard's gradient
@@ -208,7 +214,12 @@ def _patch_conv_with_oracle():
     from oracle import gtconv as og
 
     convmod.get_csr = lambda ei, ns, nd: _CpuPlan(ei, ns, nd)
-    ops.gt_conv = lambda q, k, v, e, plan: og.gt_conv_unfused(q, k, v, e, plan.edge_index, (plan.num_src, plan.num_dst))
+    def cpu_conv(q, k, v, e, plan, halo=None):
+        if halo is not None:
+            k, v = torch.cat([k, halo[0]]), torch.cat([v, halo[1]])
+        return og.gt_conv_unfused(q, k, v, e, plan.edge_index, (plan.num_src, plan.num_dst))
+
+    ops.gt_conv = cpu_conv
 
     def graphconv_forward(self, x, edge_attr, edge_index, size=None, plan=None):
         p = dict(self.named_parameters())
