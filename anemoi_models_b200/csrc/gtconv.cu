@@ -29,13 +29,15 @@ struct RowMap {  // how a CTA's threads map onto (dst row, 16-byte chunk)
 
 // src rows live in two pieces when the graph is dst-row sharded: rows [0, nsplit) in the rank's own k / v shard, rows
 // [nsplit, Ns) in the halo buffer received from the peers (k2 / v2).  Single GPU: nsplit = Ns and k2, v2 are never read.
-template <typename T>
-__device__ __forceinline__ const T* src_row(const T* own, const T* halo, int nsplit, size_t j, size_t D) {
-  return j < (size_t)nsplit ? own + j * D : halo + (j - (size_t)nsplit) * D;
-}
-template <typename T>
-__device__ __forceinline__ T* src_row(T* own, T* halo, int nsplit, size_t j, size_t D) {
-  return j < (size_t)nsplit ? own + j * D : halo + (j - (size_t)nsplit) * D;
+// The halo pointers handed to the kernels are VIRTUAL bases (halo - nsplit*D, computed on the host), so a row address is
+// one select of the base plus j*D.  SPLIT=false (one GPU) compiles the select away.
+template <bool SPLIT, typename T>
+__device__ __forceinline__ T* src_row(T* own, T* halo_virtual, int nsplit, size_t j, size_t D) {
+  if constexpr (SPLIT) {
+    return (j < (size_t)nsplit ? own : halo_virtual) + j * D;
+  } else {
+    return own + j * D;
+  }
 }
 
 template <int LPH>
@@ -51,7 +53,7 @@ __device__ __forceinline__ unsigned group_mask() {
 // ------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------
-template <typename T, int LPH>
+template <typename T, int LPH, bool SPLIT>
 __global__ void __launch_bounds__(kThreads)
 gtconv_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ e,
                   const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm, int Nd,
@@ -88,9 +90,9 @@ gtconv_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __r
     for (int u = 0; u < kU; ++u) {
       if (p + u < end) {
         const size_t j = (size_t)jn[u], t = (size_t)tn[u];
-        kr[u] = ldg16_keep(src_row(k, k2, nsplit, j, D) + off);
+        kr[u] = ldg16_keep(src_row<SPLIT>(k, k2, nsplit, j, D) + off);
         er[u] = ldg16(e + t * D + off);
-        vr[u] = ldg16_keep(src_row(v, v2, nsplit, j, D) + off);
+        vr[u] = ldg16_keep(src_row<SPLIT>(v, v2, nsplit, j, D) + off);
       } else {
         kr[u] = er[u] = vr[u] = make_uint4(0, 0, 0, 0);
       }
@@ -146,8 +148,8 @@ gtconv_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __r
 // ------------------------------------------------------------------------------------------------------
 // backward, dst pass
 // ------------------------------------------------------------------------------------------------------
-template <typename T, int LPH>
-__global__ void __launch_bounds__(kThreads)
+template <typename T, int LPH, bool SPLIT>
+__global__ void __launch_bounds__(kThreads, 4)
 gtconv_bwd_dst_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ e,
                       const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm,
                       const int* __restrict__ csr2csc, int Nd, RowMap rm, int H, float qscale, float scale,
@@ -198,9 +200,9 @@ gtconv_bwd_dst_kernel(const T* __restrict__ q, const T* __restrict__ k, const T*
       cs[u] = (size_t)cn[u];
       if (p + u < end) {
         const size_t j = (size_t)jn[u];
-        kr[u] = ldg16_keep(src_row(k, k2, nsplit, j, D) + off);
+        kr[u] = ldg16_keep(src_row<SPLIT>(k, k2, nsplit, j, D) + off);
         er[u] = ldg16(e + ts[u] * D + off);
-        vr[u] = ldg16_keep(src_row(v, v2, nsplit, j, D) + off);
+        vr[u] = ldg16_keep(src_row<SPLIT>(v, v2, nsplit, j, D) + off);
       } else {
         kr[u] = er[u] = vr[u] = make_uint4(0, 0, 0, 0);
       }
@@ -291,7 +293,7 @@ __device__ __forceinline__ float select_row(const float (&x)[R], int r) {
   return y;
 }
 
-template <typename T, int LPH>
+template <typename T, int LPH, bool SPLIT>
 __global__ void __launch_bounds__(kThreads)
 gtconv_fwd_rows_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ e,
                        const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm, int Nd,
@@ -353,9 +355,9 @@ gtconv_fwd_rows_kernel(const T* __restrict__ q, const T* __restrict__ k, const T
     for (int u = 0; u < kU; ++u) {
       if (p + u < end) {
         const size_t j = (size_t)jn[u], t = (size_t)tn[u];
-        kr[u] = ldg16_keep(src_row(k, k2, nsplit, j, D) + off);
+        kr[u] = ldg16_keep(src_row<SPLIT>(k, k2, nsplit, j, D) + off);
         er[u] = ldg16(e + t * D + off);
-        vr[u] = ldg16_keep(src_row(v, v2, nsplit, j, D) + off);
+        vr[u] = ldg16_keep(src_row<SPLIT>(v, v2, nsplit, j, D) + off);
       } else {
         kr[u] = er[u] = vr[u] = make_uint4(0, 0, 0, 0);
       }
@@ -407,8 +409,8 @@ gtconv_fwd_rows_kernel(const T* __restrict__ q, const T* __restrict__ k, const T
 // the mean out-degree of an encoder graph is 1.4, i.e. one dependent index->row->store chain per CTA.)
 constexpr int kSrcRows = 8;
 
-template <typename T, int LPH>
-__global__ void __launch_bounds__(kThreads)
+template <typename T, int LPH, bool SPLIT>
+__global__ void __launch_bounds__(kThreads, 6)
 gtconv_bwd_src_kernel(const T* __restrict__ q, const T* __restrict__ g, const int* __restrict__ colptr,
                       const int* __restrict__ crow, const float2* __restrict__ ads, int Ns, RowMap rm, int H,
                       T* __restrict__ dk, T* __restrict__ dv, T* __restrict__ dk2, T* __restrict__ dv2, int nsplit) {
@@ -430,12 +432,12 @@ gtconv_bwd_src_kernel(const T* __restrict__ q, const T* __restrict__ g, const in
   int cur = 0;  // row (relative to j0) the accumulators belong to
 
   auto flush_to = [&](int r) {  // store row `cur`, zero-fill the edge-less rows between, move on to row r
-    if (dk) stg16(src_row(dk, dk2, nsplit, (size_t)(j0 + cur), D) + off, pack<T>(ka));
-    if (dv) stg16(src_row(dv, dv2, nsplit, (size_t)(j0 + cur), D) + off, pack<T>(va));
+    if (dk) stg16(src_row<SPLIT>(dk, dk2, nsplit, (size_t)(j0 + cur), D) + off, pack<T>(ka));
+    if (dv) stg16(src_row<SPLIT>(dv, dv2, nsplit, (size_t)(j0 + cur), D) + off, pack<T>(va));
     for (int z = cur + 1; z < r; ++z) {
       if (j0 + z < Ns) {
-        if (dk) stg16(src_row(dk, dk2, nsplit, (size_t)(j0 + z), D) + off, zero4);
-        if (dv) stg16(src_row(dv, dv2, nsplit, (size_t)(j0 + z), D) + off, zero4);
+        if (dk) stg16(src_row<SPLIT>(dk, dk2, nsplit, (size_t)(j0 + z), D) + off, zero4);
+        if (dv) stg16(src_row<SPLIT>(dv, dv2, nsplit, (size_t)(j0 + z), D) + off, zero4);
       }
     }
 #pragma unroll
@@ -495,7 +497,7 @@ __device__ __forceinline__ float warp_sum(float x) {
   return x;
 }
 
-template <typename T>
+template <typename T, bool SPLIT>
 __global__ void __launch_bounds__(kThreads)
 gtconv_fwd_generic_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ e,
                           const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm, int Nd, int H,
@@ -525,8 +527,8 @@ gtconv_fwd_generic_kernel(const T* __restrict__ q, const T* __restrict__ k, cons
       vv[r] = 0.f;
       if (c < C) {
         const float ef = to_f<T>(e[t * D + ho + c]);
-        kk = to_f<T>(src_row(k, k2, nsplit, j, D)[ho + c]) + ef;
-        vv[r] = to_f<T>(src_row(v, v2, nsplit, j, D)[ho + c]) + ef;
+        kk = to_f<T>(src_row<SPLIT>(k, k2, nsplit, j, D)[ho + c]) + ef;
+        vv[r] = to_f<T>(src_row<SPLIT>(v, v2, nsplit, j, D)[ho + c]) + ef;
       }
       part = fmaf(qf[r], kk, part);
     }
@@ -547,7 +549,7 @@ gtconv_fwd_generic_kernel(const T* __restrict__ q, const T* __restrict__ k, cons
   if (lane == 0) lse2[(size_t)d * H + h] = end > beg ? m + log2f(l + 1e-16f) : 0.f;
 }
 
-template <typename T>
+template <typename T, bool SPLIT>
 __global__ void __launch_bounds__(kThreads)
 gtconv_bwd_dst_generic_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ e,
                               const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm,
@@ -583,8 +585,8 @@ gtconv_bwd_dst_generic_kernel(const T* __restrict__ q, const T* __restrict__ k, 
       float vv = 0.f;
       if (c < C) {
         const float ef = to_f<T>(e[t * D + ho + c]);
-        kk[r] = to_f<T>(src_row(k, k2, nsplit, j, D)[ho + c]) + ef;
-        vv = to_f<T>(src_row(v, v2, nsplit, j, D)[ho + c]) + ef;
+        kk[r] = to_f<T>(src_row<SPLIT>(k, k2, nsplit, j, D)[ho + c]) + ef;
+        vv = to_f<T>(src_row<SPLIT>(v, v2, nsplit, j, D)[ho + c]) + ef;
       }
       ps = fmaf(qf[r], kk[r], ps);
       pg = fmaf(gf[r], vv, pg);
@@ -609,7 +611,7 @@ gtconv_bwd_dst_generic_kernel(const T* __restrict__ q, const T* __restrict__ k, 
   }
 }
 
-template <typename T>
+template <typename T, bool SPLIT>
 __global__ void __launch_bounds__(kThreads)
 gtconv_bwd_src_generic_kernel(const T* __restrict__ q, const T* __restrict__ g, const int* __restrict__ colptr,
                               const int* __restrict__ crow, const float2* __restrict__ ads, int Ns, int H, int C,
@@ -639,8 +641,8 @@ gtconv_bwd_src_generic_kernel(const T* __restrict__ q, const T* __restrict__ g, 
   for (int r = 0; r < kGenR; ++r) {
     const int c = lane + 32 * r;
     if (c < C) {
-      if (dk) src_row(dk, dk2, nsplit, (size_t)j, D)[ho + c] = from_f<T>(ka[r]);
-      if (dv) src_row(dv, dv2, nsplit, (size_t)j, D)[ho + c] = from_f<T>(va[r]);
+      if (dk) src_row<SPLIT>(dk, dk2, nsplit, (size_t)j, D)[ho + c] = from_f<T>(ka[r]);
+      if (dv) src_row<SPLIT>(dv, dv2, nsplit, (size_t)j, D)[ho + c] = from_f<T>(va[r]);
     }
   }
 }
@@ -693,55 +695,62 @@ struct ConvArgs {
   cudaStream_t st;
 };
 
-template <typename T, int LPH>
+// virtual base of a halo buffer: row j >= n_own lives at base + j*D  (never dereferenced for j < n_own)
+template <typename T>
+static T* vbase(T* halo, const ConvArgs& a) {
+  if (!halo) return nullptr;
+  return reinterpret_cast<T*>(reinterpret_cast<uintptr_t>(halo) - (uintptr_t)a.n_own * (uintptr_t)a.H * (uintptr_t)a.C * sizeof(T));
+}
+
+template <typename T, int LPH, bool SPLIT>
 static void launch_fwd(const Plan& pl, const ConvArgs& a) {
   if (a.low_degree) {
     const int groups = (a.Nd + kDstRows - 1) / kDstRows;
     dim3 grid((groups + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
-    gtconv_fwd_rows_kernel<T, LPH><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.k, (const T*)a.v, (const T*)a.e,
+    gtconv_fwd_rows_kernel<T, LPH, SPLIT><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.k, (const T*)a.v, (const T*)a.e,
                                                                a.rowptr, a.col, a.perm, a.Nd, pl.rm, a.H, a.qscale, (T*)a.out_w,
-                                                               a.lse2_w, (const T*)a.k_halo, (const T*)a.v_halo, a.n_own);
+                                                               a.lse2_w, vbase((const T*)a.k_halo, a), vbase((const T*)a.v_halo, a), a.n_own);
   } else {
     dim3 grid((a.Nd + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
-    gtconv_fwd_kernel<T, LPH><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.k, (const T*)a.v, (const T*)a.e, a.rowptr,
+    gtconv_fwd_kernel<T, LPH, SPLIT><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.k, (const T*)a.v, (const T*)a.e, a.rowptr,
                                                           a.col, a.perm, a.Nd, pl.rm, a.H, a.qscale, (T*)a.out_w, a.lse2_w,
-                                                          (const T*)a.k_halo, (const T*)a.v_halo, a.n_own);
+                                                          vbase((const T*)a.k_halo, a), vbase((const T*)a.v_halo, a), a.n_own);
   }
 }
-template <typename T, int LPH>
+template <typename T, int LPH, bool SPLIT>
 static void launch_bwd_dst(const Plan& pl, const ConvArgs& a) {
   // (a multi-row dst pass was measured on B200: no gain at in-degree 3, slower at in-degree 8 -- one row per group here)
   dim3 grid((a.Nd + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
-  gtconv_bwd_dst_kernel<T, LPH><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.k, (const T*)a.v, (const T*)a.e, a.rowptr,
+  gtconv_bwd_dst_kernel<T, LPH, SPLIT><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.k, (const T*)a.v, (const T*)a.e, a.rowptr,
                                                             a.col, a.perm, a.csr2csc, a.Nd, pl.rm, a.H, a.qscale, a.scale,
                                                             (const T*)a.out, a.lse2_in, (const T*)a.g, (T*)a.dq, (T*)a.de, a.ads,
-                                                            (const T*)a.k_halo, (const T*)a.v_halo, a.n_own);
+                                                            vbase((const T*)a.k_halo, a), vbase((const T*)a.v_halo, a), a.n_own);
 }
-template <typename T, int LPH>
+template <typename T, int LPH, bool SPLIT>
 static void launch_bwd_src(const Plan& pl, const ConvArgs& a) {
   const int groups = (a.Ns + kSrcRows - 1) / kSrcRows;
   dim3 grid((groups + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
-  gtconv_bwd_src_kernel<T, LPH><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.g, a.colptr, a.crow, a.ads, a.Ns, pl.rm,
-                                                            a.H, (T*)a.dk, (T*)a.dv, (T*)a.dk_halo, (T*)a.dv_halo, a.n_own);
+  gtconv_bwd_src_kernel<T, LPH, SPLIT><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.g, a.colptr, a.crow, a.ads, a.Ns, pl.rm,
+                                                            a.H, (T*)a.dk, (T*)a.dv, vbase((T*)a.dk_halo, a), vbase((T*)a.dv_halo, a), a.n_own);
 }
-template <typename T>
+template <typename T, bool SPLIT>
 static void launch_generic(int which, const ConvArgs& a) {
   const int wpb = kThreads / 32;
   if (which == 0) {
     const unsigned grid = (unsigned)(((long long)a.Nd * a.H + wpb - 1) / wpb);
-    gtconv_fwd_generic_kernel<T><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.k, (const T*)a.v, (const T*)a.e, a.rowptr,
+    gtconv_fwd_generic_kernel<T, SPLIT><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.k, (const T*)a.v, (const T*)a.e, a.rowptr,
                                                              a.col, a.perm, a.Nd, a.H, a.C, a.qscale, (T*)a.out_w, a.lse2_w,
-                                                             (const T*)a.k_halo, (const T*)a.v_halo, a.n_own);
+                                                             vbase((const T*)a.k_halo, a), vbase((const T*)a.v_halo, a), a.n_own);
   } else if (which == 1) {
     const unsigned grid = (unsigned)(((long long)a.Nd * a.H + wpb - 1) / wpb);
-    gtconv_bwd_dst_generic_kernel<T><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.k, (const T*)a.v, (const T*)a.e,
+    gtconv_bwd_dst_generic_kernel<T, SPLIT><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.k, (const T*)a.v, (const T*)a.e,
                                                                  a.rowptr, a.col, a.perm, a.csr2csc, a.Nd, a.H, a.C, a.qscale,
                                                                  a.scale, (const T*)a.out, a.lse2_in, (const T*)a.g, (T*)a.dq,
-                                                                 (T*)a.de, a.ads, (const T*)a.k_halo, (const T*)a.v_halo, a.n_own);
+                                                                 (T*)a.de, a.ads, vbase((const T*)a.k_halo, a), vbase((const T*)a.v_halo, a), a.n_own);
   } else {
     const unsigned grid = (unsigned)(((long long)a.Ns * a.H + wpb - 1) / wpb);
-    gtconv_bwd_src_generic_kernel<T><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.g, a.colptr, a.crow, a.ads, a.Ns, a.H,
-                                                                 a.C, (T*)a.dk, (T*)a.dv, (T*)a.dk_halo, (T*)a.dv_halo, a.n_own);
+    gtconv_bwd_src_generic_kernel<T, SPLIT><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.g, a.colptr, a.crow, a.ads, a.Ns, a.H,
+                                                                 a.C, (T*)a.dk, (T*)a.dv, vbase((T*)a.dk_halo, a), vbase((T*)a.dv_halo, a), a.n_own);
   }
 }
 
@@ -758,12 +767,18 @@ static void launch_generic(int which, const ConvArgs& a) {
 // which: 0 = forward, 1 = backward dst pass, 2 = backward src pass
 static int run_conv(int which, int dtype, const ConvArgs& a, const char* name) {
   const Plan pl = make_plan(a.H, a.C, dtype == AB2_F32 ? 4 : 2);
+  const bool split = a.n_own < a.Ns;
   if (pl.vector) {
-#define CALL(T, L)                                \
-  do {                                            \
-    if (which == 0) launch_fwd<T, L>(pl, a);      \
-    else if (which == 1) launch_bwd_dst<T, L>(pl, a); \
-    else launch_bwd_src<T, L>(pl, a);             \
+#define CALL3(T, L, S)                                   \
+  do {                                                   \
+    if (which == 0) launch_fwd<T, L, S>(pl, a);          \
+    else if (which == 1) launch_bwd_dst<T, L, S>(pl, a); \
+    else launch_bwd_src<T, L, S>(pl, a);                 \
+  } while (0)
+#define CALL(T, L)                 \
+  do {                             \
+    if (split) CALL3(T, L, true);  \
+    else CALL3(T, L, false);       \
   } while (0)
     if (dtype == AB2_F32) {
       AB2_DISPATCH_LPH(float, pl.lph, CALL)
@@ -771,10 +786,13 @@ static int run_conv(int which, int dtype, const ConvArgs& a, const char* name) {
       AB2_DISPATCH_LPH(__nv_bfloat16, pl.lph, CALL)
     }
 #undef CALL
+#undef CALL3
   } else if (dtype == AB2_F32) {
-    launch_generic<float>(which, a);
+    if (split) launch_generic<float, true>(which, a);
+    else launch_generic<float, false>(which, a);
   } else {
-    launch_generic<__nv_bfloat16>(which, a);
+    if (split) launch_generic<__nv_bfloat16, true>(which, a);
+    else launch_generic<__nv_bfloat16, false>(which, a);
   }
   AB2_LAUNCH_OK(name);
   return AB2_OK;

@@ -275,8 +275,13 @@ def run_ours(args):
     peak, peak_src = peaks()
     dom = max(kt, key=kt.get)
     achieved = ab[dom] / (kt[dom] * 1e-3) / 1e9
+    traffic = None  # dram__bytes_read+write per launch from the committed `ncu --set full` capture of this same workload
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if world == 1 and args.workload == "encoder" and os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(f"gtconv_{dom}_kernel", {}).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": f"gtconv_{dom}_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ab[dom], "launch_ms": round(kt[dom], 4)}
     kern = {n: {"ms": round(kt[n], 4), "algorithmic_GB": round(ab[n] / 1e9, 3), "GBps": round(ab[n] / (kt[n] * 1e-3) / 1e9, 1),
                 "frac_of_peak": round(ab[n] / (kt[n] * 1e-3) / 1e9 / peak, 4)} for n in kt}
@@ -427,6 +432,117 @@ def run_graphconv(args):
     print(json.dumps(line), flush=True)
 
 
+def run_model(args):
+    """Report line (not the headline): AIFS-like n320/o96 encoder-processor-decoder training step (BASELINE configs[3]) built
+    from this repo's drop-in blocks the way the reference's mappers/processor wire them (mapper.py:245-272,
+    processor.py:317-343): node embeddings, trainable edge features (3 geometric + 8 trainable columns), GT mapper block
+    n320->o96, 16 GT processor blocks on o96 (8-NN) in 8 checkpointed chunks, GT mapper block o96->n320 (3-NN), output
+    extractor; bf16 autocast, fwd + bwd + fused AdamW step, activation checkpointing per mapper / chunk as in
+    models/encoder_processor_decoder.py:159-166 and processor.py:73-77."""
+    from torch.utils.checkpoint import checkpoint
+
+    import anemoi_models_b200 as b2
+    from anemoi_models_b200 import synthetic as S
+    from anemoi_models_b200.graph import get_csr
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(0)
+    hid, heads, layers, chunks, nvar = D, H, args.model_layers, 8, 100
+    hidden_xyz, _ = S.octahedral_grid(DST_N)
+    data_xyz = S.fibonacci_sphere(SRC_POINTS)
+    Nh, Ndata = len(hidden_xyz), SRC_POINTS
+    radius = 0.6 * S.max_nn_distance(hidden_xyz)
+    graphs = {"enc": (S.cutoff_edges(data_xyz, hidden_xyz, radius), Ndata, Nh),
+              "proc": (S.knn_edges(hidden_xyz, hidden_xyz, 8, exclude_self=True), Nh, Nh),
+              "dec": (S.knn_edges(hidden_xyz, data_xyz, 3), Nh, Ndata)}
+    ei = {k_: torch.from_numpy(g_[0]).to(dev) for k_, g_ in graphs.items()}
+    for k_, g_ in graphs.items():
+        get_csr(ei[k_], g_[1], g_[2])  # one-off plan build, outside the step like the reference's constant edge buffers
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            nn = torch.nn
+            self.emb_data = nn.Linear(nvar + 4, hid)
+            self.emb_hidden = nn.Linear(4, hid)
+            self.emb_data_dec = nn.Linear(nvar + 4, hid)
+            self.edge_geo = nn.ParameterDict({k_: nn.Parameter(torch.rand(ei[k_].shape[1], 3), requires_grad=False) for k_ in ei})
+            self.edge_train = nn.ParameterDict({k_: nn.Parameter(torch.randn(ei[k_].shape[1], 8) * 0.1) for k_ in ei})
+            self.enc = b2.GraphTransformerMapperBlock(hid, 4 * hid, hid, edge_dim=11, num_heads=heads)
+            self.proc = nn.ModuleList([b2.GraphTransformerProcessorBlock(hid, 4 * hid, hid, edge_dim=11, num_heads=heads)
+                                       for _ in range(layers)])
+            self.dec = b2.GraphTransformerMapperBlock(hid, 4 * hid, hid, edge_dim=11, num_heads=heads)
+            self.extract = nn.Sequential(nn.LayerNorm(hid), nn.Linear(hid, nvar))
+
+        def edge_attr(self, k_):
+            return torch.cat([self.edge_geo[k_], self.edge_train[k_]], dim=-1)  # TrainableTensor (layers/graph.py:37-44)
+
+        def forward(self, x_data, x_hidden):
+            def run_enc(xd, xh):
+                (s, d), _ = self.enc((self.emb_data(xd), self.emb_hidden(xh)), self.edge_attr("enc"), ei["enc"],
+                                     (None, None, None), 1, size=(Ndata, Nh))
+                return d
+
+            def run_chunk(i0, x):
+                ea = self.edge_attr("proc")
+                for blk in self.proc[i0:i0 + layers // chunks]:
+                    x, _ = blk(x, ea, ei["proc"], (None, None, None), 1)
+                return x
+
+            def run_dec(xh, xd):
+                (s, d), _ = self.dec((xh, self.emb_data_dec(xd)), self.edge_attr("dec"), ei["dec"], (None, None, None), 1,
+                                     size=(Nh, Ndata))
+                return self.extract(d)
+
+            latent = checkpoint(run_enc, x_data, x_hidden, use_reentrant=False)
+            x = latent
+            for c in range(chunks):
+                x = checkpoint(run_chunk, c * (layers // chunks), x, use_reentrant=False)
+            x = x + latent
+            return checkpoint(run_dec, x, x_data, use_reentrant=False)
+
+    model = Model().to(dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
+    x_data = torch.randn(Ndata, nvar + 4, device=dev)
+    x_hidden = torch.randn(Nh, 4, device=dev)
+    target = torch.randn(Ndata, nvar, device=dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = model(x_data, x_hidden)
+        loss = (y.float() - target).square().mean()
+        loss.backward()
+        opt.step()
+        return loss
+
+    sampler = ClockSampler(0)
+    for _ in range(max(3, min(args.warmup, 3))):
+        step()
+    torch.cuda.synchronize()
+    n = max(1, min(args.steps, 10))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with sampler:
+        ev0.record()
+        for _ in range(n):
+            loss = step()
+        ev1.record()
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / n
+    nparams = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    etot = sum(ei[k_].shape[1] * (layers if k_ == "proc" else 1) for k_ in ei)
+    line = {"metric": "aifs_like_n320_o96_train_step_ms", "value": ms, "unit": "ms/step", "n_gpus": 1, "steps": n, "warmup": 3,
+            "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"AIFS-like enc-proc-dec step: GT mapper n320->o96 (E={ei['enc'].shape[1]}), {layers} GT processor layers on "
+                                   f"o96 8-NN (E={ei['proc'].shape[1]}) in {chunks} checkpointed chunks, GT mapper o96->n320 3-NN "
+                                   f"(E={ei['dec'].shape[1]}); hidden {hid}, {heads} heads, MLP x4, bf16 autocast, fwd+bwd (with "
+                                   f"checkpoint recompute) + fused AdamW; {nparams / 1e6:.0f} M parameters (report line)",
+                       "conv_edges_per_step": int(etot), "loss": float(loss)},
+            "clocks": sampler.summary(), "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2**30, 1)}
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -456,13 +572,16 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=16, help="dst-row chunks of the streamed host-buffer call (1 = unstreamed)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graphconv-dim", type=int, default=512)
-    ap.add_argument("--workload", default="encoder", choices=["encoder", "decoder", "processor", "graphconv"],
+    ap.add_argument("--model-layers", type=int, default=16)
+    ap.add_argument("--workload", default="encoder", choices=["encoder", "decoder", "processor", "graphconv", "model"],
                     help="encoder = BASELINE configs[1] (the headline); the others are extra report lines")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "graphconv":
         run_graphconv(args)
+    elif args.workload == "model":
+        run_model(args)
     else:
         run_ours(args)
 

@@ -25,6 +25,16 @@ try:
 except Exception as ex: print("parse fail", ex)
 PY
 done
+for w in graphconv model; do
+  timeout 900 python bench.py --steps 20 --warmup 3 --workload $w > $OUT/bench_$w.json 2> $OUT/bench_$w.err; echo "bench $w exit $?"; tail -3 $OUT/bench_$w.err
+  python - <<PY
+import json
+try:
+    d=json.loads(open("$OUT/bench_$w.json").read().strip().splitlines()[-1])
+    print("$w", d["metric"], d["value"], "ms/step %.3f"%d["ms_per_step"], d.get("roofline"), d.get("peak_mem_GB"))
+except Exception as ex: print("parse fail", ex)
+PY
+done
 if [ "${NCU:-0}" == "1" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $OUT/ncu_launch.log 2>&1
