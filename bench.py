@@ -530,6 +530,19 @@ def run_model(args):
         ev1.record()
         torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / n
+    breakdown = None
+    if args.profile:
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize()
+        rows = sorted(prof.key_averages(), key=lambda r: -r.device_time_total)
+        total = sum(r.device_time_total for r in rows)
+        breakdown = [{"kernel": r.key[:90], "ms": round(r.device_time_total / 1e3, 3), "calls": r.count,
+                      "share": round(r.device_time_total / max(total, 1), 4)} for r in rows[:25]]
+        mine = sum(r.device_time_total for r in rows if "ab2::" in r.key)
+        breakdown.insert(0, {"kernel": "ALL ab2:: kernels (this repo)", "ms": round(mine / 1e3, 3), "share": round(mine / max(total, 1), 4)})
     nparams = sum(p.numel() for p in model.parameters() if p.requires_grad)
     etot = sum(ei[k_].shape[1] * (layers if k_ == "proc" else 1) for k_ in ei)
     line = {"metric": "aifs_like_n320_o96_train_step_ms", "value": ms, "unit": "ms/step", "n_gpus": 1, "steps": n, "warmup": 3,
@@ -538,8 +551,9 @@ def run_model(args):
                                    f"o96 8-NN (E={ei['proc'].shape[1]}) in {chunks} checkpointed chunks, GT mapper o96->n320 3-NN "
                                    f"(E={ei['dec'].shape[1]}); hidden {hid}, {heads} heads, MLP x4, bf16 autocast, fwd+bwd (with "
                                    f"checkpoint recompute) + fused AdamW; {nparams / 1e6:.0f} M parameters (report line)",
-                       "conv_edges_per_step": int(etot), "loss": float(loss)},
-            "clocks": sampler.summary(), "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2**30, 1)}
+                       "conv_edges_per_step": int(etot), "loss": float(loss.detach())},
+            "clocks": sampler.summary(), "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2**30, 1),
+            "kernel_breakdown": breakdown}
     print(json.dumps(line), flush=True)
 
 
@@ -573,6 +587,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graphconv-dim", type=int, default=512)
     ap.add_argument("--model-layers", type=int, default=16)
+    ap.add_argument("--profile", action="store_true", help="model workload: add a per-kernel device-time breakdown of one step")
     ap.add_argument("--workload", default="encoder", choices=["encoder", "decoder", "processor", "graphconv", "model"],
                     help="encoder = BASELINE configs[1] (the headline); the others are extra report lines")
     args = ap.parse_args()
