@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libanemoi_b200.so")
-SOURCES = ["abi.cu", "csr_build.cu", "gtconv.cu", "graphconv.cu", "host_api.cu"]
+SOURCES = ["abi.cu", "csr_build.cu", "gtconv.cu", "gtconv_tma.cu", "graphconv.cu", "host_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
@@ -36,7 +36,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     objdir = os.path.join(LIBDIR, "obj")
     os.makedirs(objdir, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(HERE), "include", "anemoi_b200.h")]
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "gtconv_args.cuh"),
+               os.path.join(os.path.dirname(HERE), "include", "anemoi_b200.h")]
     nvcc = _nvcc()
 
     def compile_one(src):

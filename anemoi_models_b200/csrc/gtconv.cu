@@ -14,18 +14,11 @@
 #include <cmath>
 #include <cstdlib>
 
-#include "common.cuh"
+#include "gtconv_args.cuh"
 
 namespace ab2 {
 
 constexpr int kThreads = 128;  // CTA size of the vector kernels
-constexpr int kU = 4;          // edges in flight per thread (3 x 16 B loads each)
-
-struct RowMap {  // how a CTA's threads map onto (dst row, 16-byte chunk)
-  int tpd;       // threads per row handled by one CTA (= heads-per-slice * LPH)
-  int rpb;       // rows per CTA
-  int chunks;    // 16-byte chunks in a full row (= D*sizeof(T)/16)
-};
 
 // src rows live in two pieces when the graph is dst-row sharded: rows [0, nsplit) in the rank's own k / v shard, rows
 // [nsplit, Ns) in the halo buffer received from the peers (k2 / v2).  Single GPU: nsplit = Ns and k2, v2 are never read.
@@ -678,23 +671,6 @@ static Plan make_plan(int H, int C, int elt) {
   return pl;
 }
 
-// everything a conv launch needs (host side)
-struct ConvArgs {
-  const void *q, *k, *v, *e;        // k, v: the rank's own src rows [0, n_own)
-  const void *k_halo, *v_halo;      // src rows [n_own, Ns) (NULL on one GPU)
-  const int *rowptr, *col, *perm, *colptr, *csr2csc, *crow;
-  int Ns, Nd, n_own, H, C;
-  int64_t E;
-  float qscale, scale;
-  const void *out, *g;
-  const float* lse2_in;
-  void *out_w, *dq, *dk, *dv, *dk_halo, *dv_halo, *de;
-  float* lse2_w;
-  float2* ads;
-  bool low_degree;
-  cudaStream_t st;
-};
-
 // virtual base of a halo buffer: row j >= n_own lives at base + j*D  (never dereferenced for j < n_own)
 template <typename T>
 static T* vbase(T* halo, const ConvArgs& a) {
@@ -768,6 +744,14 @@ static void launch_generic(int which, const ConvArgs& a) {
 static int run_conv(int which, int dtype, const ConvArgs& a, const char* name) {
   const Plan pl = make_plan(a.H, a.C, dtype == AB2_F32 ? 4 : 2);
   const bool split = a.n_own < a.Ns;
+  if (pl.vector && which == 0 && !a.low_degree && try_launch_fwd_tma(dtype, pl.lph, a)) {
+    AB2_LAUNCH_OK(name);
+    return AB2_OK;
+  }
+  if (pl.vector && which == 1 && try_launch_bwd_dst_tma(dtype, pl.lph, a)) {
+    AB2_LAUNCH_OK(name);
+    return AB2_OK;
+  }
   if (pl.vector) {
 #define CALL3(T, L, S)                                   \
   do {                                                   \

@@ -37,6 +37,27 @@ NUM_CHUNKS_INFERENCE = int(os.environ.get("ANEMOI_INFERENCE_NUM_CHUNKS", "1"))
 _halo_cache = TensorKeyedCache()
 
 
+def _autocast_once(x: Tensor) -> Tensor:
+    """Under autocast every nn.Linear casts its input to the autocast dtype; LayerNorm outputs fp32.  Casting the
+    normalised rows ONCE before they feed several projections gives bit-identical results and saves the repeated
+    full-tensor casts (4 per block, each a pass over [N, D])."""
+    if x.is_cuda and torch.is_autocast_enabled("cuda"):
+        return x.to(torch.get_autocast_dtype("cuda"))
+    return x
+
+
+def _linear_padded_k(lin: nn.Linear, x: Tensor, multiple: int = 8) -> Tensor:
+    """lin(x) with the contraction dim zero-padded to a multiple of 8 (exactly the same sums).  edge_dim is 11 in the
+    reference configs; an unaligned K sends a bf16 GEMM to a legacy alignment-1 kernel (measured: 48 ms of a 330 ms
+    AIFS-like step for lin_edge and its backward)."""
+    k = x.shape[-1]
+    pad = (-k) % multiple
+    if pad == 0 or not x.is_cuda:
+        return lin(x)
+    F = torch.nn.functional
+    return F.linear(F.pad(x, (0, pad)), F.pad(lin.weight, (0, pad)), lin.bias)
+
+
 def _group_active(group) -> bool:
     return group is not None and bool(group) and dist.get_world_size(group=group) > 1
 
@@ -159,7 +180,7 @@ class GraphTransformerBaseBlock(BaseBlock, ABC):
         """conv output rows [(own dst rows), H*C] for projected q [Nd_r,D], k/v [Ns_r,D] and RAW edge_attr."""
         H, C = self.num_heads, self.out_channels_conv
         if not _group_active(model_comm_group):
-            edges = self.lin_edge(edge_attr)
+            edges = _linear_padded_k(self.lin_edge, edge_attr)
             q, k, v, e = self.shard_qkve_heads(query, key, value, edges, shapes, batch_size, model_comm_group)
             out = self.conv(query=q, key=k, value=v, edge_attr=e, edge_index=edge_index, size=size)
             return self.shard_output_seq(out, shapes, batch_size, model_comm_group)
@@ -172,7 +193,7 @@ class GraphTransformerBaseBlock(BaseBlock, ABC):
                                          lambda: build_bipartite_halo_plan(edge_index, sb, db, rank))
         # raw attributes of the edges this rank owns (they arrive sharded by original edge order), then project locally
         ea_local = select_sharded_edges(edge_attr, shapes_edge, plan.edge_ids, model_comm_group)
-        e = self.lin_edge(ea_local).view(-1, H, C)
+        e = _linear_padded_k(self.lin_edge, ea_local).view(-1, H, C)
         q, k, v = query.view(-1, H, C), key.view(-1, H, C), value.view(-1, H, C)
         size = (plan.n_src, plan.num_dst_local)
         if q.is_cuda:
@@ -203,7 +224,7 @@ class GraphTransformerMapperBlock(GraphTransformerBaseBlock):
     def forward(self, x: Tuple[Tensor, Tensor], edge_attr: Tensor, edge_index: Tensor, shapes: tuple, batch_size: int,
                 model_comm_group=None, size: Optional[Tuple[int, int]] = None):
         x_skip = x
-        x = (self.layer_norm1(x[0]), self.layer_norm2(x[1]))
+        x = (_autocast_once(self.layer_norm1(x[0])), _autocast_once(self.layer_norm2(x[1])))
         x_r = self.lin_self(x[1])
         query = self.lin_query(x[1])
         key = self.lin_key(x[0])
@@ -228,7 +249,7 @@ class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
     def forward(self, x: Tensor, edge_attr: Tensor, edge_index: Tensor, shapes: tuple, batch_size: int,
                 model_comm_group=None, size: Optional[Tuple[int, int]] = None):
         x_skip = x
-        x = self.layer_norm1(x)
+        x = _autocast_once(self.layer_norm1(x))
         x_r = self.lin_self(x)
         query = self.lin_query(x)
         key = self.lin_key(x)

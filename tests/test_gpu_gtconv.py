@@ -68,7 +68,9 @@ def _random_case(seed, ns, nd, E, H, C, zipf=False):
 
 # (H, C) pairs chosen to hit every lanes-per-head specialisation for fp32 (C*4/16) and bf16 (C*2/16), the
 # head-sliced launch (H*LPH > 128 threads) and the generic any-C kernels
-SHAPES = [(16, 64), (16, 16), (4, 8), (2, 4), (8, 32), (4, 128), (2, 256), (16, 128), (3, 5), (2, 24), (1, 40)]
+SHAPES = [(16, 64), (16, 16), (4, 8), (2, 4), (8, 32), (4, 128), (2, 256), (16, 128), (3, 5), (2, 24), (1, 40),
+          # 2 KB rows (bulk-copy pipelined kernels): every lanes-per-head value
+          (8, 128), (32, 32), (32, 16), (64, 16), (128, 8), (16, 32)]
 
 
 @pytest.mark.parametrize("H,C", SHAPES)
@@ -82,6 +84,25 @@ def test_random_graphs_all_shapes(H, C, dtype, E):
     tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
     for key in ("out", "dq", "dk", "dv", "de"):
         assert rel_err(r[key].float(), ref[key]) < tol, (H, C, dtype, key, rel_err(r[key].float(), ref[key]))
+
+
+@pytest.mark.parametrize("dtype,H,C", [(torch.bfloat16, 16, 64), (torch.float32, 16, 32)])
+@pytest.mark.parametrize("nd,E", [(1, 5), (37, 900), (700, 9000), (5000, 30000)])
+def test_pipelined_kernel_row_shapes(dtype, H, C, nd, E):
+    """2 KB rows take the warp-specialised bulk-copy kernel: skewed in-degrees (rows with no edges, rows longer than the
+    32-edge index batch), dst counts below / around / above the number of CTAs, shuffled edge order."""
+    gen = torch.Generator().manual_seed(nd + E)
+    ns = 400
+    dst = (torch.rand(E, generator=gen) ** 3 * nd).long().clamp_(max=nd - 1)
+    src = torch.randint(0, ns, (E,), generator=gen)
+    ei = torch.stack([src, dst])
+    q, k, v, e, g = (torch.randn(n, H, C, generator=gen) for n in (nd, ns, ns, E, nd))
+    cast = (lambda x: x) if dtype == torch.float32 else (lambda x: x.bfloat16().float())
+    ref = og.gt_conv_unfused_fwd_bwd(cast(q), cast(k), cast(v), cast(e), ei, cast(g), (ns, nd))
+    r = run_b2(q, k, v, e, ei, g, (ns, nd), dtype)
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    for key in ("out", "dq", "dk", "dv", "de"):
+        assert rel_err(r[key].float(), ref[key]) < tol, (key, rel_err(r[key].float(), ref[key]))
 
 
 def test_skewed_degrees_and_f64_oracle():
