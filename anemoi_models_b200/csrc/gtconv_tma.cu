@@ -102,7 +102,8 @@ struct Ring {
 // ---- producer: walks the CSR edges of dst rows [r0, r1) and fills the ring --------------------------------------------
 // HEAD(row, stage) issues the per-row copies (q / g / out) and returns their byte count.
 template <typename T, int NHEAD, bool BWD, typename HeadFn>
-__device__ __forceinline__ void producer_loop(const Ring<NHEAD>& ring, const ConvArgs& a, int r0, int r1, HeadFn head_copies) {
+__device__ __forceinline__ void producer_loop(const Ring<NHEAD>& ring, const ConvArgs& a, int r0, int r1, uint32_t head_bytes,
+                                              HeadFn head_copies) {
   const int lane = threadIdx.x & 31;
   const T* kb = (const T*)a.k;
   const T* vb = (const T*)a.v;
@@ -161,7 +162,7 @@ __device__ __forceinline__ void producer_loop(const Ring<NHEAD>& ring, const Con
       }
       __syncwarp();
       if (lane == 0) {
-        const uint32_t tx = (first ? NHEAD * kRowBytes : 0) + (uint32_t)n * 3u * kRowBytes;
+        const uint32_t tx = (first ? head_bytes : 0u) + (uint32_t)n * 3u * kRowBytes;
         mbar_arrive_expect_tx(ring.full(s), tx);  // release: the meta stores above are visible to whoever sees the phase flip
       }
       __syncwarp();
@@ -213,7 +214,7 @@ gtconv_fwd_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) {
 
   if (threadIdx.x >= kConsumers) {
     const T* qb = (const T*)a.q;
-    producer_loop<T, 1, false>(ring, a, r0, r1, [&](int d, int s, int lane) {
+    producer_loop<T, 1, false>(ring, a, r0, r1, kRowBytes, [&](int d, int s, int lane) {
       if (lane == kU) bulk_g2s(ring.head(s, 0), qb + (size_t)d * D, kRowBytes, ring.full(s));
     });
     return;
@@ -327,12 +328,173 @@ static bool launch_fwd_tma_t(const ConvArgs& a) {
   return true;
 }
 
-static bool tma_enabled() {
+// =====================================================================================================================
+// backward, dst pass (same math as gtconv_bwd_dst_kernel in gtconv.cu)
+// =====================================================================================================================
+constexpr int kCtasPerSmBwd = 3;
+
+template <typename T, int LPH>
+__global__ void __launch_bounds__(kTmaThreads, kCtasPerSmBwd)
+gtconv_bwd_dst_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) {
+  extern __shared__ __align__(128) char smem_raw[];
+  constexpr int VEC = Vec<T>::N;
+  constexpr size_t D = kRowBytes / sizeof(T);
+  Ring<4> ring{smem_raw};  // head slots: q, g, out, lse2 (H floats)
+  const int r0 = min((long long)blockIdx.x * rows_per_cta, (long long)a.Nd);
+  const int r1 = min((long long)r0 + rows_per_cta, (long long)a.Nd);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(ring.full(s), 1);
+      mbar_init(ring.empty(s), kConsumers / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (r0 >= r1) return;
+  const uint32_t lse_bytes = (uint32_t)a.H * 4u;  // a multiple of 16: H = 128 / LPH >= 4
+
+  if (threadIdx.x >= kConsumers) {
+    const T* qb = (const T*)a.q;
+    const T* gb = (const T*)a.g;
+    const T* ob = (const T*)a.out;
+    producer_loop<T, 4, true>(ring, a, r0, r1, 3u * kRowBytes + lse_bytes, [&](int d, int s, int lane) {
+      if (lane == kU) bulk_g2s(ring.head(s, 0), qb + (size_t)d * D, kRowBytes, ring.full(s));
+      if (lane == kU + 1) bulk_g2s(ring.head(s, 1), gb + (size_t)d * D, kRowBytes, ring.full(s));
+      if (lane == kU + 2) bulk_g2s(ring.head(s, 2), ob + (size_t)d * D, kRowBytes, ring.full(s));
+      if (lane == kU + 3) bulk_g2s(ring.head(s, 3), a.lse2_in + (size_t)d * a.H, lse_bytes, ring.full(s));
+    });
+    return;
+  }
+
+  const int chunk = threadIdx.x;
+  const size_t off = (size_t)chunk * 16;
+  const unsigned mask = tma_group_mask<LPH>();
+  const int lane = threadIdx.x & 31;
+  const int h = chunk / LPH;
+  const bool leader = (chunk & (LPH - 1)) == 0;
+  T* dq = (T*)a.dq;
+  T* de = (T*)a.de;
+  float2* ads = a.ads;
+  float qf[VEC], gf[VEC], dqa[VEC];
+  float Dl = 0.f, L = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) qf[i] = gf[i] = dqa[i] = 0.f;
+  int s = 0;
+  uint32_t phase = 0;
+  while (true) {
+    mbar_wait(ring.full(s), phase);
+    const StageMeta* mt = ring.meta(s);
+    const int row = mt->row, n = mt->n, first = mt->first, last = mt->last;
+    if (row < 0) break;
+    size_t ts[kU], cs[kU];
+    uint4 kr[kU], er[kU], vr[kU];
+    uint4 qr = make_uint4(0, 0, 0, 0), gr = qr, orr = qr;
+    float Lnew = 0.f;
+    if (first) {
+      qr = lds16(ring.head(s, 0) + off);
+      gr = lds16(ring.head(s, 1) + off);
+      orr = lds16(ring.head(s, 2) + off);
+      Lnew = reinterpret_cast<const float*>(ring.head(s, 3))[h];
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      ts[u] = (size_t)mt->t[u];
+      cs[u] = (size_t)mt->cs[u];
+      if (u < n) {
+        kr[u] = lds16(ring.k(s, u) + off);
+        er[u] = lds16(ring.e(s, u) + off);
+        vr[u] = lds16(ring.v(s, u) + off);
+      } else {
+        kr[u] = er[u] = vr[u] = make_uint4(0, 0, 0, 0);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(ring.empty(s));
+    if (++s == kStages) {
+      s = 0;
+      phase ^= 1u;
+    }
+    if (first) {
+      float of[VEC];
+      unpack<T>(qr, qf);
+      unpack<T>(gr, gf);
+      unpack<T>(orr, of);
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        part = fmaf(gf[i], of[i], part);
+        dqa[i] = 0.f;
+      }
+      Dl = group_sum<LPH>(part, mask);
+      L = Lnew;
+    }
+    float sc[kU], gv[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      float kf[VEC], ef[VEC], vf[VEC];
+      unpack<T>(kr[u], kf);
+      unpack<T>(er[u], ef);
+      unpack<T>(vr[u], vf);
+      float ps = 0.f, pg = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        ps = fmaf(qf[i], kf[i] + ef[i], ps);
+        pg = fmaf(gf[i], vf[i] + ef[i], pg);
+      }
+      sc[u] = ps;
+      gv[u] = pg;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      sc[u] = group_sum<LPH>(sc[u], mask);
+      gv[u] = group_sum<LPH>(gv[u], mask);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (u < n) {
+        const float aw = fast_exp2(fmaf(sc[u], a.qscale, -L));
+        const float dss = aw * (gv[u] - Dl) * a.scale;
+        float kf[VEC], ef[VEC];
+        unpack<T>(kr[u], kf);
+        unpack<T>(er[u], ef);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) dqa[i] = fmaf(dss, kf[i] + ef[i], dqa[i]);
+        if (de) {
+          float o[VEC];
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) o[i] = fmaf(aw, gf[i], dss * qf[i]);
+          stg16(reinterpret_cast<char*>(de + ts[u] * D) + off, pack<T>(o));
+        }
+        if (ads && leader) ads[cs[u] * a.H + h] = make_float2(aw, dss);
+      }
+    }
+    if (last && dq) stg16(reinterpret_cast<char*>(dq + (size_t)row * D) + off, pack<T>(dqa));
+  }
+}
+
+template <typename T, int LPH>
+static bool launch_bwd_dst_tma_t(const ConvArgs& a) {
+  static bool configured = false;
+  auto kern = gtconv_bwd_dst_tma_kernel<T, LPH>;
+  const size_t smem = Ring<4>::kBytes + 128;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+    configured = true;
+  }
+  const int ctas = std::max(1, std::min(a.Nd, num_sms() * kCtasPerSmBwd));
+  const int rows_per_cta = (a.Nd + ctas - 1) / ctas;
+  const int grid = (a.Nd + rows_per_cta - 1) / rows_per_cta;
+  kern<<<grid, kTmaThreads, smem, a.st>>>(a, rows_per_cta);
+  return true;
+}
+
+// AB2_TMA: bit 0 = forward, bit 1 = backward dst pass (default 3); 0 sends 2 KB rows to the LDG kernels as well
+static int tma_mask() {
   static const int v = [] {
     const char* s = getenv("AB2_TMA");
-    return s ? atoi(s) : 1;
+    return s ? atoi(s) : 3;
   }();
-  return v != 0;
+  return v;
 }
 
 // halo pointers become virtual bases here as well (row j >= n_own lives at base + j*D)
@@ -346,7 +508,7 @@ static ConvArgs with_virtual_halo(const ConvArgs& a, size_t elt) {
 
 bool try_launch_fwd_tma(int dtype, int lph, const ConvArgs& a) {
   const size_t elt = dtype == AB2_F32 ? 4 : 2;
-  if (!tma_enabled() || (size_t)a.H * a.C * elt != kRowBytes || a.Nd <= 0 || a.E <= 0) return false;
+  if (!(tma_mask() & 1) || (size_t)a.H * a.C * elt != kRowBytes || a.Nd <= 0 || a.E <= 0) return false;
   const ConvArgs b = with_virtual_halo(a, elt);
   if (dtype == AB2_BF16) {
     switch (lph) {
@@ -369,10 +531,27 @@ bool try_launch_fwd_tma(int dtype, int lph, const ConvArgs& a) {
 }
 
 bool try_launch_bwd_dst_tma(int dtype, int lph, const ConvArgs& a) {
-  (void)dtype;
-  (void)lph;
-  (void)a;
-  return false;  // the dst pass of the backward still runs on the LDG kernel
+  const size_t elt = dtype == AB2_F32 ? 4 : 2;
+  if (!(tma_mask() & 2) || (size_t)a.H * a.C * elt != kRowBytes || a.Nd <= 0 || a.E <= 0) return false;
+  const ConvArgs b = with_virtual_halo(a, elt);
+  if (dtype == AB2_BF16) {
+    switch (lph) {
+      case 1: return launch_bwd_dst_tma_t<__nv_bfloat16, 1>(b);
+      case 2: return launch_bwd_dst_tma_t<__nv_bfloat16, 2>(b);
+      case 4: return launch_bwd_dst_tma_t<__nv_bfloat16, 4>(b);
+      case 8: return launch_bwd_dst_tma_t<__nv_bfloat16, 8>(b);
+      case 16: return launch_bwd_dst_tma_t<__nv_bfloat16, 16>(b);
+      default: return launch_bwd_dst_tma_t<__nv_bfloat16, 32>(b);
+    }
+  }
+  switch (lph) {
+    case 1: return launch_bwd_dst_tma_t<float, 1>(b);
+    case 2: return launch_bwd_dst_tma_t<float, 2>(b);
+    case 4: return launch_bwd_dst_tma_t<float, 4>(b);
+    case 8: return launch_bwd_dst_tma_t<float, 8>(b);
+    case 16: return launch_bwd_dst_tma_t<float, 16>(b);
+    default: return launch_bwd_dst_tma_t<float, 32>(b);
+  }
 }
 
 }  // namespace ab2
