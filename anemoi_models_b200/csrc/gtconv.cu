@@ -740,15 +740,21 @@ static void launch_generic(int which, const ConvArgs& a) {
     default: CALL(T, 32); break;                                         \
   }
 
+static bool fwd_prefers_tma(int dtype, int H, int C, int64_t E, int64_t Nd);
+
 // which: 0 = forward, 1 = backward dst pass, 2 = backward src pass
 static int run_conv(int which, int dtype, const ConvArgs& a, const char* name) {
   const Plan pl = make_plan(a.H, a.C, dtype == AB2_F32 ? 4 : 2);
   const bool split = a.n_own < a.Ns;
-  if (pl.vector && which == 0 && !a.low_degree && try_launch_fwd_tma(dtype, pl.lph, a)) {
+  if (pl.vector && which == 0 && fwd_prefers_tma(dtype, a.H, a.C, a.E, a.Nd) && try_launch_fwd_tma(dtype, pl.lph, a)) {
     AB2_LAUNCH_OK(name);
     return AB2_OK;
   }
   if (pl.vector && which == 1 && try_launch_bwd_dst_tma(dtype, pl.lph, a)) {
+    AB2_LAUNCH_OK(name);
+    return AB2_OK;
+  }
+  if (pl.vector && which == 2 && try_launch_bwd_src_tma(dtype, pl.lph, a)) {
     AB2_LAUNCH_OK(name);
     return AB2_OK;
   }
@@ -793,6 +799,21 @@ static bool use_row_blocks(int64_t E, int64_t Nd) {
   return Nd > 0 && E < 6 * Nd;
 }
 
+// Forward kernel choice for 2 KB rows, measured on B200 (profiles/r01, A/B run r01i):
+//   mean in-degree 18.6 (encoder):  LDG 0.698 ms  vs bulk-copy pipeline 0.728 ms  -> LDG
+//   mean in-degree  8   (processor): LDG 0.302 ms  vs pipeline 0.223 ms            -> pipeline
+//   mean in-degree  3   (decoder):  row-block LDG 1.85 ms vs pipeline 1.52 ms      -> pipeline
+// (the backward dst pass is faster on the pipeline at every degree: 1.00 -> 0.97, 0.455 -> 0.346, 3.62 -> 2.27 ms)
+static bool fwd_prefers_tma(int dtype, int H, int C, int64_t E, int64_t Nd) {
+  if (!tma_applicable(0, dtype, H, C)) return false;
+  static const int forced = [] {
+    const char* s = getenv("AB2_TMA");
+    return s ? atoi(s) : 3;
+  }();
+  if (forced & 4) return true;  // bit 2: pipeline at every degree (A/B runs)
+  return E < 12 * Nd;
+}
+
 static int check_common(const char* fn, int dtype, int64_t Ns, int64_t Nd, int64_t E, int H, int C) {
   if (dtype != AB2_F32 && dtype != AB2_BF16) return fail(AB2_ERR_INVALID, "%s: dtype must be AB2_F32 or AB2_BF16", fn);
   if (Ns < 0 || Nd < 0 || E < 0 || H <= 0 || C <= 0) return fail(AB2_ERR_INVALID, "%s: negative or zero dimension", fn);
@@ -827,6 +848,28 @@ static int check_halo(const char* fn, const void* k_halo, const void* v_halo, in
 }  // namespace ab2
 
 using namespace ab2;
+
+// Name of the kernel a call with these shapes dispatches to (for benchmark / profile bookkeeping).
+extern "C" const char* ab2_gtconv_variant(int which, int dtype, int64_t Nd, int64_t E, int H, int C) {
+  static thread_local char buf[96];
+  const Plan pl = make_plan(H, C, dtype == AB2_F32 ? 4 : 2);
+  const char* t = dtype == AB2_F32 ? "float" : "__nv_bfloat16";
+  const char* base;
+  if (!pl.vector) {
+    base = which == 0 ? "gtconv_fwd_generic_kernel" : which == 1 ? "gtconv_bwd_dst_generic_kernel" : "gtconv_bwd_src_generic_kernel";
+    snprintf(buf, sizeof(buf), "%s<%s>", base, t);
+    return buf;
+  }
+  const bool low = use_row_blocks(E, Nd);
+  if (which == 0)
+    base = fwd_prefers_tma(dtype, H, C, E, Nd) ? "gtconv_fwd_tma_kernel" : low ? "gtconv_fwd_rows_kernel" : "gtconv_fwd_kernel";
+  else if (which == 1)
+    base = tma_applicable(1, dtype, H, C) ? "gtconv_bwd_dst_tma_kernel" : "gtconv_bwd_dst_kernel";
+  else
+    base = tma_applicable(2, dtype, H, C) ? "gtconv_bwd_src_tma_kernel" : "gtconv_bwd_src_kernel";
+  snprintf(buf, sizeof(buf), "%s<%s, %d>", base, t, pl.lph);
+  return buf;
+}
 
 extern "C" int ab2_gtconv_fwd_halo(const void* q, const void* k, const void* v, const void* k_halo, const void* v_halo,
                                    int64_t n_own, const void* e, int dtype, const int32_t* rowptr, const int32_t* col,

@@ -32,5 +32,7 @@ struct ConvArgs {
 // gtconv_tma.cu: returns true when the pipelined kernel was launched (row = 2048 bytes, vector layout), false -> use the LDG kernel
 bool try_launch_fwd_tma(int dtype, int lph, const ConvArgs& a);
 bool try_launch_bwd_dst_tma(int dtype, int lph, const ConvArgs& a);
+bool try_launch_bwd_src_tma(int dtype, int lph, const ConvArgs& a);
+bool tma_applicable(int which, int dtype, int H, int C);  // which: 0 = forward, 1 = backward dst pass, 2 = backward src pass
 
 }  // namespace ab2

@@ -488,11 +488,192 @@ static bool launch_bwd_dst_tma_t(const ConvArgs& a) {
   return true;
 }
 
-// AB2_TMA: bit 0 = forward, bit 1 = backward dst pass (default 3); 0 sends 2 KB rows to the LDG kernels as well
+// =====================================================================================================================
+// backward, src pass: dk_j = sum ds*q_i, dv_j = sum a*g_i over the outgoing edges of src row j (CSC order).
+// Producer: per chunk of <= kU consecutive CSC edges of one src row, bulk-copies q[crow], g[crow] (2 KB each) and the
+// chunk's slice of the (a, ds) workspace (contiguous in CSC order).  Consumers accumulate and write the row once.
+// =====================================================================================================================
+constexpr int kCtasPerSmSrc = 5;
+constexpr int kAdsSlot = 4096;  // kU * H * 8 bytes with H <= 128
+
+struct SrcRing {
+  static constexpr int kStageBytes = 2 * kU * kRowBytes + kAdsSlot;
+  static constexpr size_t kBytes = (size_t)kStages * kStageBytes + kStages * sizeof(StageMeta) + 2 * kStages * sizeof(uint64_t);
+  char* base;
+  __device__ char* q(int s, int u) const { return base + (size_t)s * kStageBytes + (size_t)u * kRowBytes; }
+  __device__ char* g(int s, int u) const { return q(s, kU + u); }
+  __device__ char* w(int s) const { return q(s, 2 * kU); }
+  __device__ StageMeta* meta(int s) const { return reinterpret_cast<StageMeta*>(base + (size_t)kStages * kStageBytes) + s; }
+  __device__ uint64_t* full(int s) const {
+    return reinterpret_cast<uint64_t*>(base + (size_t)kStages * kStageBytes + kStages * sizeof(StageMeta)) + s;
+  }
+  __device__ uint64_t* empty(int s) const { return full(s) + kStages; }
+};
+
+template <typename T, int LPH>
+__global__ void __launch_bounds__(kTmaThreads, kCtasPerSmSrc)
+gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) {
+  extern __shared__ __align__(128) char smem_raw[];
+  constexpr int VEC = Vec<T>::N;
+  constexpr size_t D = kRowBytes / sizeof(T);
+  SrcRing ring{smem_raw};
+  const int r0 = min((long long)blockIdx.x * rows_per_cta, (long long)a.Ns);
+  const int r1 = min((long long)r0 + rows_per_cta, (long long)a.Ns);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(ring.full(s), 1);
+      mbar_init(ring.empty(s), kConsumers / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (r0 >= r1) return;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x >= kConsumers) {
+    // ---- producer warp
+    const T* qb = (const T*)a.q;
+    const T* gb = (const T*)a.g;
+    const uint32_t edge_w = (uint32_t)a.H * 8u;  // bytes of (a, ds) per edge
+    int s = 0;
+    uint32_t phase = 0;
+    int pb = a.colptr[r0];
+    const int pend = a.colptr[r1];
+    int i0 = pb + lane < pend ? a.crow[pb + lane] : 0;
+    int i1 = pb + 32 + lane < pend ? a.crow[pb + 32 + lane] : 0;
+    int ptr_base = r0 + 1;
+    int next_ptr = a.colptr[min(ptr_base + lane, r1)];
+    int beg = pb;
+    for (int j = r0; j < r1; ++j) {
+      if (j + 1 - ptr_base >= 32) {
+        ptr_base = j + 1;
+        next_ptr = a.colptr[min(ptr_base + lane, r1)];
+      }
+      const int end = __shfl_sync(0xffffffffu, next_ptr, j + 1 - ptr_base);
+      int p = beg;
+      do {
+        const int n = min(kU, end - p);
+        if (p >= pb + 32) {
+          i0 = i1;
+          pb += 32;
+          i1 = pb + 32 + lane < pend ? a.crow[pb + 32 + lane] : 0;
+        }
+        mbar_wait(ring.empty(s), phase ^ 1u);
+        const int pp = p + (lane < kU ? lane : 0) - pb;
+        const int ia = __shfl_sync(0xffffffffu, i0, pp & 31), ib = __shfl_sync(0xffffffffu, i1, pp & 31);
+        const int i = pp < 32 ? ia : ib;
+        if (lane == 0) {
+          StageMeta* m = ring.meta(s);
+          m->row = j;
+          m->n = n;
+          m->first = p == beg;
+          m->last = p + n >= end;
+          mbar_arrive_expect_tx(ring.full(s), (uint32_t)n * (2u * kRowBytes + edge_w));
+        }
+        __syncwarp();
+        if (lane < n) {
+          bulk_g2s(ring.q(s, lane), qb + (size_t)i * D, kRowBytes, ring.full(s));
+          bulk_g2s(ring.g(s, lane), gb + (size_t)i * D, kRowBytes, ring.full(s));
+        }
+        if (lane == kU && n > 0) bulk_g2s(ring.w(s), a.ads + (size_t)p * a.H, (uint32_t)n * edge_w, ring.full(s));
+        p += n;
+        if (++s == kStages) {
+          s = 0;
+          phase ^= 1u;
+        }
+      } while (p < end);
+      beg = end;
+    }
+    mbar_wait(ring.empty(s), phase ^ 1u);
+    if (lane == 0) {
+      ring.meta(s)->row = -1;
+      mbar_arrive_expect_tx(ring.full(s), 0);
+    }
+    return;
+  }
+
+  // ---- consumers
+  const int chunk = threadIdx.x;
+  const size_t off = (size_t)chunk * 16;
+  const int h = chunk / LPH;
+  T* dk = (T*)a.dk;
+  T* dv = (T*)a.dv;
+  T* dk2 = (T*)a.dk_halo;  // virtual bases
+  T* dv2 = (T*)a.dv_halo;
+  float ka[VEC], va[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) ka[i] = va[i] = 0.f;
+  int s = 0;
+  uint32_t phase = 0;
+  while (true) {
+    mbar_wait(ring.full(s), phase);
+    const StageMeta* mt = ring.meta(s);
+    const int row = mt->row, n = mt->n, first = mt->first, last = mt->last;
+    if (row < 0) break;
+    uint4 qr[kU], gr[kU];
+    float2 w[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (u < n) {
+        qr[u] = lds16(ring.q(s, u) + off);
+        gr[u] = lds16(ring.g(s, u) + off);
+        w[u] = reinterpret_cast<const float2*>(ring.w(s))[u * a.H + h];
+      } else {
+        qr[u] = gr[u] = make_uint4(0, 0, 0, 0);
+        w[u] = make_float2(0.f, 0.f);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(ring.empty(s));
+    if (++s == kStages) {
+      s = 0;
+      phase ^= 1u;
+    }
+    if (first) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) ka[i] = va[i] = 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      float qf[VEC], gf[VEC];
+      unpack<T>(qr[u], qf);
+      unpack<T>(gr[u], gf);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        ka[i] = fmaf(w[u].y, qf[i], ka[i]);
+        va[i] = fmaf(w[u].x, gf[i], va[i]);
+      }
+    }
+    if (last) {
+      const bool own = row < a.n_own;
+      if (dk) stg16(reinterpret_cast<char*>((own ? dk : dk2) + (size_t)row * D) + off, pack<T>(ka));
+      if (dv) stg16(reinterpret_cast<char*>((own ? dv : dv2) + (size_t)row * D) + off, pack<T>(va));
+    }
+  }
+}
+
+template <typename T, int LPH>
+static bool launch_bwd_src_tma_t(const ConvArgs& a) {
+  static bool configured = false;
+  auto kern = gtconv_bwd_src_tma_kernel<T, LPH>;
+  const size_t smem = SrcRing::kBytes + 128;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+    configured = true;
+  }
+  const int ctas = std::max(1, std::min(a.Ns, num_sms() * kCtasPerSmSrc));
+  const int rows_per_cta = (a.Ns + ctas - 1) / ctas;
+  const int grid = (a.Ns + rows_per_cta - 1) / rows_per_cta;
+  kern<<<grid, kTmaThreads, smem, a.st>>>(a, rows_per_cta);
+  return true;
+}
+
+// AB2_TMA: bit 0 = forward (subject to the degree rule in gtconv.cu), bit 1 = backward dst pass, bit 2 = forward at every
+// degree, bit 3 = backward src pass; default 11 (= 1|2|8); 0 sends 2 KB rows to the LDG kernels as well
 static int tma_mask() {
   static const int v = [] {
     const char* s = getenv("AB2_TMA");
-    return s ? atoi(s) : 3;
+    return s ? atoi(s) : 11;
   }();
   return v;
 }
@@ -504,6 +685,11 @@ static ConvArgs with_virtual_halo(const ConvArgs& a, size_t elt) {
   if (a.k_halo) b.k_halo = reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(a.k_halo) - shift);
   if (a.v_halo) b.v_halo = reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(a.v_halo) - shift);
   return b;
+}
+
+bool tma_applicable(int which, int dtype, int H, int C) {
+  const size_t elt = dtype == AB2_F32 ? 4 : 2;
+  return (tma_mask() & (which == 0 ? 1 : which == 1 ? 2 : 8)) && (size_t)H * C * elt == kRowBytes && H <= 128;
 }
 
 bool try_launch_fwd_tma(int dtype, int lph, const ConvArgs& a) {
@@ -554,4 +740,33 @@ bool try_launch_bwd_dst_tma(int dtype, int lph, const ConvArgs& a) {
   }
 }
 
+}  // namespace ab2
+
+namespace ab2 {
+bool try_launch_bwd_src_tma(int dtype, int lph, const ConvArgs& a) {
+  const size_t elt = dtype == AB2_F32 ? 4 : 2;
+  if (!tma_applicable(2, dtype, a.H, a.C) || a.Ns <= 0 || a.E <= 0 || (!a.dk && !a.dv)) return false;
+  ConvArgs b = a;
+  const uintptr_t shift = (uintptr_t)a.n_own * (uintptr_t)a.H * (uintptr_t)a.C * elt;
+  if (a.dk_halo) b.dk_halo = reinterpret_cast<void*>(reinterpret_cast<uintptr_t>(a.dk_halo) - shift);
+  if (a.dv_halo) b.dv_halo = reinterpret_cast<void*>(reinterpret_cast<uintptr_t>(a.dv_halo) - shift);
+  if (dtype == AB2_BF16) {
+    switch (lph) {
+      case 1: return launch_bwd_src_tma_t<__nv_bfloat16, 1>(b);
+      case 2: return launch_bwd_src_tma_t<__nv_bfloat16, 2>(b);
+      case 4: return launch_bwd_src_tma_t<__nv_bfloat16, 4>(b);
+      case 8: return launch_bwd_src_tma_t<__nv_bfloat16, 8>(b);
+      case 16: return launch_bwd_src_tma_t<__nv_bfloat16, 16>(b);
+      default: return launch_bwd_src_tma_t<__nv_bfloat16, 32>(b);
+    }
+  }
+  switch (lph) {
+    case 1: return launch_bwd_src_tma_t<float, 1>(b);
+    case 2: return launch_bwd_src_tma_t<float, 2>(b);
+    case 4: return launch_bwd_src_tma_t<float, 4>(b);
+    case 8: return launch_bwd_src_tma_t<float, 8>(b);
+    case 16: return launch_bwd_src_tma_t<float, 16>(b);
+    default: return launch_bwd_src_tma_t<float, 32>(b);
+  }
+}
 }  // namespace ab2

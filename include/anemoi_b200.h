@@ -107,6 +107,10 @@ int ab2_gtconv_bwd(const void* q, const void* k, const void* v, const void* e, i
                    const float* lse2, const void* g, void* dq, void* dk, void* dv, void* de, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* Name of the kernel a forward (which=0), backward dst pass (1) or backward src pass (2) with these shapes dispatches to
+ * (thread-local string; for benchmark and profile bookkeeping). */
+const char* ab2_gtconv_variant(int which, int dtype, int64_t Nd, int64_t E, int H, int C);
+
 /* dst-row-sharded variants (one process per GPU).  The rank's edges index a COMPACT src space of Ns = n_own + n_halo
  * rows: [0, n_own) are the rank's own k / v rows (k, v), [n_own, Ns) the halo rows received from the peers (k_halo,
  * v_halo -- e.g. the receive buffer of an NCCL all-to-all, or peer memory mapped through NVLink).  No concatenation

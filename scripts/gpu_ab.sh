@@ -19,9 +19,9 @@ except Exception as ex: print("$name parse fail", ex, open("$OUT/$name.err").rea
 PY
 }
 for w in encoder processor decoder; do
+  run ${w}_tma11 $w AB2_TMA=11
   run ${w}_tma3 $w AB2_TMA=3
-  run ${w}_tma0 $w AB2_TMA=0
-  run ${w}_tma1 $w AB2_TMA=1
 done
-run decoder_tma3_norows decoder AB2_TMA=3 AB2_ROW_BLOCKS=0
-run decoder_tma0_norows decoder AB2_TMA=0 AB2_ROW_BLOCKS=0
+run encoder_tma15 encoder AB2_TMA=15
+run encoder_tma11_b encoder AB2_TMA=11
+run encoder_tma8 encoder AB2_TMA=8
