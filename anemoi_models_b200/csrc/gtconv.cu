@@ -741,6 +741,7 @@ static void launch_generic(int which, const ConvArgs& a) {
   }
 
 static bool fwd_prefers_tma(int dtype, int H, int C, int64_t E, int64_t Nd);
+static bool src_prefers_tma(int dtype, int H, int C, int64_t E, int64_t Ns);
 
 // which: 0 = forward, 1 = backward dst pass, 2 = backward src pass
 static int run_conv(int which, int dtype, const ConvArgs& a, const char* name) {
@@ -754,7 +755,7 @@ static int run_conv(int which, int dtype, const ConvArgs& a, const char* name) {
     AB2_LAUNCH_OK(name);
     return AB2_OK;
   }
-  if (pl.vector && which == 2 && try_launch_bwd_src_tma(dtype, pl.lph, a)) {
+  if (pl.vector && which == 2 && src_prefers_tma(dtype, a.H, a.C, a.E, a.Ns) && try_launch_bwd_src_tma(dtype, pl.lph, a)) {
     AB2_LAUNCH_OK(name);
     return AB2_OK;
   }
@@ -814,6 +815,13 @@ static bool fwd_prefers_tma(int dtype, int H, int C, int64_t E, int64_t Nd) {
   return E < 12 * Nd;
 }
 
+// Backward src pass for 2 KB rows, measured on B200 (A/B run r01j): a pipeline stage holds edges of ONE src row, so at a
+// mean out-degree of 1.4 (encoder) stages are nearly empty: LDG (8-row blocks) 0.65 ms vs pipeline 0.79 ms; at out-degree 8
+// (processor) the pipeline wins, 0.190 -> 0.139 ms; at out-degree 40 (decoder) both sit at the L2/HBM gather limit (1.04 ms).
+static bool src_prefers_tma(int dtype, int H, int C, int64_t E, int64_t Ns) {
+  return tma_applicable(2, dtype, H, C) && E >= 4 * Ns;
+}
+
 static int check_common(const char* fn, int dtype, int64_t Ns, int64_t Nd, int64_t E, int H, int C) {
   if (dtype != AB2_F32 && dtype != AB2_BF16) return fail(AB2_ERR_INVALID, "%s: dtype must be AB2_F32 or AB2_BF16", fn);
   if (Ns < 0 || Nd < 0 || E < 0 || H <= 0 || C <= 0) return fail(AB2_ERR_INVALID, "%s: negative or zero dimension", fn);
@@ -850,7 +858,7 @@ static int check_halo(const char* fn, const void* k_halo, const void* v_halo, in
 using namespace ab2;
 
 // Name of the kernel a call with these shapes dispatches to (for benchmark / profile bookkeeping).
-extern "C" const char* ab2_gtconv_variant(int which, int dtype, int64_t Nd, int64_t E, int H, int C) {
+extern "C" const char* ab2_gtconv_variant(int which, int dtype, int64_t Ns, int64_t Nd, int64_t E, int H, int C) {
   static thread_local char buf[96];
   const Plan pl = make_plan(H, C, dtype == AB2_F32 ? 4 : 2);
   const char* t = dtype == AB2_F32 ? "float" : "__nv_bfloat16";
@@ -866,7 +874,7 @@ extern "C" const char* ab2_gtconv_variant(int which, int dtype, int64_t Nd, int6
   else if (which == 1)
     base = tma_applicable(1, dtype, H, C) ? "gtconv_bwd_dst_tma_kernel" : "gtconv_bwd_dst_kernel";
   else
-    base = tma_applicable(2, dtype, H, C) ? "gtconv_bwd_src_tma_kernel" : "gtconv_bwd_src_kernel";
+    base = src_prefers_tma(dtype, H, C, E, Ns) ? "gtconv_bwd_src_tma_kernel" : "gtconv_bwd_src_kernel";
   snprintf(buf, sizeof(buf), "%s<%s, %d>", base, t, pl.lph);
   return buf;
 }

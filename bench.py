@@ -279,10 +279,10 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if world == 1 and args.workload == "encoder" and os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(L.ab2_gtconv_variant({"fwd": 0, "bwd_dst": 1, "bwd_src": 2}[dom], 1, nd_loc, E, H, C).decode().split("<")[0],
+            traffic = json.load(f).get(L.ab2_gtconv_variant({"fwd": 0, "bwd_dst": 1, "bwd_src": 2}[dom], 1, n_src, nd_loc, E, H, C).decode().split("<")[0],
                                        {}).get("dram_bytes_per_launch")
     which = {"fwd": 0, "bwd_dst": 1, "bwd_src": 2}
-    kname = {n: L.ab2_gtconv_variant(which[n], 1, nd_loc, E, H, C).decode() for n in kt}
+    kname = {n: L.ab2_gtconv_variant(which[n], 1, n_src, nd_loc, E, H, C).decode() for n in kt}
     roofline = {"bound": "hbm", "kernel": kname[dom], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ab[dom], "launch_ms": round(kt[dom], 4)}

@@ -109,7 +109,7 @@ int ab2_gtconv_bwd(const void* q, const void* k, const void* v, const void* e, i
 
 /* Name of the kernel a forward (which=0), backward dst pass (1) or backward src pass (2) with these shapes dispatches to
  * (thread-local string; for benchmark and profile bookkeeping). */
-const char* ab2_gtconv_variant(int which, int dtype, int64_t Nd, int64_t E, int H, int C);
+const char* ab2_gtconv_variant(int which, int dtype, int64_t Ns, int64_t Nd, int64_t E, int H, int C);
 
 /* dst-row-sharded variants (one process per GPU).  The rank's edges index a COMPACT src space of Ns = n_own + n_halo
  * rows: [0, n_own) are the rank's own k / v rows (k, v), [n_own, Ns) the halo rows received from the peers (k_halo,
