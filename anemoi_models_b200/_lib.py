@@ -30,6 +30,7 @@ SIGNATURES = {
     "ab2_gtconv_bwd_workspace_bytes": (_sz, [_i64, _i32]),
     "ab2_gtconv_bwd_dst": (_i32, [_vp] * 4 + [_i32] + [_vp] * 4 + [_i64] * 3 + [_i32, _i32] + [_vp] * 5 + [_vp, _sz, _vp]),
     "ab2_gtconv_bwd_src": (_i32, [_vp] * 2 + [_i32] + [_vp] * 2 + [_i64] * 3 + [_i32, _i32] + [_vp] * 4),
+    "ab2_gtconv_bwd_src_range": (_i32, [_vp] * 2 + [_i32] + [_vp] * 2 + [_i64] * 3 + [_i32, _i32] + [_vp] * 3 + [_i64, _i64, _vp]),
     "ab2_gtconv_bwd": (_i32, [_vp] * 4 + [_i32] + [_vp] * 6 + [_i64] * 3 + [_i32, _i32] + [_vp] * 7 + [_vp, _sz, _vp]),
     "ab2_edge_gather_add_act": (_i32, [_vp] * 4 + [_i64] * 3 + [_i32] * 3 + [_vp] * 3),
     "ab2_edge_gather_add_act_bwd": (_i32, [_vp] * 6 + [_i64] * 3 + [_i32] * 3 + [_vp] * 4),

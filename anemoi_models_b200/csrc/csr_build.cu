@@ -259,11 +259,12 @@ __global__ void finalize_csr_kernel(const int64_t* __restrict__ src_row, const i
   }
 }
 
-__global__ void finalize_csc_kernel(const int* __restrict__ cpos, const int* __restrict__ rowidx, int n, int* __restrict__ crow,
-                                    int* __restrict__ csr2csc) {
+__global__ void finalize_csc_kernel(const int* __restrict__ cpos, const int* __restrict__ rowidx, const int* __restrict__ col, int n,
+                                    int* __restrict__ crow, int* __restrict__ csr2csc) {
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
     const int p = cpos[t];
-    crow[t] = rowidx[p];
+    crow[2 * t] = rowidx[p];   // dst of src-sorted position t
+    crow[2 * t + 1] = col[p];  // its src (lets a kernel stream CSC edges without walking colptr)
     if (csr2csc) csr2csc[p] = t;  // inverse permutation of cpos
   }
 }
@@ -393,7 +394,7 @@ extern "C" int ab2_csr_build(const int64_t* edge_index, int64_t E, int64_t Ns, i
     if (int rc = stable_sort_by_key<int32_t>(col, E, (int)Ns, nullptr, 0, colptr, cpos, flags + 2, w, st)) return rc;
     if (E > 0) {
       const int grid = (int)std::min<int64_t>((E + 255) / 256, (int64_t)sms * 16);
-      finalize_csc_kernel<<<grid, 256, 0, st>>>(cpos, rowidx, (int)E, crow, csr2csc);
+      finalize_csc_kernel<<<grid, 256, 0, st>>>(cpos, rowidx, col, (int)E, crow, csr2csc);
       AB2_LAUNCH_OK("finalize_csc_kernel");
     }
   }

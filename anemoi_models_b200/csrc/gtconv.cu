@@ -405,11 +405,12 @@ constexpr int kSrcRows = 8;
 template <typename T, int LPH, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 6)
 gtconv_bwd_src_kernel(const T* __restrict__ q, const T* __restrict__ g, const int* __restrict__ colptr,
-                      const int* __restrict__ crow, const float2* __restrict__ ads, int Ns, RowMap rm, int H,
+                      const int* __restrict__ crow, const float2* __restrict__ ads, int src_lo, int Ns, RowMap rm, int H,
                       T* __restrict__ dk, T* __restrict__ dv, T* __restrict__ dk2, T* __restrict__ dv2, int nsplit) {
+  // covers src rows [src_lo, Ns)
   constexpr int VEC = Vec<T>::N;
   const int lr = threadIdx.x / rm.tpd;
-  const long long j0 = ((long long)blockIdx.x * rm.rpb + lr) * kSrcRows;
+  const long long j0 = (long long)src_lo + ((long long)blockIdx.x * rm.rpb + lr) * kSrcRows;
   if (lr >= rm.rpb || j0 >= Ns) return;
   const int chunk = blockIdx.y * rm.tpd + (threadIdx.x - lr * rm.tpd);
   const size_t D = (size_t)rm.chunks * VEC;
@@ -445,7 +446,7 @@ gtconv_bwd_src_kernel(const T* __restrict__ q, const T* __restrict__ g, const in
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       if (tb + u < tend) {
-        const size_t i = (size_t)crow[tb + u];
+        const size_t i = (size_t)crow[2 * (tb + u)];
         w[u] = __ldg(ads + (size_t)(tb + u) * H + h);
         qr[u] = ldg16_keep(q + i * D + off);
         gr[u] = ldg16_keep(g + i * D + off);
@@ -607,19 +608,19 @@ gtconv_bwd_dst_generic_kernel(const T* __restrict__ q, const T* __restrict__ k, 
 template <typename T, bool SPLIT>
 __global__ void __launch_bounds__(kThreads)
 gtconv_bwd_src_generic_kernel(const T* __restrict__ q, const T* __restrict__ g, const int* __restrict__ colptr,
-                              const int* __restrict__ crow, const float2* __restrict__ ads, int Ns, int H, int C,
+                              const int* __restrict__ crow, const float2* __restrict__ ads, int src_lo, int Ns, int H, int C,
                               T* __restrict__ dk, T* __restrict__ dv, T* __restrict__ dk2, T* __restrict__ dv2, int nsplit) {
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-  if (w >= (long long)Ns * H) return;
-  const int j = (int)(w / H), h = (int)(w % H);
+  if (w >= (long long)(Ns - src_lo) * H) return;
+  const int j = src_lo + (int)(w / H), h = (int)(w % H);
   const size_t D = (size_t)H * C, ho = (size_t)h * C;
   float ka[kGenR], va[kGenR];
 #pragma unroll
   for (int r = 0; r < kGenR; ++r) ka[r] = va[r] = 0.f;
   const int beg = colptr[j], end = colptr[j + 1];
   for (int t = beg; t < end; ++t) {
-    const size_t i = (size_t)crow[t];
+    const size_t i = (size_t)crow[2 * (size_t)t];
     const float2 w2 = ads[(size_t)t * H + h];
 #pragma unroll
     for (int r = 0; r < kGenR; ++r) {
@@ -704,9 +705,9 @@ static void launch_bwd_dst(const Plan& pl, const ConvArgs& a) {
 }
 template <typename T, int LPH, bool SPLIT>
 static void launch_bwd_src(const Plan& pl, const ConvArgs& a) {
-  const int groups = (a.Ns + kSrcRows - 1) / kSrcRows;
+  const int groups = (a.src_hi - a.src_lo + kSrcRows - 1) / kSrcRows;
   dim3 grid((groups + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
-  gtconv_bwd_src_kernel<T, LPH, SPLIT><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.g, a.colptr, a.crow, a.ads, a.Ns, pl.rm,
+  gtconv_bwd_src_kernel<T, LPH, SPLIT><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.g, a.colptr, a.crow, a.ads, a.src_lo, a.src_hi, pl.rm,
                                                             a.H, (T*)a.dk, (T*)a.dv, vbase((T*)a.dk_halo, a), vbase((T*)a.dv_halo, a), a.n_own);
 }
 template <typename T, bool SPLIT>
@@ -724,8 +725,8 @@ static void launch_generic(int which, const ConvArgs& a) {
                                                                  a.scale, (const T*)a.out, a.lse2_in, (const T*)a.g, (T*)a.dq,
                                                                  (T*)a.de, a.ads, vbase((const T*)a.k_halo, a), vbase((const T*)a.v_halo, a), a.n_own);
   } else {
-    const unsigned grid = (unsigned)(((long long)a.Ns * a.H + wpb - 1) / wpb);
-    gtconv_bwd_src_generic_kernel<T, SPLIT><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.g, a.colptr, a.crow, a.ads, a.Ns, a.H,
+    const unsigned grid = (unsigned)(((long long)(a.src_hi - a.src_lo) * a.H + wpb - 1) / wpb);
+    gtconv_bwd_src_generic_kernel<T, SPLIT><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.g, a.colptr, a.crow, a.ads, a.src_lo, a.src_hi, a.H,
                                                                  a.C, (T*)a.dk, (T*)a.dv, vbase((T*)a.dk_halo, a), vbase((T*)a.dv_halo, a), a.n_own);
   }
 }
@@ -815,11 +816,12 @@ static bool fwd_prefers_tma(int dtype, int H, int C, int64_t E, int64_t Nd) {
   return E < 12 * Nd;
 }
 
-// Backward src pass for 2 KB rows, measured on B200 (A/B run r01j): a pipeline stage holds edges of ONE src row, so at a
-// mean out-degree of 1.4 (encoder) stages are nearly empty: LDG (8-row blocks) 0.65 ms vs pipeline 0.79 ms; at out-degree 8
-// (processor) the pipeline wins, 0.190 -> 0.139 ms; at out-degree 40 (decoder) both sit at the L2/HBM gather limit (1.04 ms).
+// Backward src pass for 2 KB rows: the pipelined kernel packs kU consecutive CSC edges per stage regardless of row
+// boundaries (first version, one src row per stage, lost to the LDG kernel at out-degree 1.4: 0.79 vs 0.65 ms, run r01j).
 static bool src_prefers_tma(int dtype, int H, int C, int64_t E, int64_t Ns) {
-  return tma_applicable(2, dtype, H, C) && E >= 4 * Ns;
+  (void)E;
+  (void)Ns;
+  return tma_applicable(2, dtype, H, C);
 }
 
 static int check_common(const char* fn, int dtype, int64_t Ns, int64_t Nd, int64_t E, int H, int C) {
@@ -840,6 +842,7 @@ static ConvArgs base_args(const void* q, const void* k, const void* v, const voi
   a.n_own = (int)((k_halo || v_halo) ? n_own : Ns);
   a.rowptr = rowptr; a.col = col; a.perm = perm;
   a.Ns = (int)Ns; a.Nd = (int)Nd; a.E = E; a.H = H; a.C = C;
+  a.src_lo = 0; a.src_hi = (int)Ns;
   a.scale = 1.f / sqrtf((float)C);
   a.qscale = kLog2e * a.scale;
   a.low_degree = use_row_blocks(E, Nd);
@@ -919,7 +922,7 @@ static int bwd_dst_impl(ConvArgs a, int dtype, const int32_t* csr2csc, const voi
 
 static int bwd_src_impl(ConvArgs a, int dtype, const int32_t* colptr, const int32_t* crow, const void* g, const void* ads_ws, void* dk,
                         void* dv, void* dk_halo, void* dv_halo) {
-  if (a.Ns == 0 || (!dk && !dv && !dk_halo && !dv_halo)) return AB2_OK;
+  if (a.Ns == 0 || a.src_hi <= a.src_lo || (!dk && !dv && !dk_halo && !dv_halo)) return AB2_OK;
   if (!colptr || !ads_ws || (a.E > 0 && (!a.q || !g || !crow))) return fail(AB2_ERR_INVALID, "gtconv_bwd_src: null pointer argument");
   if (a.n_own < a.Ns && ((dk && !dk_halo) || (dv && !dv_halo)))
     return fail(AB2_ERR_INVALID, "gtconv_bwd_src: halo rows present but dk_halo / dv_halo missing");
@@ -944,6 +947,17 @@ extern "C" int ab2_gtconv_bwd_src(const void* q, const void* g, int dtype, const
   if (int rc = check_common("gtconv_bwd_src", dtype, Ns, Nd, E, H, C)) return rc;
   return bwd_src_impl(base_args(q, nullptr, nullptr, nullptr, nullptr, Ns, nullptr, nullptr, nullptr, nullptr, Ns, Nd, E, H, C, stream),
                       dtype, colptr, crow, g, ads_ws, dk, dv, nullptr, nullptr);
+}
+
+extern "C" int ab2_gtconv_bwd_src_range(const void* q, const void* g, int dtype, const int32_t* colptr, const int32_t* crow,
+                                        int64_t Ns, int64_t Nd, int64_t E, int H, int C, const void* ads_ws, void* dk, void* dv,
+                                        int64_t row_begin, int64_t row_end, void* stream) {
+  if (int rc = check_common("gtconv_bwd_src_range", dtype, Ns, Nd, E, H, C)) return rc;
+  if (row_begin < 0 || row_end > Ns || row_begin > row_end) return fail(AB2_ERR_INVALID, "gtconv_bwd_src_range: bad row range");
+  ConvArgs a = base_args(q, nullptr, nullptr, nullptr, nullptr, Ns, nullptr, nullptr, nullptr, nullptr, Ns, Nd, E, H, C, stream);
+  a.src_lo = (int)row_begin;
+  a.src_hi = (int)row_end;
+  return bwd_src_impl(a, dtype, colptr, crow, g, ads_ws, dk, dv, nullptr, nullptr);
 }
 
 extern "C" int ab2_gtconv_bwd_halo(const void* q, const void* k, const void* v, const void* k_halo, const void* v_halo,

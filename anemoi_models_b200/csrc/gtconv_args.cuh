@@ -18,6 +18,7 @@ struct ConvArgs {
   const void *k_halo, *v_halo;      // src rows [n_own, Ns) (NULL on one GPU)
   const int *rowptr, *col, *perm, *colptr, *csr2csc, *crow;
   int Ns, Nd, n_own, H, C;
+  int src_lo, src_hi;               // src rows the backward src pass covers ([0, Ns) unless a caller streams row ranges)
   int64_t E;
   float qscale, scale;
   const void *out, *g;

@@ -517,8 +517,8 @@ gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) 
   constexpr int VEC = Vec<T>::N;
   constexpr size_t D = kRowBytes / sizeof(T);
   SrcRing ring{smem_raw};
-  const int r0 = min((long long)blockIdx.x * rows_per_cta, (long long)a.Ns);
-  const int r1 = min((long long)r0 + rows_per_cta, (long long)a.Ns);
+  const int r0 = min((long long)a.src_lo + (long long)blockIdx.x * rows_per_cta, (long long)a.src_hi);
+  const int r1 = min((long long)r0 + rows_per_cta, (long long)a.src_hi);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(ring.full(s), 1);
@@ -531,68 +531,55 @@ gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) 
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x >= kConsumers) {
-    // ---- producer warp
+    // ---- producer warp: every stage carries kU consecutive CSC edges of the CTA's row range, whatever rows they belong to
+    // (meta.t[u] = src row of edge u), so stages stay full at an out-degree of 1-2 as well
     const T* qb = (const T*)a.q;
     const T* gb = (const T*)a.g;
-    const uint32_t edge_w = (uint32_t)a.H * 8u;  // bytes of (a, ds) per edge
+    const int2* cedge = reinterpret_cast<const int2*>(a.crow);  // (dst, src) per src-sorted position
+    const uint32_t edge_w = (uint32_t)a.H * 8u;                 // bytes of (a, ds) per edge
     int s = 0;
     uint32_t phase = 0;
     int pb = a.colptr[r0];
     const int pend = a.colptr[r1];
-    int i0 = pb + lane < pend ? a.crow[pb + lane] : 0;
-    int i1 = pb + 32 + lane < pend ? a.crow[pb + 32 + lane] : 0;
-    int ptr_base = r0 + 1;
-    int next_ptr = a.colptr[min(ptr_base + lane, r1)];
-    int beg = pb;
-    for (int j = r0; j < r1; ++j) {
-      if (j + 1 - ptr_base >= 32) {
-        ptr_base = j + 1;
-        next_ptr = a.colptr[min(ptr_base + lane, r1)];
+    int2 e0 = pb + lane < pend ? cedge[pb + lane] : make_int2(0, 0);
+    int2 e1 = pb + 32 + lane < pend ? cedge[pb + 32 + lane] : make_int2(0, 0);
+    for (int p = pb; p < pend; p += kU) {
+      const int n = min(kU, pend - p);
+      if (p >= pb + 32) {
+        e0 = e1;
+        pb += 32;
+        e1 = pb + 32 + lane < pend ? cedge[pb + 32 + lane] : make_int2(0, 0);
       }
-      const int end = __shfl_sync(0xffffffffu, next_ptr, j + 1 - ptr_base);
-      int p = beg;
-      do {
-        const int n = min(kU, end - p);
-        if (p >= pb + 32) {
-          i0 = i1;
-          pb += 32;
-          i1 = pb + 32 + lane < pend ? a.crow[pb + 32 + lane] : 0;
-        }
-        mbar_wait(ring.empty(s), phase ^ 1u);
-        const int pp = p + (lane < kU ? lane : 0) - pb;
-        const int ia = __shfl_sync(0xffffffffu, i0, pp & 31), ib = __shfl_sync(0xffffffffu, i1, pp & 31);
-        const int i = pp < 32 ? ia : ib;
-        if (lane == 0) {
-          StageMeta* m = ring.meta(s);
-          m->row = j;
-          m->n = n;
-          m->first = p == beg;
-          m->last = p + n >= end;
-          mbar_arrive_expect_tx(ring.full(s), (uint32_t)n * (2u * kRowBytes + edge_w));
-        }
-        __syncwarp();
-        if (lane < n) {
-          bulk_g2s(ring.q(s, lane), qb + (size_t)i * D, kRowBytes, ring.full(s));
-          bulk_g2s(ring.g(s, lane), gb + (size_t)i * D, kRowBytes, ring.full(s));
-        }
-        if (lane == kU && n > 0) bulk_g2s(ring.w(s), a.ads + (size_t)p * a.H, (uint32_t)n * edge_w, ring.full(s));
-        p += n;
-        if (++s == kStages) {
-          s = 0;
-          phase ^= 1u;
-        }
-      } while (p < end);
-      beg = end;
+      mbar_wait(ring.empty(s), phase ^ 1u);
+      const int pp = p + (lane < kU ? lane : 0) - pb;
+      const int ia = __shfl_sync(0xffffffffu, e0.x, pp & 31), ib = __shfl_sync(0xffffffffu, e1.x, pp & 31);
+      const int ra = __shfl_sync(0xffffffffu, e0.y, pp & 31), rb = __shfl_sync(0xffffffffu, e1.y, pp & 31);
+      const int i = pp < 32 ? ia : ib, r = pp < 32 ? ra : rb;
+      StageMeta* m = ring.meta(s);
+      if (lane < kU) m->t[lane] = r;
+      if (lane == 0) m->n = n;
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(ring.full(s), (uint32_t)n * (2u * kRowBytes + edge_w));
+      __syncwarp();
+      if (lane < n) {
+        bulk_g2s(ring.q(s, lane), qb + (size_t)i * D, kRowBytes, ring.full(s));
+        bulk_g2s(ring.g(s, lane), gb + (size_t)i * D, kRowBytes, ring.full(s));
+      }
+      if (lane == kU) bulk_g2s(ring.w(s), a.ads + (size_t)p * a.H, (uint32_t)n * edge_w, ring.full(s));
+      if (++s == kStages) {
+        s = 0;
+        phase ^= 1u;
+      }
     }
     mbar_wait(ring.empty(s), phase ^ 1u);
     if (lane == 0) {
-      ring.meta(s)->row = -1;
+      ring.meta(s)->n = -1;
       mbar_arrive_expect_tx(ring.full(s), 0);
     }
     return;
   }
 
-  // ---- consumers
+  // ---- consumers: one accumulator pair, flushed whenever the src row changes; rows without edges get zeros
   const int chunk = threadIdx.x;
   const size_t off = (size_t)chunk * 16;
   const int h = chunk / LPH;
@@ -603,17 +590,35 @@ gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) 
   float ka[VEC], va[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) ka[i] = va[i] = 0.f;
+  int cur = r0;
+  auto flush_to = [&](int r) {  // store row `cur`, zero rows cur+1 .. r-1, continue with row r
+    {
+      const bool own = cur < a.n_own;
+      if (dk) stg16(reinterpret_cast<char*>((own ? dk : dk2) + (size_t)cur * D) + off, pack<T>(ka));
+      if (dv) stg16(reinterpret_cast<char*>((own ? dv : dv2) + (size_t)cur * D) + off, pack<T>(va));
+    }
+    for (int z = cur + 1; z < r; ++z) {
+      const bool own = z < a.n_own;
+      if (dk) stg16(reinterpret_cast<char*>((own ? dk : dk2) + (size_t)z * D) + off, make_uint4(0, 0, 0, 0));
+      if (dv) stg16(reinterpret_cast<char*>((own ? dv : dv2) + (size_t)z * D) + off, make_uint4(0, 0, 0, 0));
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) ka[i] = va[i] = 0.f;
+    cur = r;
+  };
   int s = 0;
   uint32_t phase = 0;
   while (true) {
     mbar_wait(ring.full(s), phase);
     const StageMeta* mt = ring.meta(s);
-    const int row = mt->row, n = mt->n, first = mt->first, last = mt->last;
-    if (row < 0) break;
+    const int n = mt->n;
+    if (n < 0) break;
     uint4 qr[kU], gr[kU];
     float2 w[kU];
+    int rows[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
+      rows[u] = mt->t[u];
       if (u < n) {
         qr[u] = lds16(ring.q(s, u) + off);
         gr[u] = lds16(ring.g(s, u) + off);
@@ -629,27 +634,22 @@ gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) 
       s = 0;
       phase ^= 1u;
     }
-    if (first) {
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) ka[i] = va[i] = 0.f;
-    }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      float qf[VEC], gf[VEC];
-      unpack<T>(qr[u], qf);
-      unpack<T>(gr[u], gf);
+      if (u < n) {
+        if (rows[u] != cur) flush_to(rows[u]);
+        float qf[VEC], gf[VEC];
+        unpack<T>(qr[u], qf);
+        unpack<T>(gr[u], gf);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        ka[i] = fmaf(w[u].y, qf[i], ka[i]);
-        va[i] = fmaf(w[u].x, gf[i], va[i]);
+        for (int i = 0; i < VEC; ++i) {
+          ka[i] = fmaf(w[u].y, qf[i], ka[i]);
+          va[i] = fmaf(w[u].x, gf[i], va[i]);
+        }
       }
     }
-    if (last) {
-      const bool own = row < a.n_own;
-      if (dk) stg16(reinterpret_cast<char*>((own ? dk : dk2) + (size_t)row * D) + off, pack<T>(ka));
-      if (dv) stg16(reinterpret_cast<char*>((own ? dv : dv2) + (size_t)row * D) + off, pack<T>(va));
-    }
   }
+  flush_to(r1);  // last row with edges, then the trailing edge-less rows of the range
 }
 
 template <typename T, int LPH>
@@ -661,9 +661,10 @@ static bool launch_bwd_src_tma_t(const ConvArgs& a) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
     configured = true;
   }
-  const int ctas = std::max(1, std::min(a.Ns, num_sms() * kCtasPerSmSrc));
-  const int rows_per_cta = (a.Ns + ctas - 1) / ctas;
-  const int grid = (a.Ns + rows_per_cta - 1) / rows_per_cta;
+  const int nrows = a.src_hi - a.src_lo;
+  const int ctas = std::max(1, std::min(nrows, num_sms() * kCtasPerSmSrc));
+  const int rows_per_cta = (nrows + ctas - 1) / ctas;
+  const int grid = (nrows + rows_per_cta - 1) / rows_per_cta;
   kern<<<grid, kTmaThreads, smem, a.st>>>(a, rows_per_cta);
   return true;
 }
@@ -745,7 +746,7 @@ bool try_launch_bwd_dst_tma(int dtype, int lph, const ConvArgs& a) {
 namespace ab2 {
 bool try_launch_bwd_src_tma(int dtype, int lph, const ConvArgs& a) {
   const size_t elt = dtype == AB2_F32 ? 4 : 2;
-  if (!tma_applicable(2, dtype, a.H, a.C) || a.Ns <= 0 || a.E <= 0 || (!a.dk && !a.dv)) return false;
+  if (!tma_applicable(2, dtype, a.H, a.C) || a.src_hi <= a.src_lo || a.E <= 0 || (!a.dk && !a.dv)) return false;
   ConvArgs b = a;
   const uintptr_t shift = (uintptr_t)a.n_own * (uintptr_t)a.H * (uintptr_t)a.C * elt;
   if (a.dk_halo) b.dk_halo = reinterpret_cast<void*>(reinterpret_cast<uintptr_t>(a.dk_halo) - shift);

@@ -183,8 +183,7 @@ extern "C" int ab2_gtconv_fwd_bwd_host_streamed(const void* q_host, const void* 
     TRY(cudaEventRecord(ev_dst, comp));
     // ---- src pass for the src rows whose edges are all behind us
     if (rc == AB2_OK && src_final > src_done) {
-      rc = ab2_gtconv_bwd_src(w.q, w.g, dtype, colptr + src_done, crow, src_final - src_done, Nd, E, H, C, w.ads,
-                              w.dk + src_done * row, w.dv + src_done * row, comp);
+      rc = ab2_gtconv_bwd_src_range(w.q, w.g, dtype, colptr, crow, Ns, Nd, E, H, C, w.ads, w.dk, w.dv, src_done, src_final, comp);
     }
     TRY(cudaEventRecord(ev_src, comp));
     // ---- download

@@ -67,7 +67,7 @@ class GraphCSR:
         self.rowidx = torch.empty(E, **i32)
         self.colptr = torch.empty(num_src + 1, **i32)
         self.cpos = torch.empty(E, **i32)
-        self.crow = torch.empty(E, **i32)
+        self.crow = torch.empty((E, 2), **i32)  # (dst, src) of src-sorted position t
         self.csr2csc = torch.empty(E, **i32)
         flags = torch.empty(4, **i32)
         ws_bytes = L.ab2_csr_workspace_bytes(E, num_src, num_dst)

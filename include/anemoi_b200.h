@@ -52,7 +52,7 @@ const char* ab2_last_error(void);
  * rowidx     : int32 [E]      dst id of sorted position p
  * colptr     : int32 [Ns+1]   segment offsets of each src in the src-sorted order
  * cpos       : int32 [E]      CSR position p of src-sorted position t (ascending within a src)
- * crow       : int32 [E]      dst id of src-sorted position t
+ * crow       : int32 [E,2]    (dst id, src id) of src-sorted position t
  * csr2csc    : int32 [E]      src-sorted position t of CSR position p (inverse of cpos); may be NULL
  * flags      : int32 [4]      [0] = 1 if perm is the identity; [1] = number of edges with src/dst out of range
  * Requires E, Ns, Nd < 2^31.  Result is bit-exact equal to torch.sort(edge_index[1], stable=True).
@@ -101,6 +101,11 @@ int ab2_gtconv_bwd_dst(const void* q, const void* k, const void* v, const void* 
                        size_t ads_ws_bytes, void* stream);
 int ab2_gtconv_bwd_src(const void* q, const void* g, int dtype, const int32_t* colptr, const int32_t* crow, int64_t Ns,
                        int64_t Nd, int64_t E, int H, int C, const void* ads_ws, void* dk, void* dv, void* stream);
+/* src pass restricted to src rows [row_begin, row_end) (all pointers unshifted) -- lets a caller that streams dst chunks
+ * finalise dk / dv for the src rows whose edges are all behind it. */
+int ab2_gtconv_bwd_src_range(const void* q, const void* g, int dtype, const int32_t* colptr, const int32_t* crow, int64_t Ns,
+                             int64_t Nd, int64_t E, int H, int C, const void* ads_ws, void* dk, void* dv,
+                             int64_t row_begin, int64_t row_end, void* stream);
 int ab2_gtconv_bwd(const void* q, const void* k, const void* v, const void* e, int dtype, const int32_t* rowptr,
                    const int32_t* col, const int32_t* perm, const int32_t* colptr, const int32_t* csr2csc,
                    const int32_t* crow, int64_t Ns, int64_t Nd, int64_t E, int H, int C, const void* out,

@@ -23,7 +23,8 @@ def _check_plan(ei_np, ns, nd):
     colptr, pos, row = og.csc_of_csr(rowptr, col, ns)
     assert np.array_equal(plan.colptr.cpu().numpy(), colptr)
     assert np.array_equal(plan.cpos.cpu().numpy(), pos)
-    assert np.array_equal(plan.crow.cpu().numpy(), row)
+    assert np.array_equal(plan.crow.cpu().numpy()[:, 0], row)
+    assert np.array_equal(plan.crow.cpu().numpy()[:, 1], col[pos])
     inv = np.empty_like(pos)
     inv[pos] = np.arange(len(pos), dtype=pos.dtype)
     assert np.array_equal(plan.csr2csc.cpu().numpy(), inv)

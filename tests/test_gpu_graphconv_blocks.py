@@ -162,12 +162,15 @@ def test_host_buffer_entry_points_match_device_path():
     from anemoi_models_b200.graph import get_csr
 
     torch.manual_seed(3)
-    ns, nd, E, H, C = 500, 200, 4000, 4, 16
+    ns, nd, E = 500, 200, 4000
     ei = torch.stack([torch.randint(0, ns, (E,)), torch.randint(0, nd, (E,))])
     ei_sorted = ei[:, torch.sort(ei[1], stable=True).indices]
-    for edges, chunks in ((ei, 16), (ei_sorted, 1), (ei_sorted, 7), (ei_sorted, 16), (ei_sorted, 500)):
+    cases = [(e_, c_, 4, 16, dt) for e_, c_ in ((ei, 16), (ei_sorted, 1), (ei_sorted, 7), (ei_sorted, 16), (ei_sorted, 500))
+             for dt in (torch.float32, torch.bfloat16)]
+    cases += [(ei_sorted, 7, 16, 64, torch.bfloat16), (ei_sorted, 16, 16, 32, torch.float32)]  # 2 KB rows: pipelined kernels
+    for edges, chunks, H, C, dtype in cases:
         edges = edges.cuda()
-        for dtype in (torch.float32, torch.bfloat16):
+        for _ in (0,):
             q, k, v, e, g = (torch.randn(s, H, C).to(dtype).pin_memory() for s in (nd, ns, ns, E, nd))
             plan = get_csr(edges, ns, nd)
             assert plan.perm_is_identity == (edges is not ei.cuda() and bool(torch.equal(edges.cpu(), ei_sorted)))
