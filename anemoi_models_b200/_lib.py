@@ -32,6 +32,13 @@ SIGNATURES = {
     "ab2_gtconv_bwd_src": (_i32, [_vp] * 2 + [_i32] + [_vp] * 2 + [_i64] * 3 + [_i32, _i32] + [_vp] * 4),
     "ab2_gtconv_bwd_src_range": (_i32, [_vp] * 2 + [_i32] + [_vp] * 2 + [_i64] * 3 + [_i32, _i32] + [_vp] * 3 + [_i64, _i64, _vp]),
     "ab2_gtconv_bwd": (_i32, [_vp] * 4 + [_i32] + [_vp] * 6 + [_i64] * 3 + [_i32, _i32] + [_vp] * 7 + [_vp, _sz, _vp]),
+    "ab2_ipc_alloc": (_i32, [_sz, _vp, _vp]),
+    "ab2_ipc_open": (_i32, [_vp, _vp]),
+    "ab2_ipc_close": (_i32, [_vp]),
+    "ab2_ipc_free": (_i32, [_vp]),
+    "ab2_memcpy_d2d": (_i32, [_vp, _vp, _sz, _vp]),
+    "ab2_peer_push_rows": (_i32, [_vp] * 5 + [_i64, _i32, _vp, _vp, _i32, _vp]),
+    "ab2_rows_add": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "ab2_edge_gather_add_act": (_i32, [_vp] * 4 + [_i64] * 3 + [_i32] * 3 + [_vp] * 3),
     "ab2_edge_gather_add_act_bwd": (_i32, [_vp] * 6 + [_i64] * 3 + [_i32] * 3 + [_vp] * 4),
     "ab2_edge_ln_res_segsum": (_i32, [_vp] * 4 + [_f32] + [_vp] * 2 + [_i64] * 2 + [_i32] * 2 + [_vp] * 5),

@@ -137,12 +137,17 @@ class _GTConvShardedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, e, plan: GraphCSR, hplan, group):
         from .distributed.halo import exchange_rows
+        from .distributed.peer import get_peer_exchange
 
-        k_halo = exchange_rows(k, hplan, group)
-        v_halo = exchange_rows(v, hplan, group)
+        px = get_peer_exchange(hplan, group, k.shape[1] * k.shape[2] * k.element_size(), k.device)
+        if px is not None:  # NVLink peer-memory push (one kernel + a stream-ordered barrier)
+            k_halo, v_halo = px.forward(k, v)
+        else:  # NCCL all-to-all
+            k_halo = exchange_rows(k, hplan, group)
+            v_halo = exchange_rows(v, hplan, group)
         out, lse2 = _conv_forward(q, k, v, k_halo, v_halo, e, plan)
         ctx.save_for_backward(q, k, v, e, out, lse2, k_halo, v_halo)
-        ctx.plan, ctx.hplan, ctx.group = plan, hplan, group
+        ctx.plan, ctx.hplan, ctx.group, ctx.px = plan, hplan, group, px
         return out
 
     @staticmethod
@@ -152,10 +157,13 @@ class _GTConvShardedFn(torch.autograd.Function):
         q, k, v, e, out, lse2, k_halo, v_halo = ctx.saved_tensors
         n = ctx.needs_input_grad
         dq, dk, dv, de, dkh, dvh = _conv_backward(q, k, v, k_halo, v_halo, e, out, lse2, g, ctx.plan, (n[0], n[1], n[2], n[3]))
-        if n[1]:
-            return_rows(dkh, ctx.hplan, ctx.group, dk)
-        if n[2]:
-            return_rows(dvh, ctx.hplan, ctx.group, dv)
+        if ctx.px is not None and n[1] and n[2]:
+            ctx.px.backward(dkh, dvh, dk, dv)
+        else:
+            if n[1]:
+                return_rows(dkh, ctx.hplan, ctx.group, dk)
+            if n[2]:
+                return_rows(dvh, ctx.hplan, ctx.group, dv)
         return dq, dk, dv, de, None, None, None
 
 

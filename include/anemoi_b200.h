@@ -132,6 +132,27 @@ int ab2_gtconv_bwd_halo(const void* q, const void* k, const void* v, const void*
                         void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Halo exchange over NVLink peer memory (one process per GPU on one node).  Replaces the list-form all_to_all of
+ * distributed/transformer.py:21-82 / the all_gather of distributed/primitives.py:57-109 on this path.
+ * Buffers that peers write into are whole cudaMalloc allocations owned by the library (CUDA IPC cannot export a
+ * sub-allocation of a caching allocator): ab2_ipc_alloc / ab2_ipc_free; peers map them with ab2_ipc_open / _close.
+ * ------------------------------------------------------------------------------------------------- */
+#define AB2_MAX_PEERS 16
+int ab2_ipc_alloc(size_t bytes, void** dev_ptr, void* handle_out /* 64 bytes */);
+int ab2_ipc_open(const void* handle /* 64 bytes */, void** dev_ptr);
+int ab2_ipc_close(void* dev_ptr);
+int ab2_ipc_free(void* dev_ptr);
+int ab2_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
+/* For r in [0, n): row (src_row ? src_row[r] : r) of the local planes src_a / src_b (row_bytes each, src_b may be NULL)
+ * is stored to row dst_row[r] of rank peer[r]'s planes plane_a[peer] / plane_b[peer] (HOST arrays of npeers device
+ * pointers: IPC mappings of the peers' buffers, own entry = local buffer).  One kernel, every SM, posted NVLink writes. */
+int ab2_peer_push_rows(const void* src_a, const void* src_b, const int32_t* src_row, const int32_t* peer,
+                       const int32_t* dst_row, int64_t n, int row_bytes, void* const* plane_a, void* const* plane_b,
+                       int npeers, void* stream);
+/* dst[idx[s]] += src[s], s in [0, n); the ids of one call must be distinct (plain read-modify-write, fp32 add). */
+int ab2_rows_add(void* dst, const int64_t* idx, const void* src, int64_t n, int D, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * GraphConv edge path (layers/conv.py:61-76): the parts of
  *   edges_new = edge_mlp(cat[x_i, x_j, e]) + e ;  out = scatter_sum(edges_new, dst)
  * that are not plain GEMMs.  The first Linear(3D->D) is split as x_i Wi^T + x_j Wj^T + e We^T so the node

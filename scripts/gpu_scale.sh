@@ -6,7 +6,7 @@ mkdir -p $OUT
 python -c "import __graft_entry__ as g; g.build()" > $OUT/build.log 2>&1
 nvidia-smi topo -m > $OUT/topo.txt 2>&1
 timeout 600 python -m pytest tests/test_gpu_multi.py -x -q -m gpu > $OUT/pytest_multi.log 2>&1; echo "pytest exit $?"; tail -3 $OUT/pytest_multi.log
-for n in 1 2 4 8; do
+for n in ${SCALE_NS:-1 2 4 8}; do
   if [ $n == 1 ]; then
     timeout 600 python bench.py --gpus 1 --steps 50 --warmup 5 --no-cpu-baseline > $OUT/bench_n1.json 2> $OUT/bench_n1.err
   else

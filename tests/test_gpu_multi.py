@@ -28,8 +28,9 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, halo):
     try:
+        os.environ["AB2_HALO"] = halo
         for p in (ROOT, os.path.join(ROOT, "tests")):
             if p not in sys.path:
                 sys.path.insert(0, p)
@@ -125,13 +126,14 @@ def _sharded_blocks(rank, world):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 @pytest.mark.parametrize("world", [2, 4])
-def test_sharded_blocks_nccl(world):
+@pytest.mark.parametrize("halo", ["p2p", "nccl"])  # NVLink peer-memory push (default) and the NCCL all-to-all
+def test_sharded_blocks_nccl(world, halo):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, halo)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=600) for _ in procs]
