@@ -39,6 +39,13 @@ def _worker(rank, world, port, q, halo):
         torch.cuda.set_device(rank)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
         _sharded_blocks(rank, world)
+        if halo == "p2p":  # the peer-memory transport must really have been used (no silent NCCL fallback)
+            from anemoi_models_b200.layers import block as b2block
+
+            plans = [item[3] for item in b2block._halo_cache._items.values()]
+            peers = [px for pl in plans for px in getattr(pl, "_peer", {}).values()]
+            assert peers and all(px is not None and px.fwd_epoch > 0 and px.bwd_epoch > 0 for px in peers), \
+                "NVLink peer-memory halo exchange was not used"
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, None))
