@@ -816,12 +816,12 @@ static bool fwd_prefers_tma(int dtype, int H, int C, int64_t E, int64_t Nd) {
   return E < 12 * Nd;
 }
 
-// Backward src pass for 2 KB rows: the pipelined kernel packs kU consecutive CSC edges per stage regardless of row
-// boundaries (first version, one src row per stage, lost to the LDG kernel at out-degree 1.4: 0.79 vs 0.65 ms, run r01j).
+// Backward src pass for 2 KB rows, measured on B200 (A/B runs r01j, r01n): at a mean out-degree of 1.4 (encoder) the LDG
+// kernel (8-row blocks) wins, 0.65 ms vs 0.79 (pipeline, one src row per stage) / 0.86 (pipeline, kU edges per stage whatever
+// their rows -- the version kept); at out-degree 8 (processor) the pipeline wins, 0.190 -> 0.139 ms; at out-degree 40
+// (decoder) both sit at the L2/HBM gather limit (1.04 ms).
 static bool src_prefers_tma(int dtype, int H, int C, int64_t E, int64_t Ns) {
-  (void)E;
-  (void)Ns;
-  return tma_applicable(2, dtype, H, C);
+  return tma_applicable(2, dtype, H, C) && E >= 4 * Ns;
 }
 
 static int check_common(const char* fn, int dtype, int64_t Ns, int64_t Nd, int64_t E, int H, int C) {
