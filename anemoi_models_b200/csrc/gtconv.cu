@@ -924,8 +924,8 @@ static int bwd_src_impl(ConvArgs a, int dtype, const int32_t* colptr, const int3
                         void* dv, void* dk_halo, void* dv_halo) {
   if (a.Ns == 0 || a.src_hi <= a.src_lo || (!dk && !dv && !dk_halo && !dv_halo)) return AB2_OK;
   if (!colptr || !ads_ws || (a.E > 0 && (!a.q || !g || !crow))) return fail(AB2_ERR_INVALID, "gtconv_bwd_src: null pointer argument");
-  if (a.n_own < a.Ns && ((dk && !dk_halo) || (dv && !dv_halo)))
-    return fail(AB2_ERR_INVALID, "gtconv_bwd_src: halo rows present but dk_halo / dv_halo missing");
+  if (a.n_own < a.src_hi && ((dk && !dk_halo) || (dv && !dv_halo)))
+    return fail(AB2_ERR_INVALID, "gtconv_bwd_src: halo rows in range but dk_halo / dv_halo missing");
   a.colptr = colptr; a.crow = crow; a.g = g;
   a.ads = (float2*)ads_ws;
   a.dk = dk; a.dv = dv; a.dk_halo = dk_halo; a.dv_halo = dv_halo;
@@ -958,6 +958,31 @@ extern "C" int ab2_gtconv_bwd_src_range(const void* q, const void* g, int dtype,
   a.src_lo = (int)row_begin;
   a.src_hi = (int)row_end;
   return bwd_src_impl(a, dtype, colptr, crow, g, ads_ws, dk, dv, nullptr, nullptr);
+}
+
+extern "C" int ab2_gtconv_bwd_dst_halo(const void* q, const void* k, const void* v, const void* k_halo, const void* v_halo,
+                                       int64_t n_own, const void* e, int dtype, const int32_t* rowptr, const int32_t* col,
+                                       const int32_t* perm, const int32_t* csr2csc, int64_t Ns, int64_t Nd, int64_t E, int H, int C,
+                                       const void* out, const float* lse2, const void* g, void* dq, void* de, void* ads_ws,
+                                       size_t ads_ws_bytes, void* stream) {
+  if (int rc = check_common("gtconv_bwd_dst", dtype, Ns, Nd, E, H, C)) return rc;
+  if (int rc = check_halo("gtconv_bwd_dst", k_halo, v_halo, n_own, Ns)) return rc;
+  return bwd_dst_impl(base_args(q, k, v, k_halo, v_halo, n_own, e, rowptr, col, perm, Ns, Nd, E, H, C, stream), dtype, csr2csc, out,
+                      lse2, g, dq, de, ads_ws, ads_ws_bytes);
+}
+
+extern "C" int ab2_gtconv_bwd_src_range_halo(const void* q, const void* g, int dtype, const int32_t* colptr, const int32_t* crow,
+                                             int64_t n_own, int64_t Ns, int64_t Nd, int64_t E, int H, int C, const void* ads_ws,
+                                             void* dk, void* dv, void* dk_halo, void* dv_halo, int64_t row_begin,
+                                             int64_t row_end, void* stream) {
+  if (int rc = check_common("gtconv_bwd_src_range", dtype, Ns, Nd, E, H, C)) return rc;
+  if (row_begin < 0 || row_end > Ns || row_begin > row_end || n_own < 0 || n_own > Ns)
+    return fail(AB2_ERR_INVALID, "gtconv_bwd_src_range: bad row range / n_own");
+  ConvArgs a = base_args(q, nullptr, nullptr, nullptr, nullptr, Ns, nullptr, nullptr, nullptr, nullptr, Ns, Nd, E, H, C, stream);
+  a.n_own = (int)n_own;
+  a.src_lo = (int)row_begin;
+  a.src_hi = (int)row_end;
+  return bwd_src_impl(a, dtype, colptr, crow, g, ads_ws, dk, dv, dk_halo, dv_halo);
 }
 
 extern "C" int ab2_gtconv_bwd_halo(const void* q, const void* k, const void* v, const void* k_halo, const void* v_halo,

@@ -100,28 +100,104 @@ class PeerExchange:
         self.token = torch.zeros(1, device=device)
         self.fwd_epoch = 0
         self.bwd_epoch = 0
+        # ---- overlap: the exchange runs on a side stream while the conv works on the INTERIOR dst rows (rows none of whose
+        # edges references a halo src row); the boundary rows follow once the halo has landed
+        self.stream = torch.cuda.Stream(device=device)
+        self.overlap = os.environ.get("AB2_OVERLAP", "1") != "0"
+        le = plan.local_edge_index
+        b_rows = torch.unique(le[1][le[0] >= plan.n_own]).cpu().tolist()
+        nd = plan.num_dst_local
+        best = (0, 0)
+        prev = -1
+        for r in b_rows + [nd]:  # longest run of consecutive non-boundary rows
+            if r - (prev + 1) > best[1] - best[0]:
+                best = (prev + 1, r)
+            prev = r
+        self.interior = best
+        self._ranges = {}
         dist.all_reduce(self.token, group=group)  # everyone has mapped everyone before the first push
 
     def _local(self, kind: str, parity: int, plane: str) -> int:
         return self.base + self.offs[(kind, parity, plane)]
 
-    def forward(self, k: Tensor, v: Tensor) -> Tuple[Tensor, Tensor]:
-        """push the rows of k / v the peers need, receive mine: returns (k_halo, v_halo) [n_halo, ...] (fresh tensors)."""
+    def ranges(self, csr):
+        """[(d0, d1, edges)] for the interior block and the boundary blocks before / after it (edge counts from csr.rowptr)."""
+        key = id(csr)
+        if key not in self._ranges:
+            nd = self.plan.num_dst_local
+            i_lo, i_hi = self.interior
+            pts = [0, i_lo, i_hi, nd]
+            rp = csr.rowptr[torch.tensor(pts, device=csr.rowptr.device)].tolist()
+            blocks = [(pts[i], pts[i + 1], rp[i + 1] - rp[i]) for i in range(3)]
+            self._ranges[key] = {"interior": blocks[1], "boundary": [b for b in (blocks[0], blocks[2]) if b[1] > b[0]]}
+        return self._ranges[key]
+
+    def forward_async(self, k: Tensor, v: Tensor):
+        """forward() on the side stream; returns (k_halo, v_halo, event to wait for before touching them)."""
+        main = torch.cuda.current_stream(self.device)
+        outs = tuple(torch.empty((self.plan.n_halo,) + tuple(r.shape[1:]), dtype=r.dtype, device=r.device) for r in (k, v))
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            k_halo, v_halo = self.forward(k, v, outs)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        return k_halo, v_halo, done
+
+    def backward_async(self, dk_halo: Tensor, dv_halo: Tensor):
+        """push the halo gradients on the side stream; returns (buffer parity, event)."""
+        L = _lib.lib()
+        main = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        b = self.bwd_epoch & 1
+        self.bwd_epoch += 1
+        ta, tb = self.tables[("inbox", b)]
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            with torch.cuda.device(self.device):
+                _lib.check(L.ab2_peer_push_rows(_lib.ptr(dk_halo), _lib.ptr(dv_halo), 0, _lib.ptr(self.owner_of_halo),
+                                                _lib.ptr(self.inbox_row_of_halo), self.plan.n_halo, self.row_bytes, ta, tb, self.P,
+                                                self.stream.cuda_stream))
+                dist.all_reduce(self.token, group=self.group)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        return b, done
+
+    def backward_finish(self, b: int, dk: Tensor, dv: Tensor) -> None:
+        """add what the peers pushed into inbox `b` into dk / dv (current stream; caller has waited for the event)."""
+        L = _lib.lib()
+        st = _lib.current_stream(self.device)
+        D = self.row_bytes // dk.element_size()
+        dt = _lib.dtype_code(dk.dtype)
+        off = 0
+        with torch.cuda.device(self.device):
+            for cnt in self.plan.send_counts:
+                if cnt:
+                    idx_ptr = self.send_idx64.data_ptr() + off * 8
+                    for plane, dst in (("a", dk), ("b", dv)):
+                        _lib.check(L.ab2_rows_add(_lib.ptr(dst), idx_ptr, self._local("inbox", b, plane) + off * self.row_bytes, cnt,
+                                                  D, dt, st))
+                off += cnt
+
+    def forward(self, k: Tensor, v: Tensor, outs=None) -> Tuple[Tensor, Tensor]:
+        """push the rows of k / v the peers need, receive mine: returns (k_halo, v_halo) [n_halo, ...] (fresh tensors).
+        Runs on the current stream."""
         L = _lib.lib()
         plan = self.plan
         b = self.fwd_epoch & 1
         self.fwd_epoch += 1
         st = _lib.current_stream(self.device)
         ta, tb = self.tables[("halo", b)]
+        if outs is None:
+            outs = tuple(torch.empty((plan.n_halo,) + tuple(r.shape[1:]), dtype=r.dtype, device=r.device) for r in (k, v))
         with torch.cuda.device(self.device):
             _lib.check(L.ab2_peer_push_rows(_lib.ptr(k), _lib.ptr(v), _lib.ptr(self.send_idx32), _lib.ptr(self.peer_of_send),
                                             _lib.ptr(self.dst_row_of_send), self.send_idx32.numel(), self.row_bytes, ta, tb, self.P, st))
             dist.all_reduce(self.token, group=self.group)
-            outs = []
-            for plane, ref in (("a", k), ("b", v)):
-                t = torch.empty((plan.n_halo,) + tuple(ref.shape[1:]), dtype=ref.dtype, device=ref.device)
+            for plane, t in zip(("a", "b"), outs):
                 _lib.check(L.ab2_memcpy_d2d(_lib.ptr(t), self._local("halo", b, plane), plan.n_halo * self.row_bytes, st))
-                outs.append(t)
         return outs[0], outs[1]
 
     def backward(self, dk_halo: Tensor, dv_halo: Tensor, dk: Tensor, dv: Tensor) -> None:

@@ -129,6 +129,94 @@ def gt_conv(query: Tensor, key: Tensor, value: Tensor, edge_attr: Tensor, plan: 
     return _GTConvFn.apply(q, k, v, e, k_halo, v_halo, plan)
 
 
+def _fwd_rows(q, k, v, kh, vh, e, plan, out, lse2, d0, d1, edges):
+    """forward on dst rows [d0, d1) (own src rows k / v, halo rows kh / vh)."""
+    if d1 <= d0:
+        return
+    L = _lib.lib()
+    Nd, H, C = q.shape
+    row, es = H * C * q.element_size(), q.element_size()
+    n_own, Ns = k.shape[0], k.shape[0] + kh.shape[0]
+    _lib.check(L.ab2_gtconv_fwd_halo(q.data_ptr() + d0 * row, _lib.ptr(k), _lib.ptr(v), _lib.ptr(kh), _lib.ptr(vh), n_own, _lib.ptr(e),
+                                     _lib.dtype_code(q.dtype), plan.rowptr.data_ptr() + d0 * 4, _lib.ptr(plan.col), _lib.ptr(plan.perm),
+                                     Ns, d1 - d0, max(int(edges), 1), H, C, out.data_ptr() + d0 * row, lse2.data_ptr() + d0 * H * 4,
+                                     _lib.current_stream(q.device)))
+
+
+def _bwd_dst_rows(q, k, v, kh, vh, e, plan, out, lse2, g, dq, de, ws, d0, d1, edges):
+    if d1 <= d0:
+        return
+    L = _lib.lib()
+    Nd, H, C = q.shape
+    row = H * C * q.element_size()
+    n_own, Ns = k.shape[0], k.shape[0] + kh.shape[0]
+    _lib.check(L.ab2_gtconv_bwd_dst_halo(q.data_ptr() + d0 * row, _lib.ptr(k), _lib.ptr(v), _lib.ptr(kh), _lib.ptr(vh), n_own,
+                                         _lib.ptr(e), _lib.dtype_code(q.dtype), plan.rowptr.data_ptr() + d0 * 4, _lib.ptr(plan.col),
+                                         _lib.ptr(plan.perm), _lib.ptr(plan.csr2csc), Ns, d1 - d0, max(int(edges), 1), H, C,
+                                         out.data_ptr() + d0 * row, lse2.data_ptr() + d0 * H * 4, g.data_ptr() + d0 * row,
+                                         dq.data_ptr() + d0 * row, _lib.ptr(de), _lib.ptr(ws), ws.numel(),
+                                         _lib.current_stream(q.device)))
+
+
+def _bwd_src_rows(q, g, plan, n_own, Ns, ws, dk, dv, dkh, dvh, r0, r1):
+    if r1 <= r0:
+        return
+    L = _lib.lib()
+    Nd, H, C = q.shape
+    _lib.check(L.ab2_gtconv_bwd_src_range_halo(_lib.ptr(q), _lib.ptr(g), _lib.dtype_code(q.dtype), _lib.ptr(plan.colptr),
+                                               _lib.ptr(plan.crow), n_own, Ns, Nd, plan.num_edges, H, C, _lib.ptr(ws), _lib.ptr(dk),
+                                               _lib.ptr(dv), _lib.ptr(dkh), _lib.ptr(dvh), r0, r1, _lib.current_stream(q.device)))
+
+
+class _GTConvShardedOverlapFn(torch.autograd.Function):
+    """dst-row-sharded conv with the NVLink peer-memory exchange hidden behind the interior rows.
+    forward : side stream pushes k / v halo rows | main stream runs the forward on the interior dst rows, then (halo landed) the
+              boundary rows;
+    backward: dst pass on the boundary rows and src pass on the halo rows first, their gradients leave on the side stream
+              while the interior dst pass and the src pass of the own rows run, then the peers' contributions are added."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, e, plan: GraphCSR, hplan, group, px):
+        Nd, H, C = q.shape
+        out = torch.empty_like(q)
+        lse2 = torch.empty((Nd, H), dtype=torch.float32, device=q.device)
+        rng = px.ranges(plan)
+        with torch.cuda.device(q.device):
+            k_halo, v_halo, landed = px.forward_async(k, v)
+            _fwd_rows(q, k, v, k_halo, v_halo, e, plan, out, lse2, *rng["interior"])
+            torch.cuda.current_stream(q.device).wait_event(landed)
+            for blk in rng["boundary"]:
+                _fwd_rows(q, k, v, k_halo, v_halo, e, plan, out, lse2, *blk)
+        ctx.save_for_backward(q, k, v, e, out, lse2, k_halo, v_halo)
+        ctx.plan, ctx.hplan, ctx.group, ctx.px = plan, hplan, group, px
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        q, k, v, e, out, lse2, k_halo, v_halo = ctx.saved_tensors
+        plan, px = ctx.plan, ctx.px
+        L = _lib.lib()
+        Nd, H, C = q.shape
+        n_own, Ns = k.shape[0], k.shape[0] + k_halo.shape[0]
+        g = g.contiguous()
+        if g.dtype != q.dtype:
+            g = g.to(q.dtype)
+        dq, dk, dv, de = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v), torch.empty_like(e)
+        dkh, dvh = torch.empty_like(k_halo), torch.empty_like(v_halo)
+        ws = torch.empty(L.ab2_gtconv_bwd_workspace_bytes(plan.num_edges, H), dtype=torch.uint8, device=q.device)
+        rng = px.ranges(plan)
+        with torch.cuda.device(q.device):
+            for blk in rng["boundary"]:
+                _bwd_dst_rows(q, k, v, k_halo, v_halo, e, plan, out, lse2, g, dq, de, ws, *blk)
+            _bwd_src_rows(q, g, plan, n_own, Ns, ws, dk, dv, dkh, dvh, n_own, Ns)  # halo rows: only boundary edges touch them
+            parity, pushed = px.backward_async(dkh, dvh)
+            _bwd_dst_rows(q, k, v, k_halo, v_halo, e, plan, out, lse2, g, dq, de, ws, *rng["interior"])
+            _bwd_src_rows(q, g, plan, n_own, Ns, ws, dk, dv, dkh, dvh, 0, n_own)
+            torch.cuda.current_stream(q.device).wait_event(pushed)
+            px.backward_finish(parity, dk, dv)
+        return dq, dk, dv, de, None, None, None, None
+
+
 class _GTConvShardedFn(torch.autograd.Function):
     """dst-row-sharded conv with the halo exchange inside: forward pulls the k / v rows of peers this rank's edges
     reference (NCCL all-to-all over NVLink) straight into the halo buffers the kernels read; backward sends the
@@ -173,6 +261,12 @@ def gt_conv_sharded(query: Tensor, key: Tensor, value: Tensor, edge_attr: Tensor
     _check_conv_args(query, key, value, edge_attr, plan, hplan.n_halo)
     dt = _common_dtype(query, key, value, edge_attr)
     q, k, v, e = (t.to(dt).contiguous() for t in (query, key, value, edge_attr))
+    if all(t.requires_grad or not torch.is_grad_enabled() for t in (q, k, v, e)) and q.shape[0] > 0:
+        from .distributed.peer import get_peer_exchange
+
+        px = get_peer_exchange(hplan, group, k.shape[1] * k.shape[2] * k.element_size(), k.device)
+        if px is not None and px.overlap:
+            return _GTConvShardedOverlapFn.apply(q, k, v, e, plan, hplan, group, px)
     return _GTConvShardedFn.apply(q, k, v, e, plan, hplan, group)
 
 

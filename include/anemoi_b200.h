@@ -124,6 +124,17 @@ const char* ab2_gtconv_variant(int which, int dtype, int64_t Ns, int64_t Nd, int
 int ab2_gtconv_fwd_halo(const void* q, const void* k, const void* v, const void* k_halo, const void* v_halo, int64_t n_own,
                         const void* e, int dtype, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
                         int64_t Ns, int64_t Nd, int64_t E, int H, int C, void* out, float* lse2, void* stream);
+/* The two backward passes with split src rows, on their own (used to overlap the halo-gradient exchange: dst pass on
+ * the boundary dst rows, src pass on the halo rows, push, then the interior). */
+int ab2_gtconv_bwd_dst_halo(const void* q, const void* k, const void* v, const void* k_halo, const void* v_halo,
+                            int64_t n_own, const void* e, int dtype, const int32_t* rowptr, const int32_t* col,
+                            const int32_t* perm, const int32_t* csr2csc, int64_t Ns, int64_t Nd, int64_t E, int H, int C,
+                            const void* out, const float* lse2, const void* g, void* dq, void* de, void* ads_ws,
+                            size_t ads_ws_bytes, void* stream);
+int ab2_gtconv_bwd_src_range_halo(const void* q, const void* g, int dtype, const int32_t* colptr, const int32_t* crow,
+                                  int64_t n_own, int64_t Ns, int64_t Nd, int64_t E, int H, int C, const void* ads_ws,
+                                  void* dk, void* dv, void* dk_halo, void* dv_halo, int64_t row_begin, int64_t row_end,
+                                  void* stream);
 int ab2_gtconv_bwd_halo(const void* q, const void* k, const void* v, const void* k_halo, const void* v_halo, int64_t n_own,
                         const void* e, int dtype, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
                         const int32_t* colptr, const int32_t* csr2csc, const int32_t* crow, int64_t Ns, int64_t Nd,
