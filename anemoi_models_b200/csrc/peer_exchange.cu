@@ -5,6 +5,7 @@
 // a dst-row-sharded graph sends almost all of a rank's halo to ONE neighbour (latitude bands), and a single NCCL
 // send/recv pair runs on a couple of channels (~50-100 GB/s), so the all-to-all cost 1.3 ms per 100 MB tensor while
 // NVLink 5 moves it in ~0.15 ms.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -115,7 +116,13 @@ extern "C" int ab2_peer_push_rows(const void* src_a, const void* src_b, const in
     tab.a[p] = (char*)plane_a[p];
     tab.b[p] = plane_b ? (char*)plane_b[p] : nullptr;
   }
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)num_sms() * 8));
+  // NVLink-bound: a few dozen CTAs of posted stores saturate the link; keep the other SMs for the conv kernels that run
+  // concurrently on the main stream (AB2_PUSH_CTAS overrides, for experiments)
+  static const int max_ctas = [] {
+    const char* s = getenv("AB2_PUSH_CTAS");
+    return s ? std::max(1, atoi(s)) : 64;
+  }();
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)max_ctas));
   peer_push_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const char*)src_a, plane_b ? (const char*)src_b : nullptr, src_row, peer,
                                                                dst_row, n, row_bytes, tab);
   AB2_LAUNCH_OK("peer_push_rows_kernel");
