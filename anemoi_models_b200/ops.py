@@ -168,6 +168,26 @@ def _bwd_src_rows(q, g, plan, n_own, Ns, ws, dk, dv, dkh, dvh, r0, r1):
                                                _lib.ptr(dv), _lib.ptr(dkh), _lib.ptr(dvh), r0, r1, _lib.current_stream(q.device)))
 
 
+import os as _os
+
+_TRACE = _os.environ.get("AB2_TRACE", "0") == "1"
+_trace_events = []  # [(label, event)] of the last overlapped forward+backward (debug: AB2_TRACE=1)
+
+
+def _mark(label, device):
+    if _TRACE:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(device))
+        _trace_events.append((label, ev))
+
+
+def trace_summary():
+    """ms between consecutive marks of the last step (call after torch.cuda.synchronize())."""
+    out = [(b[0], a[1].elapsed_time(b[1])) for a, b in zip(_trace_events[:-1], _trace_events[1:])]
+    _trace_events.clear()
+    return out
+
+
 class _GTConvShardedOverlapFn(torch.autograd.Function):
     """dst-row-sharded conv with the NVLink peer-memory exchange hidden behind the interior rows.
     forward : side stream pushes k / v halo rows | main stream runs the forward on the interior dst rows, then (halo landed) the
@@ -182,11 +202,15 @@ class _GTConvShardedOverlapFn(torch.autograd.Function):
         lse2 = torch.empty((Nd, H), dtype=torch.float32, device=q.device)
         rng = px.ranges(plan)
         with torch.cuda.device(q.device):
+            _mark("fwd:start", q.device)
             k_halo, v_halo, landed = px.forward_async(k, v)
             _fwd_rows(q, k, v, k_halo, v_halo, e, plan, out, lse2, *rng["interior"])
+            _mark("fwd:interior", q.device)
             torch.cuda.current_stream(q.device).wait_event(landed)
+            _mark("fwd:wait_halo", q.device)
             for blk in rng["boundary"]:
                 _fwd_rows(q, k, v, k_halo, v_halo, e, plan, out, lse2, *blk)
+            _mark("fwd:boundary", q.device)
         ctx.save_for_backward(q, k, v, e, out, lse2, k_halo, v_halo)
         ctx.plan, ctx.hplan, ctx.group, ctx.px = plan, hplan, group, px
         return out
@@ -206,14 +230,20 @@ class _GTConvShardedOverlapFn(torch.autograd.Function):
         ws = torch.empty(L.ab2_gtconv_bwd_workspace_bytes(plan.num_edges, H), dtype=torch.uint8, device=q.device)
         rng = px.ranges(plan)
         with torch.cuda.device(q.device):
+            _mark("bwd:start", q.device)
             for blk in rng["boundary"]:
                 _bwd_dst_rows(q, k, v, k_halo, v_halo, e, plan, out, lse2, g, dq, de, ws, *blk)
             _bwd_src_rows(q, g, plan, n_own, Ns, ws, dk, dv, dkh, dvh, n_own, Ns)  # halo rows: only boundary edges touch them
+            _mark("bwd:boundary+halo_src", q.device)
             parity, pushed = px.backward_async(dkh, dvh)
             _bwd_dst_rows(q, k, v, k_halo, v_halo, e, plan, out, lse2, g, dq, de, ws, *rng["interior"])
+            _mark("bwd:interior_dst", q.device)
             _bwd_src_rows(q, g, plan, n_own, Ns, ws, dk, dv, dkh, dvh, 0, n_own)
+            _mark("bwd:own_src", q.device)
             torch.cuda.current_stream(q.device).wait_event(pushed)
+            _mark("bwd:wait_push", q.device)
             px.backward_finish(parity, dk, dv)
+            _mark("bwd:rows_add", q.device)
         return dq, dk, dv, de, None, None, None, None
 
 

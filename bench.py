@@ -230,6 +230,17 @@ def run_ours(args):
         ev1.record()
         barrier()
     ms = ev0.elapsed_time(ev1)
+    if os.environ.get("AB2_TRACE", "0") == "1" and world > 1:  # debug: phase times of one step on every rank
+        ops.trace_summary()
+        barrier()
+        step()
+        torch.cuda.synchronize()
+        ph = ops.trace_summary()
+        allph = [None] * world
+        dist.all_gather_object(allph, [(lab, round(t, 3)) for lab, t in ph])
+        if rank == 0:
+            for r, p_ in enumerate(allph):
+                print(f"[trace rank {r}] " + "  ".join(f"{lab}={t}" for lab, t in p_), file=sys.stderr, flush=True)
     tmax = torch.tensor([ms], device=dev, dtype=torch.float64)
     etot = torch.tensor([float(E)], device=dev, dtype=torch.float64)
     if world > 1:
