@@ -102,7 +102,10 @@ class PeerExchange:
         self.bwd_epoch = 0
         # ---- overlap: the exchange runs on a side stream while the conv works on the INTERIOR dst rows (rows none of whose
         # edges references a halo src row); the boundary rows follow once the halo has landed
-        self.stream = torch.cuda.Stream(device=device)
+        # high priority: the push kernel's few CTAs must be scheduled ahead of the tens of thousands of pending conv CTAs
+        # of the main stream (measured with AB2_TRACE: at default priority the push only ran once the conv kernel had
+        # no more CTAs to launch, i.e. the "overlapped" exchange finished last)
+        self.stream = torch.cuda.Stream(device=device, priority=-1)
         self.overlap = os.environ.get("AB2_OVERLAP", "1") != "0"
         le = plan.local_edge_index
         b_rows = torch.unique(le[1][le[0] >= plan.n_own]).cpu().tolist()
