@@ -19,6 +19,7 @@ _vp, _i64, _i32, _sz, _f32 = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_flo
 SIGNATURES = {
     "ab2_version": (_i32, []),
     "ab2_last_error": (C.c_char_p, []),
+    "ab2_launch_count": (C.c_longlong, []),
     "ab2_csr_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "ab2_csr_build": (_i32, [_vp, _i64, _i64, _i64] + [_vp] * 9 + [_vp, _sz, _vp]),
     "ab2_edge_chunks_workspace_bytes": (_sz, [_i64]),

@@ -6,7 +6,12 @@ char* last_error_buf() {
   static thread_local char buf[512] = {0};
   return buf;
 }
+long long* launch_counter() {
+  static long long n = 0;
+  return &n;
+}
 }  // namespace ab2
 
 extern "C" int ab2_version(void) { return 100; /* 0.1.0 */ }
 extern "C" const char* ab2_last_error(void) { return ab2::last_error_buf(); }
+extern "C" long long ab2_launch_count(void) { return __atomic_load_n(ab2::launch_counter(), __ATOMIC_RELAXED); }

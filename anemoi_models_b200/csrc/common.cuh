@@ -25,8 +25,10 @@ inline int fail(int code, const char* fmt, ...) {
     cudaError_t _e = (expr);                                                                           \
     if (_e != cudaSuccess) return ab2::fail(AB2_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
+long long* launch_counter();  // process-wide count of kernel launches issued by this library (defined in abi.cu)
 #define AB2_LAUNCH_OK(name)                                                                            \
   do {                                                                                                 \
+    __atomic_add_fetch(ab2::launch_counter(), 1, __ATOMIC_RELAXED);                                    \
     cudaError_t _e = cudaGetLastError();                                                               \
     if (_e != cudaSuccess) return ab2::fail(AB2_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
   } while (0)

@@ -38,6 +38,8 @@ typedef enum {
 int ab2_version(void);
 /* Thread-local description of the last non-zero status returned on this thread. */
 const char* ab2_last_error(void);
+/* Number of CUDA kernels this library has launched in this process so far (benchmark bookkeeping: gpu_launches). */
+long long ab2_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------------
  * dst-sorted CSR (+ src-sorted CSC view) of edge_index.

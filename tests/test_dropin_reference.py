@@ -1,0 +1,87 @@
+"""Drop-in check against the REAL reference package (only in the build container, where /root/reference exists; the GPU
+box skips it).  After `install()` the reference's own mappers / processors, constructed through the reference's code,
+must be built from this repo's blocks and convs, with exactly the reference's parameter names and shapes -- so a
+reference checkpoint loads unchanged."""
+import os
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+REF_SRC = "/root/reference/src"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="reference tree not present (GPU box)")
+
+
+@pytest.fixture()
+def reference_on_path():
+    added = [p for p in (os.path.join(ROOT, "oracle", "pyg_shim"), REF_SRC) if p not in sys.path]
+    for p in added:
+        sys.path.insert(0, p)
+    yield
+    import anemoi_models_b200 as b2
+
+    b2.uninstall()
+    for p in added:
+        sys.path.remove(p)
+
+
+def _fake_graph(ns, nd, e):
+    from torch_geometric.data import HeteroData
+
+    g = HeteroData()
+    g[("src", "to", "dst")].edge_index = torch.stack([torch.randint(0, ns, (e,)), torch.randint(0, nd, (e,))])
+    g[("src", "to", "dst")].edge_attr1 = torch.rand(e, 3)
+    return g[("src", "to", "dst")]
+
+
+def _state(mod):
+    return {k: tuple(v.shape) for k, v in mod.state_dict().items()}
+
+
+def test_reference_modules_pick_up_the_b200_path(reference_on_path):
+    import anemoi_models_b200 as b2
+    from anemoi.models.layers import mapper as ref_mapper
+    from anemoi.models.layers import processor as ref_processor
+
+    torch.manual_seed(0)
+    sub = _fake_graph(30, 20, 60)
+    kw = dict(in_channels_src=5, in_channels_dst=4, hidden_dim=32, trainable_size=6, num_heads=4, sub_graph=sub,
+              sub_graph_edge_attributes=["edge_attr1"], src_grid_size=30, dst_grid_size=20)
+    ref_enc = ref_mapper.GraphTransformerForwardMapper(**kw)
+    ref_proc = ref_processor.GraphTransformerProcessor(num_layers=2, num_channels=32, num_chunks=1, num_heads=4, trainable_size=6,
+                                                       sub_graph=_fake_graph(20, 20, 50), sub_graph_edge_attributes=["edge_attr1"],
+                                                       src_grid_size=20, dst_grid_size=20)
+    ref_gnn = ref_processor.GNNProcessor(num_layers=2, num_channels=32, num_chunks=1, trainable_size=6,
+                                         sub_graph=_fake_graph(20, 20, 50), sub_graph_edge_attributes=["edge_attr1"],
+                                         src_grid_size=20, dst_grid_size=20)
+    b2.install()
+    new_enc = ref_mapper.GraphTransformerForwardMapper(**kw)
+    new_proc = ref_processor.GraphTransformerProcessor(num_layers=2, num_channels=32, num_chunks=1, num_heads=4, trainable_size=6,
+                                                       sub_graph=_fake_graph(20, 20, 50), sub_graph_edge_attributes=["edge_attr1"],
+                                                       src_grid_size=20, dst_grid_size=20)
+    new_gnn = ref_processor.GNNProcessor(num_layers=2, num_channels=32, num_chunks=1, trainable_size=6,
+                                         sub_graph=_fake_graph(20, 20, 50), sub_graph_edge_attributes=["edge_attr1"],
+                                         src_grid_size=20, dst_grid_size=20)
+    # built from this repo's classes ...
+    assert isinstance(new_enc.proc, b2.GraphTransformerMapperBlock) and isinstance(new_enc.proc.conv, b2.GraphTransformerConv)
+    blocks = [m for m in new_proc.modules() if isinstance(m, b2.GraphTransformerProcessorBlock)]
+    assert len(blocks) == 2 and all(isinstance(b.conv, b2.GraphTransformerConv) for b in blocks)
+    gblocks = [m for m in new_gnn.modules() if isinstance(m, b2.GraphConvProcessorBlock)]
+    assert len(gblocks) == 2 and all(isinstance(b.conv, b2.GraphConv) for b in gblocks)
+    # ... with the reference's parameter names and shapes: checkpoints are interchangeable
+    assert _state(new_enc) == _state(ref_enc)
+    assert _state(new_proc) == _state(ref_proc)
+    assert _state(new_gnn) == _state(ref_gnn)
+    new_enc.load_state_dict(ref_enc.state_dict())
+    new_gnn.load_state_dict(ref_gnn.state_dict())
+    # the GPU partition helper is bound where the reference looks it up
+    import anemoi.models.layers.block as ref_block
+    from anemoi_models_b200.distributed import sort_edges_1hop_chunks
+
+    assert ref_block.sort_edges_1hop_chunks is sort_edges_1hop_chunks
+    b2.uninstall()
+    from anemoi.models.layers.conv import GraphTransformerConv as RefConv
+
+    assert ref_block.GraphTransformerConv is RefConv and not isinstance(ref_mapper.GraphTransformerForwardMapper(**kw).proc, b2.GraphTransformerMapperBlock)
