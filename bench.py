@@ -52,6 +52,8 @@ def dst_N_for(parts: int) -> int:
 
 
 def workload_name(parts: int, workload: str = "encoder") -> str:
+    if workload.startswith("config1"):
+        return f"BASELINE configs[0] conv shape {workload}: o96 (40,320) / o48 (10,944) grids, D=256, H=16, fp32 fwd+bwd (report line; launch-bound at this size)"
     if workload == "decoder":
         return "GT mapper decoder conv o96(40320) -> n320(542080, Fibonacci), 3-NN, D=1024, H=16, bf16 fwd+bwd (report line, not the headline)"
     if workload == "processor":
@@ -136,6 +138,18 @@ def build_shard(parts: int, part: int, workload: str = "encoder"):
         ei, ns, nd, radius = S.encoder_graph_band(ns, dst_N_for(parts), parts, part)
     else:
         assert parts == 1, "decoder / processor workloads are single-GPU report lines"
+        if workload.startswith("config1"):  # BASELINE configs[0]: o96 data grid, o48 hidden grid
+            data, _ = S.octahedral_grid(96)
+            hid48, _ = S.octahedral_grid(48)
+            if workload == "config1-enc":
+                ei, ns, nd = S.cutoff_edges(data, hid48, 0.6 * S.max_nn_distance(hid48)), len(data), len(hid48)
+            elif workload == "config1-proc":
+                ei, ns, nd = S.knn_edges(hid48, hid48, 8, exclude_self=True), len(hid48), len(hid48)
+            else:
+                ei, ns, nd = S.knn_edges(hid48, data, 3), len(hid48), len(data)
+            sb = [0, ns]
+            db = [0, nd]
+            return ei, ns, nd, sb, db
         hidden, _ = S.octahedral_grid(DST_N)
         if workload == "decoder":  # o96 -> n320, 3 nearest hidden nodes per data node
             ei, ns, nd = S.knn_edges(hidden, S.fibonacci_sphere(SRC_POINTS), 3), len(hidden), SRC_POINTS
@@ -146,7 +160,7 @@ def build_shard(parts: int, part: int, workload: str = "encoder"):
     return ei, ns, nd, sb, db
 
 
-def algorithmic_bytes(E, Ns, Nd, b=2):
+def algorithmic_bytes(E, Ns, Nd, b=2, D=D, H=H):
     """Compulsory HBM traffic, each tensor touched once per kernel (DESIGN.md 'roofline accounting')."""
     idx_fwd = 4 * (2 * E + Nd + 1)  # col + perm + rowptr
     fwd = b * (E * D + 2 * Ns * D + 2 * Nd * D) + idx_fwd + 4 * Nd * H
@@ -180,11 +194,15 @@ def run_ours(args):
         group = dist.group.WORLD
 
     L = _lib.lib()
+    cfg1 = args.workload.startswith("config1")
+    H, C = (16, 16) if cfg1 else (16, 64)
+    D = H * C
+    dt_code, esz = (0, 4) if cfg1 else (1, 2)
     ei_np, Ns_g, Nd_g, sb, db = build_shard(world, rank, args.workload)
     ei_glob = torch.from_numpy(ei_np).to(dev)
     E = ei_glob.shape[1]
     torch.manual_seed(1234 + rank)
-    bf = torch.bfloat16
+    bf = torch.float32 if cfg1 else torch.bfloat16
     nd_loc, ns_loc = db[rank + 1] - db[rank], sb[rank + 1] - sb[rank]
     q = torch.randn(nd_loc, H, C, device=dev, dtype=bf)
     g = torch.randn(nd_loc, H, C, device=dev, dtype=bf)
@@ -266,13 +284,13 @@ def run_ours(args):
 
     def kernels(ev=None):
         if ev: ev[0].record()
-        _lib.check(L.ab2_gtconv_fwd(P(q), P(kn), P(vn), P(e), 1, P(plan.rowptr), P(plan.col), P(plan.perm), n_src, nd_loc, E, H, C,
+        _lib.check(L.ab2_gtconv_fwd(P(q), P(kn), P(vn), P(e), dt_code, P(plan.rowptr), P(plan.col), P(plan.perm), n_src, nd_loc, E, H, C,
                                     P(out), P(lse2), st))
         if ev: ev[1].record()
-        _lib.check(L.ab2_gtconv_bwd_dst(P(q), P(kn), P(vn), P(e), 1, P(plan.rowptr), P(plan.col), P(plan.perm), P(plan.csr2csc),
+        _lib.check(L.ab2_gtconv_bwd_dst(P(q), P(kn), P(vn), P(e), dt_code, P(plan.rowptr), P(plan.col), P(plan.perm), P(plan.csr2csc),
                                         n_src, nd_loc, E, H, C, P(out), P(lse2), P(g), P(dq), P(de), P(ws), ws_bytes, st))
         if ev: ev[2].record()
-        _lib.check(L.ab2_gtconv_bwd_src(P(q), P(g), 1, P(plan.colptr), P(plan.crow), n_src, nd_loc, E, H, C, P(ws), P(dk), P(dv), st))
+        _lib.check(L.ab2_gtconv_bwd_src(P(q), P(g), dt_code, P(plan.colptr), P(plan.crow), n_src, nd_loc, E, H, C, P(ws), P(dk), P(dv), st))
         if ev: ev[3].record()
 
     for _ in range(3):
@@ -284,7 +302,7 @@ def run_ours(args):
         torch.cuda.synchronize()
     kt = {name: float(np.mean([evs[r][i].elapsed_time(evs[r][i + 1]) for r in range(kreps)]))
           for i, name in enumerate(("fwd", "bwd_dst", "bwd_src"))}
-    ab = algorithmic_bytes(E, n_src, nd_loc)
+    ab = algorithmic_bytes(E, n_src, nd_loc, esz, D, H)
     peak, peak_src = peaks()
     dom = max(kt, key=kt.get)
     achieved = ab[dom] / (kt[dom] * 1e-3) / 1e9
@@ -292,10 +310,10 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if world == 1 and args.workload == "encoder" and os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(L.ab2_gtconv_variant({"fwd": 0, "bwd_dst": 1, "bwd_src": 2}[dom], 1, n_src, nd_loc, E, H, C).decode().split("<")[0],
+            traffic = json.load(f).get(L.ab2_gtconv_variant({"fwd": 0, "bwd_dst": 1, "bwd_src": 2}[dom], dt_code, n_src, nd_loc, E, H, C).decode().split("<")[0],
                                        {}).get("dram_bytes_per_launch")
     which = {"fwd": 0, "bwd_dst": 1, "bwd_src": 2}
-    kname = {n: L.ab2_gtconv_variant(which[n], 1, n_src, nd_loc, E, H, C).decode() for n in kt}
+    kname = {n: L.ab2_gtconv_variant(which[n], dt_code, n_src, nd_loc, E, H, C).decode() for n in kt}
     roofline = {"bound": "hbm", "kernel": kname[dom], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ab[dom], "launch_ms": round(kt[dom], 4)}
@@ -308,7 +326,7 @@ def run_ours(args):
     e2e = None
     if world == 1:
         host = [x.cpu().pin_memory() for x in (q, k_own, v_own, e, g)]
-        need = L.ab2_gtconv_host_workspace_bytes(n_src, nd_loc, E, H, C, 1)
+        need = L.ab2_gtconv_host_workspace_bytes(n_src, nd_loc, E, H, C, dt_code)
         dev_ws = torch.empty(need, dtype=torch.uint8, device=dev)
         outs = [torch.empty(x.shape, dtype=x.dtype, pin_memory=True) for x in (q, q, k_own, v_own, e)]
 
@@ -340,11 +358,12 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if cfg1 else "bf16", "data": "synthetic",
             "config": {"workload": workload_name(world, args.workload), "edges_total": int(float(etot)), "edges_rank0": int(E),
                        "src_rows_rank0": int(n_src), "halo_rows_rank0": int(hplan.n_halo) if hplan is not None else 0, "dst_rows_rank0": int(nd_loc), "hidden": D, "heads": H,
-                       "l2": "inputs (>5 GB per step) exceed the 126 MB L2; no flush between steps",
+                       "l2": ("inputs (>5 GB per step) exceed the 126 MB L2; no flush between steps" if not cfg1 else
+                              "config-1 working set is L2-sized: steady-state (warm L2) numbers, no flush"),
                        "timed_region": "conv forward + backward (+ halo all-to-all of k,v and its backward when n_gpus>1); CSR build excluded (one-off, cached)"},
             "clocks": sampler.summary(),
             "e2e": e2e if e2e is not None else {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
@@ -604,7 +623,7 @@ def main():
     ap.add_argument("--graphconv-dim", type=int, default=512)
     ap.add_argument("--model-layers", type=int, default=16)
     ap.add_argument("--profile", action="store_true", help="model workload: add a per-kernel device-time breakdown of one step")
-    ap.add_argument("--workload", default="encoder", choices=["encoder", "decoder", "processor", "graphconv", "model"],
+    ap.add_argument("--workload", default="encoder", choices=["encoder", "decoder", "processor", "graphconv", "model", "config1-enc", "config1-proc", "config1-dec"],
                     help="encoder = BASELINE configs[1] (the headline); the others are extra report lines")
     args = ap.parse_args()
     if args.impl == "reference":

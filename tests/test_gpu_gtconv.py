@@ -263,3 +263,34 @@ def test_headline_shape_properties_bf16():
     col_dv = v1.grad.float().sum(0)
     col_g = g.float().sum(0)
     assert float((col_dv - col_g).abs().max()) < 3.0
+
+
+@pytest.mark.parametrize("which", ["enc", "proc", "dec"])
+def test_config1_graphs_full_size_fp32(which):
+    """BASELINE configs[0] (the reference's own CPU-runnable case): o96 (40,320) data grid, o48 (10,944) hidden grid,
+    D = 256, 16 heads, fp32 -- the three conv shapes of that model at FULL size against the CPU oracle
+    (encoder cut-off 0.6: E = 51,608; processor 8-NN: 87,552; decoder 3-NN: 120,960)."""
+    from anemoi_models_b200 import synthetic as S
+
+    data, _ = S.octahedral_grid(96)
+    hidden, _ = S.octahedral_grid(48)
+    if which == "enc":
+        ei_np = S.cutoff_edges(data, hidden, 0.6 * S.max_nn_distance(hidden))
+        ns, nd, expect = len(data), len(hidden), 51608
+    elif which == "proc":
+        ei_np = S.knn_edges(hidden, hidden, 8, exclude_self=True)
+        ns, nd, expect = len(hidden), len(hidden), 87552
+    else:
+        ei_np = S.knn_edges(hidden, data, 3)
+        ns, nd, expect = len(hidden), len(data), 120960
+    assert (ns, nd) in ((40320, 10944), (10944, 10944), (10944, 40320))
+    E = ei_np.shape[1]
+    assert abs(E - expect) <= 0.01 * expect, (which, E)  # SURVEY 8d edge counts (the cut-off set depends on the grid recipe)
+    gen = torch.Generator().manual_seed(0)
+    H, C = 16, 16
+    ei = torch.from_numpy(ei_np)
+    q, k, v, e, g = (torch.randn(n, H, C, generator=gen) for n in (nd, ns, ns, E, nd))
+    ref = og.gt_conv_unfused_fwd_bwd(q, k, v, e, ei, g, (ns, nd))
+    r = run_b2(q, k, v, e, ei, g, (ns, nd))
+    for key in ("out", "dq", "dk", "dv", "de"):
+        assert rel_err(r[key], ref[key]) < FP32_TOL, (which, key, rel_err(r[key], ref[key]))
