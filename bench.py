@@ -451,6 +451,17 @@ def run_graphconv(args):
         ev1.record()
         torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / args.steps
+    breakdown = None
+    if args.profile:
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize()
+        rows = sorted(prof.key_averages(), key=lambda r: -r.device_time_total)
+        total = sum(r.device_time_total for r in rows)
+        breakdown = [{"kernel": r.key[:100], "ms": round(r.device_time_total / 1e3, 3), "calls": r.count,
+                      "share": round(r.device_time_total / max(total, 1), 4)} for r in rows[:20]]
     # executed GEMM FLOPs with the split first layer: edge GEMMs pe, W1, W2 (3 x 2*E*D^2), node GEMMs pi, pj (2 x 2*N*D^2),
     # node MLP 2*N*(2D*D + D*D + D*D); backward = 2x forward
     flops_fwd = 6 * E * Dg * Dg + 4 * N * Dg * Dg + 8 * N * Dg * Dg
@@ -463,7 +474,8 @@ def run_graphconv(args):
             "config": {"workload": f"GraphConvProcessorBlock layer, multi-scale icosahedral mesh r6 (N={N}, E={E}), D={Dg}, bf16 fwd+bwd (report line)"},
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": round(tfs, 1), "peak": tpeak, "unit": "TFLOP/s", "frac": round(tfs / tpeak, 4),
-                         "traffic": None, "note": "executed GEMM FLOPs (split first layer) of the whole block over the block time; GEMMs run on cuBLASLt"}}
+                         "traffic": None, "note": "executed GEMM FLOPs (split first layer) of the whole block over the block time; GEMMs run on cuBLASLt"},
+            "kernel_breakdown": breakdown}
     print(json.dumps(line), flush=True)
 
 
