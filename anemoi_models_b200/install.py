@@ -28,10 +28,30 @@ def _rebind(module_name: str, attr: str, new) -> None:
         setattr(mod, attr, new)
 
 
-def install(blocks: bool = True, edge_partition: bool = True) -> None:
+def _cached_expand_edges(self, edge_index, edge_inc, batch_size: int):
+    """GraphEdgeMixin._expand_edges (reference layers/mapper.py:150-171) memoised per (edge_index buffer, batch size).
+
+    The reference rebuilds `cat([edge_index + i * edge_inc ...])` on every forward although both operands are constant
+    buffers; returning the SAME tensor object lets the graph-plan cache hit by identity (no rebuild, no device compare,
+    no host sync on the step path).  An in-place edit of the buffer (its `_version` changes) rebuilds."""
+    cache = self.__dict__.setdefault("_b200_expanded", {})
+    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), str(edge_index.device), int(batch_size))
+    hit = cache.get(key)
+    if hit is not None and hit[0] is edge_index and hit[1]._version == hit[2]:
+        return hit[1]
+    import torch
+
+    out = torch.cat([edge_index + i * edge_inc for i in range(batch_size)], dim=1)
+    cache.clear()
+    cache[key] = (edge_index, out, out._version)
+    return out
+
+
+def install(blocks: bool = True, edge_partition: bool = True, cache_expanded_edges: bool = True) -> None:
     """Rebind the reference's symbols.  `blocks=False` swaps only the two conv classes (single-GPU use);
     `blocks=True` also swaps the block classes, which is what enables dst-row sharding with a halo exchange when a
-    model_comm_group is passed.  `edge_partition` routes sort_edges_1hop_* through the GPU partition kernel."""
+    model_comm_group is passed.  `edge_partition` routes sort_edges_1hop_* through the GPU partition kernel;
+    `cache_expanded_edges` memoises GraphEdgeMixin._expand_edges (constant buffers) so the graph plan is found by identity."""
     from . import distributed as b2dist
     from .layers import block as b2block
     from .layers import conv as b2conv
@@ -45,6 +65,15 @@ def install(blocks: bool = True, edge_partition: bool = True) -> None:
             new = getattr(b2block, name)
             for mod in ("anemoi.models.layers.block", "anemoi.models.layers.mapper", "anemoi.models.layers.chunk"):
                 _rebind(mod, name, new)
+    if cache_expanded_edges:
+        try:
+            mapper_mod = importlib.import_module("anemoi.models.layers.mapper")
+            mixin = getattr(mapper_mod, "GraphEdgeMixin", None)
+        except ImportError:
+            mixin = None
+        if mixin is not None and hasattr(mixin, "_expand_edges"):
+            _saved.setdefault(("anemoi.models.layers.mapper", "GraphEdgeMixin._expand_edges"), mixin._expand_edges)
+            mixin._expand_edges = _cached_expand_edges
     if edge_partition:
         for name in _DIST_NAMES:
             new = getattr(b2dist, name)
@@ -55,5 +84,10 @@ def install(blocks: bool = True, edge_partition: bool = True) -> None:
 
 def uninstall() -> None:
     for (module_name, attr), old in list(_saved.items()):
-        setattr(importlib.import_module(module_name), attr, old)
+        mod = importlib.import_module(module_name)
+        if "." in attr:  # a method of a class of the module
+            cls_name, meth = attr.split(".")
+            setattr(getattr(mod, cls_name), meth, old)
+        else:
+            setattr(mod, attr, old)
     _saved.clear()

@@ -76,6 +76,11 @@ def test_reference_modules_pick_up_the_b200_path(reference_on_path):
     assert _state(new_gnn) == _state(ref_gnn)
     new_enc.load_state_dict(ref_enc.state_dict())
     new_gnn.load_state_dict(ref_gnn.state_dict())
+    # constant edge buffers: the expanded edge_index is the same tensor object on every forward (plan cache hits by identity)
+    e1 = new_enc._expand_edges(new_enc.edge_index_base, new_enc.edge_inc, 2)
+    e2 = new_enc._expand_edges(new_enc.edge_index_base, new_enc.edge_inc, 2)
+    assert e1 is e2 and torch.equal(e1, ref_enc._expand_edges(ref_enc.edge_index_base, ref_enc.edge_inc, 2))
+    assert new_enc._expand_edges(new_enc.edge_index_base, new_enc.edge_inc, 1) is not e1
     # the GPU partition helper is bound where the reference looks it up
     import anemoi.models.layers.block as ref_block
     from anemoi_models_b200.distributed import sort_edges_1hop_chunks

@@ -294,3 +294,42 @@ def test_config1_graphs_full_size_fp32(which):
     r = run_b2(q, k, v, e, ei, g, (ns, nd))
     for key in ("out", "dq", "dk", "dv", "de"):
         assert rel_err(r[key], ref[key]) < FP32_TOL, (which, key, rel_err(r[key], ref[key]))
+
+
+def test_conv_step_is_cuda_graph_capturable():
+    """The C-ABI calls only enqueue work on the caller's stream (no allocation, no synchronisation), so a whole
+    forward+backward of the conv can be captured in a CUDA graph and replayed -- what a launch-bound small model
+    (BASELINE configs[0] shapes: ~0.2 ms per conv) wants."""
+    import anemoi_models_b200 as b2
+    from anemoi_models_b200.graph import get_csr
+
+    q, k, v, e, ei, g = _random_case(29, ns=400, nd=250, E=3000, H=16, C=16)
+    ref = og.gt_conv_unfused_fwd_bwd(q, k, v, e, ei, g, (400, 250))
+    conv = b2.GraphTransformerConv(out_channels=16)
+    ei_c = ei.cuda()
+    plan = get_csr(ei_c, 400, 250)  # the plan is built (and cached) outside the capture: that step synchronises once
+    ins = [x.cuda().requires_grad_(True) for x in (q, k, v, e)]
+    gc = g.cuda()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):  # warm-up outside the capture
+        for _ in range(2):
+            for x in ins:
+                x.grad = None
+            conv(*ins, ei_c, (400, 250), plan=plan).backward(gc)
+    torch.cuda.current_stream().wait_stream(side)
+    for x in ins:
+        x.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = conv(*ins, ei_c, (400, 250), plan=plan)
+        out.backward(gc)
+    for x in ins:  # new values in the static input buffers, then replay
+        x.data.mul_(-1.0)
+    graph.replay()
+    torch.cuda.synchronize()
+    ref2 = og.gt_conv_unfused_fwd_bwd(-q, -k, -v, -e, ei, g, (400, 250))
+    assert rel_err(out, ref2["out"]) < FP32_TOL
+    for x, key in zip(ins, ("dq", "dk", "dv", "de")):
+        assert rel_err(x.grad, ref2[key]) < FP32_TOL, key
+    assert rel_err(ref["out"], ref["out"]) == 0.0
