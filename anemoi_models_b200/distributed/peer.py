@@ -29,6 +29,32 @@ def _ptr_array(ptrs: List[int]):
     return arr
 
 
+def push_tables(rank: int, send_counts: List[int], recv_counts: List[int], recv_m: List[List[int]], send_m: List[List[int]]):
+    """Where this rank's rows land in its peers' buffers (pure index arithmetic, unit-tested on the CPU).
+
+    forward : send row number s (the i-th row of the block destined to peer p) -> row sum(recv_m[p][:rank]) + i of p's
+              halo planes (p numbers its halo rows by owner rank, then by ascending id -- the order of the send list);
+    backward: halo row number h (the i-th row owned by peer p) -> row sum(send_m[p][:rank]) + i of p's gradient inbox
+              (p's inbox mirrors its send list: blocks by destination rank).
+    recv_m[p] / send_m[p] are rank p's recv_counts / send_counts.  Returns four int lists."""
+    P = len(send_counts)
+    peer_of_send, dst_row = [], []
+    for p in range(P):
+        cnt = send_counts[p]
+        if recv_m[p][rank] != cnt:
+            raise ValueError("halo plans of the ranks disagree")
+        base = sum(recv_m[p][:rank])
+        peer_of_send += [p] * cnt
+        dst_row += list(range(base, base + cnt))
+    owner, inbox_row = [], []
+    for p in range(P):
+        cnt = recv_counts[p]
+        base = sum(send_m[p][:rank])
+        owner += [p] * cnt
+        inbox_row += list(range(base, base + cnt))
+    return peer_of_send, dst_row, owner, inbox_row
+
+
 class PeerExchange:
     def __init__(self, plan: HaloPlan, group, row_bytes: int, device: torch.device):
         L = _lib.lib()
@@ -40,26 +66,12 @@ class PeerExchange:
         dist.all_gather_object(info, (plan.recv_counts, plan.send_counts, n_halo, n_send), group=group)
         recv_m, send_m = [i[0] for i in info], [i[1] for i in info]
         halo_n, send_n = [i[2] for i in info], [i[3] for i in info]
-        # ---- forward push table: my send row (to peer p, i-th of its block) -> row sum(recv_m[p][:rank]) + i of p's halo planes
-        peer_of_send, dst_row = [], []
-        for p in range(P):
-            cnt = plan.send_counts[p]
-            base = sum(recv_m[p][:rank])
-            assert recv_m[p][rank] == cnt, "halo plans of the ranks disagree"
-            peer_of_send += [p] * cnt
-            dst_row += list(range(base, base + cnt))
+        peer_of_send, dst_row, owner, inbox_row = push_tables(rank, plan.send_counts, plan.recv_counts, recv_m, send_m)
         i32 = dict(dtype=torch.int32, device=device)
         self.peer_of_send = torch.tensor(peer_of_send, **i32)
         self.dst_row_of_send = torch.tensor(dst_row, **i32)
         self.send_idx32 = plan.send_idx.to(torch.int32).contiguous()
         self.send_idx64 = plan.send_idx.to(torch.int64).contiguous()
-        # ---- backward push table: my halo row h (owner p, i-th of its block) -> row sum(send_m[p][:rank]) + i of p's inbox planes
-        owner, inbox_row = [], []
-        for p in range(P):
-            cnt = plan.recv_counts[p]
-            base = sum(send_m[p][:rank])
-            owner += [p] * cnt
-            inbox_row += list(range(base, base + cnt))
         self.owner_of_halo = torch.tensor(owner, **i32)
         self.inbox_row_of_halo = torch.tensor(inbox_row, **i32)
         # ---- buffer: [halo A0 | halo B0 | halo A1 | halo B1 | inbox A0 | inbox B0 | inbox A1 | inbox B1]

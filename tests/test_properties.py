@@ -42,3 +42,42 @@ def test_halo_plans_partition_the_graph_and_agree_across_ranks(ns, nd, e, parts,
             assert torch.equal(rows, plans[q].halo_ids[qoff:qoff + cnt])
             off += cnt
     assert torch.equal(torch.sort(torch.cat(seen)).values, torch.arange(e))
+
+
+@settings(max_examples=25, deadline=None)
+@given(ns=st.integers(2, 60), nd=st.integers(2, 40), e=st.integers(1, 300), parts=st.integers(2, 8), seed=st.integers(0, 10**6))
+def test_peer_push_tables_route_every_row_home(ns, nd, e, parts, seed):
+    """Simulate the NVLink push exchange of distributed/peer.py on the CPU: after every rank has pushed, each halo buffer holds
+    exactly the rows its plan expects, and after the backward push + per-peer row-add every owner holds the sum of the
+    gradients of its rows over all ranks."""
+    from anemoi_models_b200.distributed.peer import push_tables
+
+    rng = np.random.default_rng(seed)
+    ei = torch.from_numpy(np.stack([rng.integers(0, ns, e), rng.integers(0, nd, e)]).astype(np.int64))
+    sb = [0] + [int(x) for x in np.cumsum(tensor_split_sizes(ns, parts))]
+    db = [0] + [int(x) for x in np.cumsum(tensor_split_sizes(nd, parts))]
+    plans = [build_bipartite_halo_plan(ei, sb, db, r) for r in range(parts)]
+    recv_m, send_m = [p.recv_counts for p in plans], [p.send_counts for p in plans]
+    x = torch.arange(ns, dtype=torch.float64) * 10 + 1  # row j of the (virtual) full tensor carries the value 10 j + 1
+    halo = [torch.full((max(p.n_halo, 1),), -1.0, dtype=torch.float64) for p in plans]
+    inbox = [torch.zeros(max(sum(p.send_counts), 1), dtype=torch.float64) for p in plans]
+    tables = [push_tables(r, plans[r].send_counts, plans[r].recv_counts, recv_m, send_m) for r in range(parts)]
+    for r, p in enumerate(plans):  # forward push
+        peer, dst_row, _, _ = tables[r]
+        own = x[sb[r]:sb[r + 1]]
+        for s_, (q_, d_) in enumerate(zip(peer, dst_row)):
+            halo[q_][d_] = own[p.send_idx[s_]]
+    for r, p in enumerate(plans):
+        assert torch.equal(halo[r][:p.n_halo], x[p.halo_ids])
+    grad_halo = [torch.arange(p.n_halo, dtype=torch.float64) + 100 * (r + 1) for r, p in enumerate(plans)]
+    for r, p in enumerate(plans):  # backward push
+        _, _, owner, inbox_row = tables[r]
+        for h_, (q_, d_) in enumerate(zip(owner, inbox_row)):
+            inbox[q_][d_] = grad_halo[r][h_]
+    expect = torch.zeros(ns, dtype=torch.float64)
+    for r, p in enumerate(plans):
+        expect.index_add_(0, p.halo_ids, grad_halo[r])
+    for r, p in enumerate(plans):  # row-add at the owner
+        got = torch.zeros(sb[r + 1] - sb[r], dtype=torch.float64)
+        got.index_add_(0, p.send_idx, inbox[r][:sum(p.send_counts)])
+        assert torch.equal(got, expect[sb[r]:sb[r + 1]])
