@@ -821,7 +821,8 @@ static bool fwd_prefers_tma(int dtype, int H, int C, int64_t E, int64_t Nd) {
 // their rows -- the version kept); at out-degree 8 (processor) the pipeline wins, 0.190 -> 0.139 ms; at out-degree 40
 // (decoder) both sit at the L2/HBM gather limit (1.04 ms).
 static bool src_prefers_tma(int dtype, int H, int C, int64_t E, int64_t Ns) {
-  return tma_applicable(2, dtype, H, C) && E >= 4 * Ns;
+  static const bool always = getenv("AB2_SRC_TMA_ALWAYS") != nullptr;  // A/B and profiling runs
+  return tma_applicable(2, dtype, H, C) && (always || E >= 4 * Ns);
 }
 
 static int check_common(const char* fn, int dtype, int64_t Ns, int64_t Nd, int64_t E, int H, int C) {
