@@ -99,10 +99,15 @@ struct Ring {
   __device__ uint64_t* empty(int s) const { return full(s) + kStages; }
 };
 
-// ---- producer: walks the CSR edges of dst rows [r0, r1) and fills the ring --------------------------------------------
-// HEAD(row, stage) issues the per-row copies (q / g / out) and returns their byte count.
+// ---- producer: streams the CSR edges of blocks of RB consecutive dst rows; blocks are dealt round-robin to the CTAs ------
+// Round-robin matters for L2: at any moment the rows in flight across the grid form one compact window of G*RB dst rows
+// (as in the one-row-per-CTA LDG kernels), so the k / v rows their edges share are fetched from HBM once.  A first version
+// gave every CTA one contiguous range of rows: ncu showed 12 % (forward) / 10 % (dst pass) extra DRAM reads, and 2.25 GB
+// instead of 0.27 GB in the src pass, whose q / g rows stopped being L2-resident.
+// The rowptr values and the first two 32-edge index batches of the CTA's NEXT block are requested while the current
+// block streams, so a block switch costs no exposed latency.  HEAD(row, stage, lane) issues the per-row copies.
 template <typename T, int NHEAD, bool BWD, typename HeadFn>
-__device__ __forceinline__ void producer_loop(const Ring<NHEAD>& ring, const ConvArgs& a, int r0, int r1, uint32_t head_bytes,
+__device__ __forceinline__ void producer_loop(const Ring<NHEAD>& ring, const ConvArgs& a, int RB, uint32_t head_bytes,
                                               HeadFn head_copies) {
   const int lane = threadIdx.x & 31;
   const T* kb = (const T*)a.k;
@@ -111,76 +116,97 @@ __device__ __forceinline__ void producer_loop(const Ring<NHEAD>& ring, const Con
   const T* v2 = (const T*)a.v_halo;
   const T* eb = (const T*)a.e;
   constexpr size_t D = kRowBytes / sizeof(T);
+  const int Nd = a.Nd;
+  const int nblocks = (Nd + RB - 1) / RB;  // RB <= 31: the RB+1 rowptr values of a block live in the lanes of one load
   int s = 0;
   uint32_t phase = 0;
-  int pb = a.rowptr[r0];  // base of the current 32-edge index batch
-  const int pend = a.rowptr[r1];
-  auto load_batch = [&](int base, int& j, int& t, int& c) {
+  auto load_batch = [&](int base, int pend, int& j, int& t, int& c) {
     const int p = base + lane;
     j = p < pend ? a.col[p] : 0;
     t = p < pend ? a.perm[p] : 0;
     c = (BWD && a.ads && p < pend) ? a.csr2csc[p] : 0;
   };
-  int j0, t0, c0, j1, t1, c1;
-  load_batch(pb, j0, t0, c0);
-  load_batch(pb + 32, j1, t1, c1);
-  int next_ptr = a.rowptr[min(r0 + 1 + lane, r1)];  // rowptr of the next 32 rows, refilled as rows advance
-  int ptr_base = r0 + 1;
-  int beg = pb;
-  for (int d = r0; d < r1; ++d) {
-    if (d + 1 - ptr_base >= 32) {
-      ptr_base = d + 1;
-      next_ptr = a.rowptr[min(ptr_base + lane, r1)];
+  int b = blockIdx.x;
+  if (b < nblocks) {
+    int r0 = b * RB, r1 = min(r0 + RB, Nd);
+    int ptr_cur = a.rowptr[min(r0 + lane, r1)];
+    int pb = __shfl_sync(0xffffffffu, ptr_cur, 0), pend = __shfl_sync(0xffffffffu, ptr_cur, r1 - r0);
+    int j0, t0, c0, j1, t1, c1;
+    load_batch(pb, pend, j0, t0, c0);
+    load_batch(pb + 32, pend, j1, t1, c1);
+    while (true) {
+      const int bn = b + (int)gridDim.x;
+      const bool has_next = bn < nblocks;
+      const int r0n = bn * RB, r1n = min(r0n + RB, Nd);
+      int ptr_nxt = 0;
+      if (has_next) ptr_nxt = a.rowptr[min(r0n + lane, r1n)];
+      int pbn = 0, pendn = 0, jn0 = 0, tn0 = 0, cn0 = 0, jn1 = 0, tn1 = 0, cn1 = 0;
+      bool next_loaded = false;
+      int beg = __shfl_sync(0xffffffffu, ptr_cur, 0);
+      for (int d = r0; d < r1; ++d) {
+        const int end = __shfl_sync(0xffffffffu, ptr_cur, d + 1 - r0);
+        int p = beg;
+        do {
+          const int n = min(kU, end - p);
+          if (p >= pb + 32) {  // p advances by <= kU per chunk, so one shift keeps p inside batch 0 and p + n inside batch 1
+            j0 = j1; t0 = t1; c0 = c1;
+            pb += 32;
+            load_batch(pb + 32, pend, j1, t1, c1);
+          }
+          mbar_wait(ring.empty(s), phase ^ 1u);
+          const int pp = p + (lane < kU ? lane : 0) - pb;  // 0..63
+          const int ja = __shfl_sync(0xffffffffu, j0, pp & 31), jb = __shfl_sync(0xffffffffu, j1, pp & 31);
+          const int ta = __shfl_sync(0xffffffffu, t0, pp & 31), tb = __shfl_sync(0xffffffffu, t1, pp & 31);
+          const int ca = __shfl_sync(0xffffffffu, c0, pp & 31), cb = __shfl_sync(0xffffffffu, c1, pp & 31);
+          const int j = pp < 32 ? ja : jb, t = pp < 32 ? ta : tb, c = pp < 32 ? ca : cb;
+          const bool first = p == beg, last = p + n >= end;
+          StageMeta* m = ring.meta(s);
+          if (lane == 0) {
+            m->row = d;
+            m->n = n;
+            m->first = first;
+            m->last = last;
+          }
+          if (lane < kU) {
+            m->t[lane] = t;
+            m->cs[lane] = c;
+          }
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t tx = (first ? head_bytes : 0u) + (uint32_t)n * 3u * kRowBytes;
+            mbar_arrive_expect_tx(ring.full(s), tx);  // release: the meta stores above are visible to whoever sees the phase flip
+          }
+          __syncwarp();
+          if (lane < n) {
+            const T* kp = ((size_t)j < (size_t)a.n_own ? kb : k2) + (size_t)j * D;
+            const T* vp = ((size_t)j < (size_t)a.n_own ? vb : v2) + (size_t)j * D;
+            bulk_g2s(ring.k(s, lane), kp, kRowBytes, ring.full(s));
+            bulk_g2s(ring.e(s, lane), eb + (size_t)t * D, kRowBytes, ring.full(s));
+            bulk_g2s(ring.v(s, lane), vp, kRowBytes, ring.full(s));
+          }
+          if (first) head_copies(d, s, lane);
+          p += n;
+          if (++s == kStages) {
+            s = 0;
+            phase ^= 1u;
+          }
+        } while (p < end);
+        beg = end;
+        if (has_next && !next_loaded) {  // the next block's rowptr has had a whole row's worth of stages to arrive
+          pbn = __shfl_sync(0xffffffffu, ptr_nxt, 0);
+          pendn = __shfl_sync(0xffffffffu, ptr_nxt, r1n - r0n);
+          load_batch(pbn, pendn, jn0, tn0, cn0);
+          load_batch(pbn + 32, pendn, jn1, tn1, cn1);
+          next_loaded = true;
+        }
+      }
+      if (!has_next) break;
+      b = bn; r0 = r0n; r1 = r1n;
+      ptr_cur = ptr_nxt;
+      pb = pbn; pend = pendn;
+      j0 = jn0; t0 = tn0; c0 = cn0;
+      j1 = jn1; t1 = tn1; c1 = cn1;
     }
-    const int end = __shfl_sync(0xffffffffu, next_ptr, d + 1 - ptr_base);
-    int p = beg;
-    do {
-      const int n = min(kU, end - p);
-      if (p >= pb + 32) {  // p advances by <= kU per chunk, so one shift keeps p inside batch 0 and p + n inside batch 1
-        j0 = j1; t0 = t1; c0 = c1;
-        pb += 32;
-        load_batch(pb + 32, j1, t1, c1);
-      }
-      mbar_wait(ring.empty(s), phase ^ 1u);
-      // indices of edge p+lane (lanes < n): from batch 0 or batch 1
-      const int pp = p + (lane < kU ? lane : 0) - pb;  // 0..63
-      const int ja = __shfl_sync(0xffffffffu, j0, pp & 31), jb = __shfl_sync(0xffffffffu, j1, pp & 31);
-      const int ta = __shfl_sync(0xffffffffu, t0, pp & 31), tb = __shfl_sync(0xffffffffu, t1, pp & 31);
-      const int ca = __shfl_sync(0xffffffffu, c0, pp & 31), cb = __shfl_sync(0xffffffffu, c1, pp & 31);
-      const int j = pp < 32 ? ja : jb, t = pp < 32 ? ta : tb, c = pp < 32 ? ca : cb;
-      const bool first = p == beg, last = p + n >= end;
-      StageMeta* m = ring.meta(s);
-      if (lane == 0) {
-        m->row = d;
-        m->n = n;
-        m->first = first;
-        m->last = last;
-      }
-      if (lane < kU) {
-        m->t[lane] = t;
-        m->cs[lane] = c;
-      }
-      __syncwarp();
-      if (lane == 0) {
-        const uint32_t tx = (first ? head_bytes : 0u) + (uint32_t)n * 3u * kRowBytes;
-        mbar_arrive_expect_tx(ring.full(s), tx);  // release: the meta stores above are visible to whoever sees the phase flip
-      }
-      __syncwarp();
-      if (lane < n) {
-        const T* kp = ((size_t)j < (size_t)a.n_own ? kb : k2) + (size_t)j * D;
-        const T* vp = ((size_t)j < (size_t)a.n_own ? vb : v2) + (size_t)j * D;
-        bulk_g2s(ring.k(s, lane), kp, kRowBytes, ring.full(s));
-        bulk_g2s(ring.e(s, lane), eb + (size_t)t * D, kRowBytes, ring.full(s));
-        bulk_g2s(ring.v(s, lane), vp, kRowBytes, ring.full(s));
-      }
-      if (first) head_copies(d, s, lane);
-      p += n;
-      if (++s == kStages) {
-        s = 0;
-        phase ^= 1u;
-      }
-    } while (p < end);
-    beg = end;
   }
   // end marker
   mbar_wait(ring.empty(s), phase ^ 1u);
@@ -190,18 +216,27 @@ __device__ __forceinline__ void producer_loop(const Ring<NHEAD>& ring, const Con
   }
 }
 
+// rows per block: about two 32-edge index batches worth of edges (AB2_TMA_RB overrides, for experiments)
+static int rows_per_block(int64_t E, int64_t rows) {
+  static const int forced = [] {
+    const char* s = getenv("AB2_TMA_RB");
+    return s ? atoi(s) : 0;
+  }();
+  if (forced > 0) return std::min(forced, 31);
+  const double deg = rows > 0 ? (double)E / (double)rows : 1.0;
+  return (int)std::max(1.0, std::min(31.0, std::floor(64.0 / std::max(deg, 1.0) + 0.5)));
+}
+
 // =====================================================================================================================
 // forward
 // =====================================================================================================================
 template <typename T, int LPH>
 __global__ void __launch_bounds__(kTmaThreads, kCtasPerSm)
-gtconv_fwd_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) {
+gtconv_fwd_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_block) {
   extern __shared__ __align__(128) char smem_raw[];
   constexpr int VEC = Vec<T>::N;
   constexpr size_t D = kRowBytes / sizeof(T);
   Ring<1> ring{smem_raw};
-  const int r0 = min((long long)blockIdx.x * rows_per_cta, (long long)a.Nd);
-  const int r1 = min((long long)r0 + rows_per_cta, (long long)a.Nd);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(ring.full(s), 1);
@@ -210,11 +245,10 @@ gtconv_fwd_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) {
     fence_barrier_init();
   }
   __syncthreads();
-  if (r0 >= r1) return;
 
   if (threadIdx.x >= kConsumers) {
     const T* qb = (const T*)a.q;
-    producer_loop<T, 1, false>(ring, a, r0, r1, kRowBytes, [&](int d, int s, int lane) {
+    producer_loop<T, 1, false>(ring, a, rows_per_block, kRowBytes, [&](int d, int s, int lane) {
       if (lane == kU) bulk_g2s(ring.head(s, 0), qb + (size_t)d * D, kRowBytes, ring.full(s));
     });
     return;
@@ -321,10 +355,9 @@ static bool launch_fwd_tma_t(const ConvArgs& a) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
     configured = true;
   }
-  const int ctas = std::max(1, std::min(a.Nd, num_sms() * kCtasPerSm));
-  const int rows_per_cta = (a.Nd + ctas - 1) / ctas;
-  const int grid = (a.Nd + rows_per_cta - 1) / rows_per_cta;
-  kern<<<grid, kTmaThreads, smem, a.st>>>(a, rows_per_cta);
+  const int rb = rows_per_block(a.E, a.Nd);
+  const int grid = std::max(1, std::min((a.Nd + rb - 1) / rb, num_sms() * kCtasPerSm));
+  kern<<<grid, kTmaThreads, smem, a.st>>>(a, rb);
   return true;
 }
 
@@ -335,13 +368,11 @@ constexpr int kCtasPerSmBwd = 3;
 
 template <typename T, int LPH>
 __global__ void __launch_bounds__(kTmaThreads, kCtasPerSmBwd)
-gtconv_bwd_dst_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) {
+gtconv_bwd_dst_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_block) {
   extern __shared__ __align__(128) char smem_raw[];
   constexpr int VEC = Vec<T>::N;
   constexpr size_t D = kRowBytes / sizeof(T);
   Ring<4> ring{smem_raw};  // head slots: q, g, out, lse2 (H floats)
-  const int r0 = min((long long)blockIdx.x * rows_per_cta, (long long)a.Nd);
-  const int r1 = min((long long)r0 + rows_per_cta, (long long)a.Nd);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(ring.full(s), 1);
@@ -350,14 +381,13 @@ gtconv_bwd_dst_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) 
     fence_barrier_init();
   }
   __syncthreads();
-  if (r0 >= r1) return;
   const uint32_t lse_bytes = (uint32_t)a.H * 4u;  // a multiple of 16: H = 128 / LPH >= 4
 
   if (threadIdx.x >= kConsumers) {
     const T* qb = (const T*)a.q;
     const T* gb = (const T*)a.g;
     const T* ob = (const T*)a.out;
-    producer_loop<T, 4, true>(ring, a, r0, r1, 3u * kRowBytes + lse_bytes, [&](int d, int s, int lane) {
+    producer_loop<T, 4, true>(ring, a, rows_per_block, 3u * kRowBytes + lse_bytes, [&](int d, int s, int lane) {
       if (lane == kU) bulk_g2s(ring.head(s, 0), qb + (size_t)d * D, kRowBytes, ring.full(s));
       if (lane == kU + 1) bulk_g2s(ring.head(s, 1), gb + (size_t)d * D, kRowBytes, ring.full(s));
       if (lane == kU + 2) bulk_g2s(ring.head(s, 2), ob + (size_t)d * D, kRowBytes, ring.full(s));
@@ -481,10 +511,9 @@ static bool launch_bwd_dst_tma_t(const ConvArgs& a) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
     configured = true;
   }
-  const int ctas = std::max(1, std::min(a.Nd, num_sms() * kCtasPerSmBwd));
-  const int rows_per_cta = (a.Nd + ctas - 1) / ctas;
-  const int grid = (a.Nd + rows_per_cta - 1) / rows_per_cta;
-  kern<<<grid, kTmaThreads, smem, a.st>>>(a, rows_per_cta);
+  const int rb = rows_per_block(a.E, a.Nd);
+  const int grid = std::max(1, std::min((a.Nd + rb - 1) / rb, num_sms() * kCtasPerSmBwd));
+  kern<<<grid, kTmaThreads, smem, a.st>>>(a, rb);
   return true;
 }
 
@@ -512,13 +541,11 @@ struct SrcRing {
 
 template <typename T, int LPH>
 __global__ void __launch_bounds__(kTmaThreads, kCtasPerSmSrc)
-gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) {
+gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_block) {
   extern __shared__ __align__(128) char smem_raw[];
   constexpr int VEC = Vec<T>::N;
   constexpr size_t D = kRowBytes / sizeof(T);
   SrcRing ring{smem_raw};
-  const int r0 = min((long long)a.src_lo + (long long)blockIdx.x * rows_per_cta, (long long)a.src_hi);
-  const int r1 = min((long long)r0 + rows_per_cta, (long long)a.src_hi);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(ring.full(s), 1);
@@ -527,48 +554,85 @@ gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) 
     fence_barrier_init();
   }
   __syncthreads();
-  if (r0 >= r1) return;
   const int lane = threadIdx.x & 31;
+  const int RB = rows_per_block;
+  const int nrows = a.src_hi - a.src_lo;
+  const int nblocks = (nrows + RB - 1) / RB;
 
   if (threadIdx.x >= kConsumers) {
-    // ---- producer warp: every stage carries kU consecutive CSC edges of the CTA's row range, whatever rows they belong to
-    // (meta.t[u] = src row of edge u), so stages stay full at an out-degree of 1-2 as well
+    // ---- producer warp.  Blocks of RB consecutive src rows are dealt round-robin to the CTAs (compact window of rows in
+    // flight -> the q / g rows they gather stay L2-resident).  Inside a block every stage carries kU consecutive CSC edges
+    // whatever rows they belong to (meta.t[u] = src row of edge u), so stages stay full at an out-degree of 1-2 as well.
     const T* qb = (const T*)a.q;
     const T* gb = (const T*)a.g;
     const int2* cedge = reinterpret_cast<const int2*>(a.crow);  // (dst, src) per src-sorted position
     const uint32_t edge_w = (uint32_t)a.H * 8u;                 // bytes of (a, ds) per edge
     int s = 0;
     uint32_t phase = 0;
-    int pb = a.colptr[r0];
-    const int pend = a.colptr[r1];
-    int2 e0 = pb + lane < pend ? cedge[pb + lane] : make_int2(0, 0);
-    int2 e1 = pb + 32 + lane < pend ? cedge[pb + 32 + lane] : make_int2(0, 0);
-    for (int p = pb; p < pend; p += kU) {
-      const int n = min(kU, pend - p);
-      if (p >= pb + 32) {
-        e0 = e1;
-        pb += 32;
-        e1 = pb + 32 + lane < pend ? cedge[pb + 32 + lane] : make_int2(0, 0);
-      }
-      mbar_wait(ring.empty(s), phase ^ 1u);
-      const int pp = p + (lane < kU ? lane : 0) - pb;
-      const int ia = __shfl_sync(0xffffffffu, e0.x, pp & 31), ib = __shfl_sync(0xffffffffu, e1.x, pp & 31);
-      const int ra = __shfl_sync(0xffffffffu, e0.y, pp & 31), rb = __shfl_sync(0xffffffffu, e1.y, pp & 31);
-      const int i = pp < 32 ? ia : ib, r = pp < 32 ? ra : rb;
-      StageMeta* m = ring.meta(s);
-      if (lane < kU) m->t[lane] = r;
-      if (lane == 0) m->n = n;
-      __syncwarp();
-      if (lane == 0) mbar_arrive_expect_tx(ring.full(s), (uint32_t)n * (2u * kRowBytes + edge_w));
-      __syncwarp();
-      if (lane < n) {
-        bulk_g2s(ring.q(s, lane), qb + (size_t)i * D, kRowBytes, ring.full(s));
-        bulk_g2s(ring.g(s, lane), gb + (size_t)i * D, kRowBytes, ring.full(s));
-      }
-      if (lane == kU) bulk_g2s(ring.w(s), a.ads + (size_t)p * a.H, (uint32_t)n * edge_w, ring.full(s));
-      if (++s == kStages) {
-        s = 0;
-        phase ^= 1u;
+    auto load_batch = [&](int base, int pend) { return base + lane < pend ? cedge[base + lane] : make_int2(0, 0); };
+    int b = blockIdx.x;
+    if (b < nblocks) {
+      int r0 = a.src_lo + b * RB, r1 = min(r0 + RB, a.src_hi);
+      int pb = a.colptr[r0], pend = a.colptr[r1];
+      int2 e0 = load_batch(pb, pend), e1 = load_batch(pb + 32, pend);
+      while (true) {
+        const int bn = b + (int)gridDim.x;
+        const bool has_next = bn < nblocks;
+        const int r0n = a.src_lo + bn * RB, r1n = min(r0n + RB, a.src_hi);
+        int pbn = 0, pendn = 0;
+        if (has_next) {
+          pbn = a.colptr[r0n];
+          pendn = a.colptr[r1n];
+        }
+        int2 en0 = make_int2(0, 0), en1 = en0;
+        bool next_loaded = false;
+        int p = pb, staged = 0;
+        bool first = true;
+        do {  // at least one stage per block, so that edge-less blocks get their zero rows written
+          const int n = max(0, min(kU, pend - p));
+          if (p >= pb + 32) {
+            e0 = e1;
+            pb += 32;
+            e1 = load_batch(pb + 32, pend);
+          }
+          mbar_wait(ring.empty(s), phase ^ 1u);
+          const int pp = p + (lane < kU ? lane : 0) - pb;
+          const int ia = __shfl_sync(0xffffffffu, e0.x, pp & 31), ib = __shfl_sync(0xffffffffu, e1.x, pp & 31);
+          const int ra = __shfl_sync(0xffffffffu, e0.y, pp & 31), rb = __shfl_sync(0xffffffffu, e1.y, pp & 31);
+          const int i = pp < 32 ? ia : ib, r = pp < 32 ? ra : rb;
+          StageMeta* m = ring.meta(s);
+          if (lane < kU) m->t[lane] = r;
+          if (lane == 0) {
+            m->n = n;
+            m->first = first;
+            m->row = r0;   // block = src rows [row, last)
+            m->last = r1;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive_expect_tx(ring.full(s), (uint32_t)n * (2u * kRowBytes + edge_w));
+          __syncwarp();
+          if (lane < n) {
+            bulk_g2s(ring.q(s, lane), qb + (size_t)i * D, kRowBytes, ring.full(s));
+            bulk_g2s(ring.g(s, lane), gb + (size_t)i * D, kRowBytes, ring.full(s));
+          }
+          if (lane == kU && n > 0) bulk_g2s(ring.w(s), a.ads + (size_t)p * a.H, (uint32_t)n * edge_w, ring.full(s));
+          p += n;
+          first = false;
+          if (++s == kStages) {
+            s = 0;
+            phase ^= 1u;
+          }
+          ++staged;
+          if (has_next && !next_loaded && (staged >= 4 || p >= pend)) {  // colptr of the next block has arrived by now
+            en0 = load_batch(pbn, pendn);
+            en1 = load_batch(pbn + 32, pendn);
+            next_loaded = true;
+          }
+        } while (p < pend);
+        if (!has_next) break;
+        b = bn; r0 = r0n; r1 = r1n;
+        pb = pbn; pend = pendn;
+        e0 = en0; e1 = en1;
       }
     }
     mbar_wait(ring.empty(s), phase ^ 1u);
@@ -590,7 +654,7 @@ gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) 
   float ka[VEC], va[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) ka[i] = va[i] = 0.f;
-  int cur = r0;
+  int cur = -1, blk_end = 0;  // current row and end of the current block (cur < 0: no block yet)
   auto flush_to = [&](int r) {  // store row `cur`, zero rows cur+1 .. r-1, continue with row r
     {
       const bool own = cur < a.n_own;
@@ -613,6 +677,7 @@ gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) 
     const StageMeta* mt = ring.meta(s);
     const int n = mt->n;
     if (n < 0) break;
+    const int first = mt->first, blk_r0 = mt->row, blk_r1 = mt->last;
     uint4 qr[kU], gr[kU];
     float2 w[kU];
     int rows[kU];
@@ -634,6 +699,11 @@ gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) 
       s = 0;
       phase ^= 1u;
     }
+    if (first) {  // a new block of rows starts: finish the previous one (its trailing edge-less rows included)
+      if (cur >= 0) flush_to(blk_end);
+      cur = blk_r0;
+      blk_end = blk_r1;
+    }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       if (u < n) {
@@ -649,7 +719,7 @@ gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) 
       }
     }
   }
-  flush_to(r1);  // last row with edges, then the trailing edge-less rows of the range
+  if (cur >= 0) flush_to(blk_end);
 }
 
 template <typename T, int LPH>
@@ -662,10 +732,11 @@ static bool launch_bwd_src_tma_t(const ConvArgs& a) {
     configured = true;
   }
   const int nrows = a.src_hi - a.src_lo;
-  const int ctas = std::max(1, std::min(nrows, num_sms() * kCtasPerSmSrc));
-  const int rows_per_cta = (nrows + ctas - 1) / ctas;
-  const int grid = (nrows + rows_per_cta - 1) / rows_per_cta;
-  kern<<<grid, kTmaThreads, smem, a.st>>>(a, rows_per_cta);
+  // rows per block: about 64 edges (two index batches); the src pass has no rowptr-in-lanes limit
+  const double deg = a.Ns > 0 ? (double)a.E / (double)a.Ns : 1.0;
+  const int rb = (int)std::max(1.0, std::min(256.0, std::floor(64.0 / std::max(deg, 0.25) + 0.5)));
+  const int grid = std::max(1, std::min((nrows + rb - 1) / rb, num_sms() * kCtasPerSmSrc));
+  kern<<<grid, kTmaThreads, smem, a.st>>>(a, rb);
   return true;
 }
 
