@@ -801,24 +801,20 @@ static bool use_row_blocks(int64_t E, int64_t Nd) {
   return Nd > 0 && E < 6 * Nd;
 }
 
-// Forward kernel choice for 2 KB rows, measured on B200 (profiles/r01, A/B run r01i):
-//   mean in-degree 18.6 (encoder):  LDG 0.698 ms  vs bulk-copy pipeline 0.728 ms  -> LDG
-//   mean in-degree  8   (processor): LDG 0.302 ms  vs pipeline 0.223 ms            -> pipeline
-//   mean in-degree  3   (decoder):  row-block LDG 1.85 ms vs pipeline 1.52 ms      -> pipeline
-// (the backward dst pass is faster on the pipeline at every degree: 1.00 -> 0.97, 0.455 -> 0.346, 3.62 -> 2.27 ms)
+// Forward kernel choice for 2 KB rows, measured on B200 (profiles/r01: A/B runs r01i, r01x).  With row blocks dealt round-robin
+// the bulk-copy pipeline wins at every in-degree: 18.6 (encoder) LDG 0.699 -> 0.662 ms, 8 (processor) 0.302 -> 0.208,
+// 3 (decoder) row-block LDG 1.85 -> 1.33.  (Its first version, one contiguous row range per CTA, lost on the encoder --
+// 0.728 ms -- because neighbouring dst rows were no longer in flight together and k / v rows were fetched from HBM twice.)
+// The backward dst pass: 1.00 -> 0.94, 0.455 -> 0.319, 3.62 -> 2.08 ms.  AB2_TMA bit 0 / bit 1 switch them off for A/B runs.
 static bool fwd_prefers_tma(int dtype, int H, int C, int64_t E, int64_t Nd) {
-  if (!tma_applicable(0, dtype, H, C)) return false;
-  static const int forced = [] {
-    const char* s = getenv("AB2_TMA");
-    return s ? atoi(s) : 3;
-  }();
-  if (forced & 4) return true;  // bit 2: pipeline at every degree (A/B runs)
-  return E < 12 * Nd;
+  (void)E;
+  (void)Nd;
+  return tma_applicable(0, dtype, H, C);
 }
 
-// Backward src pass for 2 KB rows, measured on B200 (A/B runs r01j, r01n): at a mean out-degree of 1.4 (encoder) the LDG
-// kernel (8-row blocks) wins, 0.65 ms vs 0.79 (pipeline, one src row per stage) / 0.86 (pipeline, kU edges per stage whatever
-// their rows -- the version kept); at out-degree 8 (processor) the pipeline wins, 0.190 -> 0.139 ms; at out-degree 40
+// Backward src pass for 2 KB rows, measured on B200 (A/B runs r01j, r01n, r01x): at a mean out-degree of 1.4 (encoder) the
+// LDG kernel (8-row blocks) and the pipeline (round-robin blocks) are within 2 % (0.657 vs 0.643 ms) -- LDG kept; at
+// out-degree 8 (processor) the pipeline with one contiguous row range per CTA wins, 0.190 -> 0.139 ms; at out-degree 40
 // (decoder) both sit at the L2/HBM gather limit (1.04 ms).
 static bool src_prefers_tma(int dtype, int H, int C, int64_t E, int64_t Ns) {
   static const bool always = getenv("AB2_SRC_TMA_ALWAYS") != nullptr;  // A/B and profiling runs
