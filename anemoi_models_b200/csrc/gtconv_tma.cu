@@ -216,9 +216,9 @@ __device__ __forceinline__ void producer_loop(const Ring<NHEAD>& ring, const Con
   }
 }
 
-// rows per block: about one 32-edge index batch worth of edges -- measured on the headline graph (in-degree 18.6, run r01x):
-// forward 0.662 ms at 2 rows per block, 0.680 at 4, 0.692 at 8 (smaller window in flight = better L2 reuse of k / v rows).
-// AB2_TMA_RB overrides, for experiments.
+// rows per block, measured on the headline graph (in-degree 18.6, runs r01x / r01y): forward 0.631 ms at 1 row per block,
+// 0.658 at 2, 0.673 at 3, 0.680 at 4, 0.692 at 8; backward dst pass 0.844 / 0.958 / 0.960 (the smaller the window of dst rows
+// in flight, the better the L2 reuse of the k / v rows neighbouring dst rows share).  AB2_TMA_RB overrides, for experiments.
 static int rows_per_block(int64_t E, int64_t rows) {
   static const int forced = [] {
     const char* s = getenv("AB2_TMA_RB");
@@ -226,6 +226,7 @@ static int rows_per_block(int64_t E, int64_t rows) {
   }();
   if (forced > 0) return std::min(forced, 31);
   const double deg = rows > 0 ? (double)E / (double)rows : 1.0;
+  if (deg >= 12.0) return 1;
   return (int)std::max(1.0, std::min(31.0, std::floor(32.0 / std::max(deg, 1.0) + 0.5)));
 }
 
@@ -543,11 +544,17 @@ struct SrcRing {
 
 template <typename T, int LPH>
 __global__ void __launch_bounds__(kTmaThreads, kCtasPerSmSrc)
-gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_block) {
+gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) {
   extern __shared__ __align__(128) char smem_raw[];
   constexpr int VEC = Vec<T>::N;
   constexpr size_t D = kRowBytes / sizeof(T);
   SrcRing ring{smem_raw};
+  // One contiguous range of src rows per CTA: at the out-degrees this kernel is chosen for (>= 4) consecutive src rows gather
+  // largely the same q / g rows, and that reuse is within the CTA's own stream of stages.  (Two other layouts were measured
+  // and dropped -- profiles/r01/ab_r01x, r01y: stages that mix edges of several rows, 0.206 vs 0.139 ms at out-degree 8,
+  // and blocks of rows dealt round-robin, 0.175 ms / at out-degree 40 1.41 vs 1.04 ms.)
+  const int r0 = (int)min((long long)a.src_lo + (long long)blockIdx.x * rows_per_cta, (long long)a.src_hi);
+  const int r1 = (int)min((long long)r0 + rows_per_cta, (long long)a.src_hi);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(ring.full(s), 1);
@@ -556,96 +563,73 @@ gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_block
     fence_barrier_init();
   }
   __syncthreads();
+  if (r0 >= r1) return;
   const int lane = threadIdx.x & 31;
-  const int RB = rows_per_block;
-  const int nrows = a.src_hi - a.src_lo;
-  const int nblocks = (nrows + RB - 1) / RB;
 
   if (threadIdx.x >= kConsumers) {
-    // ---- producer warp.  Blocks of RB consecutive src rows are dealt round-robin to the CTAs (compact window of rows in
-    // flight -> the q / g rows they gather stay L2-resident).  Inside a block every stage carries kU consecutive CSC edges
-    // whatever rows they belong to (meta.t[u] = src row of edge u), so stages stay full at an out-degree of 1-2 as well.
+    // ---- producer warp: every stage carries <= kU consecutive CSC edges of ONE src row
     const T* qb = (const T*)a.q;
     const T* gb = (const T*)a.g;
     const int2* cedge = reinterpret_cast<const int2*>(a.crow);  // (dst, src) per src-sorted position
     const uint32_t edge_w = (uint32_t)a.H * 8u;                 // bytes of (a, ds) per edge
     int s = 0;
     uint32_t phase = 0;
-    auto load_batch = [&](int base, int pend) { return base + lane < pend ? cedge[base + lane] : make_int2(0, 0); };
-    int b = blockIdx.x;
-    if (b < nblocks) {
-      int r0 = a.src_lo + b * RB, r1 = min(r0 + RB, a.src_hi);
-      int pb = a.colptr[r0], pend = a.colptr[r1];
-      int2 e0 = load_batch(pb, pend), e1 = load_batch(pb + 32, pend);
-      while (true) {
-        const int bn = b + (int)gridDim.x;
-        const bool has_next = bn < nblocks;
-        const int r0n = a.src_lo + bn * RB, r1n = min(r0n + RB, a.src_hi);
-        int pbn = 0, pendn = 0;
-        if (has_next) {
-          pbn = a.colptr[r0n];
-          pendn = a.colptr[r1n];
-        }
-        int2 en0 = make_int2(0, 0), en1 = en0;
-        bool next_loaded = false;
-        int p = pb, staged = 0;
-        bool first = true;
-        do {  // at least one stage per block, so that edge-less blocks get their zero rows written
-          const int n = max(0, min(kU, pend - p));
-          if (p >= pb + 32) {
-            e0 = e1;
-            pb += 32;
-            e1 = load_batch(pb + 32, pend);
-          }
-          mbar_wait(ring.empty(s), phase ^ 1u);
-          const int pp = p + (lane < kU ? lane : 0) - pb;
-          const int ia = __shfl_sync(0xffffffffu, e0.x, pp & 31), ib = __shfl_sync(0xffffffffu, e1.x, pp & 31);
-          const int ra = __shfl_sync(0xffffffffu, e0.y, pp & 31), rb = __shfl_sync(0xffffffffu, e1.y, pp & 31);
-          const int i = pp < 32 ? ia : ib, r = pp < 32 ? ra : rb;
-          StageMeta* m = ring.meta(s);
-          if (lane < kU) m->t[lane] = r;
-          if (lane == 0) {
-            m->n = n;
-            m->first = first;
-            m->row = r0;   // block = src rows [row, last)
-            m->last = r1;
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive_expect_tx(ring.full(s), (uint32_t)n * (2u * kRowBytes + edge_w));
-          __syncwarp();
-          if (lane < n) {
-            bulk_g2s(ring.q(s, lane), qb + (size_t)i * D, kRowBytes, ring.full(s));
-            bulk_g2s(ring.g(s, lane), gb + (size_t)i * D, kRowBytes, ring.full(s));
-          }
-          if (lane == kU && n > 0) bulk_g2s(ring.w(s), a.ads + (size_t)p * a.H, (uint32_t)n * edge_w, ring.full(s));
-          p += n;
-          first = false;
-          if (++s == kStages) {
-            s = 0;
-            phase ^= 1u;
-          }
-          ++staged;
-          if (has_next && !next_loaded && (staged >= 4 || p >= pend)) {  // colptr of the next block has arrived by now
-            en0 = load_batch(pbn, pendn);
-            en1 = load_batch(pbn + 32, pendn);
-            next_loaded = true;
-          }
-        } while (p < pend);
-        if (!has_next) break;
-        b = bn; r0 = r0n; r1 = r1n;
-        pb = pbn; pend = pendn;
-        e0 = en0; e1 = en1;
+    int pb = a.colptr[r0];
+    const int pend = a.colptr[r1];
+    auto load_batch = [&](int base) { return base + lane < pend ? cedge[base + lane].x : 0; };
+    int i0 = load_batch(pb), i1 = load_batch(pb + 32);
+    int ptr_base = r0 + 1;
+    int next_ptr = a.colptr[min(ptr_base + lane, r1)];
+    int beg = pb;
+    for (int j = r0; j < r1; ++j) {
+      if (j + 1 - ptr_base >= 32) {
+        ptr_base = j + 1;
+        next_ptr = a.colptr[min(ptr_base + lane, r1)];
       }
+      const int end = __shfl_sync(0xffffffffu, next_ptr, j + 1 - ptr_base);
+      int p = beg;
+      do {  // at least one stage per row, so that edge-less rows get their zeros written
+        const int n = min(kU, end - p);
+        if (p >= pb + 32) {
+          i0 = i1;
+          pb += 32;
+          i1 = load_batch(pb + 32);
+        }
+        mbar_wait(ring.empty(s), phase ^ 1u);
+        const int pp = p + (lane < kU ? lane : 0) - pb;
+        const int ia = __shfl_sync(0xffffffffu, i0, pp & 31), ib = __shfl_sync(0xffffffffu, i1, pp & 31);
+        const int i = pp < 32 ? ia : ib;
+        if (lane == 0) {
+          StageMeta* m = ring.meta(s);
+          m->row = j;
+          m->n = n;
+          m->first = p == beg;
+          m->last = p + n >= end;
+          mbar_arrive_expect_tx(ring.full(s), (uint32_t)n * (2u * kRowBytes + edge_w));
+        }
+        __syncwarp();
+        if (lane < n) {
+          bulk_g2s(ring.q(s, lane), qb + (size_t)i * D, kRowBytes, ring.full(s));
+          bulk_g2s(ring.g(s, lane), gb + (size_t)i * D, kRowBytes, ring.full(s));
+        }
+        if (lane == kU && n > 0) bulk_g2s(ring.w(s), a.ads + (size_t)p * a.H, (uint32_t)n * edge_w, ring.full(s));
+        p += n;
+        if (++s == kStages) {
+          s = 0;
+          phase ^= 1u;
+        }
+      } while (p < end);
+      beg = end;
     }
     mbar_wait(ring.empty(s), phase ^ 1u);
     if (lane == 0) {
-      ring.meta(s)->n = -1;
+      ring.meta(s)->row = -1;
       mbar_arrive_expect_tx(ring.full(s), 0);
     }
     return;
   }
 
-  // ---- consumers: one accumulator pair, flushed whenever the src row changes; rows without edges get zeros
+  // ---- consumers: accumulate the stages of a row, write it once
   const int chunk = threadIdx.x;
   const size_t off = (size_t)chunk * 16;
   const int h = chunk / LPH;
@@ -656,36 +640,17 @@ gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_block
   float ka[VEC], va[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) ka[i] = va[i] = 0.f;
-  int cur = -1, blk_end = 0;  // current row and end of the current block (cur < 0: no block yet)
-  auto flush_to = [&](int r) {  // store row `cur`, zero rows cur+1 .. r-1, continue with row r
-    {
-      const bool own = cur < a.n_own;
-      if (dk) stg16(reinterpret_cast<char*>((own ? dk : dk2) + (size_t)cur * D) + off, pack<T>(ka));
-      if (dv) stg16(reinterpret_cast<char*>((own ? dv : dv2) + (size_t)cur * D) + off, pack<T>(va));
-    }
-    for (int z = cur + 1; z < r; ++z) {
-      const bool own = z < a.n_own;
-      if (dk) stg16(reinterpret_cast<char*>((own ? dk : dk2) + (size_t)z * D) + off, make_uint4(0, 0, 0, 0));
-      if (dv) stg16(reinterpret_cast<char*>((own ? dv : dv2) + (size_t)z * D) + off, make_uint4(0, 0, 0, 0));
-    }
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) ka[i] = va[i] = 0.f;
-    cur = r;
-  };
   int s = 0;
   uint32_t phase = 0;
   while (true) {
     mbar_wait(ring.full(s), phase);
     const StageMeta* mt = ring.meta(s);
-    const int n = mt->n;
-    if (n < 0) break;
-    const int first = mt->first, blk_r0 = mt->row, blk_r1 = mt->last;
+    const int row = mt->row, n = mt->n, first = mt->first, last = mt->last;
+    if (row < 0) break;
     uint4 qr[kU], gr[kU];
     float2 w[kU];
-    int rows[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      rows[u] = mt->t[u];
       if (u < n) {
         qr[u] = lds16(ring.q(s, u) + off);
         gr[u] = lds16(ring.g(s, u) + off);
@@ -701,27 +666,27 @@ gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_block
       s = 0;
       phase ^= 1u;
     }
-    if (first) {  // a new block of rows starts: finish the previous one (its trailing edge-less rows included)
-      if (cur >= 0) flush_to(blk_end);
-      cur = blk_r0;
-      blk_end = blk_r1;
+    if (first) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) ka[i] = va[i] = 0.f;
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      if (u < n) {
-        if (rows[u] != cur) flush_to(rows[u]);
-        float qf[VEC], gf[VEC];
-        unpack<T>(qr[u], qf);
-        unpack<T>(gr[u], gf);
+      float qf[VEC], gf[VEC];
+      unpack<T>(qr[u], qf);
+      unpack<T>(gr[u], gf);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          ka[i] = fmaf(w[u].y, qf[i], ka[i]);
-          va[i] = fmaf(w[u].x, gf[i], va[i]);
-        }
+      for (int i = 0; i < VEC; ++i) {
+        ka[i] = fmaf(w[u].y, qf[i], ka[i]);
+        va[i] = fmaf(w[u].x, gf[i], va[i]);
       }
     }
+    if (last) {
+      const bool own = row < a.n_own;
+      if (dk) stg16(reinterpret_cast<char*>((own ? dk : dk2) + (size_t)row * D) + off, pack<T>(ka));
+      if (dv) stg16(reinterpret_cast<char*>((own ? dv : dv2) + (size_t)row * D) + off, pack<T>(va));
+    }
   }
-  if (cur >= 0) flush_to(blk_end);
 }
 
 template <typename T, int LPH>
@@ -734,16 +699,10 @@ static bool launch_bwd_src_tma_t(const ConvArgs& a) {
     configured = true;
   }
   const int nrows = a.src_hi - a.src_lo;
-  // Blocks of src rows: at a low out-degree (encoder, 1.4) ~64 edges per block dealt round-robin, so that the rows in flight
-  // form a compact window; at a high out-degree the reuse that matters is WITHIN a CTA (consecutive src rows gather the same
-  // q / g rows), so every CTA keeps one contiguous range (measured, run r01x vs r01j: out-degree 8: 0.175 vs 0.139 ms,
-  // out-degree 40: 1.41 vs 1.04 ms with round-robin blocks of ~64 edges).
-  const double deg = a.Ns > 0 ? (double)a.E / (double)a.Ns : 1.0;
-  const int ctas = num_sms() * kCtasPerSmSrc;
-  int rb = (int)std::max(1.0, std::min(256.0, std::floor(64.0 / std::max(deg, 0.25) + 0.5)));
-  if (deg >= 4.0) rb = std::max(1, (nrows + ctas - 1) / ctas);
-  const int grid = std::max(1, std::min((nrows + rb - 1) / rb, ctas));
-  kern<<<grid, kTmaThreads, smem, a.st>>>(a, rb);
+  const int ctas = std::max(1, std::min(nrows, num_sms() * kCtasPerSmSrc));
+  const int rows_per_cta = (nrows + ctas - 1) / ctas;
+  const int grid = (nrows + rows_per_cta - 1) / rows_per_cta;
+  kern<<<grid, kTmaThreads, smem, a.st>>>(a, rows_per_cta);
   return true;
 }
 
