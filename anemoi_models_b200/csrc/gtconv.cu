@@ -479,6 +479,97 @@ gtconv_bwd_src_kernel(const T* __restrict__ q, const T* __restrict__ g, const in
   flush_to(last);
 }
 
+// The same pass with the bookkeeping done ONCE PER WARP instead of once per thread (row layouts where a warp lies inside one
+// row group, i.e. tpd % 32 == 0 -- all the model's shapes).  ncu on the kernel above (run r01y, headline graph): 444 M warp
+// instructions of which 48 M are the FMAs -- the per-thread row lookup (7 compares per edge slot), the 9 colptr loads and the
+// flush loop made it ~65 % issue-bound at 3.3 TB/s of writes.  Here lane l holds the CSC offset of row l of the group and
+// lane l of an edge batch holds (dst, src) of edge l; the per-edge state every thread needs -- the dst index, "is this the
+// last edge of its src row" -- comes from one shuffle and one bit of a ballot mask.
+constexpr int kSrcRowsW = 24;  // most rows per warp group (<= 31; AB2_SRC_ROWS overrides, for experiments)
+
+template <typename T, int LPH, bool SPLIT>
+__global__ void __launch_bounds__(kThreads, 6)
+gtconv_bwd_src_warp_kernel(const T* __restrict__ q, const T* __restrict__ g, const int* __restrict__ colptr,
+                           const int2* __restrict__ cedge, const float2* __restrict__ ads, int src_lo, int Ns, RowMap rm, int H,
+                           T* __restrict__ dk, T* __restrict__ dv, T* __restrict__ dk2, T* __restrict__ dv2, int nsplit,
+                           int rows_per_group) {
+  constexpr int VEC = Vec<T>::N;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int lr = threadIdx.x / rm.tpd;
+  const long long j0l = (long long)src_lo + ((long long)blockIdx.x * rm.rpb + lr) * rows_per_group;
+  if (lr >= rm.rpb || j0l >= Ns) return;  // warp-uniform: tpd is a multiple of 32
+  const int j0 = (int)j0l;
+  const int nrows = min(rows_per_group, Ns - j0);
+  const int chunk = blockIdx.y * rm.tpd + (threadIdx.x - lr * rm.tpd);
+  const size_t D = (size_t)rm.chunks * VEC;
+  const size_t off = (size_t)chunk * VEC;
+  const T* qo = q + off;
+  const T* go = g + off;
+  const float2* wo = ads + chunk / LPH;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+
+  const int cp = colptr[j0 + min(lane, nrows)];  // lane l: CSC offset of row j0 + l
+  const int c0 = __shfl_sync(kFull, cp, 0), cend = __shfl_sync(kFull, cp, nrows);
+  int2 ed = c0 + lane < cend ? cedge[c0 + lane] : make_int2(0, -1);  // first edge batch: lane l = (dst, src) of edge c0 + l
+  {  // edge-less rows get zeros
+    const int cpn = __shfl_down_sync(kFull, cp, 1);
+    unsigned empty = __ballot_sync(kFull, lane < nrows && cpn == cp);
+    while (empty) {
+      const int z = __ffs(empty) - 1;
+      empty &= empty - 1;
+      if (dk) stg16(src_row<SPLIT>(dk, dk2, nsplit, (size_t)(j0 + z), D) + off, zero4);
+      if (dv) stg16(src_row<SPLIT>(dv, dv2, nsplit, (size_t)(j0 + z), D) + off, zero4);
+    }
+  }
+  float ka[VEC], va[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) ka[i] = va[i] = 0.f;
+
+  for (int tb = c0; tb < cend; tb += 32) {
+    const int t = tb + lane;
+    if (tb != c0) ed = t < cend ? cedge[t] : make_int2(0, -1);
+    int nsrc = __shfl_down_sync(kFull, ed.y, 1);  // src row of the next edge (-1 past the group's last edge)
+    if (lane == 31) nsrc = t + 1 < cend ? cedge[t + 1].y : -1;
+    const unsigned lastm = __ballot_sync(kFull, t < cend && nsrc != ed.y);  // bit l: edge tb + l is the last one of its row
+    const int n = min(32, cend - tb);
+    for (int u0 = 0; u0 < n; u0 += kU) {
+      uint4 qr[kU], gr[kU];
+      float2 w[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const size_t i = (size_t)__shfl_sync(kFull, ed.x, (u0 + u) & 31);
+        if (u0 + u < n) {
+          w[u] = __ldg(wo + (size_t)(tb + u0 + u) * H);
+          qr[u] = ldg16_keep(qo + i * D);
+          gr[u] = ldg16_keep(go + i * D);
+        } else {
+          w[u] = make_float2(0.f, 0.f);
+          qr[u] = gr[u] = zero4;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        float qf[VEC], gf[VEC];
+        unpack<T>(qr[u], qf);
+        unpack<T>(gr[u], gf);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          ka[i] = fmaf(w[u].y, qf[i], ka[i]);
+          va[i] = fmaf(w[u].x, gf[i], va[i]);
+        }
+        if ((lastm >> ((u0 + u) & 31)) & 1u) {  // warp-uniform; only set for u0 + u < n
+          const int row = __shfl_sync(kFull, ed.y, (u0 + u) & 31);
+          if (dk) stg16(src_row<SPLIT>(dk, dk2, nsplit, (size_t)row, D) + off, pack<T>(ka));
+          if (dv) stg16(src_row<SPLIT>(dv, dv2, nsplit, (size_t)row, D) + off, pack<T>(va));
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) ka[i] = va[i] = 0.f;
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // generic kernels: any C (one warp per (row, head), lanes stride over channels).  Used when C*sizeof(T) is not
 // a power-of-two multiple of 16 bytes (e.g. C=5, C=24) -- small test shapes; not the tuned path.
@@ -672,6 +763,15 @@ static Plan make_plan(int H, int C, int elt) {
   return pl;
 }
 
+// a warp never straddles two row groups -> the warp-cooperative src pass applies (AB2_SRC_WARP=0 keeps the per-thread kernel)
+static bool src_warp_layout(const Plan& pl) {
+  static const bool off = [] {
+    const char* s = getenv("AB2_SRC_WARP");
+    return s && atoi(s) == 0;
+  }();
+  return !off && pl.rm.tpd % 32 == 0;
+}
+
 // virtual base of a halo buffer: row j >= n_own lives at base + j*D  (never dereferenced for j < n_own)
 template <typename T>
 static T* vbase(T* halo, const ConvArgs& a) {
@@ -705,6 +805,30 @@ static void launch_bwd_dst(const Plan& pl, const ConvArgs& a) {
 }
 template <typename T, int LPH, bool SPLIT>
 static void launch_bwd_src(const Plan& pl, const ConvArgs& a) {
+  if (src_warp_layout(pl)) {
+    // rows per warp group: about one 32-edge batch, but at least ~3 waves of CTAs on a small graph.  Measured on B200 (run r01aa),
+    // headline graph (out-degree 1.4): 8 rows 0.564 ms, 12: 0.534, 16: 0.526, 24: 0.517, 31: 0.521 (per-thread kernel: 0.658);
+    // BASELINE config-1 graphs (10-40 k src rows, fp32): 16 rows per group were too few CTAs (0.063 vs 0.037 ms).
+    static const int forced = [] {
+      const char* s = getenv("AB2_SRC_ROWS");
+      const int v = s ? atoi(s) : 0;
+      return v >= 1 && v <= 31 ? v : 0;
+    }();
+    const int nsrc = a.src_hi - a.src_lo;
+    int rpg = forced;
+    if (!rpg) {
+      const double deg = nsrc > 0 ? (double)a.E / (double)std::max(a.Ns, 1) : 1.0;
+      const int by_edges = (int)std::floor(32.0 / std::max(deg, 1.0) + 0.5);
+      const int by_waves = nsrc / std::max(1, 3 * 6 * num_sms() * pl.rm.rpb);
+      rpg = std::max(2, std::min(kSrcRowsW, std::min(by_edges, by_waves)));
+    }
+    const int groups = (a.src_hi - a.src_lo + rpg - 1) / rpg;
+    dim3 grid((groups + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
+    gtconv_bwd_src_warp_kernel<T, LPH, SPLIT><<<grid, kThreads, 0, a.st>>>(
+        (const T*)a.q, (const T*)a.g, a.colptr, reinterpret_cast<const int2*>(a.crow), a.ads, a.src_lo, a.src_hi, pl.rm, a.H, (T*)a.dk,
+        (T*)a.dv, vbase((T*)a.dk_halo, a), vbase((T*)a.dv_halo, a), a.n_own, rpg);
+    return;
+  }
   const int groups = (a.src_hi - a.src_lo + kSrcRows - 1) / kSrcRows;
   dim3 grid((groups + pl.rm.rpb - 1) / pl.rm.rpb, pl.slices);
   gtconv_bwd_src_kernel<T, LPH, SPLIT><<<grid, kThreads, 0, a.st>>>((const T*)a.q, (const T*)a.g, a.colptr, a.crow, a.ads, a.src_lo, a.src_hi, pl.rm,
@@ -874,7 +998,7 @@ extern "C" const char* ab2_gtconv_variant(int which, int dtype, int64_t Ns, int6
   else if (which == 1)
     base = tma_applicable(1, dtype, H, C) ? "gtconv_bwd_dst_tma_kernel" : "gtconv_bwd_dst_kernel";
   else
-    base = src_prefers_tma(dtype, H, C, E, Ns) ? "gtconv_bwd_src_tma_kernel" : "gtconv_bwd_src_kernel";
+    base = src_prefers_tma(dtype, H, C, E, Ns) ? "gtconv_bwd_src_tma_kernel" : src_warp_layout(pl) ? "gtconv_bwd_src_warp_kernel" : "gtconv_bwd_src_kernel";
   snprintf(buf, sizeof(buf), "%s<%s, %d>", base, t, pl.lph);
   return buf;
 }

@@ -316,7 +316,10 @@ def run_ours(args):
     kname = {n: L.ab2_gtconv_variant(which[n], dt_code, n_src, nd_loc, E, H, C).decode() for n in kt}
     roofline = {"bound": "hbm", "kernel": kname[dom], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": ab[dom], "launch_ms": round(kt[dom], 4)}
+                "algorithmic_bytes_per_launch": ab[dom], "launch_ms": round(kt[dom], 4),
+                "note": "peak = measured COPY bandwidth (half reads, half writes); a read-dominated kernel can exceed it (frac > 1): "
+                        "ncu reports the same kernel at ~84 % of the 7.7 TB/s HBM3e pin rate, and traffic ~= algorithmic bytes "
+                        "(profiles/r01/ncu_gtconv_r01ab.md); write-only traffic on this GPU tops out at ~3.9 TB/s (hbm_probe_r01ab.json)"}
     kern = {n: {"kernel": kname[n], "ms": round(kt[n], 4), "algorithmic_GB": round(ab[n] / 1e9, 3), "GBps": round(ab[n] / (kt[n] * 1e-3) / 1e9, 1),
                 "frac_of_peak": round(ab[n] / (kt[n] * 1e-3) / 1e9 / peak, 4)} for n in kt}
     t_kernels = sum(kt.values())

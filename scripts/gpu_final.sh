@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-end check in ONE gpurun call: scripts/gpu_check.sh (tests, smoke, bench, ncu) + the other workloads + one A/B of the row-block size.
+# Round-end check in ONE gpurun call: scripts/gpu_check.sh (tests, smoke, bench, ncu) + the other workloads + bandwidth probe.
 TAG=${1:-final}; OUT=gpurun_out/$TAG; mkdir -p $OUT
 bash scripts/gpu_check.sh $TAG
 run() {
@@ -15,10 +15,11 @@ PY
 }
 run bench_processor processor X=1
 run bench_decoder decoder X=1
-run encoder_rb1 encoder AB2_TMA_RB=1
-run encoder_rb3 encoder AB2_TMA_RB=3
-run encoder_srctma encoder AB2_SRC_TMA_ALWAYS=1
-for w in config1-enc config1-proc config1-dec; do
-  timeout 200 python bench.py --steps 50 --warmup 5 --workload $w --no-cpu-baseline --e2e-steps 1 > $OUT/bench_$w.json 2> $OUT/bench_$w.err
-  python -c "import json;d=json.loads(open('$OUT/bench_$w.json').read().strip().splitlines()[-1]);print('$w', d['ms_per_step'], d['roofline_step']['frac'])"
-done
+run bench_config1-enc config1-enc X=1
+run bench_config1-proc config1-proc X=1
+run bench_config1-dec config1-dec X=1
+run config1-enc_r4 config1-enc AB2_SRC_ROWS=4
+run config1-proc_r4 config1-proc AB2_SRC_ROWS=4
+run config1-dec_r4 config1-dec AB2_SRC_ROWS=4
+timeout 120 python scripts/hbm_probe.py > $OUT/hbm_probe.json 2>&1; cat $OUT/hbm_probe.json
+timeout 300 python bench.py --workload graphconv --steps 20 --warmup 5 --no-cpu-baseline > $OUT/bench_graphconv.json 2> $OUT/bench_graphconv.err; tail -c 600 $OUT/bench_graphconv.json
