@@ -203,6 +203,13 @@ def run_ours(args):
     E = ei_glob.shape[1]
     torch.manual_seed(1234 + rank)
     bf = torch.float32 if cfg1 else torch.bfloat16
+    if world > 1 and args.src_split == "aligned":
+        # src ownership follows dst ownership (caller-chosen shard shapes; see distributed/halo.py aligned_bounds_from_ranges):
+        # equal-count src shards of the uniform Fibonacci grid do not align in latitude with equal-count dst shards of the
+        # octahedral grid, which makes 9-25 % of a shard halo at 4-8 ranks
+        from anemoi_models_b200.distributed.halo import aligned_src_bounds
+
+        sb = aligned_src_bounds(ei_glob, Ns_g, group)
     nd_loc, ns_loc = db[rank + 1] - db[rank], sb[rank + 1] - sb[rank]
     q = torch.randn(nd_loc, H, C, device=dev, dtype=bf)
     g = torch.randn(nd_loc, H, C, device=dev, dtype=bf)
@@ -263,9 +270,12 @@ def run_ours(args):
                 print(f"[trace rank {r}] " + "  ".join(f"{lab}={t}" for lab, t in p_), file=sys.stderr, flush=True)
     tmax = torch.tensor([ms], device=dev, dtype=torch.float64)
     etot = torch.tensor([float(E)], device=dev, dtype=torch.float64)
+    shard_stats = torch.tensor([float(ns_loc), float(hplan.n_halo if hplan is not None else 0), float(E)], device=dev, dtype=torch.float64)
+    shard_max = shard_stats.clone()
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(etot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(shard_max, op=dist.ReduceOp.MAX)
     ms_per_step = float(tmax) / args.steps
     value = float(etot) / (ms_per_step * 1e-3)
 
@@ -365,6 +375,8 @@ def run_ours(args):
             "dtype": "f32" if cfg1 else "bf16", "data": "synthetic",
             "config": {"workload": workload_name(world, args.workload), "edges_total": int(float(etot)), "edges_rank0": int(E),
                        "src_rows_rank0": int(n_src), "halo_rows_rank0": int(hplan.n_halo) if hplan is not None else 0, "dst_rows_rank0": int(nd_loc), "hidden": D, "heads": H,
+                       "src_split": (args.src_split if world > 1 else "n/a"), "own_src_rows_max_rank": int(shard_max[0]),
+                       "halo_rows_max_rank": int(shard_max[1]), "edges_max_rank": int(shard_max[2]),
                        "l2": ("inputs (>5 GB per step) exceed the 126 MB L2; no flush between steps" if not cfg1 else
                               "config-1 working set is L2-sized: steady-state (warm L2) numbers, no flush"),
                        "timed_region": "conv forward + backward (+ halo all-to-all of k,v and its backward when n_gpus>1); CSR build excluded (one-off, cached)"},
@@ -638,6 +650,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-chunks", type=int, default=16, help="dst-row chunks of the streamed host-buffer call (1 = unstreamed)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--src-split", default="aligned", choices=["aligned", "equal"],
+                    help="multi-GPU: src row ownership aligned to the dst shards (default) or the reference's equal-count tensor_split")
     ap.add_argument("--graphconv-dim", type=int, default=512)
     ap.add_argument("--model-layers", type=int, default=16)
     ap.add_argument("--profile", action="store_true", help="model workload: add a per-kernel device-time breakdown of one step")

@@ -193,6 +193,47 @@ def _halo(rank, world):
     assert torch.allclose(ea.grad, expect[eb[rank]:eb[rank + 1]])
 
 
+def _aligned_halo(rank, world):
+    """Caller-chosen src ownership aligned to the dst shards (uneven shard shapes): smaller halo, same exchange semantics."""
+    from anemoi_models_b200.distributed.halo import aligned_src_bounds, build_local_halo_plan, halo_gather
+    from anemoi_models_b200.distributed.shapes import tensor_split_sizes
+
+    group = dist.group.WORLD
+    ns, nd, deg = 4000, 300, 12
+    gen = torch.Generator().manual_seed(3)
+    # latitude-like ordering with DIFFERENT densities: dst i sits at src position ns * (i/nd)^2 (denser towards one pole)
+    centre = (ns * (torch.arange(nd).double() / nd) ** 2).long()
+    src = (centre.view(-1, 1) + torch.randint(-40, 41, (nd, deg), generator=gen)).clamp_(0, ns - 1).view(-1)
+    dst = torch.arange(nd).repeat_interleave(deg)
+    ei = torch.stack([src, dst])
+    db = [0] + np.cumsum(tensor_split_sizes(nd, world)).tolist()
+    sb_equal = [0] + np.cumsum(tensor_split_sizes(ns, world)).tolist()
+    mine = ei[:, (dst >= db[rank]) & (dst < db[rank + 1])]
+    sb = aligned_src_bounds(mine, ns, group)
+    assert sb[0] == 0 and sb[-1] == ns and all(sb[i] <= sb[i + 1] for i in range(world))
+    plan_eq = build_local_halo_plan(mine, sb_equal, db, group)
+    plan = build_local_halo_plan(mine, sb, db, group)
+    halo = torch.tensor([plan.n_halo, plan_eq.n_halo])
+    dist.all_reduce(halo)
+    assert int(halo[0]) * 4 < int(halo[1]), f"aligned ownership should shrink the halo: {halo.tolist()}"
+    x_full = torch.randn(ns, 5, generator=torch.Generator().manual_seed(1))
+    xs = x_full[sb[rank]:sb[rank + 1]].clone().requires_grad_(True)
+    got = halo_gather(xs, plan, group)
+    glob = torch.cat([torch.arange(sb[rank], sb[rank + 1]), plan.halo_ids])
+    assert torch.equal(got, x_full[glob])
+    assert torch.equal(glob[plan.local_edge_index[0]], mine[0])
+    w = torch.randn(plan.n_src, 5, generator=torch.Generator().manual_seed(20 + rank))
+    (got * w).sum().backward()
+    dense = torch.zeros(ns, 5)
+    dense[glob] = w
+    dist.all_reduce(dense)
+    assert torch.allclose(xs.grad, dense[sb[rank]:sb[rank + 1]], atol=1e-6)
+
+
+def test_aligned_halo_world3():
+    run_distributed("_aligned_halo", 3)
+
+
 def test_halo_world2():
     run_distributed("_halo", 2)
 
@@ -236,7 +277,8 @@ def _sharded_gt_blocks(rank, world):
 
     _patch_conv_with_oracle()
     group = dist.group.WORLD
-    for fixture, kind in (("block_gt_mapper.npz", "mapper"), ("block_gt_processor.npz", "processor")):
+    for fixture, kind, uneven in (("block_gt_mapper.npz", "mapper", False), ("block_gt_mapper.npz", "mapper", True),
+                                  ("block_gt_processor.npz", "processor", False)):
         z = load_golden(fixture)
         ns, nd, D, H, ed, hid = (int(x) for x in z["meta"])
         params = {k[2:]: t(v) for k, v in z.items() if k.startswith("p.")}
@@ -248,6 +290,9 @@ def _sharded_gt_blocks(rank, world):
         blk = cls(D, hid, D, edge_dim=ed, num_heads=H)
         blk.load_state_dict(params)
         sh_src = get_shape_shards(torch.empty(ns, D), 0, group)
+        if uneven:  # caller-chosen src ownership (e.g. aligned to the dst shards): shard shapes need not be tensor_split's
+            small = max(1, ns // (3 * world))
+            sh_src = [[ns - (world - 1) * small, D]] + [[small, D] for _ in range(world - 1)]
         sh_dst = get_shape_shards(torch.empty(nd, D), 0, group)
         sh_e = get_shape_shards(ea_full, 0, group)
         sb, db, eb = bounds_from_shapes(sh_src), bounds_from_shapes(sh_dst), bounds_from_shapes(sh_e)

@@ -4,7 +4,7 @@ import torch
 from hypothesis import given, settings
 from hypothesis import strategies as st
 
-from anemoi_models_b200.distributed.halo import build_bipartite_halo_plan
+from anemoi_models_b200.distributed.halo import aligned_bounds_from_ranges, build_bipartite_halo_plan
 from anemoi_models_b200.distributed.shapes import bounds_from_shapes, tensor_split_sizes
 from oracle import sharding as osh
 
@@ -81,3 +81,26 @@ def test_peer_push_tables_route_every_row_home(ns, nd, e, parts, seed):
         got = torch.zeros(sb[r + 1] - sb[r], dtype=torch.float64)
         got.index_add_(0, p.send_idx, inbox[r][:sum(p.send_counts)])
         assert torch.equal(got, expect[sb[r]:sb[r + 1]])
+
+
+@settings(max_examples=60, deadline=None)
+@given(ns=st.integers(1, 400), parts=st.integers(1, 9), seed=st.integers(0, 10**6))
+def test_aligned_src_bounds_are_a_partition_and_cut_inside_the_shared_zone(ns, parts, seed):
+    """Bounds are monotone, cover [0, ns), and on a banded graph (rank r references one window of rows, windows in rank
+    order) every cut lies between the next rank's first row and one past the previous ranks' last row: the halo of the
+    aligned split never exceeds the overlap of neighbouring windows."""
+    rng = np.random.default_rng(seed)
+    cuts = np.sort(rng.integers(0, ns + 1, parts - 1)) if parts > 1 else np.array([], dtype=np.int64)
+    edges = np.concatenate([[0], cuts, [ns]])
+    ov = int(rng.integers(0, 6))
+    lo = [max(0, int(edges[r]) - ov) for r in range(parts)]
+    hi = [min(ns - 1, int(edges[r + 1]) - 1 + ov) for r in range(parts)]
+    for r in range(parts):  # empty windows become "no edges"
+        if edges[r] == edges[r + 1]:
+            lo[r], hi[r] = 1, 0
+    b = aligned_bounds_from_ranges(lo, hi, ns)
+    assert len(b) == parts + 1 and b[0] == 0 and b[-1] == ns and all(b[i] <= b[i + 1] for i in range(parts))
+    live = [r for r in range(parts) if lo[r] <= hi[r]]
+    for a, c in zip(live[:-1], live[1:]):  # consecutive ranks that have edges
+        for cut in b[a + 1:c + 1]:
+            assert min(lo[c], hi[a] + 1) <= cut <= max(lo[c], hi[a] + 1)
