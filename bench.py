@@ -337,31 +337,57 @@ def run_ours(args):
 
     # ---- e2e: the same step through the host-buffer C-ABI call (pinned host tensors in and out), rank-local
     e2e = None
-    if world == 1:
-        host = [x.cpu().pin_memory() for x in (q, k_own, v_own, e, g)]
+    host = outs = dev_ws = None
+    err = ""
+    try:
+        # N > 1: every rank feeds ITS shard (compact src space [own | halo]: the host supplies the halo rows' k, v and gets
+        # their dk, dv back) through its own PCIe link, all ranks at once; time = max over ranks
+        if world > 1:
+            k_h = torch.cat([k_own, torch.randn(n_src - ns_loc, H, C, device=dev, dtype=bf)])
+            v_h = torch.cat([v_own, torch.randn(n_src - ns_loc, H, C, device=dev, dtype=bf)])
+        else:
+            k_h, v_h = k_own, v_own
+        host = [x.cpu().pin_memory() for x in (q, k_h, v_h, e, g)]
+        del k_h, v_h
         need = L.ab2_gtconv_host_workspace_bytes(n_src, nd_loc, E, H, C, dt_code)
         dev_ws = torch.empty(need, dtype=torch.uint8, device=dev)
-        outs = [torch.empty(x.shape, dtype=x.dtype, pin_memory=True) for x in (q, q, k_own, v_own, e)]
-
+        outs = [torch.empty(x.shape, dtype=x.dtype, pin_memory=True) for x in (host[0], host[0], host[1], host[2], host[3])]
+    except Exception as ex:  # e.g. no pinned host memory for N shards on this box
+        if world == 1:
+            raise
+        err = f"{type(ex).__name__}: {ex}"[:300]
+    ok = torch.tensor([0.0 if err else 1.0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # all ranks take the same branch (no rank waits in a collective alone)
+    if float(ok) < 1.0:
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "error": err or "host buffers could not be allocated on another rank"}
+    else:
         def host_step():
             ops.gt_conv_host(*host, plan, dev_ws=dev_ws, outs=outs, nchunks=args.e2e_chunks)
 
         host_step()
-        torch.cuda.synchronize()
+        barrier()
         n_e2e = max(1, min(args.steps, args.e2e_steps))
         with sampler:
             t0 = time.perf_counter()
             for _ in range(n_e2e):
                 host_step()  # synchronises internally: results are in host memory when it returns
             t1 = time.perf_counter()
-        e2e_ms = (t1 - t0) * 1e3 / n_e2e
-        e2e = {"value": E / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": round(e2e_ms, 3), "steps": n_e2e,
-               "h2d_bytes_per_step": int(sum(x.numel() * x.element_size() for x in host)),
-               "d2h_bytes_per_step": int(sum(x.numel() * x.element_size() for x in outs)),
+        e2e_t = torch.tensor([(t1 - t0) * 1e3 / n_e2e], device=dev, dtype=torch.float64)
+        io = torch.tensor([float(sum(x.numel() * x.element_size() for x in host)),
+                           float(sum(x.numel() * x.element_size() for x in outs))], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(io, op=dist.ReduceOp.SUM)
+        e2e_ms = float(e2e_t)
+        e2e = {"value": float(etot) / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": round(e2e_ms, 3), "steps": n_e2e,
+               "h2d_bytes_per_step": int(io[0]), "d2h_bytes_per_step": int(io[1]),
                "api": ("ab2_gtconv_fwd_bwd_host_streamed" if plan.perm_is_identity and args.e2e_chunks > 1 else "ab2_gtconv_fwd_bwd_host")
-                      + " (pinned host q,k,v,e,g in; out,dq,dk,dv,de back to pinned host; copies inside the call)",
+                      + " (pinned host q,k,v,e,g in; out,dq,dk,dv,de back to pinned host; copies inside the call"
+                      + ("; one call per rank on its shard, all ranks concurrently, max over ranks)" if world > 1 else ")"),
                "chunks": args.e2e_chunks}
-        del host, outs, dev_ws
+    del host, outs, dev_ws
 
     # ---- CPU baseline: the reference's op sequence (oracle port) on this box's host cores, bounded sample
     cpu_baseline = None
