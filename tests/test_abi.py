@@ -57,3 +57,28 @@ def test_argument_errors_are_reported_without_a_gpu():
         _lib.check(rc)
     rc = L.ab2_csr_build(0, 2**31, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)  # E too large for int32 indices
     assert rc == _lib.AB2_ERR_UNSUPPORTED
+
+
+def test_kernel_dispatch_rules_for_the_model_shapes():
+    """`ab2_gtconv_variant` answers from the same rules `run_conv` dispatches with (no GPU needed): the shapes of the AIFS-like
+    model (2 KB rows) go to the bulk-copy pipelined kernels, except the src pass at a low out-degree, which goes to the
+    warp-cooperative LDG kernel; other row widths stay on the LDG kernels; odd head widths on the generic ones."""
+    from anemoi_models_b200 import _lib
+
+    L = _lib.lib()
+
+    def names(dtype, ns, nd, e, h, c):
+        return [L.ab2_gtconv_variant(w, dtype, ns, nd, e, h, c).decode().split("<")[0] for w in range(3)]
+
+    bf16, f32 = 1, 0
+    assert names(bf16, 542080, 40320, 748256, 16, 64) == ["gtconv_fwd_tma_kernel", "gtconv_bwd_dst_tma_kernel", "gtconv_bwd_src_warp_kernel"]
+    assert names(bf16, 40320, 40320, 322560, 16, 64) == ["gtconv_fwd_tma_kernel", "gtconv_bwd_dst_tma_kernel", "gtconv_bwd_src_tma_kernel"]
+    assert names(bf16, 40320, 542080, 1626240, 16, 64) == ["gtconv_fwd_tma_kernel", "gtconv_bwd_dst_tma_kernel", "gtconv_bwd_src_tma_kernel"]
+    assert names(f32, 40320, 40320, 322560, 16, 32) == ["gtconv_fwd_tma_kernel", "gtconv_bwd_dst_tma_kernel", "gtconv_bwd_src_tma_kernel"]  # 2 KB fp32 rows
+    # BASELINE configs[0]: D = 256 fp32 (1 KB rows) -> LDG kernels; low in-degree -> 4-row forward
+    assert names(f32, 40320, 10944, 51608, 16, 16) == ["gtconv_fwd_rows_kernel", "gtconv_bwd_dst_kernel", "gtconv_bwd_src_warp_kernel"]
+    assert names(f32, 10944, 10944, 87552, 16, 16) == ["gtconv_fwd_kernel", "gtconv_bwd_dst_kernel", "gtconv_bwd_src_warp_kernel"]
+    # a row layout where a warp straddles two row groups (tpd = 24) keeps the per-thread src pass
+    assert names(f32, 100, 100, 500, 3, 32)[2] == "gtconv_bwd_src_kernel"
+    # head width that is not a power-of-two multiple of 16 bytes -> generic kernels
+    assert names(f32, 100, 100, 500, 4, 5) == ["gtconv_fwd_generic_kernel", "gtconv_bwd_dst_generic_kernel", "gtconv_bwd_src_generic_kernel"]
