@@ -38,6 +38,26 @@ def edge_chunk_order(num_dst: int, edge_index: Tensor, num_chunks: int, bounds: 
     return order[: sum(cnt)], cnt
 
 
+def get_k_hop_edges(nodes: Tensor, edge_attr: Tensor, edge_index: Tensor, num_hops: int = 1) -> Tuple[Tensor, Tensor]:
+    """reference khop_edges.py:24-47: (edge_attr, edge_index) of the edges that reach `nodes` within `num_hops` hops
+    (flow source -> target, directed), in original edge order.  One hop = the edges whose dst is in `nodes`; every further hop
+    adds the edges whose dst is a src reached so far (PyG `k_hop_subgraph(directed=True)`: the union of the per-hop masks)."""
+    if num_hops < 1:
+        raise ValueError("num_hops must be >= 1")
+    src, dst = edge_index[0], edge_index[1]
+    n = int(max(int(edge_index.max()) + 1 if edge_index.numel() else 0, int(nodes.max()) + 1 if nodes.numel() else 0))
+    frontier = nodes.to(edge_index.device).view(-1)
+    keep = torch.zeros(edge_index.shape[1], dtype=torch.bool, device=edge_index.device)
+    for _ in range(num_hops):
+        node_mask = torch.zeros(n, dtype=torch.bool, device=edge_index.device)
+        node_mask[frontier] = True
+        hop = node_mask[dst]
+        keep |= hop
+        frontier = src[hop]
+    ids = keep.nonzero().view(-1)
+    return edge_attr[ids], edge_index[:, ids]
+
+
 def sort_edges_1hop_chunks(num_nodes: Union[int, Tuple[int, int]], edge_attr: Tensor, edge_index: Tensor,
                            num_chunks: int) -> Tuple[List[Tensor], List[Tensor]]:
     """reference khop_edges.py:88-130: (list of edge_attr chunks, list of edge_index chunks)."""

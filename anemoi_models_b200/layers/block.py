@@ -24,6 +24,7 @@ from ..distributed.collectives import shard_tensor, sync_tensor
 from ..distributed.halo import (HaloPlan, build_bipartite_halo_plan, build_local_halo_plan, halo_exchange, halo_gather,
                                 select_sharded_edges)
 from ..distributed.shapes import bounds_from_shapes
+from ..distributed.transformer import shard_heads, shard_sequence
 from ..graph import TensorKeyedCache, check_edge_index, get_csr, resolve_size
 from .conv import GraphConv, GraphTransformerConv
 from .mlp import MLP, activation_class
@@ -162,18 +163,28 @@ class GraphTransformerBaseBlock(BaseBlock, ABC):
             self.node_src_mlp = nn.Sequential(nn.LayerNorm(out_channels), nn.Linear(out_channels, hidden_dim), act_func(),
                                               nn.Linear(hidden_dim, out_channels))
 
-    # -- kept for API compatibility (reference block.py:366-414).  On one rank they are pure reshapes; with a group
-    #    the reference's head all-to-all is not used by this implementation (forward() shards by dst rows instead).
+    # -- API compatibility (reference block.py:366-414).  forward() does not use the head all-to-all with a group (it shards
+    #    by dst rows and exchanges a halo, see _attend); on one rank these are pure reshapes.
     def shard_qkve_heads(self, query, key, value, edges, shapes, batch_size, model_comm_group=None):
-        if _group_active(model_comm_group):
-            raise NotImplementedError("head sharding is replaced by dst-row sharding with a halo exchange; call forward()")
+        """[(batch grid), heads*vars] rows of a sequence shard -> [(batch grid_total), heads_of_this_rank, vars]."""
         H, C = self.num_heads, self.out_channels_conv
-        return tuple(t.reshape(t.shape[0], H, C) for t in (query, key, value, edges))
+        if not _group_active(model_comm_group):
+            return tuple(t.reshape(t.shape[0], H, C) for t in (query, key, value, edges))
+        shape_src, shape_dst, shape_edges = shapes
+        out = []
+        for t, shp in ((query, shape_dst), (key, shape_src), (value, shape_src), (edges, shape_edges)):
+            t = t.reshape(batch_size, -1, H, C).transpose(1, 2)  # batch heads grid vars
+            t = shard_heads(t, shp, model_comm_group)
+            out.append(t.transpose(1, 2).reshape(-1, t.shape[1], C))
+        return tuple(out)
 
     def shard_output_seq(self, out, shapes, batch_size, model_comm_group=None):
-        if _group_active(model_comm_group):
-            raise NotImplementedError("sequence re-sharding is not needed: the conv output is already dst-row sharded")
-        return out.reshape(out.shape[0], -1)
+        """[(batch grid_total), heads_of_this_rank, vars] -> [(batch grid_shard), heads*vars]."""
+        if not _group_active(model_comm_group):
+            return out.reshape(out.shape[0], -1)
+        t = out.reshape(batch_size, -1, out.shape[-2], out.shape[-1]).transpose(1, 2)  # batch heads grid vars
+        t = shard_sequence(t, shapes[1], model_comm_group)
+        return t.transpose(1, 2).reshape(-1, t.shape[1] * t.shape[-1])
 
     def _attend(self, query: Tensor, key: Tensor, value: Tensor, edge_attr: Tensor, edge_index: Tensor, shapes: tuple,
                 batch_size: int, model_comm_group, size) -> Tensor:

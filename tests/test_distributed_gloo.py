@@ -234,6 +234,59 @@ def test_aligned_halo_world3():
     run_distributed("_aligned_halo", 3)
 
 
+def _head_sequence_resharding(rank, world):
+    """shard_heads / shard_sequence (reference distributed/transformer.py:85-133) and the blocks' shard_qkve_heads /
+    shard_output_seq (block.py:366-414): values against slices of the full tensor, round trip, and the backward duals."""
+    import anemoi_models_b200 as b2
+    from anemoi_models_b200.distributed.shapes import bounds_from_shapes, get_shape_shards, tensor_split_sizes
+    from anemoi_models_b200.distributed.transformer import shard_heads, shard_sequence
+
+    group = dist.group.WORLD
+    gen = torch.Generator().manual_seed(7)
+    B, H, N, C = 2, 5, 23, 4  # 5 heads over 2 or 3 ranks: uneven head counts; 23 rows: uneven sequence shards
+    full = torch.randn(B, H, N, C, generator=gen)
+    shapes = get_shape_shards(torch.empty(N, 1), 0, group)
+    nb = bounds_from_shapes(shapes)
+    hb = [0] + np.cumsum(tensor_split_sizes(H, world)).tolist()
+    mine = full[:, :, nb[rank]:nb[rank + 1]].clone().requires_grad_(True)
+    got = shard_heads(mine, shapes, group)
+    assert torch.equal(got, full[:, hb[rank]:hb[rank + 1]])
+    back = shard_sequence(got, shapes, group)
+    assert torch.equal(back, mine)
+    w = torch.randn(B, H, N, C, generator=gen)
+    (got * w[:, hb[rank]:hb[rank + 1]]).sum().backward()  # d/d mine = w restricted to my rows (every head)
+    assert torch.equal(mine.grad, w[:, :, nb[rank]:nb[rank + 1]])
+    x2 = full[:, hb[rank]:hb[rank + 1]].clone().requires_grad_(True)
+    y2 = shard_sequence(x2, shapes, group)
+    assert torch.equal(y2, full[:, :, nb[rank]:nb[rank + 1]])
+    (y2 * w[:, :, nb[rank]:nb[rank + 1]]).sum().backward()
+    assert torch.equal(x2.grad, w[:, hb[rank]:hb[rank + 1]])
+    assert shard_heads(mine, shapes, None) is mine or torch.equal(shard_heads(mine, shapes, None), mine)  # no group: identity
+
+    # block-level helpers, batch_size = 1 (the reference asserts that with a group, block.py:501-504)
+    Hh, Cc, ns, nd, E = 6, 8, 17, 11, 29
+    blk = b2.GraphTransformerProcessorBlock(Hh * Cc, 16, Hh * Cc, edge_dim=3, num_heads=Hh)
+    fq, fk, fe = (torch.randn(n, Hh * Cc, generator=gen) for n in (nd, ns, E))
+    sh = tuple(get_shape_shards(torch.empty(n, 1), 0, group) for n in (ns, nd, E))
+    b_s, b_d, b_e = (bounds_from_shapes(x) for x in sh)
+    q, k, v, e = blk.shard_qkve_heads(fq[b_d[rank]:b_d[rank + 1]], fk[b_s[rank]:b_s[rank + 1]], fk[b_s[rank]:b_s[rank + 1]] * 2,
+                                      fe[b_e[rank]:b_e[rank + 1]], sh, 1, group)
+    hb = [0] + np.cumsum(tensor_split_sizes(Hh, world)).tolist()
+    sl = slice(hb[rank], hb[rank + 1])
+    assert torch.equal(q, fq.view(nd, Hh, Cc)[:, sl]) and torch.equal(k, fk.view(ns, Hh, Cc)[:, sl])
+    assert torch.equal(v, 2 * fk.view(ns, Hh, Cc)[:, sl]) and torch.equal(e, fe.view(E, Hh, Cc)[:, sl])
+    out = blk.shard_output_seq(q, sh, 1, group)  # my heads of all dst rows -> all heads of my dst rows
+    assert torch.equal(out, fq[b_d[rank]:b_d[rank + 1]])
+
+
+def test_head_sequence_resharding_world2():
+    run_distributed("_head_sequence_resharding", 2)
+
+
+def test_head_sequence_resharding_world3():
+    run_distributed("_head_sequence_resharding", 3)
+
+
 def test_halo_world2():
     run_distributed("_halo", 2)
 

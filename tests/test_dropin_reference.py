@@ -90,3 +90,37 @@ def test_reference_modules_pick_up_the_b200_path(reference_on_path):
     from anemoi.models.layers.conv import GraphTransformerConv as RefConv
 
     assert ref_block.GraphTransformerConv is RefConv and not isinstance(ref_mapper.GraphTransformerForwardMapper(**kw).proc, b2.GraphTransformerMapperBlock)
+
+
+def test_index_helpers_equal_the_reference_functions(reference_on_path):
+    """get_k_hop_edges, get_shape_shards / change_channels_in_shape, and the single-rank reshapes of shard_qkve_heads /
+    shard_output_seq against the reference's own functions (imported from /root/reference, PyG through the oracle's shim)."""
+    import anemoi_models_b200 as b2
+    from anemoi.models.distributed import khop_edges as ref_khop
+    from anemoi.models.distributed import shapes as ref_shapes
+    from anemoi.models.layers import block as ref_block
+    from anemoi_models_b200 import distributed as b2dist
+
+    gen = torch.Generator().manual_seed(11)
+    ei = torch.randint(0, 25, (2, 90), generator=gen)
+    ea = torch.randn(90, 4, generator=gen)
+    nodes = torch.tensor([0, 7, 8, 21])
+    for hops in (1, 2):
+        ref_ea, ref_ei = ref_khop.get_k_hop_edges(nodes, ea, ei, num_hops=hops)
+        got_ea, got_ei = b2dist.get_k_hop_edges(nodes, ea, ei, num_hops=hops)
+        assert torch.equal(ref_ea, got_ea) and torch.equal(ref_ei, got_ei)
+    x = torch.empty(23, 6)
+    assert ref_shapes.get_shape_shards(x, 0, None) == b2dist.get_shape_shards(x, 0, None)
+    sl = [[5, 6], [4, 6]]
+    assert ref_shapes.change_channels_in_shape(sl, 9) == b2dist.change_channels_in_shape(sl, 9)
+
+    torch.manual_seed(0)
+    kw = dict(in_channels=24, hidden_dim=16, out_channels=24, edge_dim=3, num_heads=4)
+    ref_blk, new_blk = ref_block.GraphTransformerProcessorBlock(**kw), b2.GraphTransformerProcessorBlock(**kw)
+    q, k, v, e = (torch.randn(n, 24, generator=gen) for n in (10, 14, 14, 30))  # batch_size 2: 5 / 7 / 15 rows per sample
+    shapes = ([[14, 24]], [[10, 24]], [[30, 24]])
+    ref_out = ref_blk.shard_qkve_heads(q, k, v, e, shapes, 2, None)
+    new_out = new_blk.shard_qkve_heads(q, k, v, e, shapes, 2, None)
+    for a, b in zip(ref_out, new_out):
+        assert torch.equal(a, b)
+    assert torch.equal(ref_blk.shard_output_seq(ref_out[0], shapes, 2, None), new_blk.shard_output_seq(new_out[0], shapes, 2, None))

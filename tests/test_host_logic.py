@@ -147,3 +147,22 @@ def test_install_rebinds_and_restores_reference_symbols():
             blockmod.GraphTransformerConv = old
         for name in made:
             sys.modules.pop(name, None)
+
+
+@pytest.mark.parametrize("hops", [1, 2, 3])
+def test_get_k_hop_edges_matches_pyg_semantics(hops):
+    """reference khop_edges.py:24-47 over PyG's k_hop_subgraph(directed=True) (restated in oracle/pyg_shim): same edges, same order."""
+    from torch_geometric.utils import k_hop_subgraph, mask_to_index  # the oracle's shim (tests/conftest.py puts it on the path)
+
+    from anemoi_models_b200.distributed import get_k_hop_edges
+
+    gen = torch.Generator().manual_seed(hops)
+    n, E = 40, 150
+    ei = torch.randint(0, n, (2, E), generator=gen)
+    ea = torch.randn(E, 3, generator=gen)
+    nodes = torch.tensor([3, 4, 5, 17])
+    _, ei_ref, _, mask = k_hop_subgraph(node_idx=nodes, num_hops=hops, edge_index=ei, directed=True)
+    got_ea, got_ei = get_k_hop_edges(nodes, ea, ei, num_hops=hops)
+    assert torch.equal(got_ei, ei_ref) and torch.equal(got_ea, ea[mask_to_index(mask)])
+    with pytest.raises(ValueError):
+        get_k_hop_edges(nodes, ea, ei, num_hops=0)
