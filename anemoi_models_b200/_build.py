@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libanemoi_b200.so")
-SOURCES = ["abi.cu", "csr_build.cu", "gtconv.cu", "gtconv_tma.cu", "graphconv.cu", "host_api.cu", "peer_exchange.cu"]
+SOURCES = ["abi.cu", "csr_build.cu", "gtconv.cu", "gtconv_tma.cu", "gtconv_fold.cu", "graphconv.cu", "host_api.cu", "peer_exchange.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",

@@ -25,6 +25,9 @@ SIGNATURES = {
     "ab2_edge_chunks_workspace_bytes": (_sz, [_i64]),
     "ab2_edge_chunks": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "ab2_gtconv_fwd": (_i32, [_vp] * 4 + [_i32] + [_vp] * 3 + [_i64] * 3 + [_i32, _i32, _vp, _vp, _vp]),
+    "ab2_gtconv_fold_fwd": (_i32, [_vp] * 5 + [_i32] + [_vp] * 3 + [_i64] * 3 + [_i32, _i32] + [_vp] * 4),
+    "ab2_gtconv_fold_bwd_dst": (_i32, [_vp] * 6 + [_i32] + [_vp] * 4 + [_i64] * 3 + [_i32, _i32] + [_vp] * 7),
+    "ab2_edge_raw_grad": (_i32, [_vp] * 6 + [_i64, _i64, _i32, _vp, _vp]),
     "ab2_gtconv_variant": (C.c_char_p, [_i32, _i32, _i64, _i64, _i64, _i32, _i32]),
     "ab2_gtconv_fwd_halo": (_i32, [_vp] * 5 + [_i64] + [_vp] + [_i32] + [_vp] * 3 + [_i64] * 3 + [_i32, _i32, _vp, _vp, _vp]),
     "ab2_gtconv_bwd_dst_halo": (_i32, [_vp] * 5 + [_i64] + [_vp] + [_i32] + [_vp] * 4 + [_i64] * 3 + [_i32, _i32] + [_vp] * 5 + [_vp, _sz, _vp]),

@@ -34,6 +34,7 @@ LOGGER = logging.getLogger(__name__)
 # Number of mapper chunks used during inference -- read at import like the reference (block.py:39).  The fused conv
 # has no E x D temporaries, so chunking changes neither memory nor results; the variable stays accepted.
 NUM_CHUNKS_INFERENCE = int(os.environ.get("ANEMOI_INFERENCE_NUM_CHUNKS", "1"))
+_EDGE_FOLD = os.environ.get("AB2_EDGE_FOLD", "0") == "1"  # round-2 draft path, see ops.gt_conv_folded
 
 _halo_cache = TensorKeyedCache()
 
@@ -191,6 +192,15 @@ class GraphTransformerBaseBlock(BaseBlock, ABC):
         """conv output rows [(own dst rows), H*C] for projected q [Nd_r,D], k/v [Ns_r,D] and RAW edge_attr."""
         H, C = self.num_heads, self.out_channels_conv
         if not _group_active(model_comm_group):
+            if _EDGE_FOLD and query.is_cuda and edge_attr.shape[1] < 16:
+                # round-2 draft (AB2_EDGE_FOLD=1, off by default): lin_edge folded into the conv, no [E, H*C] edge tensor
+                from .. import ops
+
+                check_edge_index(edge_index)
+                ns, nd = resolve_size(size, key.shape[0], query.shape[0])
+                out = ops.gt_conv_folded(query.view(-1, H, C), key.view(-1, H, C), value.view(-1, H, C), edge_attr,
+                                         self.lin_edge.weight, self.lin_edge.bias, get_csr(edge_index, ns, nd))
+                return out.reshape(out.shape[0], H * C)
             edges = _linear_padded_k(self.lin_edge, edge_attr)
             q, k, v, e = self.shard_qkve_heads(query, key, value, edges, shapes, batch_size, model_comm_group)
             out = self.conv(query=q, key=k, value=v, edge_attr=e, edge_index=edge_index, size=size)

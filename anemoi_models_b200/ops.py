@@ -129,6 +129,111 @@ def gt_conv(query: Tensor, key: Tensor, value: Tensor, edge_attr: Tensor, plan: 
     return _GTConvFn.apply(q, k, v, e, k_halo, v_halo, plan)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# ROUND-2 DRAFT (AB2_EDGE_FOLD=1; kernels not yet run on a GPU): conv with the block's lin_edge folded in -- see
+# csrc/gtconv_fold.cu.  The three kernel calls are module-level functions so that the CPU tests can check this host glue
+# (padding, the [Nd]-sized einsums with W, gradient assembly) against the reference with a torch emulation of the kernels.
+# ---------------------------------------------------------------------------------------------------------------------
+FOLD_COLS = 16  # raw edge features + one constant-1 column that carries the bias, zero padded
+
+
+def _fold_fwd_kernel(q, k, v, rawp, qw, plan):
+    L = _lib.lib()
+    Nd, H, C = q.shape
+    out = torch.empty_like(q)
+    lse2 = torch.empty((Nd, H), dtype=torch.float32, device=q.device)
+    R = torch.empty((Nd, H, FOLD_COLS), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(L.ab2_gtconv_fold_fwd(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(rawp), _lib.ptr(qw), _lib.dtype_code(q.dtype),
+                                         _lib.ptr(plan.rowptr), _lib.ptr(plan.col), _lib.ptr(plan.perm), k.shape[0], Nd, plan.num_edges,
+                                         H, C, _lib.ptr(out), _lib.ptr(lse2), _lib.ptr(R), _lib.current_stream(q.device)))
+    return out, lse2, R
+
+
+def _fold_bwd_kernels(q, k, v, rawp, qw, gw, out, lse2, g, plan):
+    """-> dq_part [Nd,H,C], S [Nd,H,16] (already / sqrt(C)), dk, dv [Ns,H,C], draw [E,16]"""
+    L = _lib.lib()
+    Nd, H, C = q.shape
+    Ns, E = k.shape[0], plan.num_edges
+    dq = torch.empty_like(q)
+    S = torch.empty((Nd, H, FOLD_COLS), dtype=torch.float32, device=q.device)
+    dk, dv = torch.empty_like(k), torch.empty_like(v)
+    draw = torch.empty((E, FOLD_COLS), dtype=torch.float32, device=q.device)
+    ads = torch.empty((max(E, 1), H, 2), dtype=torch.float32, device=q.device)
+    st = _lib.current_stream(q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(L.ab2_gtconv_fold_bwd_dst(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(rawp), _lib.ptr(qw), _lib.ptr(gw),
+                                             _lib.dtype_code(q.dtype), _lib.ptr(plan.rowptr), _lib.ptr(plan.col), _lib.ptr(plan.perm),
+                                             _lib.ptr(plan.csr2csc), Ns, Nd, E, H, C, _lib.ptr(out), _lib.ptr(lse2), _lib.ptr(g),
+                                             _lib.ptr(dq), _lib.ptr(S), _lib.ptr(ads), st))
+        _lib.check(L.ab2_gtconv_bwd_src(_lib.ptr(q), _lib.ptr(g), _lib.dtype_code(q.dtype), _lib.ptr(plan.colptr), _lib.ptr(plan.crow),
+                                        Ns, Nd, E, H, C, _lib.ptr(ads), _lib.ptr(dk), _lib.ptr(dv), st))
+        _lib.check(L.ab2_edge_raw_grad(_lib.ptr(ads), _lib.ptr(qw), _lib.ptr(gw), _lib.ptr(plan.rowptr), _lib.ptr(plan.perm),
+                                       _lib.ptr(plan.csr2csc), Nd, E, H, _lib.ptr(draw), st))
+    return dq, S, dk, dv, draw
+
+
+def _fold_pad(raw: Tensor, weight: Tensor, bias: Optional[Tensor], H: int, C: int) -> Tuple[Tensor, Tensor]:
+    """raw [E,ed] -> [E,16] fp32 with a constant-1 column at index ed; W [H*C,ed], b [H*C] -> [H,C,16] fp32 with b in column ed."""
+    E, ed = raw.shape
+    if ed + 1 > FOLD_COLS:
+        raise ValueError(f"folded lin_edge supports at most {FOLD_COLS - 1} raw edge features, got {ed}")
+    rawp = raw.new_zeros((E, FOLD_COLS), dtype=torch.float32)
+    rawp[:, :ed] = raw
+    rawp[:, ed] = 1.0
+    Wp = weight.new_zeros((H * C, FOLD_COLS), dtype=torch.float32)
+    Wp[:, :ed] = weight
+    if bias is not None:
+        Wp[:, ed] = bias
+    return rawp, Wp.view(H, C, FOLD_COLS)
+
+
+class _GTConvFoldedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q: Tensor, k: Tensor, v: Tensor, raw: Tensor, weight: Tensor, bias: Optional[Tensor], plan: GraphCSR) -> Tensor:
+        Nd, H, C = q.shape
+        rawp, Wp = _fold_pad(raw, weight, bias, H, C)
+        qw = torch.einsum("ihc,hcm->ihm", q.float(), Wp).contiguous()
+        out_part, lse2, R = _fold_fwd_kernel(q, k, v, rawp, qw, plan)
+        out = (out_part.float() + torch.einsum("ihm,hcm->ihc", R, Wp)).to(q.dtype)
+        ctx.save_for_backward(q, k, v, rawp, Wp, qw, out, lse2, R)
+        ctx.plan, ctx.ed, ctx.has_bias = plan, raw.shape[1], bias is not None
+        ctx.in_dtypes = (raw.dtype, weight.dtype, bias.dtype if bias is not None else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        q, k, v, rawp, Wp, qw, out, lse2, R = ctx.saved_tensors
+        Nd, H, C = q.shape
+        ed = ctx.ed
+        g = g.contiguous().to(q.dtype)
+        gw = torch.einsum("ihc,hcm->ihm", g.float(), Wp).contiguous()
+        dq_part, S, dk, dv, draw = _fold_bwd_kernels(q, k, v, rawp, qw, gw, out, lse2, g, ctx.plan)
+        dq = (dq_part.float() + torch.einsum("ihm,hcm->ihc", S, Wp)).to(q.dtype)
+        dWp = torch.einsum("ihc,ihm->hcm", g.float(), R) + torch.einsum("ihc,ihm->hcm", q.float(), S)  # S carries 1/sqrt(C)
+        dWp = dWp.reshape(H * C, FOLD_COLS)
+        rd, wd, bd = ctx.in_dtypes
+        dW = dWp[:, :ed].to(wd)
+        db = dWp[:, ed].to(bd) if ctx.has_bias else None
+        return dq, dk, dv, draw[:, :ed].to(rd), dW, db, None
+
+
+def gt_conv_folded(query: Tensor, key: Tensor, value: Tensor, raw_edge_attr: Tensor, weight: Tensor, bias: Optional[Tensor],
+                   plan: GraphCSR) -> Tensor:
+    """`conv(q, k, v, lin_edge(raw_edge_attr))` (reference block.py:497 + conv.py:98-142) without the [E,H,C] edge tensor;
+    q [Nd,H,C], k/v [Ns,H,C], raw_edge_attr [E,ed] (ed <= 15, original edge order), weight [H*C, ed], bias [H*C] or None."""
+    _require_cuda(query, key, value, raw_edge_attr, weight, bias)
+    if raw_edge_attr.dim() != 2 or raw_edge_attr.shape[0] != plan.num_edges:
+        raise ValueError(f"raw_edge_attr must be [E={plan.num_edges}, ed], got {tuple(raw_edge_attr.shape)}")
+    if weight.shape != (query.shape[1] * query.shape[2], raw_edge_attr.shape[1]):
+        raise ValueError(f"weight must be [{query.shape[1] * query.shape[2]}, {raw_edge_attr.shape[1]}], got {tuple(weight.shape)}")
+    if query.shape[0] != plan.num_dst or key.shape[0] != plan.num_src or key.shape != value.shape:
+        raise ValueError("node counts do not match the graph plan")
+    dt = _common_dtype(query, key, value)
+    q, k, v = (t.to(dt).contiguous() for t in (query, key, value))
+    return _GTConvFoldedFn.apply(q, k, v, raw_edge_attr, weight, bias, plan)
+
+
 def _fwd_rows(q, k, v, kh, vh, e, plan, out, lse2, d0, d1, edges):
     """forward on dst rows [d0, d1) (own src rows k / v, halo rows kh / vh)."""
     if d1 <= d0:

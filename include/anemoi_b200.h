@@ -195,6 +195,26 @@ int ab2_edge_ln_res_segsum_bwd(const void* g_edges /* may be NULL */, const void
                                int nparts, float* dgamma, float* dbeta, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * ROUND-2 DRAFT (off by default, AB2_EDGE_FOLD=1; not yet run on a GPU): GraphTransformerConv with the block's
+ * `lin_edge` folded in.  Replaces reference layers/block.py:497 (`edges = self.lin_edge(edge_attr)`) + conv.py:98-142:
+ * the conv takes the RAW edge features raw [E,16] (fp32; ed <= 15 columns + a constant-1 column that carries the bias,
+ * zero padded) and per-dst projections qw = W_h^T q_i, gw = W_h^T g_i ([Nd,H,16] fp32, computed by the caller with one
+ * small GEMM) instead of e [E,H,C]; it returns out_part = sum_t a_t v_j and R = sum_t a_t raw_t ([Nd,H,16]); the caller adds
+ * W_h R.  Backward dst pass: dq_part = sum_t ds_t k_j / sqrt(C), S = sum_t ds_t raw_t / sqrt(C), and the (a, ds/sqrt(C)) workspace
+ * `ads` [E,H] float2 (src-sorted order) that ab2_gtconv_bwd_src and ab2_edge_raw_grad consume.
+ * ------------------------------------------------------------------------------------------------- */
+int ab2_gtconv_fold_fwd(const void* q, const void* k, const void* v, const float* raw, const float* qw, int dtype,
+                        const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t Ns, int64_t Nd, int64_t E,
+                        int H, int C, void* out, float* lse2, float* R, void* stream);
+int ab2_gtconv_fold_bwd_dst(const void* q, const void* k, const void* v, const float* raw, const float* qw, const float* gw,
+                            int dtype, const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* csr2csc,
+                            int64_t Ns, int64_t Nd, int64_t E, int H, int C, const void* out, const float* lse2, const void* g,
+                            void* dq, float* S, void* ads, void* stream);
+/* d raw_t[m] = sum_h a_t,h gw_i[h][m] + ads_t,h.y qw_i[h][m]  ->  draw [E,16] fp32 in ORIGINAL edge order (lin_edge's input gradient) */
+int ab2_edge_raw_grad(const void* ads, const float* qw, const float* gw, const int32_t* rowptr, const int32_t* perm,
+                      const int32_t* csr2csc, int64_t Nd, int64_t E, int H, float* draw, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Host-buffer entry point (what a reference-side plugin with CPU tensors calls): one GraphTransformerConv
  * forward+backward with q,k,v,e,g in PINNED HOST memory and out,dq,dk,dv,de written back to host memory.
  * Device staging buffers are supplied by the caller (dev_ws, >= ab2_gtconv_host_workspace_bytes()).

@@ -222,3 +222,72 @@ def graph_conv_unfused(x, edge_attr: Tensor, edge_index: Tensor, p: dict, prefix
     idx = dst.view(-1, 1).expand_as(edges_new)
     out = edges_new.new_zeros((nd, edges_new.shape[1])).scatter_add_(0, idx, edges_new)
     return out, edges_new
+
+
+# --------------------------------------------------------------------------------------------------
+# GraphTransformerConv with `lin_edge` folded in (round-2 kernel design) -- numpy float64
+# --------------------------------------------------------------------------------------------------
+def gt_conv_edge_folded_f64(q, k, v, raw, W, b, edge_index, g=None, num_dst: Optional[int] = None):
+    """The same conv when `edge_attr` is the block's `lin_edge(raw)` (block.py:497: e_t = W raw_t + b, W [H*C, ed]),
+    WITHOUT ever forming an [E, H, C] tensor.  With W_h [C, ed], b_h [C] the rows of head h:
+
+      q_i.e_t      = (W_h^T q_i).raw_t + q_i.b_h            -> per-dst vector  qW_i = W_h^T q_i  (ed values), scalar qb_i
+      sum_t a_t e_t = W_h (sum_t a_t raw_t) + b_h sum_t a_t  -> per-dst accumulator R_i = sum_t a_t raw_t (ed values), A_i = sum_t a_t
+      g_i.e_t      = (W_h^T g_i).raw_t + g_i.b_h            -> gW_i, gb_i
+      dq_i         = (sum_t ds_t k_j + W_h S_i + b_h sum_t ds_t)/sqrt(C),   S_i = sum_t ds_t raw_t
+      de_t = a_t g_i + ds_t q_i/sqrt(C) is never formed; what lin_edge's backward needs from it is
+      dW_h   = sum_i g_i (x) R_i + q_i (x) S_i / sqrt(C)
+      db_h   = sum_i g_i A_i + q_i (sum_t ds_t)/sqrt(C)
+      draw_t = sum_h a_t gW_i + ds_t qW_i / sqrt(C)
+    Per edge the kernels then touch k_j, v_j and the ed raw values only.  Returns the same keys as `gt_conv_csr_f64`
+    plus dW, db, draw (and no `de`)."""
+    f = lambda t: np.asarray(t.detach().cpu().to(torch.float64).numpy() if isinstance(t, Tensor) else t, dtype=np.float64)
+    q, k, v, raw, W, b = f(q), f(k), f(v), f(raw), f(W), f(b)
+    ei = np.asarray(edge_index.cpu().numpy() if isinstance(edge_index, Tensor) else edge_index).astype(np.int64)
+    nd = q.shape[0] if num_dst is None else num_dst
+    H, C = q.shape[1], q.shape[2]
+    ed = raw.shape[1]
+    Wh, bh = W.reshape(H, C, ed), b.reshape(H, C)
+    src, dst = ei[0], ei[1]
+    scale = 1.0 / math.sqrt(C)
+    qW = np.einsum("ihc,hcm->ihm", q, Wh)  # [Nd,H,ed]
+    qb = np.einsum("ihc,hc->ih", q, bh)
+    s = ((q[dst] * k[src]).sum(-1) + (qW[dst] * raw[:, None, :]).sum(-1) + qb[dst]) * scale  # [E,H]
+    m = np.full((nd, H), -np.inf)
+    np.maximum.at(m, dst, s)
+    m_safe = np.where(np.isfinite(m), m, 0.0)
+    p = np.exp(s - m_safe[dst])
+    l = np.zeros((nd, H))
+    np.add.at(l, dst, p)
+    a = p / (l[dst] + 1e-16)
+    out = np.zeros((nd, H, C))
+    np.add.at(out, dst, a[..., None] * v[src])
+    R = np.zeros((nd, H, ed))
+    np.add.at(R, dst, a[..., None] * raw[:, None, :])
+    A = np.zeros((nd, H))
+    np.add.at(A, dst, a)
+    out = out + np.einsum("ihm,hcm->ihc", R, Wh) + A[..., None] * bh[None]
+    res = {"out": out, "lse": m_safe + np.log(l + 1e-16), "alpha": a}
+    if g is not None:
+        g = f(g)
+        gW = np.einsum("ihc,hcm->ihm", g, Wh)
+        gb = np.einsum("ihc,hc->ih", g, bh)
+        Dl = (g * out).sum(-1)
+        gv = (g[dst] * v[src]).sum(-1) + (gW[dst] * raw[:, None, :]).sum(-1) + gb[dst]
+        ds = a * (gv - Dl[dst])
+        S = np.zeros((nd, H, ed))
+        np.add.at(S, dst, ds[..., None] * raw[:, None, :])
+        Z = np.zeros((nd, H))
+        np.add.at(Z, dst, ds)
+        dq = np.zeros_like(q)
+        np.add.at(dq, dst, ds[..., None] * k[src])
+        dq = (dq + np.einsum("ihm,hcm->ihc", S, Wh) + Z[..., None] * bh[None]) * scale
+        dk = np.zeros_like(k)
+        np.add.at(dk, src, ds[..., None] * q[dst] * scale)
+        dv = np.zeros_like(v)
+        np.add.at(dv, src, a[..., None] * g[dst])
+        dW = (np.einsum("ihc,ihm->hcm", g, R) + np.einsum("ihc,ihm->hcm", q, S) * scale).reshape(H * C, ed)
+        db = (np.einsum("ihc,ih->hc", g, A) + np.einsum("ihc,ih->hc", q, Z) * scale).reshape(H * C)
+        draw = (a[..., None] * gW[dst]).sum(1) + (ds[..., None] * qW[dst]).sum(1) * scale
+        res.update(dq=dq, dk=dk, dv=dv, dW=dW, db=db, draw=draw, ds=ds, R=R, S=S)
+    return res

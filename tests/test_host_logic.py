@@ -166,3 +166,60 @@ def test_get_k_hop_edges_matches_pyg_semantics(hops):
     assert torch.equal(got_ei, ei_ref) and torch.equal(got_ea, ea[mask_to_index(mask)])
     with pytest.raises(ValueError):
         get_k_hop_edges(nodes, ea, ei, num_hops=0)
+
+
+def test_folded_lin_edge_host_glue_against_reference(monkeypatch):
+    """Round-2 draft (ops.gt_conv_folded): the host side -- padding with the bias column, the [Nd]-sized einsums with W, the
+    assembly of dq / dW / db / d raw -- checked on the CPU with a torch emulation standing in for the three CUDA kernel calls,
+    against the reference op sequence conv(q, k, v, lin_edge(raw)) with autograd."""
+    import math
+    from types import SimpleNamespace
+
+    from anemoi_models_b200 import ops
+    from oracle import gtconv as og
+
+    gen = torch.Generator().manual_seed(9)
+    ns, nd, E, H, C, ed = 31, 17, 140, 4, 8, 11
+    ei = torch.stack([torch.randint(0, ns, (E,), generator=gen), torch.randint(0, nd - 1, (E,), generator=gen)])
+    src, dst = ei[0], ei[1]
+    state = {}
+
+    def seg_sum(x, index, n):
+        return x.new_zeros((n,) + tuple(x.shape[1:])).index_add_(0, index, x)
+
+    def emul_fwd(q, k, v, rawp, qw, plan):
+        s = ((q[dst] * k[src]).sum(-1) + (qw[dst] * rawp[:, None, :]).sum(-1)) / math.sqrt(C)
+        a = og.segment_softmax(s, dst, nd)
+        state["a"] = a
+        return seg_sum(a[..., None] * v[src], dst, nd), torch.zeros(nd, H), seg_sum(a[..., None] * rawp[:, None, :], dst, nd)
+
+    def emul_bwd(q, k, v, rawp, qw, gw, out, lse2, g, plan):
+        a = state["a"]
+        Dl = (g * out).sum(-1)
+        gv = (g[dst] * v[src]).sum(-1) + (gw[dst] * rawp[:, None, :]).sum(-1)
+        dss = a * (gv - Dl[dst]) / math.sqrt(C)
+        draw = (a[..., None] * gw[dst]).sum(1) + (dss[..., None] * qw[dst]).sum(1)
+        return (seg_sum(dss[..., None] * k[src], dst, nd), seg_sum(dss[..., None] * rawp[:, None, :], dst, nd),
+                seg_sum(dss[..., None] * q[dst], src, ns), seg_sum(a[..., None] * g[dst], src, ns), draw)
+
+    monkeypatch.setattr(ops, "_fold_fwd_kernel", emul_fwd)
+    monkeypatch.setattr(ops, "_fold_bwd_kernels", emul_bwd)
+    for with_bias in (True, False):
+        q, k, v = (torch.randn(n, H, C, generator=gen) for n in (nd, ns, ns))
+        raw = torch.rand(E, ed, generator=gen)
+        lin = torch.nn.Linear(ed, H * C, bias=with_bias)
+        g = torch.randn(nd, H, C, generator=gen)
+        ref_in = [t.clone().requires_grad_(True) for t in (q, k, v, raw)]
+        ref = og.gt_conv_unfused(ref_in[0], ref_in[1], ref_in[2], lin(ref_in[3]).view(E, H, C), ei, (ns, nd))
+        ref.backward(g)
+        ref_grads = [t.grad for t in ref_in] + [lin.weight.grad.clone()] + ([lin.bias.grad.clone()] if with_bias else [])
+        lin.zero_grad()
+        got_in = [t.clone().requires_grad_(True) for t in (q, k, v, raw)]
+        out = ops._GTConvFoldedFn.apply(*got_in, lin.weight, lin.bias, SimpleNamespace(num_edges=E, num_src=ns, num_dst=nd))
+        out.backward(g)
+        got_grads = [t.grad for t in got_in] + [lin.weight.grad] + ([lin.bias.grad] if with_bias else [])
+        assert torch.allclose(out, ref, atol=2e-5)
+        for a_, b_ in zip(got_grads, ref_grads):
+            assert a_.shape == b_.shape and float((a_ - b_).abs().max()) <= 2e-5 * max(1.0, float(b_.abs().max()))
+    with pytest.raises(ValueError):
+        ops._fold_pad(torch.zeros(3, 16), torch.zeros(8, 16), None, 2, 4)

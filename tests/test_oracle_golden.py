@@ -122,3 +122,28 @@ def test_halo_plan_covers_every_needed_row():
         for r, p in enumerate(plans):
             assert np.array_equal(np.unique(ei[0, p["edge_ids"]]), p["needed_src"])
             assert sum(len(v) for v in p["recv_from"].values()) == len(p["needed_src"])
+
+
+def test_edge_folded_formulation_equals_the_reference_op_sequence():
+    """oracle.gt_conv_edge_folded_f64 (lin_edge folded into the conv, no [E,H,C] tensor) against the reference's op sequence
+    `conv(q, k, v, lin_edge(raw))` with autograd, float64: outputs and every gradient incl. lin_edge's weight, bias and input."""
+    import numpy as np
+    import torch
+
+    from oracle import gtconv as og
+
+    gen = torch.Generator().manual_seed(5)
+    ns, nd, E, H, C, ed = 37, 19, 160, 4, 8, 11
+    ei = torch.stack([torch.randint(0, ns, (E,), generator=gen), torch.randint(0, nd - 2, (E,), generator=gen)])  # 2 isolated dst rows
+    q, k, v = (torch.randn(n, H, C, generator=gen, dtype=torch.float64) for n in (nd, ns, ns))
+    raw = torch.rand(E, ed, generator=gen, dtype=torch.float64).requires_grad_(True)
+    lin = torch.nn.Linear(ed, H * C).double()
+    g = torch.randn(nd, H, C, generator=gen, dtype=torch.float64)
+    q_, k_, v_ = (t.clone().requires_grad_(True) for t in (q, k, v))
+    out = og.gt_conv_unfused(q_, k_, v_, lin(raw).view(E, H, C), ei, (ns, nd))
+    out.backward(g)
+    got = og.gt_conv_edge_folded_f64(q, k, v, raw, lin.weight, lin.bias, ei, g=g)
+    ref = {"out": out, "dq": q_.grad, "dk": k_.grad, "dv": v_.grad, "dW": lin.weight.grad, "db": lin.bias.grad, "draw": raw.grad}
+    for key, want in ref.items():
+        want = want.detach().numpy()
+        assert np.abs(got[key] - want).max() <= 1e-12 * max(1.0, np.abs(want).max()), key
