@@ -1,9 +1,12 @@
-// GraphTransformerConv with the block's `lin_edge` folded in (sm_100a) -- ROUND-2 DRAFT, not on the default path.
+// GraphTransformerConv with the block's `lin_edge` folded in (sm_100a) -- ROUND-2 WORK IN PROGRESS, not on the default path.
 //
-// STATUS: compiles for sm_100a; the algebra is pinned on the CPU (oracle/gtconv.py::gt_conv_edge_folded_f64 against the
-// reference op sequence, tests/test_oracle_golden.py) and the host glue against a torch emulation of these kernels
-// (tests/test_host_logic.py); the kernels themselves have NOT run on a GPU yet (the round's GPU budget was spent).  Nothing
-// calls them unless AB2_EDGE_FOLD=1 is set (ops.gt_conv_folded); tests/test_gpu_zz_fold_draft.py runs them in a subprocess.
+// STATUS: first GPU run (profiles/r01/fold_draft_r01ah.log, the last seconds of round 1's GPU budget): parity against the product path
+// conv(q, k, v, lin_edge(raw)) on four head layouts -- fp32 6e-7 .. 8e-7, bf16 5e-3 .. 6e-3 of max|ref|, outputs and all six
+// gradients -- and, at the headline sizes (random graph), 6.56 ms per forward+backward against 13.93 ms for lin_edge + conv.
+// The algebra is pinned on the CPU (oracle/gtconv.py::gt_conv_edge_folded_f64 against the reference op sequence,
+// tests/test_oracle_golden.py) and the host glue against a torch emulation of these kernels (tests/test_host_logic.py).
+// Not yet: the bulk-copy pipelined variants, halo rows, the block-level parity tests with the switch on -- so nothing calls
+// these kernels unless AB2_EDGE_FOLD=1 is set (ops.gt_conv_folded); tests/test_gpu_zz_fold_draft.py runs them in a subprocess.
 //
 // Why: at the headline shape e = lin_edge(raw) is read twice and de written once -- 3*E*D*b = 4.6 GB of the step's 11.8 GB --
 // and exists only because lin_edge (reference block.py:497, K = 11) is a separate GEMM.  e_t = W raw_t + b is LINEAR in the

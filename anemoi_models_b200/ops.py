@@ -130,7 +130,7 @@ def gt_conv(query: Tensor, key: Tensor, value: Tensor, edge_attr: Tensor, plan: 
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# ROUND-2 DRAFT (AB2_EDGE_FOLD=1; kernels not yet run on a GPU): conv with the block's lin_edge folded in -- see
+# ROUND-2 WORK IN PROGRESS (AB2_EDGE_FOLD=1; one green GPU run, profiles/r01/fold_draft_r01ah.log): conv with lin_edge folded in -- see
 # csrc/gtconv_fold.cu.  The three kernel calls are module-level functions so that the CPU tests can check this host glue
 # (padding, the [Nd]-sized einsums with W, gradient assembly) against the reference with a torch emulation of the kernels.
 # ---------------------------------------------------------------------------------------------------------------------

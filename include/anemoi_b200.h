@@ -195,7 +195,7 @@ int ab2_edge_ln_res_segsum_bwd(const void* g_edges /* may be NULL */, const void
                                int nparts, float* dgamma, float* dbeta, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
- * ROUND-2 DRAFT (off by default, AB2_EDGE_FOLD=1; not yet run on a GPU): GraphTransformerConv with the block's
+ * ROUND-2 WORK IN PROGRESS (off by default, AB2_EDGE_FOLD=1; one green GPU run so far): GraphTransformerConv with the block's
  * `lin_edge` folded in.  Replaces reference layers/block.py:497 (`edges = self.lin_edge(edge_attr)`) + conv.py:98-142:
  * the conv takes the RAW edge features raw [E,16] (fp32; ed <= 15 columns + a constant-1 column that carries the bias,
  * zero padded) and per-dst projections qw = W_h^T q_i, gw = W_h^T g_i ([Nd,H,16] fp32, computed by the caller with one

@@ -1,9 +1,9 @@
-"""ROUND-2 DRAFT kernels (csrc/gtconv_fold.cu: GraphTransformerConv with lin_edge folded in) -- first contact with a GPU.
+"""ROUND-2 work in progress (csrc/gtconv_fold.cu: GraphTransformerConv with lin_edge folded in) -- first contact with a GPU.
 
-These kernels were written after the round's GPU budget was spent, so they have never run.  They are not on the default path
-(nothing calls them unless AB2_EDGE_FOLD=1).  This test runs them in a CHILD process with a timeout, so that whatever they do
-(wrong numbers, a CUDA fault, a hang) cannot touch the CUDA context of the parity suite, and reports a failure as `xfail`:
-the suite's colour is about the product path.  A pass means: folded conv == conv(q, k, v, lin_edge(raw)) of the product path,
+These kernels were written when the round's GPU budget was nearly spent: they have run exactly once (profiles/r01/fold_draft_r01ah.log,
+all four cases green).  They are not on the default path (nothing calls them unless AB2_EDGE_FOLD=1).  This test runs them in a
+CHILD process with a timeout, so that whatever they do cannot touch the CUDA context of the parity suite, and reports a failure as
+`xfail`: the suite's colour is about the product path.  A pass means: folded conv == conv(q, k, v, lin_edge(raw)) of the product path,
 outputs and every gradient (fp32 <= 1e-5, bf16 <= 2e-2 of max|ref|), on four head layouts."""
 import os
 import subprocess
