@@ -60,6 +60,11 @@ def _linear_padded_k(lin: nn.Linear, x: Tensor, multiple: int = 8) -> Tensor:
     return F.linear(F.pad(x, (0, pad)), F.pad(lin.weight, (0, pad)), lin.bias)
 
 
+def _fold_applies(query: Tensor, edge_attr: Tensor) -> bool:
+    """round-2 switch AB2_EDGE_FOLD=1: lin_edge folded into the conv (ops.gt_conv_folded) when the raw features fit its 16 columns"""
+    return _EDGE_FOLD and query.is_cuda and edge_attr.dim() == 2 and edge_attr.shape[1] < 16
+
+
 def _group_active(group) -> bool:
     return group is not None and bool(group) and dist.get_world_size(group=group) > 1
 
@@ -192,7 +197,7 @@ class GraphTransformerBaseBlock(BaseBlock, ABC):
         """conv output rows [(own dst rows), H*C] for projected q [Nd_r,D], k/v [Ns_r,D] and RAW edge_attr."""
         H, C = self.num_heads, self.out_channels_conv
         if not _group_active(model_comm_group):
-            if _EDGE_FOLD and query.is_cuda and edge_attr.shape[1] < 16:
+            if _fold_applies(query, edge_attr):
                 # round-2 draft (AB2_EDGE_FOLD=1, off by default): lin_edge folded into the conv, no [E, H*C] edge tensor
                 from .. import ops
 

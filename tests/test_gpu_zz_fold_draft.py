@@ -80,6 +80,35 @@ for name, fn in (("lin_edge + conv (product path)", unfused), ("folded draft", f
         fn()
     t1.record(); torch.cuda.synchronize()
     print("%%-34s %%.3f ms per fwd+bwd" %% (name, t0.elapsed_time(t1) / 10), flush=True)
+
+# block level: the reference blocks' golden vectors through the AB2_EDGE_FOLD branch (fp32, <= 1e-5 of max|ref|)
+sys.path.insert(0, %(root)r + "/tests")
+from conftest import load_golden, rel_err, t
+from anemoi_models_b200.layers import block as b2block
+assert b2block._EDGE_FOLD, "AB2_EDGE_FOLD=1 must be set before the import"
+for fixture, kind in (("block_gt_mapper.npz", "mapper"), ("block_gt_processor.npz", "processor")):
+    z = load_golden(fixture)
+    ns, nd, D, H, ed, hid = (int(x) for x in z["meta"])
+    cls = b2.GraphTransformerMapperBlock if kind == "mapper" else b2.GraphTransformerProcessorBlock
+    blk = cls(D, hid, D, edge_dim=ed, num_heads=H).to(dev)
+    blk.load_state_dict({k_[2:]: t(v_) for k_, v_ in z.items() if k_.startswith("p.")})
+    ei, ea = t(z["edge_index"]).to(dev), t(z["ea"]).to(dev).requires_grad_(True)
+    launches0 = ops._lib.lib().ab2_launch_count()
+    if kind == "mapper":
+        xs, xd = t(z["xs"]).to(dev).requires_grad_(True), t(z["xd"]).to(dev).requires_grad_(True)
+        (_, out), _ = blk((xs, xd), ea, ei, ([[ns, D]], [[nd, D]], [[ea.shape[0], ed]]), 1, size=(ns, nd))
+        ref_out, grads = t(z["dst_new"]), [(xs, "dxs"), (xd, "dxd"), (ea, "dea")]
+    else:
+        xd = t(z["x"]).to(dev).requires_grad_(True)
+        out, _ = blk(xd, ea, ei, ([[nd, D]], [[nd, D]], [[ea.shape[0], ed]]), 1)
+        ref_out, grads = t(z["nodes_new"]), [(xd, "dx"), (ea, "dea")]
+    (out * t(z["gd"]).to(dev)).sum().backward()
+    assert rel_err(out, ref_out) < 1e-5, ("out", kind, rel_err(out, ref_out))
+    for x_, key in grads:
+        assert rel_err(x_.grad, t(z[key])) < 1e-5, (key, kind, rel_err(x_.grad, t(z[key])))
+    for name, p_ in blk.named_parameters():
+        assert rel_err(p_.grad, t(z["gp." + name])) < 2e-5, (name, kind)
+    print("ok block", kind, "through the folded branch; library launches:", ops._lib.lib().ab2_launch_count() - launches0, flush=True)
 print("FOLD_DRAFT_OK")
 """
 

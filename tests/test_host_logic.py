@@ -223,3 +223,48 @@ def test_folded_lin_edge_host_glue_against_reference(monkeypatch):
             assert a_.shape == b_.shape and float((a_ - b_).abs().max()) <= 2e-5 * max(1.0, float(b_.abs().max()))
     with pytest.raises(ValueError):
         ops._fold_pad(torch.zeros(3, 16), torch.zeros(8, 16), None, 2, 4)
+
+
+@pytest.mark.parametrize("fixture,kind", [("block_gt_mapper.npz", "mapper"), ("block_gt_processor.npz", "processor")])
+def test_block_folded_branch_plumbing_against_golden(monkeypatch, fixture, kind):
+    """The blocks' AB2_EDGE_FOLD branch (round-2 switch) on the CPU: `ops.gt_conv_folded` is replaced by the reference op sequence
+    on lin_edge(raw), so what is checked is the branch itself -- argument order, reshapes, size resolution, that lin_edge's
+    parameters and the raw edge features still get their gradients -- against the golden vectors of the reference block."""
+    import torch.nn.functional as F
+
+    from anemoi_models_b200 import ops
+    from anemoi_models_b200.layers import block as b2block
+    from oracle import gtconv as og
+
+    class FakePlan:
+        def __init__(self, edge_index, ns, nd):
+            self.edge_index, self.num_src, self.num_dst, self.num_edges = edge_index, ns, nd, edge_index.shape[1]
+
+    def folded_cpu(q, k, v, raw, weight, bias, plan):
+        E, (H, C) = raw.shape[0], q.shape[1:]
+        return og.gt_conv_unfused(q, k, v, F.linear(raw, weight, bias).view(E, H, C), plan.edge_index, (plan.num_src, plan.num_dst))
+
+    monkeypatch.setattr(b2block, "_fold_applies", lambda query, edge_attr: True)
+    monkeypatch.setattr(b2block, "get_csr", lambda ei, ns, nd: FakePlan(ei, ns, nd))
+    monkeypatch.setattr(ops, "gt_conv_folded", folded_cpu)
+    z = load_golden(fixture)
+    ns, nd, D, H, ed, hid = (int(x) for x in z["meta"])
+    cls = b2.GraphTransformerMapperBlock if kind == "mapper" else b2.GraphTransformerProcessorBlock
+    blk = cls(D, hid, D, edge_dim=ed, num_heads=H)
+    blk.load_state_dict({k[2:]: t(v) for k, v in z.items() if k.startswith("p.")})
+    ei, ea = t(z["edge_index"]), t(z["ea"]).requires_grad_(True)
+    if kind == "mapper":
+        xs, xd = t(z["xs"]).requires_grad_(True), t(z["xd"]).requires_grad_(True)
+        (_, out), _ = blk((xs, xd), ea, ei, ([[ns, D]], [[nd, D]], [[ea.shape[0], ed]]), 1, size=(ns, nd))
+        ref_out, grads = t(z["dst_new"]), [(xs, "dxs"), (xd, "dxd"), (ea, "dea")]
+    else:
+        xd = t(z["x"]).requires_grad_(True)
+        out, _ = blk(xd, ea, ei, ([[nd, D]], [[nd, D]], [[ea.shape[0], ed]]), 1)
+        ref_out, grads = t(z["nodes_new"]), [(xd, "dx"), (ea, "dea")]
+    (out * t(z["gd"])).sum().backward()
+    assert torch.allclose(out, ref_out, atol=2e-6)
+    for x, key in grads:
+        assert torch.allclose(x.grad, t(z[key]), atol=5e-6), key
+    for name, p in blk.named_parameters():
+        ref = t(z["gp." + name])
+        assert p.grad is not None and torch.allclose(p.grad, ref, atol=2e-5 * max(1.0, float(ref.abs().max()))), name
