@@ -3,13 +3,14 @@
 // Why: in the LDG kernels every in-flight 16 B costs four registers of the thread that will consume it, and a CTA walks a
 // dependent rowptr -> index -> row -> store chain, so at low in-degree (decoder: 3 edges per dst) they are latency-bound.
 // Here a CTA is warp-specialised:
-//   * one PRODUCER warp streams the CTA's contiguous range of CSR edges: it reads the indices (coalesced, 32 edges per load,
-//     double-buffered) and issues one `cp.async.bulk` per gathered 2 KB row (k[src], e[perm], v[src], plus q[dst] at the start
-//     of a dst row) into a shared-memory ring; completion is counted in bytes on an mbarrier (`complete_tx`);
+//   * one PRODUCER warp streams the CSR edges of the CTA's blocks of dst rows (blocks are dealt round-robin, see producer_loop):
+//     it reads the indices (coalesced, 32 edges per load, double-buffered) and issues one `cp.async.bulk` per gathered 2 KB
+//     row (k[src], e[perm], v[src], plus q[dst] at the start of a dst row) into a shared-memory ring; completion is counted in
+//     bytes on an mbarrier (`complete_tx`);
 //   * four CONSUMER warps wait on the stage's mbarrier, read their 16 B of every row with LDS.128 and run the same
 //     online-softmax / weighted-sum math as the LDG kernel (logits via lane-group shuffles, fp32 accumulation).
 // In-flight data lives in shared memory (up to ~210 KB per SM) instead of registers, index latency is off the consumers'
-// critical path, and one instruction moves a whole row.  dst rows are split statically into contiguous ranges per CTA.
+// critical path, and one instruction moves a whole row.
 #include <cmath>
 #include <cstdlib>
 
