@@ -523,6 +523,59 @@ def run_graphconv(args):
     print(json.dumps(line), flush=True)
 
 
+def run_edgepath(args):
+    """Report line (not the headline; round-2 work in progress): the edge path AS THE BLOCK RUNS IT on the headline graph --
+    `lin_edge(raw [E,11])` + conv forward+backward through the product path, against the same with lin_edge folded into the conv
+    (ops.gt_conv_folded).  Gradients flow to q, k, v, the raw edge features and lin_edge's parameters in both."""
+    from anemoi_models_b200 import ops
+    from anemoi_models_b200 import synthetic as S
+    from anemoi_models_b200.graph import GraphCSR
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    H, C, ed = 16, 64, 11
+    ei_np, ns, nd, _ = S.encoder_graph(SRC_POINTS, DST_N)
+    ei = torch.from_numpy(ei_np).to(dev)
+    E = ei.shape[1]
+    plan = GraphCSR(ei, ns, nd)
+    torch.manual_seed(0)
+    q, k, v = (torch.randn(n, H, C, device=dev, dtype=torch.bfloat16).requires_grad_(True) for n in (nd, ns, ns))
+    raw = torch.rand(E, ed, device=dev).requires_grad_(True)
+    lin = torch.nn.Linear(ed, H * C).to(dev)
+    g = torch.randn(nd, H, C, device=dev, dtype=torch.bfloat16)
+
+    def product():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            e = lin(raw)
+        ops.gt_conv(q, k, v, e.view(E, H, C), plan).backward(g)
+
+    def folded():
+        ops.gt_conv_folded(q, k, v, raw, lin.weight, lin.bias, plan).backward(g)
+
+    sampler = ClockSampler(0)
+    res = {}
+    with sampler:
+        for name, fn in (("lin_edge_plus_conv", product), ("folded", folded)):
+            for _ in range(max(args.warmup, 3)):
+                fn()
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(args.steps):
+                fn()
+            ev1.record()
+            torch.cuda.synchronize()
+            res[name] = ev0.elapsed_time(ev1) / args.steps
+    ms = res["folded"]
+    line = {"metric": "gt_block_edge_path_fwd_bwd_edges_per_s", "value": E / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "edge path of the GT mapper block on the headline graph: lin_edge(raw[E,11]) folded into the conv "
+                                   "(report line, round-2 work in progress)", "edges_total": int(E)},
+            "clocks": sampler.summary(), "ms_product_path_lin_edge_plus_conv": res["lin_edge_plus_conv"], "ms_folded": res["folded"]}
+    print(json.dumps(line), flush=True)
+
+
 def run_model(args):
     """Report line (not the headline): AIFS-like n320/o96 encoder-processor-decoder training step (BASELINE configs[3]) built
     from this repo's drop-in blocks the way the reference's mappers/processor wire them (mapper.py:245-272,
@@ -681,7 +734,7 @@ def main():
     ap.add_argument("--graphconv-dim", type=int, default=512)
     ap.add_argument("--model-layers", type=int, default=16)
     ap.add_argument("--profile", action="store_true", help="model workload: add a per-kernel device-time breakdown of one step")
-    ap.add_argument("--workload", default="encoder", choices=["encoder", "decoder", "processor", "graphconv", "model", "config1-enc", "config1-proc", "config1-dec"],
+    ap.add_argument("--workload", default="encoder", choices=["encoder", "decoder", "processor", "graphconv", "model", "edgepath", "config1-enc", "config1-proc", "config1-dec"],
                     help="encoder = BASELINE configs[1] (the headline); the others are extra report lines")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -690,6 +743,8 @@ def main():
         run_graphconv(args)
     elif args.workload == "model":
         run_model(args)
+    elif args.workload == "edgepath":
+        run_edgepath(args)
     else:
         run_ours(args)
 
