@@ -124,3 +124,102 @@ def test_index_helpers_equal_the_reference_functions(reference_on_path):
     for a, b in zip(ref_out, new_out):
         assert torch.equal(a, b)
     assert torch.equal(ref_blk.shard_output_seq(ref_out[0], shapes, 2, None), new_blk.shard_output_seq(new_out[0], shapes, 2, None))
+
+
+def _cpu_conv_patches(monkeypatch):
+    """CPU stand-ins for the CUDA conv entry points (the oracle's restatements), so that the PLUGIN path -- the reference's own
+    mapper / processor code driving this repo's blocks -- can be run end to end without a GPU."""
+    import anemoi_models_b200.layers.conv as convmod
+    from anemoi_models_b200 import ops
+    from oracle import gtconv as og
+
+    class CpuPlan:
+        def __init__(self, edge_index, ns, nd):
+            self.edge_index, self.num_src, self.num_dst, self.num_edges = edge_index, ns, nd, edge_index.shape[1]
+
+    def cpu_conv(q, k, v, e, plan, halo=None):
+        return og.gt_conv_unfused(q, k, v, e, plan.edge_index, (plan.num_src, plan.num_dst))
+
+    def graphconv_forward(self, x, edge_attr, edge_index, size=None, plan=None):
+        p = dict(self.named_parameters())
+        return og.graph_conv_unfused(x, edge_attr, edge_index, {"edge_mlp." + k[len("edge_mlp."):]: v for k, v in p.items()},
+                                     "edge_mlp.", size=size)
+
+    monkeypatch.setattr(convmod, "get_csr", lambda ei, ns, nd: CpuPlan(ei, ns, nd))
+    monkeypatch.setattr(ops, "gt_conv", cpu_conv)
+    monkeypatch.setattr(convmod.GraphConv, "forward", graphconv_forward)
+
+
+@pytest.mark.parametrize("kind", ["gt_forward_mapper", "gt_backward_mapper", "gt_processor", "gnn_processor", "gnn_forward_mapper",
+                                  "gnn_backward_mapper"])
+def test_reference_mappers_and_processors_give_the_same_numbers_through_the_plugin(reference_on_path, monkeypatch, kind):
+    """The reference's mapper / processor classes, unchanged, once with the reference's blocks and once (after install()) with
+    this repo's blocks, same weights, batch size 2: outputs, input gradients and every parameter gradient must agree.  (The conv
+    arithmetic itself is the oracle's on the CPU here; on the GPU it is pinned by tests/test_gpu_*.py.)"""
+    import anemoi_models_b200 as b2
+    from anemoi.models.layers import mapper as ref_mapper
+    from anemoi.models.layers import processor as ref_processor
+
+    ns, nd, B, hid = 30, 20, 2, 32
+    torch.manual_seed(3)
+    bip, sq = _fake_graph(ns, nd, 70), _fake_graph(nd, nd, 60)
+    rev = _fake_graph(nd, ns, 80)
+    common = dict(trainable_size=6, sub_graph_edge_attributes=["edge_attr1"])
+    if kind == "gt_forward_mapper":
+        make = lambda: ref_mapper.GraphTransformerForwardMapper(in_channels_src=5, in_channels_dst=4, hidden_dim=hid, num_heads=4, sub_graph=bip,
+                                                                src_grid_size=ns, dst_grid_size=nd, **common)
+        x = (torch.randn(B * ns, 5), torch.randn(B * nd, 4))
+    elif kind == "gt_backward_mapper":
+        make = lambda: ref_mapper.GraphTransformerBackwardMapper(in_channels_src=hid, in_channels_dst=7, hidden_dim=hid, out_channels_dst=3, num_heads=4,
+                                                                 sub_graph=rev, src_grid_size=nd, dst_grid_size=ns, **common)
+        x = (torch.randn(B * nd, hid), torch.randn(B * ns, 7))
+    elif kind == "gnn_forward_mapper":
+        make = lambda: ref_mapper.GNNForwardMapper(in_channels_src=5, in_channels_dst=4, hidden_dim=hid, sub_graph=bip, src_grid_size=ns,
+                                                   dst_grid_size=nd, **common)
+        x = (torch.randn(B * ns, 5), torch.randn(B * nd, 4))
+    elif kind == "gnn_backward_mapper":
+        make = lambda: ref_mapper.GNNBackwardMapper(in_channels_src=hid, in_channels_dst=hid, hidden_dim=hid, out_channels_dst=3, sub_graph=rev,
+                                                    src_grid_size=nd, dst_grid_size=ns, **common)
+        x = (torch.randn(B * nd, hid), torch.randn(B * ns, hid))  # the GNN backward mapper does not embed its dst input
+    elif kind == "gt_processor":
+        make = lambda: ref_processor.GraphTransformerProcessor(num_layers=2, num_channels=hid, num_chunks=1, num_heads=4, sub_graph=sq,
+                                                               src_grid_size=nd, dst_grid_size=nd, **common)
+        x = torch.randn(B * nd, hid)
+    else:
+        make = lambda: ref_processor.GNNProcessor(num_layers=2, num_channels=hid, num_chunks=1, sub_graph=sq, src_grid_size=nd,
+                                                  dst_grid_size=nd, **common)
+        x = torch.randn(B * nd, hid)
+    pair = isinstance(x, tuple)
+    shapes = ([list(x[0].shape)], [list(x[1].shape)]) if pair else ([list(x.shape)],)
+    if not pair:
+        shapes = (shapes[0], shapes[0])
+
+    def run(mod):
+        xin = tuple(t.clone().requires_grad_(True) for t in x) if pair else x.clone().requires_grad_(True)
+        out = mod(xin, batch_size=B, shard_shapes=shapes)
+        outs = [o for o in (out if isinstance(out, tuple) else (out,)) if o.requires_grad]
+        gen = torch.Generator().manual_seed(4)
+        sum((o * torch.randn(o.shape, generator=gen)).sum() for o in outs).backward()
+        grads_in = [t.grad for t in (xin if pair else (xin,))]
+        return [o.detach() for o in outs], grads_in, {n: p.grad for n, p in mod.named_parameters()}
+
+    ref_mod = make()
+    ref_out, ref_gin, ref_gp = run(ref_mod)
+    b2.install(edge_partition=False)  # the partition helper is a CUDA kernel; on one rank it only regroups the edges
+    _cpu_conv_patches(monkeypatch)
+    new_mod = make()
+    assert any(type(m).__module__.startswith("anemoi_models_b200") for m in new_mod.modules())
+    new_mod.load_state_dict(ref_mod.state_dict())
+    new_out, new_gin, new_gp = run(new_mod)
+    assert len(new_out) == len(ref_out)
+    for a, b in zip(new_out, ref_out):
+        assert torch.allclose(a, b, atol=2e-5), float((a - b).abs().max())
+    for a, b in zip(new_gin, ref_gin):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert torch.allclose(a, b, atol=2e-5 * max(1.0, float(b.abs().max())))
+    for n, g in ref_gp.items():
+        if g is None:
+            assert new_gp[n] is None or float(new_gp[n].abs().max()) == 0.0, n
+        else:
+            assert new_gp[n] is not None and torch.allclose(new_gp[n], g, atol=5e-5 * max(1.0, float(g.abs().max()))), n
