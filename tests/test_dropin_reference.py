@@ -223,3 +223,87 @@ def test_reference_mappers_and_processors_give_the_same_numbers_through_the_plug
             assert new_gp[n] is None or float(new_gp[n].abs().max()) == 0.0, n
         else:
             assert new_gp[n] is not None and torch.allclose(new_gp[n], g, atol=5e-5 * max(1.0, float(g.abs().max()))), n
+
+
+class _Idx:
+    def __init__(self, n, prognostic, full=None, diagnostic=(), names=None):
+        self._n, self.prognostic, self.full, self.diagnostic = n, list(prognostic), list(full if full is not None else range(n)), list(diagnostic)
+        self.name_to_index = names or {f"v{i}": i for i in range(n)}
+
+    def __len__(self):
+        return self._n
+
+
+def _tiny_model_inputs(kind):
+    from types import SimpleNamespace
+
+    from anemoi.utils.config import DotDict
+    from torch_geometric.data import HeteroData
+
+    gen = torch.Generator().manual_seed(21)
+    n_data, n_hid = 40, 16
+    g = HeteroData()
+    g["data"].x = torch.rand(n_data, 2, generator=gen) * 3 - 1.5
+    g["hidden"].x = torch.rand(n_hid, 2, generator=gen) * 3 - 1.5
+    for (a, na), (b, nb), e in ((("data", n_data), ("hidden", n_hid), 90), (("hidden", n_hid), ("hidden", n_hid), 64), (("hidden", n_hid), ("data", n_data), 120)):
+        st = g[(a, "to", b)]
+        st.edge_index = torch.stack([torch.randint(0, na, (e,), generator=gen), torch.randint(0, nb, (e,), generator=gen)])
+        st.edge_length = torch.rand(e, 1, generator=gen)
+        st.edge_dirs = torch.rand(e, 2, generator=gen)
+    attrs = ["edge_length", "edge_dirs"]
+    p = "anemoi.models.layers."
+    if kind == "graphtransformer":
+        enc = {"_target_": p + "mapper.GraphTransformerForwardMapper", "trainable_size": 3, "sub_graph_edge_attributes": attrs, "num_chunks": 1,
+               "num_heads": 4, "mlp_hidden_ratio": 2, "activation": "GELU"}
+        proc = {"_target_": p + "processor.GraphTransformerProcessor", "trainable_size": 3, "sub_graph_edge_attributes": attrs, "num_layers": 2,
+                "num_chunks": 2, "num_heads": 4, "mlp_hidden_ratio": 2, "activation": "GELU"}
+        dec = dict(enc, _target_=p + "mapper.GraphTransformerBackwardMapper")
+    else:
+        enc = {"_target_": p + "mapper.GNNForwardMapper", "trainable_size": 3, "sub_graph_edge_attributes": attrs, "num_chunks": 1,
+               "mlp_extra_layers": 0, "activation": "SiLU"}
+        proc = {"_target_": p + "processor.GNNProcessor", "trainable_size": 3, "sub_graph_edge_attributes": attrs, "num_layers": 2,
+                "num_chunks": 1, "mlp_extra_layers": 0, "activation": "SiLU"}
+        dec = dict(enc, _target_=p + "mapper.GNNBackwardMapper")
+    cfg = DotDict({"graph": {"data": "data", "hidden": "hidden"}, "training": {"multistep_input": 2},
+                   "model": {"num_channels": 32, "trainable_parameters": {"data": 2, "hidden": 2}, "encoder": enc, "processor": proc,
+                             "decoder": dec, "bounding": []}})
+    nvar = 4
+    idx = SimpleNamespace(internal_model=SimpleNamespace(input=_Idx(nvar, [0, 1, 2]), output=_Idx(nvar, [0, 1, 2], diagnostic=[3])))
+    x = torch.randn(2, 2, 1, n_data, nvar, generator=gen)  # batch, time, ensemble, grid, vars
+    return cfg, idx, g, x
+
+
+@pytest.mark.parametrize("kind", ["graphtransformer", "gnn"])
+def test_full_reference_model_runs_unchanged_on_the_plugin(reference_on_path, monkeypatch, kind):
+    """`AnemoiModelEncProcDec` (reference models/encoder_processor_decoder.py, unmodified; hydra / anemoi-utils stood in for by the
+    10-line shims of oracle/ref_shims): built once from the reference's blocks and once after `install()`, same state_dict --
+    forward output (batch 2, activation checkpointing as the model does it) and every parameter gradient agree."""
+    shims = os.path.join(ROOT, "oracle", "ref_shims")
+    monkeypatch.syspath_prepend(shims)
+    import anemoi_models_b200 as b2
+    from anemoi.models.models.encoder_processor_decoder import AnemoiModelEncProcDec
+
+    cfg, idx, graph, x = _tiny_model_inputs(kind)
+    torch.manual_seed(0)
+    ref = AnemoiModelEncProcDec(model_config=cfg, data_indices=idx, graph_data=graph)
+    ref_out = ref(x)
+    gen = torch.Generator().manual_seed(1)
+    w = torch.randn(ref_out.shape, generator=gen)
+    (ref_out * w).sum().backward()
+
+    b2.install(edge_partition=False)
+    _cpu_conv_patches(monkeypatch)
+    new = AnemoiModelEncProcDec(model_config=cfg, data_indices=idx, graph_data=graph)
+    assert sum(type(m).__module__.startswith("anemoi_models_b200.layers.block") for m in new.modules()) >= 4
+    assert _state(new) == _state(ref)
+    new.load_state_dict(ref.state_dict())
+    new_out = new(x)
+    (new_out * w).sum().backward()
+    assert new_out.shape == ref_out.shape and torch.allclose(new_out, ref_out, atol=3e-5), float((new_out - ref_out).abs().max())
+    ref_g = {n: p.grad for n, p in ref.named_parameters()}
+    for n, p in new.named_parameters():
+        g = ref_g[n]
+        if g is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
+        else:
+            assert p.grad is not None and torch.allclose(p.grad, g, atol=1e-4 * max(1.0, float(g.abs().max()))), n
