@@ -307,3 +307,59 @@ def test_full_reference_model_runs_unchanged_on_the_plugin(reference_on_path, mo
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
         else:
             assert p.grad is not None and torch.allclose(p.grad, g, atol=1e-4 * max(1.0, float(g.abs().max()))), n
+
+
+def test_hierarchical_reference_model_runs_unchanged_on_the_plugin(reference_on_path, monkeypatch):
+    """`AnemoiModelEncProcDecHierarchical` (reference models/hierarchical.py:30-308, unmodified): two hidden levels with level
+    processors, down- and up-scale mappers -- the same kernels at more call sites."""
+    from types import SimpleNamespace
+
+    monkeypatch.syspath_prepend(os.path.join(ROOT, "oracle", "ref_shims"))
+    import anemoi_models_b200 as b2
+    from anemoi.models.models.hierarchical import AnemoiModelEncProcDecHierarchical
+    from anemoi.utils.config import DotDict
+    from torch_geometric.data import HeteroData
+
+    gen = torch.Generator().manual_seed(33)
+    sizes = {"data": 36, "hidden_1": 18, "hidden_2": 8}
+    g = HeteroData()
+    for name, n in sizes.items():
+        g[name].x = torch.rand(n, 2, generator=gen) * 3 - 1.5
+    for a, b, e in (("data", "hidden_1", 80), ("hidden_1", "hidden_1", 60), ("hidden_2", "hidden_2", 30), ("hidden_1", "hidden_2", 40),
+                    ("hidden_2", "hidden_1", 50), ("hidden_1", "data", 100)):
+        st = g[(a, "to", b)]
+        st.edge_index = torch.stack([torch.randint(0, sizes[a], (e,), generator=gen), torch.randint(0, sizes[b], (e,), generator=gen)])
+        st.edge_length = torch.rand(e, 1, generator=gen)
+    p = "anemoi.models.layers."
+    enc = {"_target_": p + "mapper.GraphTransformerForwardMapper", "trainable_size": 2, "sub_graph_edge_attributes": ["edge_length"],
+           "num_chunks": 1, "num_heads": 4, "mlp_hidden_ratio": 2, "activation": "GELU"}
+    proc = {"_target_": p + "processor.GraphTransformerProcessor", "trainable_size": 2, "sub_graph_edge_attributes": ["edge_length"],
+            "num_layers": 2, "num_chunks": 1, "num_heads": 4, "mlp_hidden_ratio": 2, "activation": "GELU"}
+    cfg = DotDict({"graph": {"data": "data", "hidden": ["hidden_1", "hidden_2"]}, "training": {"multistep_input": 1},
+                   "model": {"num_channels": 16, "trainable_parameters": {"hidden": 2}, "enable_hierarchical_level_processing": True,
+                             "level_process_num_layers": 1, "encoder": enc, "processor": proc,
+                             "decoder": dict(enc, _target_=p + "mapper.GraphTransformerBackwardMapper"), "bounding": []}})
+    idx = SimpleNamespace(internal_model=SimpleNamespace(input=_Idx(3, [0, 1]), output=_Idx(3, [0, 1], diagnostic=[2])))
+    x = torch.randn(2, 1, 1, sizes["data"], 3, generator=gen)
+
+    torch.manual_seed(0)
+    ref = AnemoiModelEncProcDecHierarchical(model_config=cfg, data_indices=idx, graph_data=g)
+    ref_out = ref(x)
+    w = torch.randn(ref_out.shape, generator=torch.Generator().manual_seed(2))
+    (ref_out * w).sum().backward()
+    b2.install(edge_partition=False)
+    _cpu_conv_patches(monkeypatch)
+    new = AnemoiModelEncProcDecHierarchical(model_config=cfg, data_indices=idx, graph_data=g)
+    assert sum(type(m).__module__.startswith("anemoi_models_b200.layers.block") for m in new.modules()) >= 7
+    assert _state(new) == _state(ref)
+    new.load_state_dict(ref.state_dict())
+    new_out = new(x)
+    (new_out * w).sum().backward()
+    assert torch.allclose(new_out, ref_out, atol=3e-5), float((new_out - ref_out).abs().max())
+    ref_g = {n: p_.grad for n, p_ in ref.named_parameters()}
+    for n, p_ in new.named_parameters():
+        gref = ref_g[n]
+        if gref is None:
+            assert p_.grad is None or float(p_.grad.abs().max()) == 0.0, n
+        else:
+            assert p_.grad is not None and torch.allclose(p_.grad, gref, atol=1e-4 * max(1.0, float(gref.abs().max()))), n
