@@ -65,6 +65,13 @@ def install(blocks: bool = True, edge_partition: bool = True, cache_expanded_edg
             new = getattr(b2block, name)
             for mod in ("anemoi.models.layers.block", "anemoi.models.layers.mapper", "anemoi.models.layers.chunk"):
                 _rebind(mod, name, new)
+        # the reference's tests check `isinstance(block.node_mlp, MLP)` against the name they import from layers/mlp.py
+        # (tests/layers/block/test_block_graphconv.py:50, 86): same constructor, same state_dict keys
+        from .layers import mlp as b2mlp
+
+        for mod in ("anemoi.models.layers.mlp", "anemoi.models.layers.block", "anemoi.models.layers.mapper", "anemoi.models.layers.chunk",
+                    "anemoi.models.layers.processor", "anemoi.models.layers.conv"):
+            _rebind(mod, "MLP", b2mlp.MLP)
     if cache_expanded_edges:
         try:
             mapper_mod = importlib.import_module("anemoi.models.layers.mapper")

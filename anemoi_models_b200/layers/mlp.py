@@ -47,17 +47,18 @@ class MLP(nn.Module):
                  activation: str = "SiLU", final_activation: bool = False, layer_norm: bool = True,
                  checkpoints: bool = False) -> None:
         super().__init__()
-        act_func = activation_class(activation)
-        mlp1 = nn.Sequential(nn.Linear(in_features, hidden_dim), act_func())
-        for _ in range(n_extra_layers + 1):
-            mlp1.append(nn.Linear(hidden_dim, hidden_dim))
-            mlp1.append(act_func())
-        mlp1.append(nn.Linear(hidden_dim, out_features))
+        act = activation_class(activation)
+        widths = [in_features] + [hidden_dim] * (n_extra_layers + 2)  # input layer + (n_extra_layers + 1) hidden layers
+        layers = []
+        for fan_in, fan_out in zip(widths[:-1], widths[1:]):
+            layers += [nn.Linear(fan_in, fan_out), act()]
+        layers.append(nn.Linear(hidden_dim, out_features))
         if final_activation:
-            mlp1.append(act_func())
+            layers.append(act())
         if layer_norm:
-            mlp1.append(AutocastLayerNorm(out_features))
-        self.model = CheckpointWrapper(mlp1) if checkpoints else mlp1
+            layers.append(AutocastLayerNorm(out_features))
+        body = nn.Sequential(*layers)  # indices = the reference's state_dict keys (model.0, model.2, ...)
+        self.model = CheckpointWrapper(body) if checkpoints else body
 
     def forward(self, x: Tensor) -> Tensor:
         return self.model(x)
