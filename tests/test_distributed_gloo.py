@@ -118,6 +118,60 @@ def _collectives(rank, world):
     assert shard_tensor(full, 0, shapes, None) is full and sync_tensor(full, 0, shapes, None) is full
 
 
+def _collectives_vs_reference(rank, world):
+    """The five tensor-parallel helpers against the REFERENCE's own functions (distributed/graph.py:20-137) in the same gloo group:
+    same inputs -> same outputs and same input gradients.  Even shard sizes only: gloo rejects the reference's uneven list
+    all_gather (this repo's padded collectives do not have that limit -- `_collectives` above runs uneven shards)."""
+    ref_src = "/root/reference/src"
+    if not os.path.isdir(ref_src):
+        return
+    sys.path.insert(0, ref_src)
+    from anemoi.models.distributed import graph as ref
+    from anemoi.models.distributed import shapes as ref_shapes
+
+    from anemoi_models_b200 import distributed as mine
+
+    group = dist.group.WORLD
+    gen = torch.Generator().manual_seed(5)
+    full = torch.randn(6 * world, 4, generator=gen)
+    shapes = mine.get_shape_shards(full, 0, group)
+    assert shapes == ref_shapes.get_shape_shards(full, 0, group)
+    n = shapes[0][0]
+    part = full[rank * n:(rank + 1) * n]
+    w_full = torch.randn(full.shape, generator=gen) * (rank + 1)
+    w_part = torch.randn(part.shape, generator=gen) * (rank + 1)
+
+    def both(name, x, w, *args, **kw):
+        outs = []
+        for mod in (ref, mine):
+            xi = x.clone().requires_grad_(True)
+            y = getattr(mod, name)(xi, *args, **kw)
+            (y * w).sum().backward()
+            outs.append((y.detach(), xi.grad))
+        (y_ref, g_ref), (y_new, g_new) = outs
+        assert y_ref.shape == y_new.shape and torch.allclose(y_ref, y_new, atol=1e-6), name
+        assert torch.allclose(g_ref, g_new, atol=1e-6), name + " (backward)"
+
+    both("shard_tensor", full, w_part, 0, shapes, group)
+    both("gather_tensor", part, w_full, 0, shapes, group)
+    both("sync_tensor", part, w_full, 0, shapes, group)
+    both("reduce_tensor", full * (rank + 1), w_full, group)
+    both("reduce_shard_tensor", full * (rank + 1), w_part, 0, shapes, group)
+    # gather_in_backward=False: only the rank's own rows of the gradient are defined (the reference leaves the rest uninitialised,
+    # primitives.py:95-104) -- compare those rows
+    outs = []
+    for mod in (ref, mine):
+        xi = full.clone().requires_grad_(True)
+        y = mod.shard_tensor(xi, 0, shapes, group, gather_in_backward=False)
+        (y * w_part).sum().backward()
+        outs.append((y.detach(), xi.grad[rank * n:(rank + 1) * n].clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.allclose(outs[0][1], outs[1][1])
+
+
+def test_collectives_match_the_reference_functions_world2():
+    run_distributed("_collectives_vs_reference", 2)
+
+
 def test_collectives_world2():
     run_distributed("_collectives", 2)
 
