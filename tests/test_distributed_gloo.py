@@ -473,3 +473,76 @@ def _sharded_graphconv_block(rank, world):
 
 def test_sharded_graphconv_block_world2():
     run_distributed("_sharded_graphconv_block", 2)
+
+
+# ------------------------------------------------------------------------------------------------------------
+def _gnn_processor_vs_reference_sharded(rank, world):
+    """The reference's GNNProcessor run SHARDED by the reference itself (its blocks, its list collectives) against the same class
+    built after install() (this repo's blocks: halo exchange instead of sync_tensor's all-gather), same weights, same 2-rank gloo
+    group: per-rank outputs, input gradients and per-rank (partial) parameter gradients must agree.  Sizes divide evenly because
+    gloo rejects the reference's uneven list all_gather."""
+    ref_src = "/root/reference/src"
+    if not os.path.isdir(ref_src):
+        return
+    sys.path.insert(0, ref_src)
+    import anemoi_models_b200 as b2
+    import anemoi_models_b200.layers.conv as convmod
+    from anemoi.models.layers import processor as ref_processor
+    from oracle import gtconv as og
+    from torch_geometric.data import HeteroData
+
+    group = dist.group.WORLD
+    n, per_chunk, hid = 40, 60, 16
+    gen = torch.Generator().manual_seed(2)
+    dst = torch.cat([torch.randint(c * n // world, (c + 1) * n // world, (per_chunk,), generator=gen) for c in range(world)])
+    src = torch.randint(0, n, (dst.numel(),), generator=gen)
+    perm = torch.randperm(dst.numel(), generator=gen)  # edges arrive in arbitrary order; every dst chunk has per_chunk of them
+    g = HeteroData()
+    st = g[("h", "to", "h")]
+    st.edge_index = torch.stack([src, dst])[:, perm]
+    st.edge_length = torch.rand(dst.numel(), 2, generator=gen)
+
+    def make():
+        torch.manual_seed(11)
+        return ref_processor.GNNProcessor(num_layers=2, num_channels=hid, num_chunks=1, trainable_size=3, sub_graph=st,
+                                          sub_graph_edge_attributes=["edge_length"], src_grid_size=n, dst_grid_size=n)
+
+    x_full = torch.randn(n, hid, generator=gen)
+    w_full = torch.randn(n, hid, generator=gen)
+    shapes = [[n // world, hid] for _ in range(world)]
+    mine = slice(rank * n // world, (rank + 1) * n // world)
+
+    def run(mod):
+        x = x_full[mine].clone().requires_grad_(True)
+        y = mod(x, batch_size=1, shard_shapes=shapes, model_comm_group=group)
+        (y * w_full[mine]).sum().backward()
+        return y.detach(), x.grad, {k: (p.grad.clone() if p.grad is not None else None) for k, p in mod.named_parameters()}
+
+    ref_mod = make()
+    y_ref, gx_ref, gp_ref = run(ref_mod)
+
+    b2.install(edge_partition=False)
+
+    def graphconv_forward(self, x, edge_attr, edge_index, size=None, plan=None):
+        p = dict(self.named_parameters())
+        return og.graph_conv_unfused(x, edge_attr, edge_index, {"edge_mlp." + k[len("edge_mlp."):]: v for k, v in p.items()},
+                                     "edge_mlp.", size=size)
+
+    convmod.GraphConv.forward = graphconv_forward
+    new_mod = make()
+    assert any(isinstance(m, b2.GraphConvProcessorBlock) for m in new_mod.modules())
+    new_mod.load_state_dict(ref_mod.state_dict())
+    y_new, gx_new, gp_new = run(new_mod)
+    b2.uninstall()
+    assert torch.allclose(y_new, y_ref, atol=2e-5), float((y_new - y_ref).abs().max())
+    assert torch.allclose(gx_new, gx_ref, atol=2e-5)
+    for k, gr in gp_ref.items():
+        gn = gp_new[k]
+        if gr is None:
+            assert gn is None or float(gn.abs().max()) == 0.0, k
+        else:
+            assert gn is not None and torch.allclose(gn, gr, atol=5e-5 * max(1.0, float(gr.abs().max()))), k
+
+
+def test_gnn_processor_sharded_matches_the_reference_sharded_world2():
+    run_distributed("_gnn_processor_vs_reference_sharded", 2)
