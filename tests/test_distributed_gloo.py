@@ -546,3 +546,87 @@ def _gnn_processor_vs_reference_sharded(rank, world):
 
 def test_gnn_processor_sharded_matches_the_reference_sharded_world2():
     run_distributed("_gnn_processor_vs_reference_sharded", 2)
+
+
+def _gnn_mappers_vs_reference_sharded(rank, world):
+    """Same comparison for the GNN forward mapper (replicated inputs, sharded inside: mapper.py:105-116) and the GNN backward mapper
+    (sharded inputs, gathered output: mapper.py:96-102)."""
+    ref_src = "/root/reference/src"
+    if not os.path.isdir(ref_src):
+        return
+    sys.path.insert(0, ref_src)
+    import anemoi_models_b200 as b2
+    import anemoi_models_b200.layers.conv as convmod
+    from anemoi.models.layers import mapper as ref_mapper
+    from oracle import gtconv as og
+    from torch_geometric.data import HeteroData
+
+    group = dist.group.WORLD
+    hid, per_chunk = 16, 50
+    gen = torch.Generator().manual_seed(6)
+
+    def graph(ns, nd):
+        dst = torch.cat([torch.randint(c * nd // world, (c + 1) * nd // world, (per_chunk,), generator=gen) for c in range(world)])
+        src = torch.randint(0, ns, (dst.numel(),), generator=gen)
+        perm = torch.randperm(dst.numel(), generator=gen)
+        st = HeteroData()[("a", "to", "b")]
+        st.edge_index = torch.stack([src, dst])[:, perm]
+        st.edge_length = torch.rand(dst.numel(), 2, generator=gen)
+        return st
+
+    def graphconv_forward(self, x, edge_attr, edge_index, size=None, plan=None):
+        p = dict(self.named_parameters())
+        return og.graph_conv_unfused(x, edge_attr, edge_index, {"edge_mlp." + k[len("edge_mlp."):]: v for k, v in p.items()},
+                                     "edge_mlp.", size=size)
+
+    ns, nd = 40, 20
+    cases = []
+    fwd_graph, bwd_graph = graph(ns, nd), graph(nd, ns)
+    cases.append(("forward", lambda: ref_mapper.GNNForwardMapper(in_channels_src=5, in_channels_dst=4, hidden_dim=hid, trainable_size=3, sub_graph=fwd_graph,
+                                                                  sub_graph_edge_attributes=["edge_length"], src_grid_size=ns, dst_grid_size=nd),
+                  (torch.randn(ns, 5, generator=gen), torch.randn(nd, 4, generator=gen)), ([[ns // world, 5]] * world, [[nd // world, 4]] * world), False))
+    cases.append(("backward", lambda: ref_mapper.GNNBackwardMapper(in_channels_src=hid, in_channels_dst=hid, hidden_dim=hid, out_channels_dst=3, trainable_size=3,
+                                                                    sub_graph=bwd_graph, sub_graph_edge_attributes=["edge_length"], src_grid_size=nd,
+                                                                    dst_grid_size=ns),
+                  (torch.randn(nd, hid, generator=gen), torch.randn(ns, hid, generator=gen)), ([[nd // world, hid]] * world, [[ns // world, hid]] * world), True))
+    orig_forward = convmod.GraphConv.forward
+    for name, make, x_full, shapes, sharded_inputs in cases:
+        def run(mod):
+            if sharded_inputs:
+                xs = tuple(t[rank * t.shape[0] // world:(rank + 1) * t.shape[0] // world].clone().requires_grad_(True) for t in x_full)
+            else:
+                xs = tuple(t.clone().requires_grad_(True) for t in x_full)
+            out = mod(xs, batch_size=1, shard_shapes=shapes, model_comm_group=group)
+            outs = [o for o in (out if isinstance(out, tuple) else (out,)) if o.requires_grad]
+            g2 = torch.Generator().manual_seed(8)
+            sum((o * torch.randn(o.shape, generator=g2)).sum() for o in outs).backward()
+            return [o.detach() for o in outs], [t.grad for t in xs], {k: (p.grad.clone() if p.grad is not None else None) for k, p in mod.named_parameters()}
+
+        torch.manual_seed(13)
+        ref_mod = make()
+        o_ref, gx_ref, gp_ref = run(ref_mod)
+        b2.install(edge_partition=False)
+        convmod.GraphConv.forward = graphconv_forward
+        new_mod = make()
+        assert any(isinstance(m, b2.GraphConvMapperBlock) for m in new_mod.modules()), name
+        new_mod.load_state_dict(ref_mod.state_dict())
+        o_new, gx_new, gp_new = run(new_mod)
+        convmod.GraphConv.forward = orig_forward
+        b2.uninstall()
+        assert len(o_new) == len(o_ref), name
+        for a, b in zip(o_new, o_ref):
+            assert a.shape == b.shape and torch.allclose(a, b, atol=2e-5), (name, float((a - b).abs().max()))
+        for a, b in zip(gx_new, gx_ref):
+            assert (a is None) == (b is None), name
+            if a is not None:
+                assert torch.allclose(a, b, atol=2e-5 * max(1.0, float(b.abs().max()))), name
+        for k, gr in gp_ref.items():
+            gn = gp_new[k]
+            if gr is None:
+                assert gn is None or float(gn.abs().max()) == 0.0, (name, k)
+            else:
+                assert gn is not None and torch.allclose(gn, gr, atol=5e-5 * max(1.0, float(gr.abs().max()))), (name, k)
+
+
+def test_gnn_mappers_sharded_match_the_reference_sharded_world2():
+    run_distributed("_gnn_mappers_vs_reference_sharded", 2)
