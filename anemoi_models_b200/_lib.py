@@ -15,6 +15,18 @@ AB2_ERR_INVALID, AB2_ERR_UNSUPPORTED, AB2_ERR_CUDA = 1, 2, 3
 
 _vp, _i64, _i32, _sz, _f32 = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_float
 
+
+
+class Gemm(C.Structure):
+    """`ab2_gemm` of include/anemoi_b200.h"""
+
+    _fields_ = [("M", _i64), ("N", _i64), ("K", _i64), ("a", _vp), ("lda", _i64), ("b", _vp), ("ldb", _i64), ("a_mn", C.c_int32),
+                ("b_mn", C.c_int32), ("out", _vp * 4), ("ld_out", _i64), ("seg_cols", C.c_int32), ("out_f32", C.c_int32),
+                ("bias", _vp), ("row_scale", _vp), ("row_shift", _vp), ("col_vec", _vp), ("pre_out", _vp), ("dact_pre", _vp),
+                ("residual", _vp), ("ld_res", _i64), ("res_f32", C.c_int32), ("act", C.c_int32), ("splits", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 # name -> (restype, argtypes); must list every symbol of include/anemoi_b200.h (tests/test_abi.py checks it)
 SIGNATURES = {
     "ab2_version": (_i32, []),
@@ -50,6 +62,8 @@ SIGNATURES = {
     "ab2_edge_ln_res_segsum": (_i32, [_vp] * 4 + [_f32] + [_vp] * 2 + [_i64] * 2 + [_i32] * 2 + [_vp] * 5),
     "ab2_ln_bwd_parts": (_i32, []),
     "ab2_edge_ln_res_segsum_bwd": (_i32, [_vp] * 7 + [_i64] * 2 + [_i32] * 2 + [_vp] * 3 + [_i32] + [_vp] * 3),
+    "ab2_gemm_workspace_bytes": (_sz, [C.POINTER(Gemm)]),
+    "ab2_gemm_bf16": (_i32, [C.POINTER(Gemm), _vp, _sz, _vp]),
     "ab2_gtconv_host_workspace_bytes": (_sz, [_i64] * 3 + [_i32] * 3),
     "ab2_gtconv_fwd_bwd_host_streamed": (_i32, [_vp] * 5 + [_i32] + [_vp] * 6 + [_i64] * 3 + [_i32] * 2 + [_vp] * 5 + [_vp, _i32, _vp, _sz, _vp]),
     "ab2_gtconv_fwd_bwd_host": (_i32, [_vp] * 5 + [_i32] + [_vp] * 6 + [_i64] * 3 + [_i32] * 2 + [_vp] * 5 + [_vp, _sz, _vp]),

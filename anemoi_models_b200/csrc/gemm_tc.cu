@@ -1,0 +1,610 @@
+// Dense node-side contractions on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), sm_100a.
+//
+// Replaces, inside the graph blocks of the reference (paths relative to src/anemoi/models/):
+//   layers/block.py:491-499, 615-620   lin_self / lin_query / lin_key / lin_value  (concatenated: [q|self], [k|v], one GEMM each)
+//   layers/block.py:531-533, 630       projection(out + x_r) + x_skip               (bias + residual epilogue)
+//   layers/block.py:349-354, 537, 633  node_dst_mlp: Linear -> act -> Linear + res   (bias + activation / bias + residual epilogues)
+//   layers/conv.py:53-59 + mlp.py:74-84 GraphConv.edge_mlp Linear layers             (bias + activation epilogues)
+// and their backward (dgrad with the activation derivative in the epilogue, split-K wgrad).
+//
+//   D[M,N] = epilogue( A[M,K] . B[N,K]^T ),  bf16 operands, fp32 accumulation in tensor memory.
+//
+// Structure (one persistent CTA per SM, 10 warps):
+//   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B boxes) of the A / B k-blocks into a shared-memory ring,
+//               completion counted in bytes on the stage's `full` mbarrier;
+//   warp 1      MMA issuer: ONE thread issues tcgen05.mma.cta_group::1.kind::f16 (128 x BN x 16 per instruction) on the staged
+//               tiles; tcgen05.commit releases the stage (`empty`) and, after the last k-block, publishes the accumulator
+//               (`tmem_full`).  The warp also owns the TMEM allocation (512 columns = two accumulator stages of BN <= 256);
+//   warps 2..9  epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) of the finished accumulator while the MMA warp
+//               already works on the next tile in the other TMEM stage; bias / LayerNorm-fold / activation (+ pre-activation
+//               side output) / activation-derivative / residual, bf16 or fp32 stores, outputs optionally split by column
+//               segments (q | self, k | v land in separate tensors).
+// Operands may be K-major (contraction contiguous in memory: x [M,K], W [N,K]) or MN-major (contraction strided: W as the
+// B operand of dgrad, dY^T and x as the operands of wgrad), selected per operand in the instruction descriptor; no transposes
+// are materialised.  wgrad splits the (long) contraction over CTAs into fp32 partials that a second kernel sums in a fixed
+// order (deterministic, no atomics).
+#include <cuda.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace ab2 {
+namespace tc {
+
+constexpr int BM = 128;     // accumulator rows per CTA tile = TMEM lanes
+constexpr int BK = 64;      // 64 bf16 = 128 B = one SWIZZLE_128B atom along the contraction
+constexpr int UMMA_K = 16;  // contraction per tcgen05.mma for 16-bit operands
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kBoxBytes = 64 * 64 * 2;  // one 64 x 64 bf16 box (MN-major operands are loaded box by box)
+
+template <int BN>
+struct Cfg {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes;  // 4 at BN=256, 6 at BN=128, 8 at BN=64
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + slack for the 1024 B alignment
+};
+
+struct Epi {
+  void* out[4];          // column segment s of the result goes to out[s] (row stride ld_out elements)
+  long long ld_out;
+  int seg_cols;          // width of a column segment (multiple of 32); >= N for a single output
+  int out_f32;           // 1: fp32 stores, 0: bf16
+  const float* bias;     // [N] or null
+  const float* row_scale;  // [M] or null:  acc = row_scale[m] * acc + row_shift[m] * col_vec[n]   (LayerNorm folded into the GEMM)
+  const float* row_shift;  // [M]
+  const float* col_vec;    // [N]
+  int act;               // 0 SiLU, 1 GELU(erf), 2 ReLU, 3 identity  (ops.ACT_CODES)
+  void* pre_out;         // bf16 [M,N] (ld = N): pre-activation side output, kept for backward; null to skip
+  const void* dact_pre;  // bf16 [M,N] (ld = N): result *= act'(dact_pre)  (dgrad through an activation); null to skip
+  const void* residual;  // [M,N] row stride ld_res, bf16 or fp32; added last
+  long long ld_res;
+  int res_f32;
+};
+
+struct Args {
+  int M, N, K;
+  int tiles_m, tiles_n, splits, kb_per_split, kb_total;
+  long long split_stride;  // elements between the fp32 partials of two splits (split-K only)
+  int k_lbo, k_sbo, mn_lbo, mn_sbo;  // descriptor byte offsets (fixed by the tile layout; overridable for bring-up probes only)
+  Epi epi;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.b32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol error must end in a trapped launch (cudaErrorLaunchFailure), never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor (SWIZZLE_128B, descriptor version 1 = sm_100): start address, leading / stride byte
+// offsets in 16 B units.  K-major tile [rows][64]: rows are 128 B apart inside an 8-row swizzle atom, atoms 1024 B apart
+// (SBO); LBO is not used.  MN-major tile = 64 x 64 boxes [k][64 mn]: 8 k-rows form an atom, atoms 1024 B apart along k
+// (SBO), the next 64 mn-elements live in the next box, 8192 B further (LBO).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  const uint32_t lo = ((addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+  const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ float act_fn(float x, int act) {
+  switch (act) {
+    case 0: return x / (1.f + __expf(-x));
+    case 1: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+    case 2: return fmaxf(x, 0.f);
+    default: return x;
+  }
+}
+__device__ __forceinline__ float act_grad(float x, int act) {
+  switch (act) {
+    case 0: {
+      const float s = 1.f / (1.f + __expf(-x));
+      return s * (1.f + x * (1.f - s));
+    }
+    case 1: return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+    case 2: return x > 0.f ? 1.f : 0.f;
+    default: return 1.f;
+  }
+}
+
+// ---- the kernel --------------------------------------------------------------------------------------------------
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                             const __grid_constant__ CUtensorMap tmB, const Args g) {
+  using C = Cfg<BN>;
+  constexpr int S = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms are 1024 B aligned
+  const uint32_t bars = base + S * C::kStageBytes;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (S + s); };
+  auto tfull = [&](int a) { return bars + 8u * (2 * S + a); };
+  auto tempty = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * S + 4);
+  auto sA = [&](int s) { return base + s * C::kStageBytes; };
+  auto sB = [&](int s) { return base + s * C::kStageBytes + C::kABytes; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull(a), 1);
+      mbar_init(tempty(a), kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: 512 columns (the whole SM's tensor memory; one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int num_tiles = g.tiles_m * g.tiles_n * g.splits;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t c = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int split = t % g.splits, r = t / g.splits;
+        const int n0 = (r % g.tiles_n) * BN, m0 = (r / g.tiles_n) * BM;
+        const int kb0 = split * g.kb_per_split, kb1 = min(kb0 + g.kb_per_split, g.kb_total);
+        for (int kb = kb0; kb < kb1; ++kb, ++c) {
+          const int s = c % S;
+          mbar_wait(empty(s), ((c / S) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(full(s), C::kStageBytes);
+          if constexpr (!A_MN) {
+            tma_load_2d(sA(s), &tmA, full(s), kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i) tma_load_2d(sA(s) + i * kBoxBytes, &tmA, full(s), m0 + 64 * i, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sB(s), &tmB, full(s), kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(sB(s) + i * kBoxBytes, &tmB, full(s), n0 + 64 * i, kb * BK);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A / B bf16, operand majors, N >> 3 at bit 17, M >> 4 at bit 24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      constexpr uint32_t kAStep = A_MN ? (UMMA_K * 128) : (UMMA_K * 2);  // bytes per UMMA_K along the contraction
+      constexpr uint32_t kBStep = B_MN ? (UMMA_K * 128) : (UMMA_K * 2);
+      uint32_t c = 0, it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int split = t % g.splits;
+        const int kb0 = split * g.kb_per_split, kb1 = min(kb0 + g.kb_per_split, g.kb_total);
+        const uint32_t a = it & 1u;
+        mbar_wait(tempty(a), ((it >> 1) & 1u) ^ 1u);  // the epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * BN;
+        for (int kb = kb0; kb < kb1; ++kb, ++c) {
+          const int s = c % S;
+          mbar_wait(full(s), (c / S) & 1u);
+          tc_fence_after();
+          const uint64_t da = A_MN ? smem_desc(sA(s), g.mn_lbo, g.mn_sbo) : smem_desc(sA(s), g.k_lbo, g.k_sbo);
+          const uint64_t db = B_MN ? smem_desc(sB(s), g.mn_lbo, g.mn_sbo) : smem_desc(sB(s), g.k_lbo, g.k_sbo);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            tc_mma(d_tmem, da + (uint64_t)((k * kAStep) >> 4), db + (uint64_t)((k * kBStep) >> 4), idesc,
+                   (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(empty(s));  // stage reusable once these MMAs have read it
+        }
+        tc_commit(tfull(a));  // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue =====
+    const int e = warp - 2;
+    const int quad = warp & 3;  // a warp may only touch TMEM lanes [32 * (warp % 4), +32)
+    const int half = e >> 2;    // two warps per lane quadrant: each takes half of the BN columns
+    constexpr int kChunks = BN / 32 / 2;
+    const Epi& ep = g.epi;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int split = t % g.splits, r = t / g.splits;
+      const int n0 = (r % g.tiles_n) * BN, m0 = (r / g.tiles_n) * BM;
+      const uint32_t a = it & 1u;
+      mbar_wait(tfull(a), (it >> 1) & 1u);
+      tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < g.M;
+      float rs = 1.f, rt = 0.f;
+      if (ep.row_scale != nullptr && row_ok) {
+        rs = ep.row_scale[row];
+        rt = ep.row_shift[row];
+      }
+#pragma unroll 1
+      for (int ch = 0; ch < kChunks; ++ch) {
+        const int cc = (half * kChunks + ch) * 32;
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + a * BN + cc, v);
+        tc_wait_ld();
+        if (ch == kChunks - 1) {  // this warp has read its share of the stage: hand it back before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty(a));
+        }
+        const int col0 = n0 + cc;
+        if (!row_ok || col0 >= g.N) continue;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (ep.row_scale != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + j < g.N) {
+              const float4 cv = __ldg(reinterpret_cast<const float4*>(ep.col_vec + col0 + j));
+              f[j] = rs * f[j] + rt * cv.x;
+              f[j + 1] = rs * f[j + 1] + rt * cv.y;
+              f[j + 2] = rs * f[j + 2] + rt * cv.z;
+              f[j + 3] = rs * f[j + 3] + rt * cv.w;
+            }
+          }
+        }
+        if (ep.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + j < g.N) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+              f[j] += b.x;
+              f[j + 1] += b.y;
+              f[j + 2] += b.z;
+              f[j + 3] += b.w;
+            }
+          }
+        }
+        if (ep.dact_pre != nullptr) {
+          const __nv_bfloat16* pp = reinterpret_cast<const __nv_bfloat16*>(ep.dact_pre) + (size_t)row * g.N + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col0 + j < g.N) {
+              float p[8];
+              unpack<__nv_bfloat16>(ldg16(pp + j), p);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) f[j + u] *= act_grad(p[u], ep.act);
+            }
+          }
+        } else if (ep.act != 3) {
+          if (ep.pre_out != nullptr) {
+            __nv_bfloat16* pp = reinterpret_cast<__nv_bfloat16*>(ep.pre_out) + (size_t)row * g.N + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (col0 + j < g.N) {
+                float p[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) p[u] = f[j + u];
+                stg16(pp + j, pack<__nv_bfloat16>(p));
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            // the activation sees the bf16-rounded pre-activation when one is kept, so that backward (which only has the
+            // rounded value) differentiates exactly the function forward applied
+            const float x = ep.pre_out != nullptr ? __bfloat162float(__float2bfloat16_rn(f[j])) : f[j];
+            f[j] = act_fn(x, ep.act);
+          }
+        }
+        if (ep.residual != nullptr) {
+          if (ep.res_f32) {
+            const float* rp = reinterpret_cast<const float*>(ep.residual) + (size_t)row * ep.ld_res + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (col0 + j < g.N) {
+                float p[4];
+                unpack<float>(ldg16(rp + j), p);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) f[j + u] += p[u];
+              }
+            }
+          } else {
+            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (size_t)row * ep.ld_res + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (col0 + j < g.N) {
+                float p[8];
+                unpack<__nv_bfloat16>(ldg16(rp + j), p);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) f[j + u] += p[u];
+              }
+            }
+          }
+        }
+        const int seg = col0 / ep.seg_cols;
+        const int cs = col0 - seg * ep.seg_cols;
+        if (ep.out_f32) {
+          float* op = reinterpret_cast<float*>(ep.out[seg]) + (size_t)split * g.split_stride + (size_t)row * ep.ld_out + cs;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + j < g.N) {
+              float p[4] = {f[j], f[j + 1], f[j + 2], f[j + 3]};
+              stg16(op + j, pack<float>(p));
+            }
+          }
+        } else {
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(ep.out[seg]) + (size_t)row * ep.ld_out + cs;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col0 + j < g.N) {
+              float p[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) p[u] = f[j + u];
+              stg16(op + j, pack<__nv_bfloat16>(p));
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// out[i] = sum_s part[s][i]  (fixed order), cast to bf16 or kept fp32
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, long long n, int splits, long long stride, void* out,
+                                     int out_f32) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  float4 acc = *reinterpret_cast<const float4*>(part + i);
+  for (int s = 1; s < splits; ++s) {
+    const float4 p = *reinterpret_cast<const float4*>(part + (long long)s * stride + i);
+    acc.x += p.x;
+    acc.y += p.y;
+    acc.z += p.z;
+    acc.w += p.w;
+  }
+  if (out_f32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + i) = acc;
+  } else {
+    uint2 o = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + i) = o;
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows `ld` elements apart; box = 64 x box_rows, SWIZZLE_128B
+static int make_map(CUtensorMap* m, const void* ptr, long long inner, long long outer, long long ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return fail(AB2_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (ld * 2) % 16 != 0)
+    return fail(AB2_ERR_INVALID, "gemm operand must be 16-byte aligned with a row stride that is a multiple of 8 elements");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(AB2_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return AB2_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Args& a, cudaStream_t st) {
+  using C = Cfg<BN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  static std::mutex mu;
+  static bool configured[64] = {false};
+  int dev = 0;
+  AB2_CUDA_OK(cudaGetDevice(&dev));
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev < 64 && !configured[dev]) {
+      AB2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+      configured[dev] = true;
+    }
+  }
+  const int tiles = a.tiles_m * a.tiles_n * a.splits;
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  const char* env = getenv("AB2_GEMM_GRID");
+  if (env != nullptr && atoi(env) > 0 && atoi(env) < grid) grid = atoi(env);
+  kern<<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, a);
+  AB2_LAUNCH_OK("gemm_tc_kernel");
+  return AB2_OK;
+}
+
+}  // namespace tc
+}  // namespace ab2
+
+using namespace ab2;
+
+extern "C" size_t ab2_gemm_workspace_bytes(const ab2_gemm* d) {
+  if (d == nullptr || d->splits <= 1) return 0;
+  return (size_t)d->splits * (size_t)d->M * (size_t)d->N * sizeof(float);
+}
+
+extern "C" int ab2_gemm_bf16(const ab2_gemm* d, void* workspace, size_t workspace_bytes, void* stream) {
+  if (d == nullptr) return fail(AB2_ERR_INVALID, "ab2_gemm_bf16: null descriptor");
+  const long long M = d->M, N = d->N, K = d->K;
+  if (M < 0 || N <= 0 || K <= 0 || M >= (1LL << 31) || N >= (1LL << 31) || K >= (1LL << 31))
+    return fail(AB2_ERR_INVALID, "ab2_gemm_bf16: bad sizes M=%lld N=%lld K=%lld", M, N, K);
+  if (M == 0) return AB2_OK;
+  if (N % 8 != 0) return fail(AB2_ERR_UNSUPPORTED, "ab2_gemm_bf16: N must be a multiple of 8 (got %lld)", N);
+  if (d->a == nullptr || d->b == nullptr || d->out[0] == nullptr) return fail(AB2_ERR_INVALID, "ab2_gemm_bf16: null operand");
+  const int splits = d->splits > 1 ? d->splits : 1;
+  tc::Args a;
+  memset(&a, 0, sizeof(a));
+  a.M = (int)M;
+  a.N = (int)N;
+  a.K = (int)K;
+  const int BN = (N > 128) ? 256 : (N > 64 ? 128 : 64);
+  a.tiles_m = (int)((M + tc::BM - 1) / tc::BM);
+  a.tiles_n = (int)((N + BN - 1) / BN);
+  a.kb_total = (int)((K + tc::BK - 1) / tc::BK);
+  a.splits = splits;
+  a.kb_per_split = (a.kb_total + splits - 1) / splits;
+  a.k_lbo = 16;
+  a.k_sbo = 1024;
+  a.mn_lbo = tc::kBoxBytes;
+  a.mn_sbo = 1024;
+  if (const char* dbg = getenv("AB2_GEMM_DESC")) sscanf(dbg, "%d,%d,%d,%d", &a.k_lbo, &a.k_sbo, &a.mn_lbo, &a.mn_sbo);
+  if ((long long)a.kb_per_split * (splits - 1) >= a.kb_total && splits > 1)
+    return fail(AB2_ERR_INVALID, "ab2_gemm_bf16: %d splits leave an empty split for %d k-blocks", splits, a.kb_total);
+  tc::Epi& e = a.epi;
+  for (int i = 0; i < 4; ++i) e.out[i] = d->out[i];
+  e.ld_out = d->ld_out;
+  e.seg_cols = d->seg_cols > 0 ? d->seg_cols : (int)(((N + 31) / 32) * 32);
+  if (e.seg_cols % 32 != 0) return fail(AB2_ERR_INVALID, "ab2_gemm_bf16: seg_cols must be a multiple of 32");
+  const long long nseg = (N + e.seg_cols - 1) / e.seg_cols;
+  if (nseg > 4) return fail(AB2_ERR_INVALID, "ab2_gemm_bf16: at most 4 output segments");
+  for (int i = 0; i < nseg; ++i)
+    if (e.out[i] == nullptr) return fail(AB2_ERR_INVALID, "ab2_gemm_bf16: output segment %d is null", i);
+  e.out_f32 = d->out_f32;
+  e.bias = d->bias;
+  e.row_scale = d->row_scale;
+  e.row_shift = d->row_shift;
+  e.col_vec = d->col_vec;
+  if (e.row_scale != nullptr && (e.row_shift == nullptr || e.col_vec == nullptr))
+    return fail(AB2_ERR_INVALID, "ab2_gemm_bf16: row_scale needs row_shift and col_vec");
+  e.act = d->act;
+  e.pre_out = d->pre_out;
+  e.dact_pre = d->dact_pre;
+  e.residual = d->residual;
+  e.ld_res = d->ld_res;
+  e.res_f32 = d->res_f32;
+  void* final_out = e.out[0];
+  if (splits > 1) {
+    if (nseg != 1 || e.bias || e.row_scale || e.act != 3 || e.dact_pre || e.residual || e.pre_out)
+      return fail(AB2_ERR_INVALID, "ab2_gemm_bf16: split-K supports a plain single output only");
+    const size_t need = (size_t)splits * M * N * sizeof(float);
+    if (workspace == nullptr || workspace_bytes < need)
+      return fail(AB2_ERR_INVALID, "ab2_gemm_bf16: split-K workspace too small (%zu < %zu)", workspace_bytes, need);
+    if (d->ld_out != N) return fail(AB2_ERR_INVALID, "ab2_gemm_bf16: split-K needs a contiguous output (ld_out == N)");
+    e.out[0] = workspace;
+    e.out_f32 = 1;
+    a.split_stride = M * N;
+  }
+  CUtensorMap ta, tb;
+  int rc;
+  // K-major operand: memory [rows][K] -> inner = K, outer = rows, box 64 x tile rows.  MN-major: memory [K][rows] -> inner =
+  // rows, outer = K, 64 x 64 boxes.
+  rc = d->a_mn ? tc::make_map(&ta, d->a, M, K, d->lda, 64) : tc::make_map(&ta, d->a, K, M, d->lda, tc::BM);
+  if (rc) return rc;
+  rc = d->b_mn ? tc::make_map(&tb, d->b, N, K, d->ldb, 64) : tc::make_map(&tb, d->b, K, N, d->ldb, BN);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+#define AB2_GEMM_DISPATCH(BNV)                                                        \
+  do {                                                                                \
+    if (!d->a_mn && !d->b_mn) rc = tc::launch<BNV, false, false>(ta, tb, a, st);      \
+    else if (!d->a_mn && d->b_mn) rc = tc::launch<BNV, false, true>(ta, tb, a, st);   \
+    else if (d->a_mn && d->b_mn) rc = tc::launch<BNV, true, true>(ta, tb, a, st);     \
+    else rc = tc::launch<BNV, true, false>(ta, tb, a, st);                            \
+  } while (0)
+  if (BN == 256) AB2_GEMM_DISPATCH(256);
+  else if (BN == 128) AB2_GEMM_DISPATCH(128);
+  else AB2_GEMM_DISPATCH(64);
+#undef AB2_GEMM_DISPATCH
+  if (rc) return rc;
+  if (splits > 1) {
+    const long long n = M * N;  // N % 8 == 0 -> n % 4 == 0
+    const int threads = 256;
+    const long long blocks = (n / 4 + threads - 1) / threads;
+    tc::splitk_reduce_kernel<<<(unsigned)blocks, threads, 0, st>>>(reinterpret_cast<const float*>(workspace), n, splits, M * N, final_out,
+                                                                    d->out_f32);
+    AB2_LAUNCH_OK("splitk_reduce_kernel");
+  }
+  return AB2_OK;
+}

@@ -109,6 +109,35 @@ def build_local_halo_plan(edge_index_local: Tensor, src_bounds: List[int], dst_b
                     halo_ids=halo_ids)
 
 
+def cached_plan(owner, key, edge_index: Tensor, group, builder):
+    """Halo plan of `edge_index` kept ON THE CALLING MODULE (`owner.__dict__`), one entry per key (shard bounds, rank).
+
+    Building a plan and, later, its peer-memory exchange involves collectives, so whether to build must be the same decision on
+    every rank.  A process-wide LRU keyed by tensor content (the round-1 design) made that decision locally: had eviction
+    order or a content match ever differed between ranks, one rank would have entered the collective alone.  Here:
+      * the very same tensor object with an unchanged version -> hit, no device work, no host sync (the steady state: the
+        expanded edge_index and the 1-hop partition are memoised, see install.py / khop_edges.py);
+      * anything else -> every rank compares its tensor with the stored one and the group agrees (MIN all-reduce) whether
+        all of them may keep their plan; otherwise all rebuild.  SPMD ranks walk through the same modules in the same
+        order, so they reach this point together."""
+    from ..graph import tensor_version
+
+    store = owner.__dict__.setdefault("_b200_halo_plans", {})
+    hit = store.get(key)
+    if hit is not None and hit[0] is edge_index and hit[1] == tensor_version(edge_index):
+        return hit[2]
+    same = (hit is not None and hit[0].shape == edge_index.shape and hit[0].device == edge_index.device
+            and hit[0].dtype == edge_index.dtype and hit[1] == tensor_version(hit[0]) and bool(torch.equal(hit[0], edge_index)))
+    flag = torch.tensor([1 if same else 0], dtype=torch.int64, device=edge_index.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 1:
+        plan = hit[2]
+    else:
+        plan = builder()
+    store[key] = (edge_index, tensor_version(edge_index), plan)
+    return plan
+
+
 def aligned_bounds_from_ranges(lo: Sequence[int], hi: Sequence[int], n_src: int) -> List[int]:
     """Contiguous src ownership that follows dst ownership: cut between rank r and r+1 in the middle of the zone both
     reference.  lo[r] / hi[r] = smallest / largest src row referenced by the edges into rank r's dst shard (lo > hi: none).

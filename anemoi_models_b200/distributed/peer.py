@@ -55,6 +55,10 @@ def push_tables(rank: int, send_counts: List[int], recv_counts: List[int], recv_
     return peer_of_send, dst_row, owner, inbox_row
 
 
+class PeerSetupFailed(RuntimeError):
+    """Raised on EVERY rank of the group when the peer-memory set-up failed on any of them (the decision is collective)."""
+
+
 class PeerExchange:
     def __init__(self, plan: HaloPlan, group, row_bytes: int, device: torch.device):
         L = _lib.lib()
@@ -86,23 +90,46 @@ class PeerExchange:
                         o += (nbytes + 255) // 256 * 256
             return offs, o
         self.offs, total = layout(n_halo, n_send)
-        base_ptr = C.c_void_p()
-        handle = (C.c_ubyte * 64)()
-        with torch.cuda.device(device):
-            _lib.check(L.ab2_ipc_alloc(total, C.byref(base_ptr), handle))
-        self.base = base_ptr.value
-        handles = [None] * P
-        dist.all_gather_object(handles, bytes(handle), group=group)
+        # ---- local phases (may fail on SOME ranks: IPC not permitted, a GPU pair without P2P) are kept apart from the
+        # collective ones: every rank walks through the same sequence of collectives whatever happened locally, and the
+        # outcome is agreed on with one MIN all-reduce before anything is used.  A rank that raised half-way would
+        # otherwise sit in a different collective than its peers (mismatched NCCL calls: a hang, not a fallback).
+        self.base = 0
         self.peer_base: List[int] = []
-        for p in range(P):
-            if p == rank:
-                self.peer_base.append(self.base)
-            else:
-                hp = (C.c_ubyte * 64)(*handles[p])
-                mapped = C.c_void_p()
-                with torch.cuda.device(device):
-                    _lib.check(L.ab2_ipc_open(hp, C.byref(mapped)))
-                self.peer_base.append(mapped.value)
+        self._mapped: List[int] = []
+        self._closed = False
+        err: Optional[Exception] = None
+        handle = (C.c_ubyte * 64)()
+        try:
+            base_ptr = C.c_void_p()
+            with torch.cuda.device(device):
+                _lib.check(L.ab2_ipc_alloc(total, C.byref(base_ptr), handle))
+            self.base = base_ptr.value
+        except Exception as exc:  # noqa: BLE001 -- reported through the agreed flag below
+            err = exc
+        handles = [None] * P
+        dist.all_gather_object(handles, (bytes(handle), err is None), group=group)
+        if err is None and all(h[1] for h in handles):
+            try:
+                for p in range(P):
+                    if p == rank:
+                        self.peer_base.append(self.base)
+                    else:
+                        hp = (C.c_ubyte * 64)(*handles[p][0])
+                        mapped = C.c_void_p()
+                        with torch.cuda.device(device):
+                            _lib.check(L.ab2_ipc_open(hp, C.byref(mapped)))
+                        self._mapped.append(mapped.value)
+                        self.peer_base.append(mapped.value)
+            except Exception as exc:  # noqa: BLE001
+                err = exc
+        elif err is None:
+            err = RuntimeError("a peer could not allocate its exchange buffer")
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int64, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # also: everyone has mapped everyone before the first push
+        if int(ok.item()) == 0:
+            self.close()
+            raise PeerSetupFailed(str(err) if err is not None else "peer-memory setup failed on another rank")
         peer_offs = [layout(halo_n[p], send_n[p])[0] for p in range(P)]
         self.tables = {}
         for kind in ("halo", "inbox"):
@@ -130,7 +157,26 @@ class PeerExchange:
             prev = r
         self.interior = best
         self._ranges = {}
-        dist.all_reduce(self.token, group=group)  # everyone has mapped everyone before the first push
+
+    def close(self) -> None:
+        """Unmap the peers' buffers and free the own one (idempotent; called on a failed set-up and when the plan goes away).
+        Peers may still hold a mapping of the freed buffer: CUDA keeps the allocation alive until the last mapping closes."""
+        if getattr(self, "_closed", True):
+            return
+        self._closed = True
+        try:
+            L = _lib.lib()
+            with torch.cuda.device(self.device):
+                for ptr in self._mapped:
+                    L.ab2_ipc_close(C.c_void_p(ptr))
+                if self.base:
+                    L.ab2_ipc_free(C.c_void_p(self.base))
+        except Exception:  # noqa: BLE001 -- interpreter shutdown: the driver reclaims everything with the process
+            pass
+        self._mapped, self.base = [], 0
+
+    def __del__(self):
+        self.close()
 
     def _local(self, kind: str, parity: int, plane: str) -> int:
         return self.base + self.offs[(kind, parity, plane)]
@@ -249,16 +295,15 @@ def get_peer_exchange(plan: HaloPlan, group, row_bytes: int, device: torch.devic
     px = None
     usable = (os.environ.get("AB2_HALO", "p2p") != "nccl" and device.type == "cuda" and dist.get_backend(group) == "nccl"
               and row_bytes % 16 == 0 and plan.world <= 16)
-    ok = torch.tensor([1 if usable else 0], device=device)
-    if usable:
+    # `usable` depends on the environment of each process: agree on it first, so that either every rank enters the
+    # constructor (whose collectives are unconditional, see there) or none does
+    ok = torch.tensor([1 if usable else 0], dtype=torch.int64, device=device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 1:
         try:
             px = PeerExchange(plan, group, row_bytes, device)
-        except Exception as exc:  # IPC not permitted / peers not NVLink-reachable: agree on the NCCL path below
+        except PeerSetupFailed as exc:  # raised on every rank alike
             LOGGER.warning("peer-memory halo exchange unavailable (%s); using the NCCL all-to-all", exc)
-            ok.zero_()
             px = None
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-    if int(ok.item()) == 0:
-        px = None
     cache[key] = px
     return px

@@ -85,6 +85,12 @@ class GraphCSR:
         self._host_meta = {}
 
 
+def tensor_version(t: Tensor) -> int:
+    """`t._version`, or -1 for tensors created under `torch.inference_mode()` (they do not track a version counter and
+    reading it raises; Lightning's validate / predict loops and inference runners build `edge_index` that way)."""
+    return -1 if t.is_inference() else t._version
+
+
 class TensorKeyedCache:
     """Small LRU of objects derived from an index tensor (+ a hashable extra key).
 
@@ -105,7 +111,7 @@ class TensorKeyedCache:
             entries = list(self._items.items())
         for pass_no in (0, 1):
             for key, (src, ver, ext, value) in reversed(entries):
-                if ext != extra or ver != src._version:
+                if ext != extra or ver != tensor_version(src):
                     continue
                 if pass_no == 0:
                     hit = src is tensor
@@ -120,7 +126,7 @@ class TensorKeyedCache:
         value = builder()
         with self._lock:
             self._serial += 1
-            self._items[self._serial] = (tensor, tensor._version, extra, value)
+            self._items[self._serial] = (tensor, tensor_version(tensor), extra, value)
             while len(self._items) > self._max:
                 self._items.popitem(last=False)
         return value

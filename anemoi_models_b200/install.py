@@ -34,16 +34,21 @@ def _cached_expand_edges(self, edge_index, edge_inc, batch_size: int):
     The reference rebuilds `cat([edge_index + i * edge_inc ...])` on every forward although both operands are constant
     buffers; returning the SAME tensor object lets the graph-plan cache hit by identity (no rebuild, no device compare,
     no host sync on the step path).  An in-place edit of the buffer (its `_version` changes) rebuilds."""
-    cache = self.__dict__.setdefault("_b200_expanded", {})
-    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), str(edge_index.device), int(batch_size))
-    hit = cache.get(key)
-    if hit is not None and hit[0] is edge_index and hit[1]._version == hit[2]:
-        return hit[1]
     import torch
 
-    out = torch.cat([edge_index + i * edge_inc for i in range(batch_size)], dim=1)
+    from .graph import tensor_version
+
+    cache = self.__dict__.setdefault("_b200_expanded", {})
+    key = (edge_index.data_ptr(), tensor_version(edge_index), tuple(edge_index.shape), str(edge_index.device), int(batch_size))
+    hit = cache.get(key)
+    if hit is not None and hit[0] is edge_index and tensor_version(hit[1]) == hit[2]:
+        return hit[1]
+    # built OUTSIDE inference mode even when the caller is inside it (Lightning validate / predict): the cached tensor is
+    # then an ordinary tensor that later training forwards may use, and its version counter exists
+    with torch.inference_mode(False):
+        out = torch.cat([edge_index + i * edge_inc for i in range(batch_size)], dim=1)
     cache.clear()
-    cache[key] = (edge_index, out, out._version)
+    cache[key] = (edge_index, out, tensor_version(out))
     return out
 
 

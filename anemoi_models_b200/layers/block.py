@@ -21,11 +21,11 @@ import torch.distributed as dist
 from torch import Tensor, nn
 
 from ..distributed.collectives import shard_tensor, sync_tensor
-from ..distributed.halo import (HaloPlan, build_bipartite_halo_plan, build_local_halo_plan, halo_exchange, halo_gather,
-                                select_sharded_edges)
+from ..distributed.halo import (HaloPlan, build_bipartite_halo_plan, build_local_halo_plan, cached_plan, halo_exchange,
+                                halo_gather, select_sharded_edges)
 from ..distributed.shapes import bounds_from_shapes
 from ..distributed.transformer import shard_heads, shard_sequence
-from ..graph import TensorKeyedCache, check_edge_index, get_csr, resolve_size
+from ..graph import check_edge_index, get_csr, resolve_size
 from .conv import GraphConv, GraphTransformerConv
 from .mlp import MLP, activation_class
 
@@ -35,8 +35,6 @@ LOGGER = logging.getLogger(__name__)
 # has no E x D temporaries, so chunking changes neither memory nor results; the variable stays accepted.
 NUM_CHUNKS_INFERENCE = int(os.environ.get("ANEMOI_INFERENCE_NUM_CHUNKS", "1"))
 _EDGE_FOLD = os.environ.get("AB2_EDGE_FOLD", "0") == "1"  # round-2 draft path, see ops.gt_conv_folded
-
-_halo_cache = TensorKeyedCache()
 
 
 def _autocast_once(x: Tensor) -> Tensor:
@@ -106,8 +104,8 @@ class GraphConvBaseBlock(BaseBlock):
         check_edge_index(edge_index)
         sb, db = bounds_from_shapes(shapes_src), bounds_from_shapes(shapes_dst)
         rank = dist.get_rank(group=model_comm_group)
-        plan: HaloPlan = _halo_cache.get(edge_index, ("local", tuple(sb), tuple(db), rank),
-                                         lambda: build_local_halo_plan(edge_index, sb, db, model_comm_group))
+        plan: HaloPlan = cached_plan(self, ("local", tuple(sb), tuple(db), rank), edge_index, model_comm_group,
+                                     lambda: build_local_halo_plan(edge_index, sb, db, model_comm_group))
         x_need = halo_gather(x_src, plan, model_comm_group)  # replaces sync_tensor's full all-gather (block.py:203)
         return self.conv((x_need, x_dst), edge_attr, plan.local_edge_index, size=(plan.n_src, plan.num_dst_local))
 
@@ -215,8 +213,8 @@ class GraphTransformerBaseBlock(BaseBlock, ABC):
         shapes_src, shapes_dst, shapes_edge = shapes
         sb, db = bounds_from_shapes(shapes_src), bounds_from_shapes(shapes_dst)
         rank = dist.get_rank(group=model_comm_group)
-        plan: HaloPlan = _halo_cache.get(edge_index, ("bipartite", tuple(sb), tuple(db), rank),
-                                         lambda: build_bipartite_halo_plan(edge_index, sb, db, rank))
+        plan: HaloPlan = cached_plan(self, ("bipartite", tuple(sb), tuple(db), rank), edge_index, model_comm_group,
+                                     lambda: build_bipartite_halo_plan(edge_index, sb, db, rank))
         # raw attributes of the edges this rank owns (they arrive sharded by original edge order), then project locally
         ea_local = select_sharded_edges(edge_attr, shapes_edge, plan.edge_ids, model_comm_group)
         e = _linear_padded_k(self.lin_edge, ea_local).view(-1, H, C)

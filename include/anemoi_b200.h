@@ -242,6 +242,54 @@ int ab2_gtconv_fwd_bwd_host_streamed(const void* q_host, const void* k_host, con
                                      void* dq_host, void* dk_host, void* dv_host, void* de_host, const int64_t* meta_host,
                                      int nchunks, void* dev_ws, size_t dev_ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Dense node-side contractions on tcgen05 tensor cores (TMEM accumulators, TMA-staged operands).
+ * Replaces the nn.Linear calls inside the graph blocks: layers/block.py:491-499, 615-620 (lin_self / lin_query / lin_key /
+ * lin_value), :531-533, 630 (projection + skip), :349-354, 537, 633 (node_dst_mlp), layers/conv.py:53-59 + layers/mlp.py:74-84
+ * (GraphConv.edge_mlp), and their autograd backward.
+ *
+ *   D[M,N] = epilogue( A[M,K] . B[N,K]^T )        bf16 operands, fp32 accumulation
+ *
+ * Operand layouts: a_mn = 0: A is [M,K] row-major (row stride lda);  a_mn = 1: A is stored as [K,M] (row stride lda).
+ *                  b_mn = 0: B is [N,K] row-major (nn.Linear weight); b_mn = 1: B is stored as [K,N].
+ *   forward  y = x W^T        : a = x  (a_mn 0), b = W  (b_mn 0)
+ *   dgrad    dx = dy W        : a = dy (a_mn 0), b = W  (b_mn 1; W is [K_gemm = out_features, N_gemm = in_features])
+ *   wgrad    dW = dy^T x      : a = dy (a_mn 1), b = x  (b_mn 1), splits > 1 (contraction over the rows)
+ * Epilogue, in this order (every pointer optional):
+ *   acc = row_scale[m] * acc + row_shift[m] * col_vec[n]     (LayerNorm folded into the GEMM: rstd, -rstd*mean, colsum(W'))
+ *   acc += bias[n]
+ *   dact_pre != NULL : acc *= act'(dact_pre[m,n])            (dgrad through an activation; bf16 [M,N])
+ *   else act != 3    : pre_out[m,n] = acc (bf16, optional side output kept for backward);  acc = act(acc)
+ *   acc += residual[m, n]                                    (bf16 or fp32, row stride ld_res)
+ *   out[n / seg_cols][m, n % seg_cols] = acc                 (bf16 or fp32; up to 4 column segments, row stride ld_out)
+ * act: 0 SiLU, 1 GELU(erf), 2 ReLU, 3 identity.  Requirements: N % 8 == 0, lda / ldb multiples of 8, 16-byte aligned pointers,
+ * seg_cols % 32 == 0 (0 = one output).  splits > 1 (split-K): plain single fp32/bf16 output, fp32 partials in `workspace`
+ * (ab2_gemm_workspace_bytes), summed in a fixed order by a second kernel -- deterministic.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct ab2_gemm {
+  int64_t M, N, K;
+  const void* a;
+  int64_t lda;
+  const void* b;
+  int64_t ldb;
+  int32_t a_mn, b_mn;
+  void* out[4];
+  int64_t ld_out;
+  int32_t seg_cols, out_f32;
+  const float* bias;
+  const float* row_scale;
+  const float* row_shift;
+  const float* col_vec;
+  void* pre_out;
+  const void* dact_pre;
+  const void* residual;
+  int64_t ld_res;
+  int32_t res_f32, act;
+  int32_t splits, reserved;
+} ab2_gemm;
+size_t ab2_gemm_workspace_bytes(const ab2_gemm* d);
+int ab2_gemm_bf16(const ab2_gemm* d, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

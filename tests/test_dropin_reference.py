@@ -363,3 +363,54 @@ def test_hierarchical_reference_model_runs_unchanged_on_the_plugin(reference_on_
             assert p_.grad is None or float(p_.grad.abs().max()) == 0.0, n
         else:
             assert p_.grad is not None and torch.allclose(p_.grad, gref, atol=1e-4 * max(1.0, float(gref.abs().max()))), n
+
+
+@pytest.mark.parametrize("kind", ["gt_forward_mapper", "gt_processor", "gnn_processor"])
+def test_plugin_forward_under_inference_mode(reference_on_path, monkeypatch, kind):
+    """Lightning's validate / predict loops and inference runners call the model under `torch.inference_mode()`: tensors made
+    there do not track a version counter (reading `_version` raises).  The memoised `_expand_edges` and the plan cache must
+    work there, give the numbers of a `no_grad` forward, and leave tensors a later TRAINING forward can use."""
+    import anemoi_models_b200 as b2
+    from anemoi.models.layers import mapper as ref_mapper
+    from anemoi.models.layers import processor as ref_processor
+    from anemoi_models_b200.graph import TensorKeyedCache
+
+    ns, nd, B, hid = 30, 20, 2, 32
+    torch.manual_seed(5)
+    common = dict(trainable_size=6, sub_graph_edge_attributes=["edge_attr1"])
+    b2.install(edge_partition=False)
+    _cpu_conv_patches(monkeypatch)
+    if kind == "gt_forward_mapper":
+        mod = ref_mapper.GraphTransformerForwardMapper(in_channels_src=5, in_channels_dst=4, hidden_dim=hid, num_heads=4,
+                                                       sub_graph=_fake_graph(ns, nd, 70), src_grid_size=ns, dst_grid_size=nd, **common)
+        x = (torch.randn(B * ns, 5), torch.randn(B * nd, 4))
+        shapes = ([list(x[0].shape)], [list(x[1].shape)])
+    else:
+        cls = ref_processor.GraphTransformerProcessor if kind == "gt_processor" else ref_processor.GNNProcessor
+        extra = dict(num_heads=4) if kind == "gt_processor" else {}
+        mod = cls(num_layers=2, num_channels=hid, num_chunks=1, sub_graph=_fake_graph(nd, nd, 60), src_grid_size=nd, dst_grid_size=nd,
+                  **extra, **common)
+        x = torch.randn(B * nd, hid)
+        shapes = ([list(x.shape)], [list(x.shape)])
+
+    def first(o):
+        return o[1] if isinstance(o, tuple) else o
+
+    with torch.inference_mode():
+        a1 = first(mod(x, batch_size=B, shard_shapes=shapes))
+        a2 = first(mod(x, batch_size=B, shard_shapes=shapes))  # second call: cache hits
+    with torch.no_grad():
+        ref = first(mod(x, batch_size=B, shard_shapes=shapes))
+    assert torch.equal(a1, a2) and torch.allclose(a1, ref, atol=1e-6)
+    # a training forward + backward afterwards still works (nothing cached is an inference tensor that autograd would reject)
+    out = first(mod(x, batch_size=B, shard_shapes=shapes))
+    out.sum().backward()
+    assert any(p.grad is not None for p in mod.parameters())
+    # the plan cache itself, keyed by an inference tensor
+    cache = TensorKeyedCache()
+    with torch.inference_mode():
+        ei = torch.cat([torch.randint(0, 5, (2, 7)), torch.randint(0, 5, (2, 3))], dim=1)
+        assert ei.is_inference()
+        v1 = cache.get(ei, ("k",), lambda: object())
+        assert cache.get(ei, ("k",), lambda: object()) is v1
+        assert cache.get(ei.clone(), ("k",), lambda: object()) is v1  # same content, other object
