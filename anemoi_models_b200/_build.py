@@ -13,7 +13,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libanemoi_b200.so")
 WIP_SOURCES = ["wip/gtconv_fold_tma.cu"]  # round-2 work in progress: must keep compiling, never linked / never called
 SOURCES = ["abi.cu", "csr_build.cu", "gtconv.cu", "gtconv_tma.cu", "gtconv_fold.cu", "graphconv.cu", "host_api.cu", "peer_exchange.cu",
-           "gemm_tc.cu"]
+           "gemm_tc.cu", "layernorm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",

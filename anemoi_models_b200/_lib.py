@@ -64,6 +64,10 @@ SIGNATURES = {
     "ab2_edge_ln_res_segsum_bwd": (_i32, [_vp] * 7 + [_i64] * 2 + [_i32] * 2 + [_vp] * 3 + [_i32] + [_vp] * 3),
     "ab2_gemm_workspace_bytes": (_sz, [C.POINTER(Gemm)]),
     "ab2_gemm_bf16": (_i32, [C.POINTER(Gemm), _vp, _sz, _vp]),
+    "ab2_ln_parts": (_i32, []),
+    "ab2_layernorm_fwd": (_i32, [_vp, _i32, _vp, _vp, _f32, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "ab2_layernorm_bwd": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ab2_colsum": (_i32, [_vp, _i32, _i64, _i32, _i64, _vp, _vp, _vp]),
     "ab2_gtconv_host_workspace_bytes": (_sz, [_i64] * 3 + [_i32] * 3),
     "ab2_gtconv_fwd_bwd_host_streamed": (_i32, [_vp] * 5 + [_i32] + [_vp] * 6 + [_i64] * 3 + [_i32] * 2 + [_vp] * 5 + [_vp, _i32, _vp, _sz, _vp]),
     "ab2_gtconv_fwd_bwd_host": (_i32, [_vp] * 5 + [_i32] + [_vp] * 6 + [_i64] * 3 + [_i32] * 2 + [_vp] * 5 + [_vp, _sz, _vp]),

@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
 
 #include "../../include/anemoi_b200.h"
 
@@ -32,6 +33,22 @@ long long* launch_counter();  // process-wide count of kernel launches issued by
     cudaError_t _e = cudaGetLastError();                                                               \
     if (_e != cudaSuccess) return ab2::fail(AB2_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
   } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: set it once per (kernel instantiation, device), under a
+// mutex (calls arrive from the main thread and from autograd's worker threads).  Expands inside the launcher of ONE kernel
+// instantiation, so the function-local statics are per kernel.  Evaluates to false when the attribute cannot be set.
+#define AB2_ENSURE_DYN_SMEM(kern, bytes)                                                                          \
+  ([&]() -> bool {                                                                                                \
+    static std::mutex mu_;                                                                                        \
+    static bool done_[64] = {false};                                                                              \
+    int dev_ = 0;                                                                                                 \
+    if (cudaGetDevice(&dev_) != cudaSuccess) return false;                                                        \
+    std::lock_guard<std::mutex> lock_(mu_);                                                                       \
+    if (dev_ >= 0 && dev_ < 64 && done_[dev_]) return true;                                                       \
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)) != cudaSuccess) return false; \
+    if (dev_ >= 0 && dev_ < 64) done_[dev_] = true;                                                               \
+    return true;                                                                                                  \
+  }())
 
 inline int num_sms() {
   static int n = 0;

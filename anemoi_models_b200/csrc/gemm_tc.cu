@@ -9,16 +9,22 @@
 //
 //   D[M,N] = epilogue( A[M,K] . B[N,K]^T ),  bf16 operands, fp32 accumulation in tensor memory.
 //
-// Structure (one persistent CTA per SM, 10 warps):
+// Structure (one persistent CTA per SM, 10 warps; CG = 2: the two CTAs of a cluster -- the two SMs of a TPC -- work as ONE
+// 256 x BN tile with tcgen05.mma.cta_group::2: each CTA stages its 128 rows of A and its HALF of B, so the B bytes pulled
+// from L2 and the shared-memory reads per flop are halved; measured: 1-CTA 128 x 256 tiles are L2-feed-bound at 75-85 % of
+// cuBLAS, profiles/r02/gemm_probe_r02a.jsonl):
 //   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B boxes) of the A / B k-blocks into a shared-memory ring,
-//               completion counted in bytes on the stage's `full` mbarrier;
-//   warp 1      MMA issuer: ONE thread issues tcgen05.mma.cta_group::1.kind::f16 (128 x BN x 16 per instruction) on the staged
-//               tiles; tcgen05.commit releases the stage (`empty`) and, after the last k-block, publishes the accumulator
-//               (`tmem_full`).  The warp also owns the TMEM allocation (512 columns = two accumulator stages of BN <= 256);
+//               completion counted in bytes on the stage's `full` mbarrier (CG = 2: both CTAs' copies signal the LEADER's);
+//   warp 1      MMA issuer (leader CTA): ONE thread issues tcgen05.mma.kind::f16 (128*CG x BN x 16 per instruction) on the
+//               staged tiles; tcgen05.commit releases the stage (`empty`, multicast to both CTAs) and, after the last k-block,
+//               publishes the accumulator (`tmem_full`).  The warp also owns the TMEM allocation (512 columns = two
+//               accumulator stages of BN <= 256);
 //   warps 2..9  epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) of the finished accumulator while the MMA warp
 //               already works on the next tile in the other TMEM stage; bias / LayerNorm-fold / activation (+ pre-activation
-//               side output) / activation-derivative / residual, bf16 or fp32 stores, outputs optionally split by column
-//               segments (q | self, k | v land in separate tensors).
+//               side output) / activation-derivative / residual; bf16 results are transposed through a per-warp shared-memory
+//               patch so that global stores are row-contiguous 64 B runs (a thread owns a ROW of the accumulator: storing
+//               straight from registers writes 32 rows x 16 B per instruction, half a sector each -- measured 2-4x slower on
+//               epilogue-bound shapes); outputs optionally split by column segments (q | self, k | v land in separate tensors).
 // Operands may be K-major (contraction contiguous in memory: x [M,K], W [N,K]) or MN-major (contraction strided: W as the
 // B operand of dgrad, dY^T and x as the operands of wgrad), selected per operand in the instruction descriptor; no transposes
 // are materialised.  wgrad splits the (long) contraction over CTAs into fp32 partials that a second kernel sums in a fixed
@@ -41,14 +47,19 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kBoxBytes = 64 * 64 * 2;  // one 64 x 64 bf16 box (MN-major operands are loaded box by box)
 
-template <int BN>
+constexpr int kPatchStride = 80;                      // bytes per row of an epilogue patch: 64 B of bf16 + 16 B pad (bank spread)
+constexpr int kPatchBytes = 32 * kPatchStride;        // 32 rows x 32 bf16 columns per epilogue warp
+
+template <int BN, int CG>
 struct Cfg {
+  static constexpr int kBRows = BN / CG;  // rows of B this CTA stages (CG = 2: half of the tile's columns)
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes;  // 4 at BN=256, 6 at BN=128, 8 at BN=64
+  static constexpr int kStagesRaw = (192 * 1024) / kStageBytes;  // CG=1: 4 / 6 / 8 at BN = 256 / 128 / 64; CG=2: 6 / 8 / 9
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kBarBytes = 1024;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + slack for the 1024 B alignment
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kEpiWarps * kPatchBytes + 1024;  // + 1024 B alignment slack
 };
 
 struct Epi {
@@ -113,6 +124,52 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                "l"(map), "r"(bar), "r"(c0), "r"(c1)
                : "memory");
 }
+// CG = 2: the copy lands in THIS CTA's shared memory, its bytes are counted on the LEADER CTA's mbarrier (cluster address)
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {  // shared::cluster address of `addr` in CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit_cg2(uint32_t bar) {  // arrives on the barrier at this offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_cg2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void sts16(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds16(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -152,32 +209,86 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
   return ((uint64_t)hi << 32) | lo;
 }
 
-__device__ __forceinline__ float act_fn(float x, int act) {
-  switch (act) {
-    case 0: return x / (1.f + __expf(-x));
-    case 1: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
-    case 2: return fmaxf(x, 0.f);
-    default: return x;
+// erf with |error| < 2e-7 (Abramowitz & Stegun 7.1.26): one reciprocal, one exp2 and 7 FMAs instead of libdevice's ~30-instruction
+// erff -- far below the bf16 resolution of anything stored here
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float r = 1.f - p * t * fast_exp2(-ax * ax * kLog2e);
+  return copysignf(r, x);
+}
+template <int ACT>
+__device__ __forceinline__ float act_fn(float x) {
+  if constexpr (ACT == 0) return x * __frcp_rn(1.f + fast_exp2(-x * kLog2e));
+  else if constexpr (ACT == 1) return 0.5f * x * (1.f + erf_fast(x * 0.70710678118654752f));
+  else if constexpr (ACT == 2) return fmaxf(x, 0.f);
+  else return x;
+}
+template <int ACT>
+__device__ __forceinline__ float act_grad(float x) {
+  if constexpr (ACT == 0) {
+    const float s = __frcp_rn(1.f + fast_exp2(-x * kLog2e));
+    return s * (1.f + x * (1.f - s));
+  } else if constexpr (ACT == 1) {
+    return 0.5f * (1.f + erf_fast(x * 0.70710678118654752f)) + x * 0.3989422804014327f * fast_exp2(-0.5f * x * x * kLog2e);
+  } else if constexpr (ACT == 2) {
+    return x > 0.f ? 1.f : 0.f;
+  } else {
+    return 1.f;
   }
 }
-__device__ __forceinline__ float act_grad(float x, int act) {
-  switch (act) {
-    case 0: {
-      const float s = 1.f / (1.f + __expf(-x));
-      return s * (1.f + x * (1.f - s));
-    }
-    case 1: return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
-    case 2: return x > 0.f ? 1.f : 0.f;
-    default: return 1.f;
-  }
+// the activation code is a runtime argument: dispatch ONCE per 32-value chunk (warp-uniform), never per element -- a per-element
+// `switch` made ptxas emit every activation's code for every element (measured: ~165 instructions per element, epilogue-bound GEMMs
+// at 15-35 % of cuBLAS, profiles/r02/gemm_probe_r02c.jsonl)
+template <int ACT>
+__device__ __forceinline__ void act_chunk(float (&f)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = act_fn<ACT>(f[j]);
+}
+__device__ __forceinline__ void act_chunk_rt(float (&f)[32], int act) {
+  if (act == 0) act_chunk<0>(f);
+  else if (act == 1) act_chunk<1>(f);
+  else if (act == 2) act_chunk<2>(f);
+}
+template <int ACT>
+__device__ __forceinline__ void act_grad_mul8(float (&f)[32], int j, const float (&p)[8]) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) f[j + u] *= act_grad<ACT>(p[u]);
 }
 
 // ---- the kernel --------------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN>
+// bf16 chunk of 32 rows x 32 columns held one ROW per lane (f[j] = column j of row `lane`) -> global memory, through the warp's
+// shared-memory patch so that each store instruction writes 8 rows x 64 contiguous bytes.
+__device__ __forceinline__ void store_chunk_bf16(uint32_t patch, int lane, const float (&f)[32], __nv_bfloat16* out, long long ld,
+                                                 int row0, int rows_left, int cols_left) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    float p[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) p[u] = f[j + u];
+    sts16(patch + lane * kPatchStride + j * 2, pack<__nv_bfloat16>(p));
+  }
+  __syncwarp();
+  const int c16 = lane & 3, rsub = lane >> 2;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + rsub;
+    const uint4 v = lds16(patch + r * kPatchStride + c16 * 16);
+    if (r < rows_left && c16 * 8 < cols_left) stg16(out + (size_t)(row0 + r) * ld + c16 * 8, v);
+  }
+  __syncwarp();
+}
+
+template <int BN, bool A_MN, bool B_MN, int CG>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, const Args g) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
   constexpr int S = C::kStages;
+  constexpr int TM = BM * CG;  // rows of the tile the CTA pair (or the single CTA) accumulates
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms are 1024 B aligned
   const uint32_t bars = base + S * C::kStageBytes;
@@ -186,28 +297,38 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   auto tfull = [&](int a) { return bars + 8u * (2 * S + a); };
   auto tempty = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * S + 4);
+  const uint32_t patches = bars + C::kBarBytes;
   auto sA = [&](int s) { return base + s * C::kStageBytes; };
   auto sB = [&](int s) { return base + s * C::kStageBytes + C::kABytes; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta = CG == 2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs, owns the full / tmem_empty barriers)
+  const int cluster_id = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_clusters = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full(s), 1);
+      mbar_init(full(s), CG);  // one arrival per CTA's producer (the leader's carries the byte count of both)
       mbar_init(empty(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull(a), 1);
-      mbar_init(tempty(a), kEpiWarps);
+      mbar_init(tempty(a), CG * kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers exist before anything can signal them
   if (warp == 1) {  // TMEM: 512 columns (the whole SM's tensor memory; one CTA per SM)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -218,44 +339,55 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t c = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         const int split = t % g.splits, r = t / g.splits;
-        const int n0 = (r % g.tiles_n) * BN, m0 = (r / g.tiles_n) * BM;
+        const int n0 = (r % g.tiles_n) * BN + (int)cta * C::kBRows, m0 = (r / g.tiles_n) * TM + (int)cta * BM;
         const int kb0 = split * g.kb_per_split, kb1 = min(kb0 + g.kb_per_split, g.kb_total);
         for (int kb = kb0; kb < kb1; ++kb, ++c) {
           const int s = c % S;
           mbar_wait(empty(s), ((c / S) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(full(s), C::kStageBytes);
+          uint32_t fb = full(s);
+          if constexpr (CG == 2) fb = mapa(fb, 0);
+          auto load = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1) {
+            if constexpr (CG == 2) tma_load_2d_cg2(dst, m, fb, c0, c1); else tma_load_2d(dst, m, fb, c0, c1);
+          };
           if constexpr (!A_MN) {
-            tma_load_2d(sA(s), &tmA, full(s), kb * BK, m0);
+            load(sA(s), &tmA, kb * BK, m0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BM / 64; ++i) tma_load_2d(sA(s) + i * kBoxBytes, &tmA, full(s), m0 + 64 * i, kb * BK);
+            for (int i = 0; i < BM / 64; ++i) load(sA(s) + i * kBoxBytes, &tmA, m0 + 64 * i, kb * BK);
           }
           if constexpr (!B_MN) {
-            tma_load_2d(sB(s), &tmB, full(s), kb * BK, n0);
+            load(sB(s), &tmB, kb * BK, n0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i) tma_load_2d(sB(s) + i * kBoxBytes, &tmB, full(s), n0 + 64 * i, kb * BK);
+            for (int i = 0; i < C::kBRows / 64; ++i) load(sB(s) + i * kBoxBytes, &tmB, n0 + 64 * i, kb * BK);
+          }
+          // copies first, arrival second: the peer's arrival on the leader's barrier is a remote operation and must not sit in
+          // front of its own loads (a `.release.cluster` arrival there cost an ERRBAR per k-block: 34 % tensor-pipe activity)
+          if constexpr (CG == 2) {
+            if (cta == 0) mbar_arrive_expect_tx(full(s), 2 * C::kStageBytes); else mbar_arrive_cluster(fb);
+          } else {
+            mbar_arrive_expect_tx(fb, C::kStageBytes);
           }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer (one thread of the leader CTA) =====
+    if (lane == 0 && cta == 0) {
       // instruction descriptor: D fp32, A / B bf16, operand majors, N >> 3 at bit 17, M >> 4 at bit 24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       constexpr uint32_t kAStep = A_MN ? (UMMA_K * 128) : (UMMA_K * 2);  // bytes per UMMA_K along the contraction
       constexpr uint32_t kBStep = B_MN ? (UMMA_K * 128) : (UMMA_K * 2);
       uint32_t c = 0, it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
         const int split = t % g.splits;
         const int kb0 = split * g.kb_per_split, kb1 = min(kb0 + g.kb_per_split, g.kb_total);
         const uint32_t a = it & 1u;
-        mbar_wait(tempty(a), ((it >> 1) & 1u) ^ 1u);  // the epilogue has drained this accumulator stage
+        mbar_wait(tempty(a), ((it >> 1) & 1u) ^ 1u);  // the epilogue (of both CTAs) has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * BN;
         for (int kb = kb0; kb < kb1; ++kb, ++c) {
@@ -266,12 +398,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           const uint64_t db = B_MN ? smem_desc(sB(s), g.mn_lbo, g.mn_sbo) : smem_desc(sB(s), g.k_lbo, g.k_sbo);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            tc_mma(d_tmem, da + (uint64_t)((k * kAStep) >> 4), db + (uint64_t)((k * kBStep) >> 4), idesc,
-                   (kb > kb0 || k > 0) ? 1u : 0u);
+            const uint64_t dak = da + (uint64_t)((k * kAStep) >> 4), dbk = db + (uint64_t)((k * kBStep) >> 4);
+            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+            if constexpr (CG == 2) tc_mma_cg2(d_tmem, dak, dbk, idesc, acc); else tc_mma(d_tmem, dak, dbk, idesc, acc);
           }
-          tc_commit(empty(s));  // stage reusable once these MMAs have read it
+          // stage reusable (in both CTAs) once these MMAs have read it
+          if constexpr (CG == 2) tc_commit_cg2(empty(s)); else tc_commit(empty(s));
         }
-        tc_commit(tfull(a));  // accumulator complete
+        if constexpr (CG == 2) tc_commit_cg2(tfull(a)); else tc_commit(tfull(a));  // accumulator complete
+      }
+      if constexpr (CG == 2) {
+        // the peer's epilogue arrives on THIS CTA's tmem_empty barriers: see its last arrivals in before leaving
+        if (it >= 1) mbar_wait(tempty((it - 1) & 1u), ((it - 1) >> 1) & 1u);
+        if (it >= 2) mbar_wait(tempty((it - 2) & 1u), ((it - 2) >> 1) & 1u);
       }
     }
     __syncwarp();
@@ -282,14 +421,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int half = e >> 2;    // two warps per lane quadrant: each takes half of the BN columns
     constexpr int kChunks = BN / 32 / 2;
     const Epi& ep = g.epi;
+    const uint32_t patch = patches + e * kPatchBytes;
     uint32_t it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
       const int split = t % g.splits, r = t / g.splits;
-      const int n0 = (r % g.tiles_n) * BN, m0 = (r / g.tiles_n) * BM;
+      const int n0 = (r % g.tiles_n) * BN, m0 = (r / g.tiles_n) * TM + (int)cta * BM;
       const uint32_t a = it & 1u;
       mbar_wait(tfull(a), (it >> 1) & 1u);
       tc_fence_after();
-      const int row = m0 + quad * 32 + lane;
+      const int row0 = m0 + quad * 32;  // first row of this warp's 32 x 32 chunks
+      const int row = row0 + lane;
       const bool row_ok = row < g.M;
       float rs = 1.f, rt = 0.f;
       if (ep.row_scale != nullptr && row_ok) {
@@ -305,17 +446,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         if (ch == kChunks - 1) {  // this warp has read its share of the stage: hand it back before the stores
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty(a));
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_cluster(mapa(tempty(a), 0)); else mbar_arrive(tempty(a));
+          }
         }
         const int col0 = n0 + cc;
-        if (!row_ok || col0 >= g.N) continue;
+        if (row0 >= g.M || col0 >= g.N) continue;  // warp-uniform
+        const int cols_left = g.N - col0, rows_left = g.M - row0;
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
         if (ep.row_scale != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            if (col0 + j < g.N) {
+            if (j < cols_left) {
               const float4 cv = __ldg(reinterpret_cast<const float4*>(ep.col_vec + col0 + j));
               f[j] = rs * f[j] + rt * cv.x;
               f[j + 1] = rs * f[j + 1] + rt * cv.y;
@@ -327,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         if (ep.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            if (col0 + j < g.N) {
+            if (j < cols_left) {
               const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
               f[j] += b.x;
               f[j + 1] += b.y;
@@ -337,45 +481,37 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           }
         }
         if (ep.dact_pre != nullptr) {
-          const __nv_bfloat16* pp = reinterpret_cast<const __nv_bfloat16*>(ep.dact_pre) + (size_t)row * g.N + col0;
+          if (row_ok) {
+            const __nv_bfloat16* pp = reinterpret_cast<const __nv_bfloat16*>(ep.dact_pre) + (size_t)row * g.N + col0;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (col0 + j < g.N) {
-              float p[8];
-              unpack<__nv_bfloat16>(ldg16(pp + j), p);
-#pragma unroll
-              for (int u = 0; u < 8; ++u) f[j + u] *= act_grad(p[u], ep.act);
+            for (int j = 0; j < 32; j += 8) {
+              if (j < cols_left) {
+                float p[8];
+                unpack<__nv_bfloat16>(ldg16_keep(pp + j), p);
+                if (ep.act == 0) act_grad_mul8<0>(f, j, p);
+                else if (ep.act == 1) act_grad_mul8<1>(f, j, p);
+                else if (ep.act == 2) act_grad_mul8<2>(f, j, p);
+              }
             }
           }
         } else if (ep.act != 3) {
           if (ep.pre_out != nullptr) {
-            __nv_bfloat16* pp = reinterpret_cast<__nv_bfloat16*>(ep.pre_out) + (size_t)row * g.N + col0;
+            // the activation sees the bf16-rounded pre-activation, so that backward (which only has the rounded value)
+            // differentiates exactly the function forward applied
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (col0 + j < g.N) {
-                float p[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) p[u] = f[j + u];
-                stg16(pp + j, pack<__nv_bfloat16>(p));
-              }
-            }
+            for (int j = 0; j < 32; ++j) f[j] = __bfloat162float(__float2bfloat16_rn(f[j]));
+            store_chunk_bf16(patch, lane, f, reinterpret_cast<__nv_bfloat16*>(ep.pre_out) + col0, g.N, row0, rows_left, cols_left);
           }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            // the activation sees the bf16-rounded pre-activation when one is kept, so that backward (which only has the
-            // rounded value) differentiates exactly the function forward applied
-            const float x = ep.pre_out != nullptr ? __bfloat162float(__float2bfloat16_rn(f[j])) : f[j];
-            f[j] = act_fn(x, ep.act);
-          }
+          act_chunk_rt(f, ep.act);
         }
-        if (ep.residual != nullptr) {
+        if (ep.residual != nullptr && row_ok) {
           if (ep.res_f32) {
             const float* rp = reinterpret_cast<const float*>(ep.residual) + (size_t)row * ep.ld_res + col0;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              if (col0 + j < g.N) {
+              if (j < cols_left) {
                 float p[4];
-                unpack<float>(ldg16(rp + j), p);
+                unpack<float>(ldg16_keep(rp + j), p);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) f[j + u] += p[u];
               }
@@ -384,9 +520,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (size_t)row * ep.ld_res + col0;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              if (col0 + j < g.N) {
+              if (j < cols_left) {
                 float p[8];
-                unpack<__nv_bfloat16>(ldg16(rp + j), p);
+                unpack<__nv_bfloat16>(ldg16_keep(rp + j), p);
 #pragma unroll
                 for (int u = 0; u < 8; ++u) f[j + u] += p[u];
               }
@@ -396,35 +532,31 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const int seg = col0 / ep.seg_cols;
         const int cs = col0 - seg * ep.seg_cols;
         if (ep.out_f32) {
-          float* op = reinterpret_cast<float*>(ep.out[seg]) + (size_t)split * g.split_stride + (size_t)row * ep.ld_out + cs;
+          if (row_ok) {
+            float* op = reinterpret_cast<float*>(ep.out[seg]) + (size_t)split * g.split_stride + (size_t)row * ep.ld_out + cs;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (col0 + j < g.N) {
-              float p[4] = {f[j], f[j + 1], f[j + 2], f[j + 3]};
-              stg16(op + j, pack<float>(p));
+            for (int j = 0; j < 32; j += 4) {
+              if (j < cols_left) {
+                float p[4] = {f[j], f[j + 1], f[j + 2], f[j + 3]};
+                stg16(op + j, pack<float>(p));
+              }
             }
           }
         } else {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(ep.out[seg]) + (size_t)row * ep.ld_out + cs;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (col0 + j < g.N) {
-              float p[8];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) p[u] = f[j + u];
-              stg16(op + j, pack<__nv_bfloat16>(p));
-            }
-          }
+          store_chunk_bf16(patch, lane, f, reinterpret_cast<__nv_bfloat16*>(ep.out[seg]) + cs, ep.ld_out, row0, rows_left, cols_left);
         }
       }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if constexpr (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -482,26 +614,30 @@ static int make_map(CUtensorMap* m, const void* ptr, long long inner, long long 
   return AB2_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CG>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Args& a, cudaStream_t st) {
-  using C = Cfg<BN>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
-  static std::mutex mu;
-  static bool configured[64] = {false};
-  int dev = 0;
-  AB2_CUDA_OK(cudaGetDevice(&dev));
-  {
-    std::lock_guard<std::mutex> lock(mu);
-    if (dev < 64 && !configured[dev]) {
-      AB2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-      configured[dev] = true;
-    }
-  }
+  using C = Cfg<BN, CG>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CG>;
+  if (!AB2_ENSURE_DYN_SMEM(kern, C::kSmemBytes)) return fail(AB2_ERR_CUDA, "gemm_tc_kernel: cannot reserve %d B of shared memory", C::kSmemBytes);
   const int tiles = a.tiles_m * a.tiles_n * a.splits;
-  int grid = tiles < num_sms() ? tiles : num_sms();
+  const int slots = num_sms() / CG;  // CTAs (CG = 1) or CTA pairs (CG = 2) that can be resident
+  int grid = tiles < slots ? tiles : slots;
   const char* env = getenv("AB2_GEMM_GRID");
   if (env != nullptr && atoi(env) > 0 && atoi(env) < grid) grid = atoi(env);
-  kern<<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, a);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(grid * CG));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  AB2_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, a));
   AB2_LAUNCH_OK("gemm_tc_kernel");
   return AB2_OK;
 }
@@ -530,8 +666,10 @@ extern "C" int ab2_gemm_bf16(const ab2_gemm* d, void* workspace, size_t workspac
   a.M = (int)M;
   a.N = (int)N;
   a.K = (int)K;
-  const int BN = (N > 128) ? 256 : (N > 64 ? 128 : 64);
-  a.tiles_m = (int)((M + tc::BM - 1) / tc::BM);
+  const int BN = (N > 128) ? 256 : 128;
+  int CG = 2;  // CTA pairs (cta_group::2) unless asked otherwise (A/B experiments)
+  if (const char* cg = getenv("AB2_GEMM_CG")) CG = atoi(cg) == 1 ? 1 : 2;
+  a.tiles_m = (int)((M + tc::BM * CG - 1) / (tc::BM * CG));
   a.tiles_n = (int)((N + BN - 1) / BN);
   a.kb_total = (int)((K + tc::BK - 1) / tc::BK);
   a.splits = splits;
@@ -579,23 +717,24 @@ extern "C" int ab2_gemm_bf16(const ab2_gemm* d, void* workspace, size_t workspac
   }
   CUtensorMap ta, tb;
   int rc;
-  // K-major operand: memory [rows][K] -> inner = K, outer = rows, box 64 x tile rows.  MN-major: memory [K][rows] -> inner =
-  // rows, outer = K, 64 x 64 boxes.
+  // K-major operand: memory [rows][K] -> inner = K, outer = rows, box 64 x (rows this CTA stages).  MN-major: memory [K][rows]
+  // -> inner = rows, outer = K, 64 x 64 boxes.
   rc = d->a_mn ? tc::make_map(&ta, d->a, M, K, d->lda, 64) : tc::make_map(&ta, d->a, K, M, d->lda, tc::BM);
   if (rc) return rc;
-  rc = d->b_mn ? tc::make_map(&tb, d->b, N, K, d->ldb, 64) : tc::make_map(&tb, d->b, K, N, d->ldb, BN);
+  rc = d->b_mn ? tc::make_map(&tb, d->b, N, K, d->ldb, 64) : tc::make_map(&tb, d->b, K, N, d->ldb, BN / CG);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-#define AB2_GEMM_DISPATCH(BNV)                                                        \
-  do {                                                                                \
-    if (!d->a_mn && !d->b_mn) rc = tc::launch<BNV, false, false>(ta, tb, a, st);      \
-    else if (!d->a_mn && d->b_mn) rc = tc::launch<BNV, false, true>(ta, tb, a, st);   \
-    else if (d->a_mn && d->b_mn) rc = tc::launch<BNV, true, true>(ta, tb, a, st);     \
-    else rc = tc::launch<BNV, true, false>(ta, tb, a, st);                            \
+#define AB2_GEMM_DISPATCH(BNV, CGV)                                                       \
+  do {                                                                                    \
+    if (!d->a_mn && !d->b_mn) rc = tc::launch<BNV, false, false, CGV>(ta, tb, a, st);     \
+    else if (!d->a_mn && d->b_mn) rc = tc::launch<BNV, false, true, CGV>(ta, tb, a, st);  \
+    else if (d->a_mn && d->b_mn) rc = tc::launch<BNV, true, true, CGV>(ta, tb, a, st);    \
+    else rc = tc::launch<BNV, true, false, CGV>(ta, tb, a, st);                           \
   } while (0)
-  if (BN == 256) AB2_GEMM_DISPATCH(256);
-  else if (BN == 128) AB2_GEMM_DISPATCH(128);
-  else AB2_GEMM_DISPATCH(64);
+  if (BN == 256 && CG == 2) AB2_GEMM_DISPATCH(256, 2);
+  else if (BN == 256) AB2_GEMM_DISPATCH(256, 1);
+  else if (CG == 2) AB2_GEMM_DISPATCH(128, 2);
+  else AB2_GEMM_DISPATCH(128, 1);
 #undef AB2_GEMM_DISPATCH
   if (rc) return rc;
   if (splits > 1) {

@@ -352,13 +352,9 @@ gtconv_fwd_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_block) {
 
 template <typename T, int LPH>
 static bool launch_fwd_tma_t(const ConvArgs& a) {
-  static bool configured = false;
   auto kern = gtconv_fwd_tma_kernel<T, LPH>;
   const size_t smem = Ring<1>::kBytes + 128;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
-    configured = true;
-  }
+  if (!AB2_ENSURE_DYN_SMEM(kern, smem)) return false;
   const int rb = rows_per_block(a.E, a.Nd);
   const int grid = std::max(1, std::min((a.Nd + rb - 1) / rb, num_sms() * kCtasPerSm));
   kern<<<grid, kTmaThreads, smem, a.st>>>(a, rb);
@@ -508,13 +504,9 @@ gtconv_bwd_dst_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_block
 
 template <typename T, int LPH>
 static bool launch_bwd_dst_tma_t(const ConvArgs& a) {
-  static bool configured = false;
   auto kern = gtconv_bwd_dst_tma_kernel<T, LPH>;
   const size_t smem = Ring<4>::kBytes + 128;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
-    configured = true;
-  }
+  if (!AB2_ENSURE_DYN_SMEM(kern, smem)) return false;
   const int rb = rows_per_block(a.E, a.Nd);
   const int grid = std::max(1, std::min((a.Nd + rb - 1) / rb, num_sms() * kCtasPerSmBwd));
   kern<<<grid, kTmaThreads, smem, a.st>>>(a, rb);
@@ -692,13 +684,9 @@ gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) 
 
 template <typename T, int LPH>
 static bool launch_bwd_src_tma_t(const ConvArgs& a) {
-  static bool configured = false;
   auto kern = gtconv_bwd_src_tma_kernel<T, LPH>;
   const size_t smem = SrcRing::kBytes + 128;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
-    configured = true;
-  }
+  if (!AB2_ENSURE_DYN_SMEM(kern, smem)) return false;
   const int nrows = a.src_hi - a.src_lo;
   const int ctas = std::max(1, std::min(nrows, num_sms() * kCtasPerSmSrc));
   const int rows_per_cta = (nrows + ctas - 1) / ctas;

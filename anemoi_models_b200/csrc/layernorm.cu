@@ -1,0 +1,323 @@
+// LayerNorm forward / backward over node rows, and a deterministic column sum (bias gradients), sm_100a.
+//
+// Replaces, around the tensor-core GEMMs of the graph blocks (reference paths relative to src/anemoi/models/):
+//   layers/block.py:487-489, 611 (layer_norm1 / layer_norm2), :349-354 (node_dst_mlp[0]) -- nn.LayerNorm, which under autocast
+//   runs in fp32 and is followed by a separate fp32 -> bf16 cast in front of every nn.Linear (measured in round 1 on the
+//   AIFS-like step: 41 ms of LayerNorm kernels + 41 ms of `direct_copy` casts of a 280 ms step).  Here one pass reads the row
+//   (fp32 or bf16), keeps it in registers, and writes the normalised row in the dtype the GEMM consumes (bf16) together with
+//   mean / rstd for backward.  HBM-bound: b_in + b_out bytes per element.
+// Backward: dx = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat)); dgamma / dbeta are column sums accumulated in
+// registers per CTA over a fixed slice of the rows, written as partials and reduced by a second kernel in a fixed order
+// (deterministic, no atomics).
+#include "common.cuh"
+
+namespace ab2 {
+
+constexpr int kLnWarps = 4;
+constexpr int kLnParts = 296;  // CTAs of the backward / column-sum kernels = partial rows (2 per SM)
+
+template <typename T>
+__device__ __forceinline__ void load_row_vec(const T* p, float (&f)[8]);
+template <>
+__device__ __forceinline__ void load_row_vec<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  unpack<__nv_bfloat16>(ldg16(p), f);
+}
+template <>
+__device__ __forceinline__ void load_row_vec<float>(const float* p, float (&f)[8]) {
+  float a[4], b[4];
+  unpack<float>(ldg16(p), a);
+  unpack<float>(ldg16(p + 4), b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[i] = a[i];
+    f[4 + i] = b[i];
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store_row_vec(T* p, const float (&f)[8]);
+template <>
+__device__ __forceinline__ void store_row_vec<__nv_bfloat16>(__nv_bfloat16* p, const float (&f)[8]) {
+  stg16(p, pack<__nv_bfloat16>(f));
+}
+template <>
+__device__ __forceinline__ void store_row_vec<float>(float* p, const float (&f)[8]) {
+  float a[4] = {f[0], f[1], f[2], f[3]}, b[4] = {f[4], f[5], f[6], f[7]};
+  stg16(p, pack<float>(a));
+  stg16(p + 4, pack<float>(b));
+}
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+// one warp per row; lane l owns the 8-element groups l, l + 32, ... (VPL of them): D <= VPL * 256
+template <typename TX, typename TY, int VPL>
+__global__ void __launch_bounds__(kLnWarps * 32) layernorm_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta, float eps, long long M, int D,
+                                                                     TY* __restrict__ y, float* __restrict__ mean_out,
+                                                                     float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * kLnWarps + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * kLnWarps;
+  const int ngroups = D >> 3;
+  float gm[VPL][8], bt[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int gidx = lane + 32 * i;
+    if (gidx < ngroups) {
+      load_row_vec<float>(gamma + gidx * 8, gm[i]);
+      load_row_vec<float>(beta + gidx * 8, bt[i]);
+    }
+  }
+  for (long long row = warp0; row < M; row += nwarps) {
+    float v[VPL][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int gidx = lane + 32 * i;
+      if (gidx < ngroups) {
+        load_row_vec<TX>(x + row * D + gidx * 8, v[i]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[i][u];
+      }
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      if (lane + 32 * i < ngroups) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float d = v[i][u] - mean;
+          q += d * d;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int gidx = lane + 32 * i;
+      if (gidx < ngroups) {
+        float o[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) o[u] = (v[i][u] - mean) * rstd * gm[i][u] + bt[i][u];
+        store_row_vec<TY>(y + row * D + gidx * 8, o);
+      }
+    }
+    if (lane == 0) {
+      if (mean_out != nullptr) mean_out[row] = mean;
+      if (rstd_out != nullptr) rstd_out[row] = rstd;
+    }
+  }
+}
+
+// backward: TG = dtype of the incoming gradient, TX = dtype of x and of dx.  partial: [gridDim.x][2][D] fp32.
+template <typename TG, typename TX, int VPL>
+__global__ void __launch_bounds__(kLnWarps * 32) layernorm_bwd_kernel(const TG* __restrict__ g, const TX* __restrict__ x,
+                                                                     const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                                     const float* __restrict__ rstd, long long M, int D,
+                                                                     const TX* __restrict__ add, TX* __restrict__ dx,
+                                                                     float* __restrict__ partial) {
+  extern __shared__ float red[];  // [kLnWarps][2][D]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int ngroups = D >> 3;
+  // fixed slice of rows per CTA, rows of a slice dealt round-robin to its warps: the summation order is a function of (M, grid)
+  const long long per = (M + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * per, r1 = min(r0 + per, M);
+  float gm[VPL][8], dg[VPL][8], db[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int gidx = lane + 32 * i;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) dg[i][u] = db[i][u] = 0.f;
+    if (gidx < ngroups) load_row_vec<float>(gamma + gidx * 8, gm[i]);
+  }
+  for (long long row = r0 + w; row < r1; row += kLnWarps) {
+    const float mu = mean[row], rs = rstd[row];
+    float gv[VPL][8], xh[VPL][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int gidx = lane + 32 * i;
+      if (gidx < ngroups) {
+        load_row_vec<TG>(g + row * D + gidx * 8, gv[i]);
+        load_row_vec<TX>(x + row * D + gidx * 8, xh[i]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          xh[i][u] = (xh[i][u] - mu) * rs;
+          dg[i][u] += gv[i][u] * xh[i][u];
+          db[i][u] += gv[i][u];
+          gv[i][u] *= gm[i][u];
+          s1 += gv[i][u];
+          s2 += gv[i][u] * xh[i][u];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)D;
+    s2 = warp_sum(s2) / (float)D;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int gidx = lane + 32 * i;
+      if (gidx < ngroups) {
+        float o[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) o[u] = rs * (gv[i][u] - s1 - xh[i][u] * s2);
+        if (add != nullptr) {  // + gradient arriving through the residual branch (same dtype as x)
+          float a[8];
+          load_row_vec<TX>(add + row * D + gidx * 8, a);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) o[u] += a[u];
+        }
+        store_row_vec<TX>(dx + row * D + gidx * 8, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int gidx = lane + 32 * i;
+    if (gidx < ngroups) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        red[(w * 2 + 0) * D + gidx * 8 + u] = dg[i][u];
+        red[(w * 2 + 1) * D + gidx * 8 + u] = db[i][u];
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < kLnWarps; ++ww) acc += red[ww * 2 * D + c];
+    partial[(size_t)blockIdx.x * 2 * D + c] = acc;
+  }
+}
+
+// out[c] = sum_p partial[p][c], c < n, fixed order
+__global__ void partial_reduce_kernel(const float* __restrict__ partial, int parts, int n, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  float acc = 0.f;
+  for (int p = 0; p < parts; ++p) acc += partial[(size_t)p * n + c];
+  out[c] = acc;
+}
+
+// column sums of a [M, N] matrix (row stride ld): partial[blockIdx.x][N]; thread t owns columns 8t .. 8t+7 of a 8*blockDim-wide
+// column block, rows of the CTA's fixed slice in order
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ a, long long M, int N, long long ld, float* __restrict__ partial) {
+  const long long per = (M + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * per, r1 = min(r0 + per, M);
+  for (int c0 = threadIdx.x * 8; c0 < N; c0 += blockDim.x * 8) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    long long row = r0;
+    for (; row + 4 <= r1; row += 4) {  // 4 independent 16 B loads in flight per thread
+      float f[4][8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) load_row_vec<T>(a + (row + i) * ld + c0, f[i]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] += f[i][u];
+    }
+    for (; row < r1; ++row) {
+      float f[8];
+      load_row_vec<T>(a + row * ld + c0, f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += f[u];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) partial[(size_t)blockIdx.x * N + c0 + u] = acc[u];
+  }
+}
+
+template <typename TX, typename TY>
+static int ln_fwd_dispatch(const void* x, const float* gamma, const float* beta, float eps, long long M, int D, void* y, float* mean,
+                           float* rstd, cudaStream_t st) {
+  const int vpl = (D / 8 + 31) / 32;
+  long long blocks = (M + kLnWarps - 1) / kLnWarps;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+#define AB2_LN_FWD(V)                                                                                                       \
+  layernorm_fwd_kernel<TX, TY, V><<<(unsigned)blocks, kLnWarps * 32, 0, st>>>((const TX*)x, gamma, beta, eps, M, D, (TY*)y, mean, rstd)
+  if (vpl <= 1) AB2_LN_FWD(1);
+  else if (vpl <= 2) AB2_LN_FWD(2);
+  else if (vpl <= 4) AB2_LN_FWD(4);
+  else if (vpl <= 8) AB2_LN_FWD(8);
+  else return fail(AB2_ERR_UNSUPPORTED, "layernorm: D = %d is wider than 2048", D);
+#undef AB2_LN_FWD
+  AB2_LAUNCH_OK("layernorm_fwd_kernel");
+  return AB2_OK;
+}
+
+template <typename TG, typename TX>
+static int ln_bwd_dispatch(const void* g, const void* x, const float* gamma, const float* mean, const float* rstd, long long M, int D,
+                           const void* add, void* dx, float* partial, cudaStream_t st) {
+  const int vpl = (D / 8 + 31) / 32;
+  const size_t smem = (size_t)kLnWarps * 2 * D * sizeof(float);
+#define AB2_LN_BWD(V)                                                                                                       \
+  layernorm_bwd_kernel<TG, TX, V><<<kLnParts, kLnWarps * 32, smem, st>>>((const TG*)g, (const TX*)x, gamma, mean, rstd, M, D, \
+                                                                         (const TX*)add, (TX*)dx, partial)
+  if (vpl <= 1) AB2_LN_BWD(1);
+  else if (vpl <= 2) AB2_LN_BWD(2);
+  else if (vpl <= 4) AB2_LN_BWD(4);
+  else return fail(AB2_ERR_UNSUPPORTED, "layernorm backward: D = %d is wider than 1024", D);
+#undef AB2_LN_BWD
+  AB2_LAUNCH_OK("layernorm_bwd_kernel");
+  return AB2_OK;
+}
+
+}  // namespace ab2
+
+using namespace ab2;
+
+extern "C" int ab2_ln_parts(void) { return kLnParts; }
+
+extern "C" int ab2_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, float eps, int64_t M, int D, void* y,
+                                 int y_dtype, float* mean, float* rstd, void* stream) {
+  if (M < 0 || D <= 0 || D % 8 != 0) return fail(AB2_ERR_UNSUPPORTED, "layernorm: D must be a positive multiple of 8 (got %d)", D);
+  if (M == 0) return AB2_OK;
+  if (x == nullptr || y == nullptr || gamma == nullptr || beta == nullptr) return fail(AB2_ERR_INVALID, "layernorm: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == AB2_BF16 && y_dtype == AB2_BF16) return ln_fwd_dispatch<__nv_bfloat16, __nv_bfloat16>(x, gamma, beta, eps, M, D, y, mean, rstd, st);
+  if (x_dtype == AB2_F32 && y_dtype == AB2_BF16) return ln_fwd_dispatch<float, __nv_bfloat16>(x, gamma, beta, eps, M, D, y, mean, rstd, st);
+  if (x_dtype == AB2_F32 && y_dtype == AB2_F32) return ln_fwd_dispatch<float, float>(x, gamma, beta, eps, M, D, y, mean, rstd, st);
+  if (x_dtype == AB2_BF16 && y_dtype == AB2_F32) return ln_fwd_dispatch<__nv_bfloat16, float>(x, gamma, beta, eps, M, D, y, mean, rstd, st);
+  return fail(AB2_ERR_INVALID, "layernorm: bad dtype");
+}
+
+extern "C" int ab2_layernorm_bwd(const void* g, int g_dtype, const void* x, int x_dtype, const float* gamma, const float* mean,
+                                 const float* rstd, int64_t M, int D, const void* add, void* dx, float* partial, float* dgamma,
+                                 float* dbeta, void* stream) {
+  if (M < 0 || D <= 0 || D % 8 != 0) return fail(AB2_ERR_UNSUPPORTED, "layernorm: D must be a positive multiple of 8 (got %d)", D);
+  if (g == nullptr || x == nullptr || gamma == nullptr || mean == nullptr || rstd == nullptr || dx == nullptr || partial == nullptr ||
+      dgamma == nullptr || dbeta == nullptr)
+    return fail(AB2_ERR_INVALID, "layernorm backward: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (g_dtype == AB2_BF16 && x_dtype == AB2_BF16) rc = ln_bwd_dispatch<__nv_bfloat16, __nv_bfloat16>(g, x, gamma, mean, rstd, M, D, add, dx, partial, st);
+  else if (g_dtype == AB2_BF16 && x_dtype == AB2_F32) rc = ln_bwd_dispatch<__nv_bfloat16, float>(g, x, gamma, mean, rstd, M, D, add, dx, partial, st);
+  else if (g_dtype == AB2_F32 && x_dtype == AB2_F32) rc = ln_bwd_dispatch<float, float>(g, x, gamma, mean, rstd, M, D, add, dx, partial, st);
+  else if (g_dtype == AB2_F32 && x_dtype == AB2_BF16) rc = ln_bwd_dispatch<float, __nv_bfloat16>(g, x, gamma, mean, rstd, M, D, add, dx, partial, st);
+  else return fail(AB2_ERR_INVALID, "layernorm backward: bad dtype");
+  if (rc) return rc;
+  // partial is [kLnParts][2][D]: dgamma = columns [0, D), dbeta = [D, 2D) of the reduced row
+  partial_reduce_kernel<<<(2 * D + 255) / 256, 256, 0, st>>>(partial, kLnParts, 2 * D, partial + (size_t)kLnParts * 2 * D);
+  AB2_LAUNCH_OK("partial_reduce_kernel");
+  AB2_CUDA_OK(cudaMemcpyAsync(dgamma, partial + (size_t)kLnParts * 2 * D, D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  AB2_CUDA_OK(cudaMemcpyAsync(dbeta, partial + (size_t)kLnParts * 2 * D + D, D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return AB2_OK;
+}
+
+extern "C" int ab2_colsum(const void* a, int dtype, int64_t M, int N, int64_t ld, float* partial, float* out, void* stream) {
+  if (M < 0 || N <= 0 || N % 8 != 0) return fail(AB2_ERR_UNSUPPORTED, "colsum: N must be a positive multiple of 8 (got %d)", N);
+  if (a == nullptr || partial == nullptr || out == nullptr) return fail(AB2_ERR_INVALID, "colsum: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == AB2_BF16) colsum_kernel<__nv_bfloat16><<<kLnParts, 256, 0, st>>>((const __nv_bfloat16*)a, M, N, ld, partial);
+  else if (dtype == AB2_F32) colsum_kernel<float><<<kLnParts, 256, 0, st>>>((const float*)a, M, N, ld, partial);
+  else return fail(AB2_ERR_INVALID, "colsum: bad dtype");
+  AB2_LAUNCH_OK("colsum_kernel");
+  partial_reduce_kernel<<<(N + 255) / 256, 256, 0, st>>>(partial, kLnParts, N, out);
+  AB2_LAUNCH_OK("partial_reduce_kernel");
+  return AB2_OK;
+}

@@ -72,3 +72,175 @@ def gemm(a: Tensor, b: Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_
     with torch.cuda.device(a.device):
         _lib.check(L.ab2_gemm_bf16(C.byref(d), _p(ws), need, _lib.current_stream(a.device)))
     return out[0] if single else out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# autograd functions used by the graph blocks
+# ---------------------------------------------------------------------------------------------------------------------
+import os as _os
+
+_TC_OFF = _os.environ.get("AB2_TC", "1") == "0"  # AB2_TC=0: keep every dense contraction on nn.Linear / cuBLASLt (A/B runs)
+
+
+def tc_applies(x: Tensor, *dims: int) -> bool:
+    """The tcgen05 path takes CUDA tensors that are bf16 or that autocast would cast to bf16, with GEMM dims that are
+    multiples of 8; everything else (fp32 parity runs, CPU, odd widths) stays on nn.Linear."""
+    if _TC_OFF or not x.is_cuda or any(d % 8 != 0 or d <= 0 for d in dims):
+        return False
+    if x.dtype == torch.bfloat16:
+        return True
+    return x.dtype == torch.float32 and torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16
+
+
+def _f32(t: Optional[Tensor]) -> Optional[Tensor]:
+    return None if t is None else t.detach().float().contiguous()
+
+
+def colsum(a: Tensor) -> Tensor:
+    """fp32 column sums of a [M, N] matrix (bias gradients), deterministic two-stage reduction."""
+    L = _lib.lib()
+    M, N = a.shape
+    parts = L.ab2_ln_parts()
+    partial = torch.empty((parts, N), dtype=torch.float32, device=a.device)
+    out = torch.empty(N, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(L.ab2_colsum(a.data_ptr(), _lib.dtype_code(a.dtype), M, N, a.stride(0), partial.data_ptr(), out.data_ptr(),
+                                _lib.current_stream(a.device)))
+    return out
+
+
+class _LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm over the last dim, output directly in the dtype the next GEMM consumes (reference block.py:487-489, 611,
+    349: LayerNorm in fp32 under autocast + the cast in front of each nn.Linear)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Tensor, eps: float, out_dtype: torch.dtype) -> Tensor:
+        L = _lib.lib()
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        M, D = x2.shape
+        gamma, beta = _f32(weight), _f32(bias)
+        y = torch.empty((M, D), dtype=out_dtype, device=x.device)
+        mean = torch.empty(M, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(M, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(L.ab2_layernorm_fwd(x2.data_ptr(), _lib.dtype_code(x2.dtype), gamma.data_ptr(), beta.data_ptr(), float(eps), M, D,
+                                           y.data_ptr(), _lib.dtype_code(out_dtype), mean.data_ptr(), rstd.data_ptr(),
+                                           _lib.current_stream(x.device)))
+        ctx.save_for_backward(x2, gamma, mean, rstd)
+        ctx.shape, ctx.pdt = tuple(x.shape), (weight.dtype, bias.dtype)
+        return y.view(ctx.shape)
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        x2, gamma, mean, rstd = ctx.saved_tensors
+        L = _lib.lib()
+        M, D = x2.shape
+        g2 = g.reshape(M, D).contiguous()
+        if g2.dtype not in (torch.float32, torch.bfloat16):
+            g2 = g2.float()
+        dx = torch.empty_like(x2)
+        parts = L.ab2_ln_parts()
+        partial = torch.empty((parts + 1) * 2 * D, dtype=torch.float32, device=x2.device)
+        dgamma = torch.empty(D, dtype=torch.float32, device=x2.device)
+        dbeta = torch.empty(D, dtype=torch.float32, device=x2.device)
+        with torch.cuda.device(x2.device):
+            _lib.check(L.ab2_layernorm_bwd(g2.data_ptr(), _lib.dtype_code(g2.dtype), x2.data_ptr(), _lib.dtype_code(x2.dtype),
+                                           gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), M, D, 0, dx.data_ptr(),
+                                           partial.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _lib.current_stream(x2.device)))
+        return dx.view(ctx.shape), dgamma.to(ctx.pdt[0]), dbeta.to(ctx.pdt[1]), None, None
+
+
+def layer_norm(x: Tensor, ln: torch.nn.LayerNorm, out_dtype: torch.dtype = torch.bfloat16) -> Tensor:
+    """`ln(x)` written in `out_dtype` (bf16: what the tensor-core GEMM behind it reads)."""
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    return _LayerNormFn.apply(x, ln.weight, ln.bias, ln.eps, out_dtype)
+
+
+def wgrad_splits(N: int, K: int, M: int) -> int:
+    """Split count of the wgrad contraction (over the M rows): enough CTA pairs to fill the GPU, at least 8 k-blocks each."""
+    pairs = ((N + 255) // 256) * ((K + 255) // 256 if K > 128 else 1)
+    kb = (M + 63) // 64
+    want = max(1, (2 * 74 + pairs - 1) // pairs)
+    s = max(1, min(want, kb // 8 if kb >= 8 else 1, 64))
+    while s > 1 and ((kb + s - 1) // s) * (s - 1) >= kb:  # no empty split
+        s -= 1
+    return s
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = op(x) W^T + b (+ residual), op(x) = x, or act(pre) when the producer handed over its pre-activation `pre` together
+    with h = act(pre) (`x` is then h).  With `act_out` the function returns (y, act(y)): the activation is applied in the
+    GEMM epilogue and the consumer differentiates through it in ITS dgrad epilogue (`pre` argument), so no elementwise
+    activation / activation-gradient pass exists.  Backward: dgrad (B operand MN-major, activation derivative fused),
+    split-K wgrad (both operands MN-major), deterministic column sum for the bias."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, pre: Optional[Tensor], weight: Tensor, bias: Optional[Tensor], residual: Optional[Tensor],
+                act_in: int, act_out: int):
+        shape = tuple(x.shape)
+        x2 = x.reshape(-1, shape[-1])
+        if x2.dtype != torch.bfloat16 or x2.stride(-1) != 1 or (x2.stride(0) % 8) != 0 or (x2.data_ptr() % 16) != 0:
+            x2 = x2.to(torch.bfloat16).contiguous()
+        M, K = x2.shape
+        N = weight.shape[0]
+        w = weight.detach().to(torch.bfloat16).contiguous()
+        b = _f32(bias)
+        res2 = None
+        if residual is not None:
+            res2 = residual.reshape(M, N)
+            if res2.dtype not in (torch.float32, torch.bfloat16) or res2.stride(-1) != 1:
+                res2 = res2.float().contiguous()
+        out_dtype = res2.dtype if res2 is not None else torch.bfloat16
+        y_pre = None
+        if act_out != ACT_NONE:
+            y_pre = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+            y = gemm(x2, w, M, N, K, bias=b, act=act_out, pre_out=y_pre, residual=res2, out_dtype=out_dtype)
+        else:
+            y = gemm(x2, w, M, N, K, bias=b, residual=res2, out_dtype=out_dtype)
+        ctx.save_for_backward(x2, pre.reshape(M, K) if pre is not None else None, w)
+        ctx.meta = (shape, act_in, weight.dtype, None if bias is None else bias.dtype, None if residual is None else residual.dtype,
+                    None if residual is None else tuple(residual.shape))
+        oshape = shape[:-1] + (N,)
+        if act_out != ACT_NONE:
+            h = y.view(oshape)
+            ctx.mark_non_differentiable(h)
+            return y_pre.view(oshape), h
+        return y.view(oshape)
+
+    @staticmethod
+    def backward(ctx, g: Tensor, _g_h=None):
+        x2, pre, w = ctx.saved_tensors
+        shape, act_in, wdt, bdt, rdt, rshape = ctx.meta
+        M, K = x2.shape
+        N = w.shape[0]
+        need = ctx.needs_input_grad
+        g_in = g.reshape(M, N)
+        g2 = g_in
+        if g2.dtype != torch.bfloat16 or g2.stride(-1) != 1 or (g2.stride(0) % 8) != 0 or (g2.data_ptr() % 16) != 0:
+            g2 = g2.to(torch.bfloat16).contiguous()
+        dx = dpre = dw = db = dres = None
+        if need[0] or need[1]:
+            # d op(x) = g W : A = g [M, N] (K-major, contraction N), B = W stored [N, K] = [contraction, out] -> MN-major
+            if pre is not None:
+                dpre = gemm(g2, w, M, K, N, b_mn=True, dact_pre=pre.contiguous(), act=act_in).view(shape)
+            else:
+                dx = gemm(g2, w, M, K, N, b_mn=True).view(shape)
+        if need[2]:
+            # dW [N, K] = g^T x : A = g stored [M, N] = [contraction, out rows] (MN-major), B = x stored [M, K] (MN-major)
+            dw = gemm(g2, x2, N, K, M, a_mn=True, b_mn=True, out_dtype=torch.float32, splits=wgrad_splits(N, K, M)).to(wdt)
+        if need[3]:
+            db = colsum(g2).to(bdt)
+        if need[4]:
+            dres = g_in.to(rdt).view(rshape)
+        return dx, dpre, dw, db, dres, None, None
+
+
+def linear(x: Tensor, lin: torch.nn.Linear, residual: Optional[Tensor] = None, act_out: int = ACT_NONE):
+    """`lin(x)` (+ residual) on the tensor-core kernel; with `act_out` returns (pre-activation, activation) for `act_linear`."""
+    return _LinearFn.apply(x, None, lin.weight, lin.bias, residual, ACT_NONE, act_out)
+
+
+def act_linear(pre: Tensor, h: Tensor, lin: torch.nn.Linear, act: int, residual: Optional[Tensor] = None, act_out: int = ACT_NONE):
+    """`lin(act(pre))` (+ residual) where h = act(pre) came out of the previous GEMM's epilogue."""
+    return _LinearFn.apply(h, pre, lin.weight, lin.bias, residual, act, act_out)

@@ -25,6 +25,7 @@ from ..distributed.halo import (HaloPlan, build_bipartite_halo_plan, build_local
                                 halo_gather, select_sharded_edges)
 from ..distributed.shapes import bounds_from_shapes
 from ..distributed.transformer import shard_heads, shard_sequence
+from .. import gemm as tcg
 from ..graph import check_edge_index, get_csr, resolve_size
 from .conv import GraphConv, GraphTransformerConv
 from .mlp import MLP, activation_class
@@ -167,6 +168,30 @@ class GraphTransformerBaseBlock(BaseBlock, ABC):
             self.node_src_mlp = nn.Sequential(nn.LayerNorm(out_channels), nn.Linear(out_channels, hidden_dim), act_func(),
                                               nn.Linear(hidden_dim, out_channels))
 
+    # -- dense node-side contractions: tcgen05 kernels (gemm.py / csrc/gemm_tc.cu) for CUDA bf16 (or bf16-autocast) inputs,
+    #    nn.LayerNorm / nn.Linear otherwise (fp32 parity runs, CPU tests with the oracle conv)
+    def _tc(self, x: Tensor) -> bool:
+        lin2 = self.node_dst_mlp[3]
+        return (tcg.tc_applies(x, self.lin_key.in_features, self.lin_key.out_features, lin2.in_features, lin2.out_features)
+                and type(self.node_dst_mlp[2]).__name__ in tcg.ACT_CODES and self.layer_norm1.elementwise_affine)
+
+    def _ln(self, ln: nn.LayerNorm, x: Tensor, tc: bool) -> Tensor:
+        return tcg.layer_norm(x, ln) if tc else _autocast_once(ln(x))
+
+    def _lin(self, lin: nn.Linear, x: Tensor, tc: bool, residual: Optional[Tensor] = None) -> Tensor:
+        if tc:
+            return tcg.linear(x, lin, residual=residual)
+        y = lin(x)
+        return y if residual is None else y + residual
+
+    def _mlp_res(self, mlp: nn.Sequential, x: Tensor, tc: bool) -> Tensor:
+        """`mlp(x) + x` for mlp = Sequential(LayerNorm, Linear, act, Linear) (reference block.py:349-354, 537, 633)."""
+        if not tc:
+            return mlp(x) + x
+        act = tcg.ACT_CODES[type(mlp[2]).__name__]
+        pre, h = tcg.linear(tcg.layer_norm(x, mlp[0]), mlp[1], act_out=act)
+        return tcg.act_linear(pre, h, mlp[3], act, residual=x)
+
     # -- API compatibility (reference block.py:366-414).  forward() does not use the head all-to-all with a group (it shards
     #    by dst rows and exchanges a halo, see _attend); on one rank these are pure reshapes.
     def shard_qkve_heads(self, query, key, value, edges, shapes, batch_size, model_comm_group=None):
@@ -248,11 +273,12 @@ class GraphTransformerMapperBlock(GraphTransformerBaseBlock):
     def forward(self, x: Tuple[Tensor, Tensor], edge_attr: Tensor, edge_index: Tensor, shapes: tuple, batch_size: int,
                 model_comm_group=None, size: Optional[Tuple[int, int]] = None):
         x_skip = x
-        x = (_autocast_once(self.layer_norm1(x[0])), _autocast_once(self.layer_norm2(x[1])))
-        x_r = self.lin_self(x[1])
-        query = self.lin_query(x[1])
-        key = self.lin_key(x[0])
-        value = self.lin_value(x[0])
+        tc = self._tc(x[0])
+        x = (self._ln(self.layer_norm1, x[0], tc), self._ln(self.layer_norm2, x[1], tc))
+        x_r = self._lin(self.lin_self, x[1], tc)
+        query = self._lin(self.lin_query, x[1], tc)
+        key = self._lin(self.lin_key, x[0], tc)
+        value = self._lin(self.lin_value, x[0], tc)
 
         if model_comm_group is not None:
             assert (model_comm_group.size() == 1 or batch_size == 1), \
@@ -260,10 +286,9 @@ class GraphTransformerMapperBlock(GraphTransformerBaseBlock):
 
         out = self._attend(query, key, value, edge_attr, edge_index, shapes, batch_size, model_comm_group, size)
 
-        out = self.projection(out + x_r)
-        out = out + x_skip[1]
-        nodes_new_dst = self.node_dst_mlp(out) + out
-        nodes_new_src = self.node_src_mlp(x_skip[0]) + x_skip[0] if self.update_src_nodes else x_skip[0]
+        out = self._lin(self.projection, out + x_r, tc, residual=x_skip[1])  # projection(out + x_r) + x_skip: one epilogue
+        nodes_new_dst = self._mlp_res(self.node_dst_mlp, out, tc)
+        nodes_new_src = self._mlp_res(self.node_src_mlp, x_skip[0], tc) if self.update_src_nodes else x_skip[0]
         return (nodes_new_src, nodes_new_dst), edge_attr
 
 
@@ -273,18 +298,18 @@ class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
     def forward(self, x: Tensor, edge_attr: Tensor, edge_index: Tensor, shapes: tuple, batch_size: int,
                 model_comm_group=None, size: Optional[Tuple[int, int]] = None):
         x_skip = x
-        x = _autocast_once(self.layer_norm1(x))
-        x_r = self.lin_self(x)
-        query = self.lin_query(x)
-        key = self.lin_key(x)
-        value = self.lin_value(x)
+        tc = self._tc(x)
+        x = self._ln(self.layer_norm1, x, tc)
+        x_r = self._lin(self.lin_self, x, tc)
+        query = self._lin(self.lin_query, x, tc)
+        key = self._lin(self.lin_key, x, tc)
+        value = self._lin(self.lin_value, x, tc)
 
         if model_comm_group is not None:
             assert (model_comm_group.size() == 1 or batch_size == 1), \
                 "Only batch size of 1 is supported when model is sharded across GPUs"
 
         out = self._attend(query, key, value, edge_attr, edge_index, shapes, batch_size, model_comm_group, size)
-        out = self.projection(out + x_r)
-        out = out + x_skip
-        nodes_new = self.node_dst_mlp(out) + out
+        out = self._lin(self.projection, out + x_r, tc, residual=x_skip)
+        nodes_new = self._mlp_res(self.node_dst_mlp, out, tc)
         return nodes_new, edge_attr

@@ -111,6 +111,55 @@ def encoder_graph_band(src_points: int, dst_N: int, parts: int, part: int, cutof
     return ei, src_points, nd, radius
 
 
+def fibonacci_max_nn_distance(M: int) -> float:
+    """largest nearest-neighbour chord distance of the M-point Fibonacci sphere (exact, one KD-tree query over all points)."""
+    return max_nn_distance(fibonacci_sphere(M))
+
+
+def o1280_to_n320_band(parts: int, part: int, src_N: int = 1280, dst_points: int = 542080, cutoff: float = 0.6,
+                       dst_bounds=None, radius: Optional[float] = None):
+    """BASELINE configs[4] / SURVEY 8d+8e "enc o1280 -> n320": src = octahedral grid o<src_N> (o1280: 6,599,680 points), dst = the
+    Fibonacci stand-in for n320 (542,080 points), every src within 0.6 x the largest nearest-neighbour distance of the dst grid.
+    Returns the edges (GLOBAL ids, grouped by dst ascending, src ascending inside a dst) into dst shard `part` of `parts`
+    (equal-count `tensor_split` shards unless `dst_bounds` gives P+1 cut points), generating only the octahedral rows of the
+    matching latitude band: (edge_index [2,E] int64, Ns, Nd, radius).  Whole graph: E = 7,458,659, in-degree 9-45."""
+    from .distributed.shapes import tensor_split_sizes
+
+    if radius is None:
+        radius = cutoff * fibonacci_max_nn_distance(dst_points)
+    if dst_bounds is None:
+        sizes = tensor_split_sizes(dst_points, parts)
+        lo = sum(sizes[:part])
+        hi = lo + sizes[part]
+    else:
+        lo, hi = int(dst_bounds[part]), int(dst_bounds[part + 1])
+    ns = octahedral_size(src_N)
+    if hi <= lo:
+        return np.zeros((2, 0), np.int64), ns, dst_points, radius
+    band = fibonacci_sphere(dst_points, lo, hi)
+    zmax, zmin = min(1.0, band[:, 2].max() + radius), max(-1.0, band[:, 2].min() - radius)
+    lat, _ = octahedral_rows(src_N)
+    z_rows = np.sin(lat)  # north -> south, decreasing
+    rows = np.nonzero((z_rows <= zmax + 1e-9) & (z_rows >= zmin - 1e-9))[0]
+    if len(rows) == 0:
+        return np.zeros((2, 0), np.int64), ns, dst_points, radius
+    r_lo, r_hi = max(0, int(rows[0]) - 1), min(2 * src_N, int(rows[-1]) + 2)
+    src_xyz, first = octahedral_grid(src_N, r_lo, r_hi)
+    ei = cutoff_edges(src_xyz, band, radius, src_offset=first, dst_offset=lo)
+    return ei, ns, dst_points, radius
+
+
+def edge_balanced_bounds(in_degree: np.ndarray, parts: int):
+    """P+1 dst cut points that give every rank (nearly) the same number of EDGES instead of the same number of dst rows
+    (`tensor_split`, the reference's shard shapes, distributed/shapes.py:19-24).  The shapes argument of the blocks takes
+    either; on the o1280 -> n320 graph (in-degree 9-45) equal-count shards leave the busiest of 8 ranks with 1.18x the mean."""
+    csum = np.concatenate([[0], np.cumsum(in_degree.astype(np.int64))])
+    total = int(csum[-1])
+    targets = [(total * r) // parts for r in range(1, parts)]
+    cuts = [int(np.searchsorted(csum, t, side="left")) for t in targets]
+    return [0] + cuts + [len(in_degree)]
+
+
 def icosahedron():
     """12 vertices / 20 faces of the unit icosahedron."""
     phi = (1.0 + np.sqrt(5.0)) / 2.0

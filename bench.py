@@ -242,6 +242,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # multi-GPU: before anything is timed, the sharded step is checked against a single-rank conv of the same sub-graph
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        parity = sharded_parity(q, k_own, v_own, e, g, ei_glob, Ns_g, sb, rank, world, plan, hplan, group, dev)
+        if parity["max_rel_err"] > 2e-2 or parity["max_rel_l2"] > 2e-2:
+            raise SystemExit(f"sharded conv differs from the single-rank conv: {parity}")
     sampler = ClockSampler(local_rank)
     for _ in range(max(args.warmup, 3)):
         step()
@@ -389,6 +395,20 @@ def run_ours(args):
                "chunks": args.e2e_chunks}
     del host, outs, dev_ws
 
+    # ---- BASELINE configs[4]: the o1280 -> n320 graph, whole graph over `world` ranks (strong scaling; extra block of the line)
+    config5 = None
+    if args.workload == "encoder" and args.config5 != "off":
+        del q, g, e, k_own, v_own, kn, vn, dq, de, dk, dv, ws, out, lse2
+        torch.cuda.empty_cache()
+        try:
+            config5 = {"equal": config5_block(world, rank, dev, group, steps=min(args.steps, 20), warmup=3, dst_split="equal",
+                                              parity=not args.no_parity_check)}
+            if world > 1:
+                config5["balanced"] = config5_block(world, rank, dev, group, steps=min(args.steps, 20), warmup=3, dst_split="balanced",
+                                                    parity=False)
+        except Exception as ex:  # noqa: BLE001 -- the headline line must still be printed
+            config5 = {"error": f"{type(ex).__name__}: {ex}"[:400]}
+
     # ---- CPU baseline: the reference's op sequence (oracle port) on this box's host cores, bounded sample
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "encoder":
@@ -416,6 +436,8 @@ def run_ours(args):
                               "note": "SURVEY 8d algorithmic bytes of fwd+bwd over the sum of the three kernel durations"},
             "kernels": kern,
             "cpu_baseline": cpu_baseline,
+            "parity": parity,
+            "config5_o1280_to_n320": config5,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -424,35 +446,254 @@ def run_ours(args):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# multi-GPU: driver-visible parity of the sharded step, and BASELINE configs[4] (o1280 -> n320, strong scaling)
+# ----------------------------------------------------------------------------------------------------------------
+def _err_pair(a, b):
+    """(max|a-b| / max(1, max|b|), ||a-b||_2 / ||b||_2) in fp64 on the device, chunked over rows (a, b may be 10+ GB)."""
+    mx, num, den, bmax = 0.0, 0.0, 0.0, 0.0
+    n = a.shape[0]
+    step = max(1, (1 << 26) // max(1, a[0].numel()))
+    for i in range(0, n, step):
+        x, y = a[i:i + step].double(), b[i:i + step].double()
+        d = x - y
+        mx = max(mx, float(d.abs().max())) if d.numel() else mx
+        bmax = max(bmax, float(y.abs().max())) if y.numel() else bmax
+        num += float((d * d).sum())
+        den += float((y * y).sum())
+    return mx / max(1.0, bmax), (num ** 0.5) / max(den ** 0.5, 1e-30)
+
+
+def sharded_parity(q, k_own, v_own, e, g, ei_glob, Ns_g, sb, rank, world, plan, hplan, group, dev):
+    """The dst-row-sharded step (halo exchange of k / v over NVLink, gradients of halo rows sent home and added) against a
+    SINGLE-RANK conv of this rank's sub-graph on the all-gathered k / v: out, dq, de compared rank by rank; dk, dv = the sum
+    over ranks of the single-rank contributions (fp32 all-reduce), compared on the rows this rank owns.  Returns the maxima
+    over tensors and ranks of (max-norm relative error, relative L2 error)."""
+    import torch.distributed as dist
+
+    from anemoi_models_b200 import ops
+    from anemoi_models_b200.graph import GraphCSR
+
+    H, C = q.shape[1], q.shape[2]
+    ins = [t.detach().clone().requires_grad_(True) for t in (q, k_own, v_own, e)]
+    out = ops.gt_conv_sharded(ins[0], ins[1], ins[2], ins[3], plan, hplan, group)
+    out.backward(g)
+    got = {"out": out.detach(), "dq": ins[0].grad, "dk": ins[1].grad, "dv": ins[2].grad, "de": ins[3].grad}
+    # all-gather the (uneven) src shards
+    sizes = [sb[r + 1] - sb[r] for r in range(world)]
+    mx = max(sizes)
+
+    def gather(t):
+        pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+        pad[: t.shape[0]] = t
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad, group=group)
+        full = torch.cat([parts[r][: sizes[r]] for r in range(world)])
+        del parts, pad
+        return full
+
+    k_full, v_full = gather(k_own).requires_grad_(True), gather(v_own).requires_grad_(True)
+    nd_loc = q.shape[0]
+    ei_ref = torch.stack([ei_glob[0], hplan.local_edge_index[1]]).contiguous()  # global src ids, local dst ids
+    ref_plan = GraphCSR(ei_ref, Ns_g, nd_loc)
+    qr, er = q.detach().clone().requires_grad_(True), e.detach().clone().requires_grad_(True)
+    out_r = ops.gt_conv(qr, k_full, v_full, er, ref_plan)
+    out_r.backward(g)
+    errs = {"out": _err_pair(got["out"], out_r.detach()), "dq": _err_pair(got["dq"], qr.grad), "de": _err_pair(got["de"], er.grad)}
+    del out_r, qr, er, ref_plan
+    lo, hi = sb[rank], sb[rank + 1]
+    for name, full in (("dk", k_full), ("dv", v_full)):
+        contrib = full.grad
+        mxe, num, den, bmax = 0.0, 0.0, 0.0, 0.0
+        chunk = 1 << 19  # rows per fp32 all-reduce (2 GB at D = 1024)
+        for r0 in range(0, Ns_g, chunk):
+            r1 = min(Ns_g, r0 + chunk)
+            tot = contrib[r0:r1].float()
+            dist.all_reduce(tot, group=group)
+            a0, a1 = max(lo, r0), min(hi, r1)
+            if a1 > a0:
+                x, y = got[name][a0 - lo:a1 - lo].double(), tot[a0 - r0:a1 - r0].double()
+                d = x - y
+                mxe, bmax = max(mxe, float(d.abs().max())), max(bmax, float(y.abs().max()))
+                num += float((d * d).sum())
+                den += float((y * y).sum())
+            del tot
+        errs[name] = (mxe / max(1.0, bmax), (num ** 0.5) / max(den ** 0.5, 1e-30))
+        full.grad = None
+    del k_full, v_full
+    worst = torch.tensor([max(v[0] for v in errs.values()), max(v[1] for v in errs.values())], device=dev, dtype=torch.float64)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=group)
+    torch.cuda.empty_cache()
+    return {"parity_checked": True, "max_rel_err": float(worst[0]), "max_rel_l2": float(worst[1]), "tolerance": 2e-2,
+            "against": "single-rank conv of each rank's sub-graph on the all-gathered k / v; dk, dv summed over ranks in fp32",
+            "rank0": {k: [float(f"{v[0]:.3e}"), float(f"{v[1]:.3e}")] for k, v in errs.items()}}
+
+
+def config5_block(world, rank, dev, group, steps, warmup, dst_split="equal", parity=True):
+    """BASELINE configs[4] / SURVEY 8e: GT mapper conv on the o1280 (6,599,680 pts) -> n320 (542,080 pts) cut-off graph, D = 1024,
+    H = 16, bf16 fwd+bwd, the WHOLE graph split over `world` ranks by dst rows (strong scaling; world = 1: the whole graph on one
+    GPU, ~85 GB).  dst shards: the reference's equal-count `tensor_split` (shapes.py:19-24) or edge-count balanced cut points."""
+    import torch.distributed as dist
+
+    from anemoi_models_b200 import ops
+    from anemoi_models_b200 import synthetic as S
+    from anemoi_models_b200.distributed.halo import aligned_src_bounds, build_local_halo_plan
+    from anemoi_models_b200.distributed.shapes import tensor_split_sizes
+    from anemoi_models_b200.graph import GraphCSR
+
+    H, C = 16, 64
+    Nd_g, Ns_g = 542080, S.octahedral_size(1280)
+    radius = 0.6 * S.fibonacci_max_nn_distance(Nd_g)
+    db = np.concatenate([[0], np.cumsum(tensor_split_sizes(Nd_g, world))]).tolist()
+    if dst_split == "balanced" and world > 1:
+        # in-degree of every dst: each rank counts its equal-count shard, the counts are all-gathered
+        ei0, _, _, _ = S.o1280_to_n320_band(world, rank, radius=radius)
+        deg = torch.from_numpy(np.bincount(ei0[1] - db[rank], minlength=db[rank + 1] - db[rank])).to(dev)
+        pad = torch.zeros(max(db[r + 1] - db[r] for r in range(world)), dtype=deg.dtype, device=dev)
+        pad[: deg.numel()] = deg
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad, group=group)
+        deg_all = torch.cat([parts[r][: db[r + 1] - db[r]] for r in range(world)]).cpu().numpy()
+        db = S.edge_balanced_bounds(deg_all, world)
+        del ei0
+    ei_np, _, _, _ = S.o1280_to_n320_band(world, rank, radius=radius, dst_bounds=db)
+    ei_glob = torch.from_numpy(ei_np).to(dev)
+    E = ei_glob.shape[1]
+    torch.manual_seed(4321 + rank)
+    if world > 1:
+        sb = aligned_src_bounds(ei_glob, Ns_g, group)
+    else:
+        sb = [0, Ns_g]
+    nd_loc, ns_loc = db[rank + 1] - db[rank], sb[rank + 1] - sb[rank]
+    bf = torch.bfloat16
+    q = torch.randn(nd_loc, H, C, device=dev, dtype=bf)
+    g = torch.randn(nd_loc, H, C, device=dev, dtype=bf)
+    e = torch.randn(E, H, C, device=dev, dtype=bf)
+    k_own = torch.randn(ns_loc, H, C, device=dev, dtype=bf)
+    v_own = torch.randn(ns_loc, H, C, device=dev, dtype=bf)
+    if world > 1:
+        hplan = build_local_halo_plan(ei_glob, sb, db, group)
+        plan = GraphCSR(hplan.local_edge_index, hplan.n_src, nd_loc)
+    else:
+        hplan, plan = None, GraphCSR(ei_glob, Ns_g, nd_loc)
+
+    def step():
+        qq, ee = q.detach().requires_grad_(True), e.detach().requires_grad_(True)
+        kk, vv = k_own.detach().requires_grad_(True), v_own.detach().requires_grad_(True)
+        out = ops.gt_conv_sharded(qq, kk, vv, ee, plan, hplan, group) if world > 1 else ops.gt_conv(qq, kk, vv, ee, plan)
+        out.backward(g)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    par = None
+    if world > 1 and parity:
+        par = sharded_parity(q, k_own, v_own, e, g, ei_glob, Ns_g, sb, rank, world, plan, hplan, group, dev)
+    for _ in range(max(3, warmup)):
+        step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        step()
+    ev1.record()
+    barrier()
+    stats = torch.tensor([ev0.elapsed_time(ev1) / steps, float(E), float(hplan.n_halo if hplan is not None else 0), float(ns_loc)],
+                         device=dev, dtype=torch.float64)
+    mx, sm = stats.clone(), stats.clone()
+    if world > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    ab = algorithmic_bytes(float(sm[1]), Ns_g, Nd_g, 2, H * C, H)["step_survey"]
+    peak, _ = peaks()
+    ms = float(mx[0])
+    del q, g, e, k_own, v_own, plan, hplan
+    torch.cuda.empty_cache()
+    return {"workload": "GT mapper conv o1280 (6,599,680) -> n320 (542,080 Fibonacci), cut-off 0.6, D=1024, H=16, bf16 fwd+bwd, whole graph "
+                        f"dst-row sharded over {world} rank(s) (strong scaling), k / v halo exchange + gradient return inside the timed region",
+            "dst_split": dst_split if world > 1 else "n/a", "src_split": "aligned" if world > 1 else "n/a", "scaling": "strong",
+            "ms_per_step": ms, "edges_total": int(sm[1]), "edges_per_s": float(sm[1]) / (ms * 1e-3), "steps": steps,
+            "edges_max_rank": int(mx[1]), "edge_imbalance_max_over_mean": float(mx[1]) / (float(sm[1]) / world),
+            "halo_rows_max_rank": int(mx[2]), "own_src_rows_max_rank": int(mx[3]),
+            "hbm_frac_of_peak_per_gpu": ab / world / (ms * 1e-3) / 1e9 / peak, "parity": par}
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # CPU arm: the reference's unfused op sequence (oracle port of conv.py + PyG) on host cores
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(ei_np, Ns, Nd, steps, warmup, frac=8):
-    """fp32, all host threads, on a contiguous 1/`frac` dst subset of the same graph (src rows compacted)."""
+def reference_conv():
+    """(GraphTransformerConv class, kind): the UNMODIFIED reference class from baseline/_ref (scripts/install_ref.sh; PyG through
+    oracle/pyg_shim) when it travelled with the snapshot -> kind "reference"; otherwise None -> the oracle port."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "anemoi", "models")):
+        return None, "port"
+    for p in (os.path.join(ROOT, "oracle", "pyg_shim"), ref):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    try:
+        from anemoi.models.layers.conv import GraphTransformerConv as RefConv
+    except Exception as exc:  # noqa: BLE001
+        print(f"[bench] reference import failed ({exc!r}); timing the oracle port instead", file=sys.stderr)
+        return None, "port"
+    return RefConv, "reference"
+
+
+def cpu_reference_sample(ei_np, Ns, Nd, steps, warmup, frac=None):
+    """The reference's own CPU path, fp32, all host threads: `GraphTransformerConv.forward` + autograd backward
+    (reference layers/conv.py:98-142 over PyG propagate / softmax / scatter) on the headline graph.  The unfused autograd
+    graph keeps ~10 [E, D] fp32 tensors (~30 GB at the headline): with >= 64 GB of free RAM the WHOLE graph is timed
+    (frac = 1, same configuration as the GPU arm), otherwise a contiguous 1/8 dst subset (src rows compacted)."""
     from oracle import gtconv as og
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    nd_s = Nd // frac
-    keep = ei_np[1] < nd_s
-    sub = ei_np[:, keep]
-    needed, inv = np.unique(sub[0], return_inverse=True)
-    ei = torch.from_numpy(np.stack([inv.astype(np.int64), sub[1]]))
-    ns_s, E = len(needed), ei.shape[1]
+    if frac is None:
+        try:
+            import psutil
+
+            frac = 1 if psutil.virtual_memory().available >= 64 * 2 ** 30 else 8
+        except Exception:  # noqa: BLE001
+            frac = 8
+    if frac > 1:
+        nd_s = Nd // frac
+        keep = ei_np[1] < nd_s
+        sub = ei_np[:, keep]
+        needed, inv = np.unique(sub[0], return_inverse=True)
+        ei = torch.from_numpy(np.stack([inv.astype(np.int64), sub[1]]))
+        ns_s = len(needed)
+    else:
+        ei, ns_s, nd_s = torch.from_numpy(np.ascontiguousarray(ei_np)), Ns, Nd
+    E = ei.shape[1]
     gen = torch.Generator().manual_seed(0)
     q = torch.randn(nd_s, H, C, generator=gen)
     k = torch.randn(ns_s, H, C, generator=gen)
     v = torch.randn(ns_s, H, C, generator=gen)
     e = torch.randn(E, H, C, generator=gen)
     g = torch.randn(nd_s, H, C, generator=gen)
+    RefConv, kind = reference_conv()
+    if RefConv is not None:
+        conv = RefConv(out_channels=C)
+        ins = [t.requires_grad_(True) for t in (q, k, v, e)]
+
+        def step():
+            for t in ins:
+                t.grad = None
+            conv(ins[0], ins[1], ins[2], ins[3], ei, size=(ns_s, nd_s)).backward(g)
+        what = "anemoi.models.layers.conv.GraphTransformerConv (unmodified, baseline/_ref) forward + autograd backward over oracle/pyg_shim"
+    else:
+        def step():
+            og.gt_conv_unfused_fwd_bwd(q, k, v, e, ei, g, (ns_s, nd_s))
+        what = "oracle/gtconv.py gt_conv_unfused = reference conv.py:98-142 + PyG op sequence on torch CPU"
     for _ in range(warmup):
-        og.gt_conv_unfused_fwd_bwd(q, k, v, e, ei, g, (ns_s, nd_s))
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        og.gt_conv_unfused_fwd_bwd(q, k, v, e, ei, g, (ns_s, nd_s))
+        step()
     dt = (time.perf_counter() - t0) / steps
-    return {"value": E / dt, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": round(dt * 1e3, 2),
-            "sample": f"contiguous 1/{frac} dst subset of the headline graph ({E} edges, {ns_s} src, {nd_s} dst), fp32, "
-                      f"{steps} timed fwd+bwd after {warmup} warm-up; oracle/gtconv.py gt_conv_unfused = reference conv.py:98-142 + PyG op sequence on torch CPU"}
+    sample = ("the whole headline graph" if frac == 1 else f"contiguous 1/{frac} dst subset of the headline graph")
+    return {"value": E / dt, "unit": UNIT, "cores": cores, "kind": kind, "ms_per_step": round(dt * 1e3, 2), "same_config": frac == 1,
+            "sample": f"{sample} ({E} edges, {ns_s} src, {nd_s} dst), fp32, {steps} timed fwd+bwd after {warmup} warm-up; {what}"}
 
 
 def run_graphconv(args):
@@ -701,6 +942,34 @@ def run_model(args):
     print(json.dumps(line), flush=True)
 
 
+def run_o1280(args):
+    """Report line: BASELINE configs[4] on its own (`--workload o1280 [--dst-split balanced]`), strong scaling over --gpus."""
+    import torch.distributed as dist
+
+    world, rank, local_rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    sampler = ClockSampler(local_rank)
+    with sampler:
+        blk = config5_block(world, rank, dev, group, steps=args.steps, warmup=args.warmup, dst_split=args.dst_split,
+                            parity=not args.no_parity_check)
+    if rank == 0:
+        line = {"metric": METRIC, "value": blk["edges_per_s"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": blk["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": {k: blk[k] for k in ("workload", "dst_split", "src_split", "edges_total", "edges_max_rank",
+                                                                     "edge_imbalance_max_over_mean", "halo_rows_max_rank", "own_src_rows_max_rank")},
+                "clocks": sampler.summary(), "roofline_step": {"frac": blk["hbm_frac_of_peak_per_gpu"], "note": "SURVEY 8d step bytes / P over the step time, of the measured HBM peak"},
+                "parity": blk["parity"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -713,7 +982,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": max(1, min(args.steps, 5)), "warmup": max(1, min(args.warmup, 2)), "ms_per_step": res["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(1), "note": "each step = bounded sample: 1/8 dst subset on host cores"},
+            "config": {"workload": workload_name(1), "note": "each step = " + res["sample"].split(",")[0] + " on host cores"},
             "cpu_baseline": res,
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -731,10 +1000,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--src-split", default="aligned", choices=["aligned", "equal"],
                     help="multi-GPU: src row ownership aligned to the dst shards (default) or the reference's equal-count tensor_split")
+    ap.add_argument("--no-parity-check", action="store_true", help="multi-GPU: skip the sharded-vs-single-rank comparison made before timing")
+    ap.add_argument("--config5", default="auto", choices=["auto", "on", "off"],
+                    help="encoder workload: also measure BASELINE configs[4] (o1280 -> n320, whole graph over the ranks) as an extra block")
+    ap.add_argument("--dst-split", default="equal", choices=["equal", "balanced"], help="o1280 workload: dst shard cut points")
     ap.add_argument("--graphconv-dim", type=int, default=512)
     ap.add_argument("--model-layers", type=int, default=16)
     ap.add_argument("--profile", action="store_true", help="model workload: add a per-kernel device-time breakdown of one step")
-    ap.add_argument("--workload", default="encoder", choices=["encoder", "decoder", "processor", "graphconv", "model", "edgepath", "config1-enc", "config1-proc", "config1-dec"],
+    ap.add_argument("--workload", default="encoder", choices=["encoder", "decoder", "processor", "graphconv", "model", "edgepath", "o1280", "config1-enc", "config1-proc", "config1-dec"],
                     help="encoder = BASELINE configs[1] (the headline); the others are extra report lines")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -745,6 +1018,8 @@ def main():
         run_model(args)
     elif args.workload == "edgepath":
         run_edgepath(args)
+    elif args.workload == "o1280":
+        run_o1280(args)
     else:
         run_ours(args)
 

@@ -290,6 +290,24 @@ typedef struct ab2_gemm {
 size_t ab2_gemm_workspace_bytes(const ab2_gemm* d);
 int ab2_gemm_bf16(const ab2_gemm* d, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * LayerNorm over node rows, feeding the GEMMs above, and the column sum used for bias gradients.
+ * Replaces nn.LayerNorm at layers/block.py:487-489, 611 (layer_norm1 / layer_norm2) and :349-354 (node_dst_mlp[0]) plus the
+ * fp32 -> bf16 cast autocast inserts in front of every nn.Linear: one pass, output in the dtype the GEMM consumes.
+ * x [M,D] (x_dtype), gamma / beta fp32 [D], y [M,D] (y_dtype), mean / rstd fp32 [M] (kept for backward; may be NULL).
+ * D % 8 == 0, D <= 2048 (forward) / 1024 (backward).
+ * Backward: g [M,D] (g_dtype) -> dx [M,D] (x_dtype) = LN-backward(g) (+ add [M,D] (x_dtype), the gradient of a residual branch,
+ * when not NULL); dgamma / dbeta fp32 [D], reduced in a fixed order through `partial` ((ab2_ln_parts() + 1) * 2 * D floats).
+ * ab2_colsum: out[n] = sum_m a[m, n] (fp32), a [M,N] with row stride ld; partial: ab2_ln_parts() * N floats.  Deterministic.
+ * ------------------------------------------------------------------------------------------------- */
+int ab2_ln_parts(void);
+int ab2_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, float eps, int64_t M, int D, void* y,
+                      int y_dtype, float* mean, float* rstd, void* stream);
+int ab2_layernorm_bwd(const void* g, int g_dtype, const void* x, int x_dtype, const float* gamma, const float* mean,
+                      const float* rstd, int64_t M, int D, const void* add, void* dx, float* partial, float* dgamma, float* dbeta,
+                      void* stream);
+int ab2_colsum(const void* a, int dtype, int64_t M, int N, int64_t ld, float* partial, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

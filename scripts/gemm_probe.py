@@ -114,7 +114,7 @@ def run_case(name):
     out = call()
     torch.cuda.synchronize()
     rec = {"case": name, "M": M, "N": N, "K": K, "a_mn": a_mn, "b_mn": b_mn, "splits": splits, "epi": epi,
-           "desc": os.environ.get("AB2_GEMM_DESC", "default")}
+           "desc": os.environ.get("AB2_GEMM_DESC", "default"), "cg": int(os.environ.get("AB2_GEMM_CG", "2"))}
     if ref is not None:
         got = torch.cat([o.float() for o in out], dim=1) if isinstance(out, list) else out.float()
         err = (got - ref).abs()
@@ -188,6 +188,9 @@ def main():
 
     for n in names:
         results[n] = launch(n)
+    if "--cg1" in sys.argv:  # the same cases on single-CTA tiles (cta_group::1), for the A/B table
+        for n in names:
+            launch(n, {"AB2_GEMM_CG": "1"})
     if "--sweep" in sys.argv:
         # descriptor byte offsets k_lbo,k_sbo,mn_lbo,mn_sbo: alternatives in case the defaults are wrong
         for n, alts in (("nn_small", ["0,1024,8192,1024", "1024,1024,8192,1024", "16,128,8192,1024"]),

@@ -52,3 +52,12 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     if a.numel() == 0:
         return 0.0
     return float((a - b).abs().max() / max(1.0, float(b.abs().max())))
+
+
+def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
+    """||a-b||_2 / ||b||_2 -- the second bound on every bf16 comparison: the max-norm measure above tolerates a large
+    relative error on near-zero elements, this one does not let a systematic error hide behind one large element."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    if a.numel() == 0:
+        return 0.0
+    return float((a - b).norm() / max(float(b.norm()), 1e-30))

@@ -38,11 +38,10 @@ def _worker(rank, world, port, q, halo):
         os.environ["MASTER_PORT"] = str(port)
         torch.cuda.set_device(rank)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-        _sharded_blocks(rank, world)
+        blocks = _sharded_blocks(rank, world)
+        plans = [entry[2] for b in blocks for entry in b.__dict__.get("_b200_halo_plans", {}).values()]
+        plans.append(_sharded_conv_2kb_rows(rank, world))
         if halo == "p2p":  # the peer-memory transport must really have been used (no silent NCCL fallback)
-            from anemoi_models_b200.layers import block as b2block
-
-            plans = [item[3] for item in b2block._halo_cache._items.values()]
             peers = [px for pl in plans for px in getattr(pl, "_peer", {}).values()]
             assert peers and all(px is not None and px.fwd_epoch > 0 and px.bwd_epoch > 0 for px in peers), \
                 "NVLink peer-memory halo exchange was not used"
@@ -129,6 +128,53 @@ def _sharded_blocks(rank, world):
         gsum = p.grad.clone()
         dist.all_reduce(gsum)
         assert float((gsum - ref_grads[k]).abs().max()) < 5e-5 * max(1.0, float(ref_grads[k].abs().max())), k
+    return [blk, gblk]
+
+
+def _sharded_conv_2kb_rows(rank, world):
+    """D = 1024 bf16 (2 KB rows: the bulk-copy pipelined kernels with a halo buffer, interior / boundary split and the peer
+    push hidden behind the interior rows) with UNEVEN, dst-aligned src shards -- the configuration of the scaling benchmark --
+    against the single-rank conv of the whole graph (every rank computes it; sizes are small)."""
+    from anemoi_models_b200 import ops
+    from anemoi_models_b200.distributed.halo import aligned_src_bounds, build_local_halo_plan
+    from anemoi_models_b200.distributed.khop_edges import edge_chunk_order
+    from anemoi_models_b200.distributed.shapes import tensor_split_sizes
+    from anemoi_models_b200.graph import GraphCSR
+    from conftest import rel_err, rel_l2
+
+    dev = torch.device("cuda", rank)
+    group = dist.group.WORLD
+    gen = torch.Generator().manual_seed(7)
+    ns, nd, H, C = 20011, 6007, 16, 64
+    ei = _graph(ns, nd, 9, gen).to(dev)
+    E = ei.shape[1]
+    bf = torch.bfloat16
+    q, g = (torch.randn(nd, H, C, generator=gen).to(dev, bf) for _ in range(2))
+    k, v = (torch.randn(ns, H, C, generator=gen).to(dev, bf) for _ in range(2))
+    e = torch.randn(E, H, C, generator=gen).to(dev, bf)
+    full = [t.clone().requires_grad_(True) for t in (q, k, v, e)]
+    ref = ops.gt_conv(*full, GraphCSR(ei, ns, nd))
+    ref.backward(g)
+    db = [0]
+    for s_ in tensor_split_sizes(nd, world):
+        db.append(db[-1] + s_)
+    order, counts = edge_chunk_order(nd, ei, world)
+    ids = torch.split(order, counts)[rank]
+    ei_loc_glob = ei[:, ids].contiguous()
+    sb = aligned_src_bounds(ei_loc_glob, ns, group)  # uneven src shards that follow the dst shards
+    assert len(set(sb[r + 1] - sb[r] for r in range(world))) > 1 or world == 1
+    hplan = build_local_halo_plan(ei_loc_glob, sb, db, group)
+    plan = GraphCSR(hplan.local_edge_index, hplan.n_src, db[rank + 1] - db[rank])
+    mine = [q[db[rank]:db[rank + 1]], k[sb[rank]:sb[rank + 1]], v[sb[rank]:sb[rank + 1]], e[ids]]
+    mine = [t.clone().requires_grad_(True) for t in mine]
+    out = ops.gt_conv_sharded(*mine, plan, hplan, group)
+    out.backward(g[db[rank]:db[rank + 1]])
+    want = [ref[db[rank]:db[rank + 1]], full[0].grad[db[rank]:db[rank + 1]], full[1].grad[sb[rank]:sb[rank + 1]],
+            full[2].grad[sb[rank]:sb[rank + 1]], full[3].grad[ids]]
+    got = [out, mine[0].grad, mine[1].grad, mine[2].grad, mine[3].grad]
+    for name, a, b in zip(("out", "dq", "dk", "dv", "de"), got, want):
+        assert rel_err(a, b) < 2e-2 and rel_l2(a, b) < 1e-2, (name, rel_err(a, b), rel_l2(a, b))
+    return hplan
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
