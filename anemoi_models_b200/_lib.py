@@ -24,7 +24,8 @@ class Gemm(C.Structure):
                 ("b_mn", C.c_int32), ("out", _vp * 4), ("ld_out", _i64), ("seg_cols", C.c_int32), ("out_f32", C.c_int32),
                 ("bias", _vp), ("row_scale", _vp), ("row_shift", _vp), ("col_vec", _vp), ("pre_out", _vp), ("dact_pre", _vp),
                 ("residual", _vp), ("ld_res", _i64), ("res_f32", C.c_int32), ("act", C.c_int32), ("splits", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("gather_a", _vp), ("gather_a_idx", _vp), ("gather_b", _vp), ("gather_b_idx", _vp),
+                ("ld_gather", _i64)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/anemoi_b200.h (tests/test_abi.py checks it)
@@ -68,6 +69,7 @@ SIGNATURES = {
     "ab2_layernorm_fwd": (_i32, [_vp, _i32, _vp, _vp, _f32, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
     "ab2_layernorm_bwd": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ab2_colsum": (_i32, [_vp, _i32, _i64, _i32, _i64, _vp, _vp, _vp]),
+    "ab2_edge_segment_sums": (_i32, [_vp] * 5 + [_i64] * 3 + [_i32, _i32, _vp, _vp, _vp]),
     "ab2_gtconv_host_workspace_bytes": (_sz, [_i64] * 3 + [_i32] * 3),
     "ab2_gtconv_fwd_bwd_host_streamed": (_i32, [_vp] * 5 + [_i32] + [_vp] * 6 + [_i64] * 3 + [_i32] * 2 + [_vp] * 5 + [_vp, _i32, _vp, _sz, _vp]),
     "ab2_gtconv_fwd_bwd_host": (_i32, [_vp] * 5 + [_i32] + [_vp] * 6 + [_i64] * 3 + [_i32] * 2 + [_vp] * 5 + [_vp, _sz, _vp]),

@@ -77,6 +77,9 @@ struct Epi {
   const void* residual;  // [M,N] row stride ld_res, bf16 or fp32; added last
   long long ld_res;
   int res_f32;
+  const __nv_bfloat16* gather[2];  // row tables added before the activation: acc += gather[i][gather_idx[i][m], n]
+  const long long* gather_idx[2];
+  long long ld_gather;
 };
 
 struct Args {
@@ -209,32 +212,48 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
   return ((uint64_t)hi << 32) | lo;
 }
 
-// erf with |error| < 2e-7 (Abramowitz & Stegun 7.1.26): one reciprocal, one exp2 and 7 FMAs instead of libdevice's ~30-instruction
-// erff -- far below the bf16 resolution of anything stored here
+__device__ __forceinline__ float rcp_approx(float x) {  // one MUFU.RCP, no refinement / denormal slow path (|rel err| ~ 1e-7)
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float tanh_approx(float x) {  // one MUFU.TANH (|rel err| <= 2^-11, far below bf16 resolution)
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// erf with |error| < 5e-7 (Abramowitz & Stegun 7.1.26): one reciprocal, one exp2 and 7 FMAs / multiplies, branch-free -- libdevice's
+// erff (and __frcp_rn's refinement + slow path) cost 27 instructions and three branches per element in the first version
 __device__ __forceinline__ float erf_fast(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float r = 1.f - p * t * fast_exp2(-ax * ax * kLog2e);
+  const float r = fmaf(-p * t, fast_exp2(ax * (ax * -kLog2e)), 1.f);
   return copysignf(r, x);
 }
+// sigmoid through the tanh unit: ONE special-function op per element (exp2 + reciprocal would be two, and at K = 512 the SFU
+// pipe (16 lanes per SM and clock) would then need as long as the MMAs of the tile)
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
 template <int ACT>
 __device__ __forceinline__ float act_fn(float x) {
-  if constexpr (ACT == 0) return x * __frcp_rn(1.f + fast_exp2(-x * kLog2e));
-  else if constexpr (ACT == 1) return 0.5f * x * (1.f + erf_fast(x * 0.70710678118654752f));
-  else if constexpr (ACT == 2) return fmaxf(x, 0.f);
+  if constexpr (ACT == 0) return x * sigmoid_fast(x);
+  else if constexpr (ACT == 1) {
+    const float h = 0.5f * x;
+    return fmaf(h, erf_fast(x * 0.70710678118654752f), h);
+  } else if constexpr (ACT == 2) return fmaxf(x, 0.f);
   else return x;
 }
 template <int ACT>
 __device__ __forceinline__ float act_grad(float x) {
   if constexpr (ACT == 0) {
-    const float s = __frcp_rn(1.f + fast_exp2(-x * kLog2e));
-    return s * (1.f + x * (1.f - s));
+    const float s = sigmoid_fast(x);
+    return s * fmaf(x, 1.f - s, 1.f);
   } else if constexpr (ACT == 1) {
-    return 0.5f * (1.f + erf_fast(x * 0.70710678118654752f)) + x * 0.3989422804014327f * fast_exp2(-0.5f * x * x * kLog2e);
+    const float cdf = fmaf(0.5f, erf_fast(x * 0.70710678118654752f), 0.5f);
+    return fmaf(x * 0.3989422804014327f, fast_exp2(x * (x * (-0.5f * kLog2e))), cdf);
   } else if constexpr (ACT == 2) {
     return x > 0.f ? 1.f : 0.f;
   } else {
@@ -261,17 +280,12 @@ __device__ __forceinline__ void act_grad_mul8(float (&f)[32], int j, const float
 }
 
 // ---- the kernel --------------------------------------------------------------------------------------------------
-// bf16 chunk of 32 rows x 32 columns held one ROW per lane (f[j] = column j of row `lane`) -> global memory, through the warp's
-// shared-memory patch so that each store instruction writes 8 rows x 64 contiguous bytes.
-__device__ __forceinline__ void store_chunk_bf16(uint32_t patch, int lane, const float (&f)[32], __nv_bfloat16* out, long long ld,
-                                                 int row0, int rows_left, int cols_left) {
+// bf16 chunk of 32 rows x 32 columns held one ROW per lane (pk[j] = columns 2j, 2j+1 of row `lane`, packed bf16x2) -> global
+// memory, through the warp's shared-memory patch so that each store instruction writes 8 rows x 64 contiguous bytes.
+__device__ __forceinline__ void store_chunk_packed(uint32_t patch, int lane, const uint32_t (&pk)[16], __nv_bfloat16* out, long long ld,
+                                                   int row0, int rows_left, int cols_left) {
 #pragma unroll
-  for (int j = 0; j < 32; j += 8) {
-    float p[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) p[u] = f[j + u];
-    sts16(patch + lane * kPatchStride + j * 2, pack<__nv_bfloat16>(p));
-  }
+  for (int j = 0; j < 4; ++j) sts16(patch + lane * kPatchStride + j * 16, make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
   __syncwarp();
   const int c16 = lane & 3, rsub = lane >> 2;
 #pragma unroll
@@ -281,6 +295,10 @@ __device__ __forceinline__ void store_chunk_bf16(uint32_t patch, int lane, const
     if (r < rows_left && c16 * 8 < cols_left) stg16(out + (size_t)(row0 + r) * ld + c16 * 8, v);
   }
   __syncwarp();
+}
+__device__ __forceinline__ void pack_chunk(const float (&f)[32], uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
 }
 
 template <int BN, bool A_MN, bool B_MN, int CG>
@@ -437,6 +455,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         rs = ep.row_scale[row];
         rt = ep.row_shift[row];
       }
+      long long grow[2] = {0, 0};  // this thread's row of each gather table (one index load per tile)
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        if (ep.gather[i] != nullptr && row_ok) grow[i] = ep.gather_idx[i][row];
 #pragma unroll 1
       for (int ch = 0; ch < kChunks; ++ch) {
         const int cc = (half * kChunks + ch) * 32;
@@ -480,6 +502,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
           }
         }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          if (ep.gather[i] != nullptr && row_ok) {
+            const __nv_bfloat16* gp = ep.gather[i] + grow[i] * ep.ld_gather + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (j < cols_left) {
+                float p[8];
+                unpack<__nv_bfloat16>(ldg16_keep(gp + j), p);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) f[j + u] += p[u];
+              }
+            }
+          }
+        }
         if (ep.dact_pre != nullptr) {
           if (row_ok) {
             const __nv_bfloat16* pp = reinterpret_cast<const __nv_bfloat16*>(ep.dact_pre) + (size_t)row * g.N + col0;
@@ -498,9 +535,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           if (ep.pre_out != nullptr) {
             // the activation sees the bf16-rounded pre-activation, so that backward (which only has the rounded value)
             // differentiates exactly the function forward applied
+            uint32_t pk[16];
+            pack_chunk(f, pk);
+            store_chunk_packed(patch, lane, pk, reinterpret_cast<__nv_bfloat16*>(ep.pre_out) + col0, g.N, row0, rows_left, cols_left);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __bfloat162float(__float2bfloat16_rn(f[j]));
-            store_chunk_bf16(patch, lane, f, reinterpret_cast<__nv_bfloat16*>(ep.pre_out) + col0, g.N, row0, rows_left, cols_left);
+            for (int j = 0; j < 16; ++j) {  // bf16 -> fp32 is a shift / a mask
+              f[2 * j] = __uint_as_float(pk[j] << 16);
+              f[2 * j + 1] = __uint_as_float(pk[j] & 0xffff0000u);
+            }
           }
           act_chunk_rt(f, ep.act);
         }
@@ -543,7 +585,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
           }
         } else {
-          store_chunk_bf16(patch, lane, f, reinterpret_cast<__nv_bfloat16*>(ep.out[seg]) + cs, ep.ld_out, row0, rows_left, cols_left);
+          uint32_t pk[16];
+          pack_chunk(f, pk);
+          store_chunk_packed(patch, lane, pk, reinterpret_cast<__nv_bfloat16*>(ep.out[seg]) + cs, ep.ld_out, row0, rows_left, cols_left);
         }
       }
     }
@@ -703,9 +747,16 @@ extern "C" int ab2_gemm_bf16(const ab2_gemm* d, void* workspace, size_t workspac
   e.residual = d->residual;
   e.ld_res = d->ld_res;
   e.res_f32 = d->res_f32;
+  e.gather[0] = reinterpret_cast<const __nv_bfloat16*>(d->gather_a);
+  e.gather[1] = reinterpret_cast<const __nv_bfloat16*>(d->gather_b);
+  e.gather_idx[0] = reinterpret_cast<const long long*>(d->gather_a_idx);
+  e.gather_idx[1] = reinterpret_cast<const long long*>(d->gather_b_idx);
+  e.ld_gather = d->ld_gather;
+  for (int i = 0; i < 2; ++i)
+    if ((e.gather[i] != nullptr) != (e.gather_idx[i] != nullptr)) return fail(AB2_ERR_INVALID, "ab2_gemm_bf16: a gather table needs its index array");
   void* final_out = e.out[0];
   if (splits > 1) {
-    if (nseg != 1 || e.bias || e.row_scale || e.act != 3 || e.dact_pre || e.residual || e.pre_out)
+    if (nseg != 1 || e.bias || e.row_scale || e.act != 3 || e.dact_pre || e.residual || e.pre_out || e.gather[0] || e.gather[1])
       return fail(AB2_ERR_INVALID, "ab2_gemm_bf16: split-K supports a plain single output only");
     const size_t need = (size_t)splits * M * N * sizeof(float);
     if (workspace == nullptr || workspace_bytes < need)

@@ -137,6 +137,31 @@ edge_act_bwd_src_kernel(const T* __restrict__ gpe, const int* __restrict__ colpt
   }
 }
 
+// out[i] = sum of g[perm[idx ? idx[s] : s]] over s in [ptr[i], ptr[i+1])   (dst segments: idx = null; src segments: idx = cpos)
+template <typename T, int N>
+__global__ void __launch_bounds__(256)
+edge_segsum_kernel(const T* __restrict__ g, const int* __restrict__ ptr, const int* __restrict__ idx, const int* __restrict__ perm,
+                   int n, int chunks, T* __restrict__ out) {
+  const size_t D = (size_t)chunks * N;
+  const int64_t total = (int64_t)n * chunks;
+  for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < total; w += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(w / chunks);
+    const size_t off = (size_t)(w - (int64_t)j * chunks) * N;
+    float acc[N];
+#pragma unroll
+    for (int x = 0; x < N; ++x) acc[x] = 0.f;
+    const int beg = ptr[j], end = ptr[j + 1];
+    for (int s = beg; s < end; ++s) {
+      const size_t t = (size_t)perm[idx ? idx[s] : s];
+      float gg[N];
+      load_chunk_keep<T, N>(g + t * D + off, gg);
+#pragma unroll
+      for (int x = 0; x < N; ++x) acc[x] += gg[x];
+    }
+    store_chunk<T, N>(out + (size_t)j * D + off, acc);
+  }
+}
+
 // ---- LayerNorm + residual + segment sum -------------------------------------------------------------------
 // one warp per dst row; lanes hold CPL chunks of the edge row in registers (D = 32*CPL*N elements max).
 __device__ __forceinline__ float wsum(float x) {
@@ -400,6 +425,37 @@ extern "C" int ab2_edge_gather_add_act_bwd(const void* g, const void* pre, const
 #undef LAUNCH
     AB2_LAUNCH_OK("edge_act_bwd_src_kernel");
   }
+  return AB2_OK;
+}
+
+extern "C" int ab2_edge_segment_sums(const void* g, const int32_t* rowptr, const int32_t* perm, const int32_t* colptr,
+                                     const int32_t* cpos, int64_t E, int64_t Ns, int64_t Nd, int D, int dtype, void* dpi, void* dpj,
+                                     void* stream) {
+  if (dtype != AB2_F32 && dtype != AB2_BF16) return fail(AB2_ERR_INVALID, "edge_segment_sums: bad dtype");
+  if (D <= 0 || E < 0) return fail(AB2_ERR_INVALID, "edge_segment_sums: bad D/E");
+  if ((E > 0 && (!g || !perm)) || (dpi && !rowptr) || (dpj && (!colptr || (E > 0 && !cpos))))
+    return fail(AB2_ERR_INVALID, "edge_segment_sums: null pointer argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int elt = dtype == AB2_F32 ? 4 : 2;
+  const bool vec = (D * elt) % 16 == 0;
+#define LAUNCH(T, N, PTR, IDX, CNT, OUT) \
+  edge_segsum_kernel<T, N><<<stream_grid((CNT) * (int64_t)(D / N), 256), 256, 0, st>>>((const T*)g, PTR, IDX, perm, (int)(CNT), D / N, (T*)(OUT))
+#define CALL(PTR, IDX, CNT, OUT)                                                          \
+  if (dtype == AB2_F32) {                                                                 \
+    if (vec) LAUNCH(float, 4, PTR, IDX, CNT, OUT); else LAUNCH(float, 1, PTR, IDX, CNT, OUT); \
+  } else {                                                                                \
+    if (vec) LAUNCH(__nv_bfloat16, 8, PTR, IDX, CNT, OUT); else LAUNCH(__nv_bfloat16, 1, PTR, IDX, CNT, OUT); \
+  }
+  if (dpi && Nd > 0) {
+    CALL(rowptr, (const int*)nullptr, Nd, dpi)
+    AB2_LAUNCH_OK("edge_segsum_kernel");
+  }
+  if (dpj && Ns > 0) {
+    CALL(colptr, cpos, Ns, dpj)
+    AB2_LAUNCH_OK("edge_segsum_kernel");
+  }
+#undef CALL
+#undef LAUNCH
   return AB2_OK;
 }
 

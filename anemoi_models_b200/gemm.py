@@ -27,7 +27,7 @@ def gemm(a: Tensor, b: Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_
          ldb: Optional[int] = None, out: Optional[Sequence[Tensor]] = None, seg_cols: int = 0, out_dtype: torch.dtype = torch.bfloat16,
          bias: Optional[Tensor] = None, row_scale: Optional[Tensor] = None, row_shift: Optional[Tensor] = None,
          col_vec: Optional[Tensor] = None, act: int = ACT_NONE, pre_out: Optional[Tensor] = None, dact_pre: Optional[Tensor] = None,
-         residual: Optional[Tensor] = None, splits: int = 1):
+         residual: Optional[Tensor] = None, splits: int = 1, gather=None):
     """D[M,N] = epilogue(A . B^T) on the tensor cores; see include/anemoi_b200.h (`ab2_gemm`).  a: [M,K] (or [K,M] when a_mn),
     b: [N,K] (or [K,N] when b_mn), bf16, last dim contiguous.  Returns the output tensor (or the list `out` when given)."""
     if not (a.is_cuda and b.is_cuda):
@@ -65,6 +65,12 @@ def gemm(a: Tensor, b: Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_
             raise TypeError("gemm residual must be fp32 or bf16, contiguous in its last dimension")
         d.residual, d.ld_res, d.res_f32 = residual.data_ptr(), residual.stride(0), int(residual.dtype == torch.float32)
     d.splits = splits
+    if gather is not None:  # ((table_a [Na, N] bf16, idx_a int64 [M]), (table_b, idx_b)): acc += table[idx[m], n], before the activation
+        (ta, ia), (tb, ib) = gather
+        for t_, i_ in ((ta, ia), (tb, ib)):
+            if t_.dtype != torch.bfloat16 or t_.stride(-1) != 1 or t_.stride(0) != ta.stride(0) or i_.dtype != torch.int64 or not i_.is_contiguous():
+                raise TypeError("gemm gather tables must be bf16 with a common row stride, indices contiguous int64")
+        d.gather_a, d.gather_a_idx, d.gather_b, d.gather_b_idx, d.ld_gather = ta.data_ptr(), ia.data_ptr(), tb.data_ptr(), ib.data_ptr(), ta.stride(0)
     ws = None
     need = L.ab2_gemm_workspace_bytes(C.byref(d))
     if need:
@@ -241,6 +247,71 @@ def linear(x: Tensor, lin: torch.nn.Linear, residual: Optional[Tensor] = None, a
     return _LinearFn.apply(x, None, lin.weight, lin.bias, residual, ACT_NONE, act_out)
 
 
+def linear_wb(x: Tensor, weight: Tensor, bias: Optional[Tensor], residual: Optional[Tensor] = None, act_out: int = ACT_NONE):
+    """`F.linear(x, weight, bias)` (+ residual) for a weight that is a slice of a parameter (GraphConv's split first layer)."""
+    return _LinearFn.apply(x, None, weight, bias, residual, ACT_NONE, act_out)
+
+
 def act_linear(pre: Tensor, h: Tensor, lin: torch.nn.Linear, act: int, residual: Optional[Tensor] = None, act_out: int = ACT_NONE):
     """`lin(act(pre))` (+ residual) where h = act(pre) came out of the previous GEMM's epilogue."""
     return _LinearFn.apply(h, pre, lin.weight, lin.bias, residual, act, act_out)
+
+
+class _EdgeFirstLayerFn(torch.autograd.Function):
+    """First layer of GraphConv's edge MLP on the split weight (reference conv.py:69, mlp.py:74):
+    pre[t] = e[t] We^T + pi[dst_t] + pj[src_t], h = act(pre) -- ONE GEMM over the edges whose epilogue gathers the two node-side
+    rows (pi, pj are L2-resident node tables), applies the activation and keeps the pre-activation.  Returns (pre, h), h not
+    differentiable (the consumer differentiates through the activation in its dgrad epilogue).
+    Backward: de = dpre We (dgrad), dWe = dpre^T e (split-K wgrad), dpi / dpj = CSR / CSC segment sums of dpre."""
+
+    @staticmethod
+    def forward(ctx, e: Tensor, pi: Tensor, pj: Tensor, w_e: Tensor, plan, act: int):
+        E, K = e.shape
+        N = w_e.shape[0]
+        e2 = e if (e.dtype == torch.bfloat16 and e.is_contiguous()) else e.to(torch.bfloat16).contiguous()
+        w = w_e.detach().to(torch.bfloat16).contiguous()
+        pi2, pj2 = pi.to(torch.bfloat16).contiguous(), pj.to(torch.bfloat16).contiguous()
+        pre = torch.empty((E, N), dtype=torch.bfloat16, device=e.device)
+        ei = plan.edge_index
+        h = gemm(e2, w, E, N, K, act=act, pre_out=pre, gather=((pi2, ei[1]), (pj2, ei[0])))
+        ctx.save_for_backward(e2, w)
+        ctx.plan, ctx.dts = plan, (e.dtype, pi.dtype, pj.dtype, w_e.dtype)
+        ctx.mark_non_differentiable(h)
+        return pre, h
+
+    @staticmethod
+    def backward(ctx, g: Tensor, _gh=None):
+        e2, w = ctx.saved_tensors
+        plan = ctx.plan
+        L = _lib.lib()
+        E, K = e2.shape
+        N = w.shape[0]
+        g2 = g if (g.dtype == torch.bfloat16 and g.is_contiguous()) else g.to(torch.bfloat16).contiguous()
+        need = ctx.needs_input_grad
+        de = gemm(g2, w, E, K, N, b_mn=True).to(ctx.dts[0]) if need[0] else None
+        dw = gemm(g2, e2, N, K, E, a_mn=True, b_mn=True, out_dtype=torch.float32, splits=wgrad_splits(N, K, E)).to(ctx.dts[3]) if need[3] else None
+        dpi = torch.empty((plan.num_dst, N), dtype=torch.bfloat16, device=g.device) if need[1] else None
+        dpj = torch.empty((plan.num_src, N), dtype=torch.bfloat16, device=g.device) if need[2] else None
+        if need[1] or need[2]:
+            with torch.cuda.device(g.device):
+                _lib.check(L.ab2_edge_segment_sums(g2.data_ptr(), plan.rowptr.data_ptr(), plan.perm.data_ptr(), plan.colptr.data_ptr(),
+                                                   plan.cpos.data_ptr(), E, plan.num_src, plan.num_dst, N, _lib.AB2_BF16, _p(dpi), _p(dpj),
+                                                   _lib.current_stream(g.device)))
+        return (de, None if dpi is None else dpi.to(ctx.dts[1]), None if dpj is None else dpj.to(ctx.dts[2]), dw, None, None)
+
+
+def edge_first_layer(e: Tensor, pi: Tensor, pj: Tensor, w_e: Tensor, plan, act: int):
+    return _EdgeFirstLayerFn.apply(e, pi, pj, w_e, plan, act)
+
+
+def mlp_tail(pre: Tensor, h: Tensor, linears, act: int) -> Tensor:
+    """The Linear layers that follow an activation already applied in a GEMM epilogue: (Linear, act)* Linear."""
+    for lin in linears[:-1]:
+        pre, h = act_linear(pre, h, lin, act, act_out=act)
+    return act_linear(pre, h, linears[-1], act)
+
+
+def mlp_forward(x: Tensor, linears, act: int) -> Tensor:
+    """Linear, act, (Linear, act)*, Linear (reference mlp.py:74-80) with every activation in a GEMM epilogue."""
+    pre, h = linear(x, linears[0], act_out=act)
+    return mlp_tail(pre, h, linears[1:], act)

@@ -110,6 +110,19 @@ class GraphConvBaseBlock(BaseBlock):
         x_need = halo_gather(x_src, plan, model_comm_group)  # replaces sync_tensor's full all-gather (block.py:203)
         return self.conv((x_need, x_dst), edge_attr, plan.local_edge_index, size=(plan.n_src, plan.num_dst_local))
 
+    def _node_update(self, x_in: Tensor, x_res: Tensor) -> Tensor:
+        """`node_mlp(x_in) + x_res` (reference block.py:217-219, 277-283): Linear-act-Linear-act-Linear-LayerNorm; bf16 CUDA inputs
+        run on the tcgen05 GEMMs (activations in the epilogues) and the LayerNorm kernel, anything else on the nn modules."""
+        body = self.node_mlp.model
+        layers = list(body) if isinstance(body, nn.Sequential) else None
+        if (layers is not None and isinstance(layers[-1], nn.LayerNorm) and layers[-1].elementwise_affine
+                and type(layers[1]).__name__ in tcg.ACT_CODES
+                and tcg.tc_applies(x_in, *[d for m in layers if isinstance(m, nn.Linear) for d in (m.in_features, m.out_features)])):
+            linears = [m for m in layers if isinstance(m, nn.Linear)]
+            y = tcg.mlp_forward(x_in, linears, tcg.ACT_CODES[type(layers[1]).__name__])
+            return tcg.layer_norm(y, layers[-1], out_dtype=y.dtype) + x_res
+        return self.node_mlp(x_in) + x_res
+
     @abstractmethod
     def forward(self, x, edge_attr, edge_index, shapes, model_comm_group=None, size=None): ...
 
@@ -120,7 +133,7 @@ class GraphConvProcessorBlock(GraphConvBaseBlock):
     def forward(self, x: Tensor, edge_attr: Tensor, edge_index: Tensor, shapes: tuple, model_comm_group=None,
                 size: Optional[Tuple[int, int]] = None):
         out, edges_new = self._conv(x, x, edge_attr, edge_index, shapes[1], shapes[1], model_comm_group, size)
-        nodes_new = self.node_mlp(torch.cat([x, out], dim=1)) + x
+        nodes_new = self._node_update(torch.cat([x, out], dim=1), x)
         return nodes_new, edges_new
 
 
@@ -130,9 +143,9 @@ class GraphConvMapperBlock(GraphConvBaseBlock):
     def forward(self, x: Tuple[Tensor, Tensor], edge_attr: Tensor, edge_index: Tensor, shapes: tuple,
                 model_comm_group=None, size: Optional[Tuple[int, int]] = None):
         out, edges_new = self._conv(x[0], x[1], edge_attr, edge_index, shapes[0], shapes[1], model_comm_group, size)
-        nodes_new_dst = self.node_mlp(torch.cat([x[1], out], dim=1)) + x[1]
+        nodes_new_dst = self._node_update(torch.cat([x[1], out], dim=1), x[1])
         # update only needed in forward mapper
-        nodes_new_src = x[0] if not self.update_src_nodes else self.node_mlp(torch.cat([x[0], x[0]], dim=1)) + x[0]
+        nodes_new_src = x[0] if not self.update_src_nodes else self._node_update(torch.cat([x[0], x[0]], dim=1), x[0])
         return (nodes_new_src, nodes_new_dst), edges_new
 
 

@@ -11,6 +11,7 @@ from typing import Optional, Tuple, Union
 import torch
 from torch import Tensor, nn
 
+from .. import gemm as tcg
 from .. import ops
 from ..graph import GraphCSR, check_edge_index, get_csr, resolve_size
 from .mlp import MLP, AutocastLayerNorm
@@ -98,6 +99,18 @@ class GraphConv(nn.Module):
             raise NotImplementedError("GraphConv: unsupported edge_mlp configuration for the fused path")
         F = torch.nn.functional
         W0 = lin0.weight
+        ln = layers[-1]
+        linears = [m for m in layers[2:-1] if isinstance(m, nn.Linear)]
+        if tcg.tc_applies(edge_attr, Din, self.out_channels) and ln.elementwise_affine:
+            # bf16 on the tcgen05 kernels: node-side projections, then ONE GEMM per edge-MLP layer whose epilogue does the
+            # gather-add of the node terms / the bias, the activation and keeps the pre-activation for backward
+            act = tcg.ACT_CODES[self.activation]
+            pi = tcg.linear_wb(x_dst, W0[:, :Din], lin0.bias)
+            pj = tcg.linear_wb(x_src, W0[:, Din:2 * Din], None)
+            pre, h = tcg.edge_first_layer(edge_attr, pi, pj, W0[:, 2 * Din:], plan, act)
+            y = tcg.mlp_tail(pre, h, linears, act)
+            edges_new, out = ops.edge_ln_res_segsum(y, edge_attr.to(y.dtype), ln.weight, ln.bias, ln.eps, plan)
+            return out.to(x_dst.dtype if x_dst.dtype != torch.float32 else y.dtype), edges_new.to(edge_attr.dtype if edge_attr.dtype != torch.float32 else y.dtype)
         # split first layer: cat order is [x_i (dst), x_j (src), edge_attr]  (reference conv.py:69)
         pi = F.linear(x_dst, W0[:, :Din], lin0.bias)
         pj = F.linear(x_src, W0[:, Din:2 * Din])
@@ -105,6 +118,5 @@ class GraphConv(nn.Module):
         h = ops.edge_gather_add_act(pi, pj, pe, plan, self.activation)
         for layer in layers[2:-1]:  # (Linear, act) x (n_extra+1), Linear -- tensor-core GEMMs
             h = layer(h)
-        ln = layers[-1]
         edges_new, out = ops.edge_ln_res_segsum(h, edge_attr, ln.weight, ln.bias, ln.eps, plan)
         return out, edges_new

@@ -258,6 +258,8 @@ int ab2_gtconv_fwd_bwd_host_streamed(const void* q_host, const void* k_host, con
  * Epilogue, in this order (every pointer optional):
  *   acc = row_scale[m] * acc + row_shift[m] * col_vec[n]     (LayerNorm folded into the GEMM: rstd, -rstd*mean, colsum(W'))
  *   acc += bias[n]
+ *   acc += gather_a[gather_a_idx[m], n] + gather_b[gather_b_idx[m], n]   (bf16 row tables, row stride ld_gather, int64 indices:
+ *                                                              GraphConv's split first layer -- pi[dst_t] + pj[src_t], conv.py:69)
  *   dact_pre != NULL : acc *= act'(dact_pre[m,n])            (dgrad through an activation; bf16 [M,N])
  *   else act != 3    : pre_out[m,n] = acc (bf16, optional side output kept for backward);  acc = act(acc)
  *   acc += residual[m, n]                                    (bf16 or fp32, row stride ld_res)
@@ -286,6 +288,11 @@ typedef struct ab2_gemm {
   int64_t ld_res;
   int32_t res_f32, act;
   int32_t splits, reserved;
+  const void* gather_a;
+  const int64_t* gather_a_idx;
+  const void* gather_b;
+  const int64_t* gather_b_idx;
+  int64_t ld_gather;
 } ab2_gemm;
 size_t ab2_gemm_workspace_bytes(const ab2_gemm* d);
 int ab2_gemm_bf16(const ab2_gemm* d, void* workspace, size_t workspace_bytes, void* stream);
@@ -307,6 +314,11 @@ int ab2_layernorm_bwd(const void* g, int g_dtype, const void* x, int x_dtype, co
                       const float* rstd, int64_t M, int D, const void* add, void* dx, float* partial, float* dgamma, float* dbeta,
                       void* stream);
 int ab2_colsum(const void* a, int dtype, int64_t M, int N, int64_t ld, float* partial, float* out, void* stream);
+/* dpi[i] = sum of g[t] over the edges t into dst i (CSR order), dpj[j] = sum over the edges out of src j (CSC order); g [E,D] in
+ * original edge order.  The node-side gradients of GraphConv's split first layer (conv.py:69) when g = d(pre-activation) already
+ * came out of a GEMM epilogue.  Either output may be NULL.  Deterministic. */
+int ab2_edge_segment_sums(const void* g, const int32_t* rowptr, const int32_t* perm, const int32_t* colptr, const int32_t* cpos,
+                          int64_t E, int64_t Ns, int64_t Nd, int D, int dtype, void* dpi, void* dpj, void* stream);
 
 #ifdef __cplusplus
 }

@@ -238,7 +238,14 @@ def test_gt_blocks_on_tensor_core_kernels_match_the_library_path(kind, mode):
     assert out_tc.dtype == out_lib.dtype
     assert rel_err(out_tc, out_ref) < 2e-2 and rel_l2(out_tc, out_ref) < 2e-2
     assert rel_l2(out_tc, out_ref) < 1.5 * rel_l2(out_lib, out_ref) + 1e-3  # no worse than the library bf16 path
+    bad = []
     for k in g_lib:
         assert (g_tc[k] is None) == (g_lib[k] is None), k
-        if g_lib[k] is not None:
-            assert rel_err(g_tc[k], g_lib[k]) < 3e-2 and rel_l2(g_tc[k], g_lib[k]) < 3e-2, (k, rel_err(g_tc[k], g_lib[k]), rel_l2(g_tc[k], g_lib[k]))
+        if g_lib[k] is None:
+            continue
+        e1, e2 = rel_err(g_tc[k], g_lib[k]), rel_l2(g_tc[k], g_lib[k])
+        # d lin_key.bias is zero in exact arithmetic (a constant added to every key of a dst shifts all its logits alike and the
+        # softmax is invariant to it): both sides hold rounding noise there, only the max-norm bound is meaningful
+        if e1 >= 3e-2 or (e2 >= 3e-2 and k != "lin_key.bias"):
+            bad.append((k, e1, e2))
+    assert not bad, bad
