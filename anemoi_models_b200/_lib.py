@@ -57,6 +57,8 @@ SIGNATURES = {
     "ab2_ipc_free": (_i32, [_vp]),
     "ab2_memcpy_d2d": (_i32, [_vp, _vp, _sz, _vp]),
     "ab2_peer_push_rows": (_i32, [_vp] * 5 + [_i64, _i32, _vp, _vp, _i32, _vp]),
+    "ab2_peer_push_rows_signal": (_i32, [_vp] * 5 + [_i64, _i32, _vp, _vp, _vp, _vp, C.c_uint32, _i32, _i32, _vp]),
+    "ab2_peer_wait_flags": (_i32, [_vp, C.c_uint32, _i32, _i32, _vp]),
     "ab2_rows_add": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "ab2_edge_gather_add_act": (_i32, [_vp] * 4 + [_i64] * 3 + [_i32] * 3 + [_vp] * 3),
     "ab2_edge_gather_add_act_bwd": (_i32, [_vp] * 6 + [_i64] * 3 + [_i32] * 3 + [_vp] * 4),

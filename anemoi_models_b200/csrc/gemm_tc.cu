@@ -43,23 +43,24 @@ namespace tc {
 constexpr int BM = 128;     // accumulator rows per CTA tile = TMEM lanes
 constexpr int BK = 64;      // 64 bf16 = 128 B = one SWIZZLE_128B atom along the contraction
 constexpr int UMMA_K = 16;  // contraction per tcgen05.mma for 16-bit operands
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kBoxBytes = 64 * 64 * 2;  // one 64 x 64 bf16 box (MN-major operands are loaded box by box)
 
 constexpr int kPatchStride = 80;                      // bytes per row of an epilogue patch: 64 B of bf16 + 16 B pad (bank spread)
 constexpr int kPatchBytes = 32 * kPatchStride;        // 32 rows x 32 bf16 columns per epilogue warp
 
-template <int BN, int CG>
+// EW = number of epilogue warps (8 or 16: two or four per scheduler -- the epilogue is a latency chain of TMEM load, gathers and
+// the shared-memory transpose, so the epilogue-heavy shapes want four; the price is one pipeline stage of shared memory)
+template <int BN, int CG, int EW>
 struct Cfg {
+  static constexpr int kThreads = 64 + 32 * EW;
   static constexpr int kBRows = BN / CG;  // rows of B this CTA stages (CG = 2: half of the tile's columns)
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesRaw = (192 * 1024) / kStageBytes;  // CG=1: 4 / 6 / 8 at BN = 256 / 128 / 64; CG=2: 6 / 8 / 9
+  static constexpr int kStagesRaw = (227 * 1024 - 2048 - EW * kPatchBytes) / kStageBytes;  // EW=16: CG=2: 5 (BN=256), 7 (BN=128); EW=8: 6 / 8
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kBarBytes = 1024;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kEpiWarps * kPatchBytes + 1024;  // + 1024 B alignment slack
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + EW * kPatchBytes + 1024;  // + 1024 B alignment slack
 };
 
 struct Epi {
@@ -301,10 +302,10 @@ __device__ __forceinline__ void pack_chunk(const float (&f)[32], uint32_t (&pk)[
   for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
 }
 
-template <int BN, bool A_MN, bool B_MN, int CG>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+template <int BN, bool A_MN, bool B_MN, int CG, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, const Args g) {
-  using C = Cfg<BN, CG>;
+  using C = Cfg<BN, CG, EW>;
   constexpr int S = C::kStages;
   constexpr int TM = BM * CG;  // rows of the tile the CTA pair (or the single CTA) accumulates
   extern __shared__ uint8_t smem_raw[];
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull(a), 1);
-      mbar_init(tempty(a), CG * kEpiWarps);
+      mbar_init(tempty(a), CG * EW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -436,8 +437,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // ===== epilogue =====
     const int e = warp - 2;
     const int quad = warp & 3;  // a warp may only touch TMEM lanes [32 * (warp % 4), +32)
-    const int half = e >> 2;    // two warps per lane quadrant: each takes half of the BN columns
-    constexpr int kChunks = BN / 32 / 2;
+    const int half = e >> 2;    // EW / 4 warps per lane quadrant: each takes an equal share of the BN columns
+    constexpr int kChunks = BN / 32 / (EW / 4);
     const Epi& ep = g.epi;
     const uint32_t patch = patches + e * kPatchBytes;
     uint32_t it = 0;
@@ -658,10 +659,10 @@ static int make_map(CUtensorMap* m, const void* ptr, long long inner, long long 
   return AB2_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, int CG>
+template <int BN, bool A_MN, bool B_MN, int CG, int EW>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Args& a, cudaStream_t st) {
-  using C = Cfg<BN, CG>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CG>;
+  using C = Cfg<BN, CG, EW>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CG, EW>;
   if (!AB2_ENSURE_DYN_SMEM(kern, C::kSmemBytes)) return fail(AB2_ERR_CUDA, "gemm_tc_kernel: cannot reserve %d B of shared memory", C::kSmemBytes);
   const int tiles = a.tiles_m * a.tiles_n * a.splits;
   const int slots = num_sms() / CG;  // CTAs (CG = 1) or CTA pairs (CG = 2) that can be resident
@@ -671,7 +672,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Args& a, c
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(grid * CG));
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(C::kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -775,17 +776,24 @@ extern "C" int ab2_gemm_bf16(const ab2_gemm* d, void* workspace, size_t workspac
   rc = d->b_mn ? tc::make_map(&tb, d->b, N, K, d->ldb, 64) : tc::make_map(&tb, d->b, K, N, d->ldb, BN / CG);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-#define AB2_GEMM_DISPATCH(BNV, CGV)                                                       \
-  do {                                                                                    \
-    if (!d->a_mn && !d->b_mn) rc = tc::launch<BNV, false, false, CGV>(ta, tb, a, st);     \
-    else if (!d->a_mn && d->b_mn) rc = tc::launch<BNV, false, true, CGV>(ta, tb, a, st);  \
-    else if (d->a_mn && d->b_mn) rc = tc::launch<BNV, true, true, CGV>(ta, tb, a, st);    \
-    else rc = tc::launch<BNV, true, false, CGV>(ta, tb, a, st);                           \
+#define AB2_GEMM_DISPATCH(BNV, CGV, EWV)                                                       \
+  do {                                                                                         \
+    if (!d->a_mn && !d->b_mn) rc = tc::launch<BNV, false, false, CGV, EWV>(ta, tb, a, st);     \
+    else if (!d->a_mn && d->b_mn) rc = tc::launch<BNV, false, true, CGV, EWV>(ta, tb, a, st);  \
+    else if (d->a_mn && d->b_mn) rc = tc::launch<BNV, true, true, CGV, EWV>(ta, tb, a, st);    \
+    else rc = tc::launch<BNV, true, false, CGV, EWV>(ta, tb, a, st);                           \
   } while (0)
-  if (BN == 256 && CG == 2) AB2_GEMM_DISPATCH(256, 2);
-  else if (BN == 256) AB2_GEMM_DISPATCH(256, 1);
-  else if (CG == 2) AB2_GEMM_DISPATCH(128, 2);
-  else AB2_GEMM_DISPATCH(128, 1);
+  // epilogue warps: 16 when the epilogue does per-element work beyond a bias (activation, activation derivative, gathers,
+  // residual), 8 (one more pipeline stage) for the plain ones; AB2_GEMM_EW overrides for A/B runs
+  int EW = (e.act != 3 || e.dact_pre || e.gather[0] || e.gather[1] || e.residual || e.row_scale) ? 16 : 8;
+  if (const char* ew = getenv("AB2_GEMM_EW")) EW = atoi(ew) == 16 ? 16 : 8;
+  if (CG == 1) {  // single-CTA tiles: A/B experiments only
+    if (BN == 256) AB2_GEMM_DISPATCH(256, 1, 8); else AB2_GEMM_DISPATCH(128, 1, 8);
+  } else if (EW == 16) {
+    if (BN == 256) AB2_GEMM_DISPATCH(256, 2, 16); else AB2_GEMM_DISPATCH(128, 2, 16);
+  } else {
+    if (BN == 256) AB2_GEMM_DISPATCH(256, 2, 8); else AB2_GEMM_DISPATCH(128, 2, 8);
+  }
 #undef AB2_GEMM_DISPATCH
   if (rc) return rc;
   if (splits > 1) {

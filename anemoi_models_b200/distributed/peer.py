@@ -88,6 +88,13 @@ class PeerExchange:
                     for plane in ("a", "b"):
                         offs[(kind, parity, plane)] = o
                         o += (nbytes + 255) // 256 * 256
+            # flag words of the barrier protocol (csrc/peer_exchange.cu): one 32-bit slot per peer and exchange kind, written by
+            # the peers; and this rank's own CTA counters of the push kernels
+            for kind in ("halo", "inbox"):
+                offs[("flags", kind)] = o
+                o += 256
+                offs[("counter", kind)] = o
+                o += 256
             return offs, o
         self.offs, total = layout(n_halo, n_send)
         # ---- local phases (may fail on SOME ranks: IPC not permitted, a GPU pair without P2P) are kept apart from the
@@ -136,6 +143,10 @@ class PeerExchange:
             for parity in (0, 1):
                 self.tables[(kind, parity)] = tuple(
                     _ptr_array([self.peer_base[p] + peer_offs[p][(kind, parity, plane)] for p in range(P)]) for plane in ("a", "b"))
+        # flag-word barrier: entry p = address of MY slot in rank p's flag array
+        self.flag_slots = {kind: _ptr_array([self.peer_base[p] + peer_offs[p][("flags", kind)] + 4 * rank for p in range(P)])
+                           for kind in ("halo", "inbox")}
+        self.use_flags = os.environ.get("AB2_BARRIER", "flags") != "nccl"  # AB2_BARRIER=nccl: the round-1 all-reduce barrier
         self.token = torch.zeros(1, device=device)
         self.fwd_epoch = 0
         self.bwd_epoch = 0
@@ -178,6 +189,19 @@ class PeerExchange:
     def __del__(self):
         self.close()
 
+    def _push(self, kind: str, epoch: int, src_a, src_b, src_row, peer, dst_row, n: int, tables, stream: int) -> None:
+        """push rows into the peers' planes and make them visible: flag-word signal + wait (default), or the NCCL barrier."""
+        L = _lib.lib()
+        ta, tb = tables
+        if self.use_flags:
+            _lib.check(L.ab2_peer_push_rows_signal(src_a, src_b, src_row, peer, dst_row, n, self.row_bytes, ta, tb,
+                                                   self.base + self.offs[("counter", kind)], self.flag_slots[kind], epoch & 0xFFFFFFFF,
+                                                   self.P, self.rank, stream))
+            _lib.check(L.ab2_peer_wait_flags(self.base + self.offs[("flags", kind)], epoch & 0xFFFFFFFF, self.P, self.rank, stream))
+        else:
+            _lib.check(L.ab2_peer_push_rows(src_a, src_b, src_row, peer, dst_row, n, self.row_bytes, ta, tb, self.P, stream))
+            dist.all_reduce(self.token, group=self.group)
+
     def _local(self, kind: str, parity: int, plane: str) -> int:
         return self.base + self.offs[(kind, parity, plane)]
 
@@ -214,14 +238,11 @@ class PeerExchange:
         ready.record(main)
         b = self.bwd_epoch & 1
         self.bwd_epoch += 1
-        ta, tb = self.tables[("inbox", b)]
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ready)
             with torch.cuda.device(self.device):
-                _lib.check(L.ab2_peer_push_rows(_lib.ptr(dk_halo), _lib.ptr(dv_halo), 0, _lib.ptr(self.owner_of_halo),
-                                                _lib.ptr(self.inbox_row_of_halo), self.plan.n_halo, self.row_bytes, ta, tb, self.P,
-                                                self.stream.cuda_stream))
-                dist.all_reduce(self.token, group=self.group)
+                self._push("inbox", self.bwd_epoch, _lib.ptr(dk_halo), _lib.ptr(dv_halo), 0, _lib.ptr(self.owner_of_halo),
+                           _lib.ptr(self.inbox_row_of_halo), self.plan.n_halo, self.tables[("inbox", b)], self.stream.cuda_stream)
             done = torch.cuda.Event()
             done.record(self.stream)
         return b, done
@@ -250,13 +271,11 @@ class PeerExchange:
         b = self.fwd_epoch & 1
         self.fwd_epoch += 1
         st = _lib.current_stream(self.device)
-        ta, tb = self.tables[("halo", b)]
         if outs is None:
             outs = tuple(torch.empty((plan.n_halo,) + tuple(r.shape[1:]), dtype=r.dtype, device=r.device) for r in (k, v))
         with torch.cuda.device(self.device):
-            _lib.check(L.ab2_peer_push_rows(_lib.ptr(k), _lib.ptr(v), _lib.ptr(self.send_idx32), _lib.ptr(self.peer_of_send),
-                                            _lib.ptr(self.dst_row_of_send), self.send_idx32.numel(), self.row_bytes, ta, tb, self.P, st))
-            dist.all_reduce(self.token, group=self.group)
+            self._push("halo", self.fwd_epoch, _lib.ptr(k), _lib.ptr(v), _lib.ptr(self.send_idx32), _lib.ptr(self.peer_of_send),
+                       _lib.ptr(self.dst_row_of_send), self.send_idx32.numel(), self.tables[("halo", b)], st)
             for plane, t in zip(("a", "b"), outs):
                 _lib.check(L.ab2_memcpy_d2d(_lib.ptr(t), self._local("halo", b, plane), plan.n_halo * self.row_bytes, st))
         return outs[0], outs[1]
@@ -268,13 +287,11 @@ class PeerExchange:
         b = self.bwd_epoch & 1
         self.bwd_epoch += 1
         st = _lib.current_stream(self.device)
-        ta, tb = self.tables[("inbox", b)]
         D = dk.numel() // max(dk.shape[0], 1) if dk.shape[0] else self.row_bytes // dk.element_size()
         dt = _lib.dtype_code(dk.dtype)
         with torch.cuda.device(self.device):
-            _lib.check(L.ab2_peer_push_rows(_lib.ptr(dk_halo), _lib.ptr(dv_halo), 0, _lib.ptr(self.owner_of_halo),
-                                            _lib.ptr(self.inbox_row_of_halo), plan.n_halo, self.row_bytes, ta, tb, self.P, st))
-            dist.all_reduce(self.token, group=self.group)
+            self._push("inbox", self.bwd_epoch, _lib.ptr(dk_halo), _lib.ptr(dv_halo), 0, _lib.ptr(self.owner_of_halo),
+                       _lib.ptr(self.inbox_row_of_halo), plan.n_halo, self.tables[("inbox", b)], st)
             off = 0
             for cnt in plan.send_counts:
                 if cnt:

@@ -163,15 +163,22 @@ def layer_norm(x: Tensor, ln: torch.nn.LayerNorm, out_dtype: torch.dtype = torch
     return _LayerNormFn.apply(x, ln.weight, ln.bias, ln.eps, out_dtype)
 
 
-def wgrad_splits(N: int, K: int, M: int) -> int:
-    """Split count of the wgrad contraction (over the M rows): enough CTA pairs to fill the GPU, at least 8 k-blocks each."""
+def wgrad_splits(N: int, K: int, M: int, slots: int = 74) -> int:
+    """Split count of the wgrad contraction (over the M rows).  dW has only (N/256) x (K/256) output tiles -- 16 for a
+    1024 x 1024 weight -- so the contraction is cut into `s` pieces to give every CTA pair work, and `s` is chosen so that the
+    tile count fills whole waves of the `slots` resident CTA pairs (160 tiles = 2.16 waves cost three rounds: measured 72 % of
+    the one-wave rate), with at least 8 k-blocks per piece and no empty piece."""
     pairs = ((N + 255) // 256) * ((K + 255) // 256 if K > 128 else 1)
     kb = (M + 63) // 64
-    want = max(1, (2 * 74 + pairs - 1) // pairs)
-    s = max(1, min(want, kb // 8 if kb >= 8 else 1, 64))
-    while s > 1 and ((kb + s - 1) // s) * (s - 1) >= kb:  # no empty split
-        s -= 1
-    return s
+    best, best_eff = 1, 0.0
+    for s_ in range(1, 65):
+        if s_ > 1 and (kb // s_ < 8 or ((kb + s_ - 1) // s_) * (s_ - 1) >= kb):
+            continue
+        tiles = pairs * s_
+        eff = tiles / (((tiles + slots - 1) // slots) * slots)
+        if eff > best_eff + 0.04:  # prefer fewer splits (fewer fp32 partials) unless the gain is real
+            best, best_eff = s_, eff
+    return best
 
 
 class _LinearFn(torch.autograd.Function):
@@ -184,6 +191,7 @@ class _LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x: Tensor, pre: Optional[Tensor], weight: Tensor, bias: Optional[Tensor], residual: Optional[Tensor],
                 act_in: int, act_out: int):
+        ctx.set_materialize_grads(False)  # the (non-differentiable) activation output would otherwise get a zero-filled [M, N] gradient
         shape = tuple(x.shape)
         x2 = x.reshape(-1, shape[-1])
         if x2.dtype != torch.bfloat16 or x2.stride(-1) != 1 or (x2.stride(0) % 8) != 0 or (x2.data_ptr() % 16) != 0:
@@ -216,6 +224,8 @@ class _LinearFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g: Tensor, _g_h=None):
+        if g is None:
+            return None, None, None, None, None, None, None
         x2, pre, w = ctx.saved_tensors
         shape, act_in, wdt, bdt, rdt, rshape = ctx.meta
         M, K = x2.shape
@@ -266,6 +276,7 @@ class _EdgeFirstLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, e: Tensor, pi: Tensor, pj: Tensor, w_e: Tensor, plan, act: int):
+        ctx.set_materialize_grads(False)
         E, K = e.shape
         N = w_e.shape[0]
         e2 = e if (e.dtype == torch.bfloat16 and e.is_contiguous()) else e.to(torch.bfloat16).contiguous()
@@ -281,6 +292,8 @@ class _EdgeFirstLayerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g: Tensor, _gh=None):
+        if g is None:
+            return None, None, None, None, None, None
         e2, w = ctx.saved_tensors
         plan = ctx.plan
         L = _lib.lib()

@@ -162,6 +162,16 @@ int ab2_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
 int ab2_peer_push_rows(const void* src_a, const void* src_b, const int32_t* src_row, const int32_t* peer,
                        const int32_t* dst_row, int64_t n, int row_bytes, void* const* plane_a, void* const* plane_b,
                        int npeers, void* stream);
+/* The same push followed, in the same kernel, by a flag-word signal: once every CTA's stores are fenced at system scope the
+ * last CTA stores `epoch` (st.release.sys) into this rank's slot of every peer's flag array (flag_slots: HOST array of npeers
+ * device pointers, entry p = address of MY slot inside peer p's buffer; counter: a zero-initialised device word of this rank).
+ * n may be 0 (signal only).  ab2_peer_wait_flags enqueues a one-warp kernel that spins (ld.acquire.sys, 20 s time-out -> trap)
+ * until the local slots of all peers have reached `epoch`; kernels behind it in `stream` then see the pushed rows.
+ * Replaces the stream-ordered 1-element NCCL all-reduce used as a barrier in round 1. */
+int ab2_peer_push_rows_signal(const void* src_a, const void* src_b, const int32_t* src_row, const int32_t* peer,
+                              const int32_t* dst_row, int64_t n, int row_bytes, void* const* plane_a, void* const* plane_b,
+                              void* counter, void* const* flag_slots, uint32_t epoch, int npeers, int my_rank, void* stream);
+int ab2_peer_wait_flags(const void* local_slots, uint32_t epoch, int npeers, int my_rank, void* stream);
 /* dst[idx[s]] += src[s], s in [0, n); the ids of one call must be distinct (plain read-modify-write, fp32 add). */
 int ab2_rows_add(void* dst, const int64_t* idx, const void* src, int64_t n, int D, int dtype, void* stream);
 
