@@ -9,6 +9,7 @@ The only exchange is the set of src rows a rank's edges reference but another ra
 """
 from __future__ import annotations
 
+import weakref
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
@@ -109,6 +110,9 @@ def build_local_halo_plan(edge_index_local: Tensor, src_bounds: List[int], dst_b
                     halo_ids=halo_ids)
 
 
+_plan_registry: dict = {}  # (id(edge_index), key) -> (weakref to the tensor, version, plan)
+
+
 def cached_plan(owner, key, edge_index: Tensor, group, builder):
     """Halo plan of `edge_index` kept ON THE CALLING MODULE (`owner.__dict__`), one entry per key (shard bounds, rank).
 
@@ -126,6 +130,13 @@ def cached_plan(owner, key, edge_index: Tensor, group, builder):
     hit = store.get(key)
     if hit is not None and hit[0] is edge_index and hit[1] == tensor_version(edge_index):
         return hit[2]
+    # another module already holds the plan of this very tensor (the 16 blocks of a processor share one edge_index): share the
+    # plan -- and with it the peer-memory buffers -- instead of building 16 copies.  Identity relations between tensors are the
+    # same on every rank (same program), so this is again the same decision everywhere.
+    reg = _plan_registry.get((id(edge_index), key))
+    if reg is not None and reg[0]() is edge_index and reg[1] == tensor_version(edge_index):
+        store[key] = (edge_index, reg[1], reg[2])
+        return reg[2]
     same = (hit is not None and hit[0].shape == edge_index.shape and hit[0].device == edge_index.device
             and hit[0].dtype == edge_index.dtype and hit[1] == tensor_version(hit[0]) and bool(torch.equal(hit[0], edge_index)))
     flag = torch.tensor([1 if same else 0], dtype=torch.int64, device=edge_index.device)
@@ -135,6 +146,9 @@ def cached_plan(owner, key, edge_index: Tensor, group, builder):
     else:
         plan = builder()
     store[key] = (edge_index, tensor_version(edge_index), plan)
+    for k_ in [k_ for k_, v_ in _plan_registry.items() if v_[0]() is None]:
+        del _plan_registry[k_]
+    _plan_registry[(id(edge_index), key)] = (weakref.ref(edge_index), tensor_version(edge_index), plan)
     return plan
 
 
@@ -239,5 +253,21 @@ class _SelectShardedEdges(torch.autograd.Function):
         return reduce_scatter_rows(full, 0, ctx.shapes, ctx.group), None, None, None
 
 
-def select_sharded_edges(edge_attr_shard: Tensor, shapes_edge, edge_ids: Tensor, group) -> Tensor:
-    return _SelectShardedEdges.apply(edge_attr_shard, shapes_edge, edge_ids, group)
+def select_sharded_edges(edge_attr_shard: Tensor, shapes_edge, edge_ids: Tensor, group, plan: Optional[HaloPlan] = None) -> Tensor:
+    """Own rows of the all-gathered raw edge attributes.  A processor hands the SAME `edge_attr` tensor to every one of its
+    blocks (reference processor.py:335-341): with `plan` given the gather + select (and, in backward, the reduce-scatter) runs
+    once per forward and the result is shared by the blocks that follow (keyed by tensor identity and version; autograd sums
+    their gradients into the one gather)."""
+    if plan is None:
+        return _SelectShardedEdges.apply(edge_attr_shard, shapes_edge, edge_ids, group)
+    from ..graph import tensor_version
+
+    hit = plan.__dict__.get("_ea_select")
+    if (hit is not None and hit[0]() is edge_attr_shard and hit[1] == tensor_version(edge_attr_shard)
+            and hit[3] == torch.is_grad_enabled()):
+        return hit[2]
+    out = _SelectShardedEdges.apply(edge_attr_shard, shapes_edge, edge_ids, group)
+    import weakref
+
+    plan.__dict__["_ea_select"] = (weakref.ref(edge_attr_shard), tensor_version(edge_attr_shard), out, torch.is_grad_enabled())
+    return out

@@ -59,6 +59,20 @@ def _linear_padded_k(lin: nn.Linear, x: Tensor, multiple: int = 8) -> Tensor:
     return F.linear(F.pad(x, (0, pad)), F.pad(lin.weight, (0, pad)), lin.bias)
 
 
+def _lin_edge(lin: nn.Linear, edge_attr: Tensor, tc: bool) -> Tensor:
+    """`lin_edge(edge_attr)` (reference block.py:497, 618).  edge_dim is 11 in the reference configs: cuBLASLt runs the forward
+    and both backward GEMMs of such a skinny contraction far below the HBM rate (measured on the headline graph: 4.9 ms per
+    forward + backward for 1.5 GB of output, bench.py --workload edgepath); on the tcgen05 kernel they are three bandwidth-bound
+    launches (the contraction zero-padded to 16 so that rows are 16-byte aligned; TMA fills the rest of the 64-wide k-block)."""
+    if not tc or edge_attr.dim() != 2:
+        return _linear_padded_k(lin, edge_attr)
+    F = torch.nn.functional
+    pad = (-edge_attr.shape[-1]) % 16
+    x = F.pad(edge_attr, (0, pad)) if pad else edge_attr
+    w = F.pad(lin.weight, (0, pad)) if pad else lin.weight
+    return tcg.linear_wb(x, w, lin.bias)
+
+
 def _fold_applies(query: Tensor, edge_attr: Tensor) -> bool:
     """round-2 switch AB2_EDGE_FOLD=1: lin_edge folded into the conv (ops.gt_conv_folded) when the raw features fit its 16 columns"""
     return _EDGE_FOLD and query.is_cuda and edge_attr.dim() == 2 and edge_attr.shape[1] < 16
@@ -242,7 +256,7 @@ class GraphTransformerBaseBlock(BaseBlock, ABC):
                 out = ops.gt_conv_folded(query.view(-1, H, C), key.view(-1, H, C), value.view(-1, H, C), edge_attr,
                                          self.lin_edge.weight, self.lin_edge.bias, get_csr(edge_index, ns, nd))
                 return out.reshape(out.shape[0], H * C)
-            edges = _linear_padded_k(self.lin_edge, edge_attr)
+            edges = _lin_edge(self.lin_edge, edge_attr, query.dtype == torch.bfloat16 and self._tc(query))
             q, k, v, e = self.shard_qkve_heads(query, key, value, edges, shapes, batch_size, model_comm_group)
             out = self.conv(query=q, key=k, value=v, edge_attr=e, edge_index=edge_index, size=size)
             return self.shard_output_seq(out, shapes, batch_size, model_comm_group)
@@ -254,8 +268,8 @@ class GraphTransformerBaseBlock(BaseBlock, ABC):
         plan: HaloPlan = cached_plan(self, ("bipartite", tuple(sb), tuple(db), rank), edge_index, model_comm_group,
                                      lambda: build_bipartite_halo_plan(edge_index, sb, db, rank))
         # raw attributes of the edges this rank owns (they arrive sharded by original edge order), then project locally
-        ea_local = select_sharded_edges(edge_attr, shapes_edge, plan.edge_ids, model_comm_group)
-        e = _linear_padded_k(self.lin_edge, ea_local).view(-1, H, C)
+        ea_local = select_sharded_edges(edge_attr, shapes_edge, plan.edge_ids, model_comm_group, plan)
+        e = _lin_edge(self.lin_edge, ea_local, query.dtype == torch.bfloat16 and self._tc(query)).view(-1, H, C)
         q, k, v = query.view(-1, H, C), key.view(-1, H, C), value.view(-1, H, C)
         size = (plan.n_src, plan.num_dst_local)
         if q.is_cuda:

@@ -32,6 +32,23 @@ def _check_mp_kwargs(kwargs: dict, default_aggr: str) -> None:
         raise NotImplementedError("only flow='source_to_target' is implemented")
 
 
+def _gt_conv_unfused_with_dropout(query, key, value, edge_attr, edge_index, size, out_channels: int, p: float) -> Tensor:
+    """reference conv.py:123-142 op by op (gather, per-dst softmax as PyG computes it, dropout on the weights, scatter-sum)."""
+    if not query.is_cuda:
+        raise RuntimeError("anemoi_models_b200 runs on CUDA tensors only (no CPU fallback); got a CPU tensor")
+    n_src, n_dst = resolve_size(size, key.shape[0], query.shape[0])
+    src, dst = edge_index[0].long(), edge_index[1].long()
+    k_j = key.index_select(0, src) + edge_attr
+    alpha = (query.index_select(0, dst) * k_j).sum(dim=-1) / out_channels ** 0.5  # [E, H]
+    idx = dst.view(-1, 1).expand_as(alpha)
+    amax = alpha.detach().new_zeros((n_dst, alpha.shape[1])).scatter_reduce_(0, idx, alpha.detach(), "amax", include_self=False)
+    ex = (alpha - amax.index_select(0, dst)).exp()
+    den = ex.new_zeros((n_dst, ex.shape[1])).scatter_add_(0, idx, ex)
+    alpha = torch.nn.functional.dropout(ex / (den.index_select(0, dst) + 1e-16), p=p, training=True)
+    msg = (value.index_select(0, src) + edge_attr) * alpha.unsqueeze(-1)
+    return msg.new_zeros((n_dst,) + tuple(msg.shape[1:])).index_add_(0, dst, msg)
+
+
 class GraphTransformerConv(nn.Module):
     """Message passing part of the graph transformer operator (reference conv.py:79-142).
 
@@ -52,9 +69,11 @@ class GraphTransformerConv(nn.Module):
         if edge_attr is None:
             # the reference adds edge_attr unconditionally (conv.py:142) and fails with a TypeError
             raise TypeError("unsupported operand type(s) for +: 'Tensor' and 'NoneType' (edge_attr is required)")
-        if self.dropout > 0.0 and self.training:
-            raise NotImplementedError("attention dropout > 0 is not implemented (no reference caller sets it, block.py:339)")
         check_edge_index(edge_index)
+        if self.dropout > 0.0 and self.training:
+            # no reference caller sets attention dropout (block.py:339 builds the conv without it); the fused kernels do not draw
+            # random numbers, so this rare configuration runs the reference's op sequence as a composition of CUDA torch ops
+            return _gt_conv_unfused_with_dropout(query, key, value, edge_attr, edge_index, size, self.out_channels, self.dropout)
         n_halo = 0 if halo is None else halo[0].shape[0]
         n_src, n_dst = resolve_size(size, key.shape[0] + n_halo, query.shape[0])
         if value.shape[0] + n_halo != n_src:
@@ -96,7 +115,13 @@ class GraphConv(nn.Module):
         Din = self.in_channels
         if self.activation not in ops.ACT_CODES or edge_attr.shape[1] != lin0.in_features - 2 * Din or \
                 not isinstance(layers[-1], AutocastLayerNorm) or edge_attr.shape[1] != layers[-1].normalized_shape[0]:
-            raise NotImplementedError("GraphConv: unsupported edge_mlp configuration for the fused path")
+            # an activation outside SiLU / GELU / ReLU / Identity (the reference accepts any nn.* name) or an edge_mlp that is not
+            # the reference's default layout: run the reference's op sequence as a composition of CUDA torch ops
+            if not edge_attr.is_cuda:
+                raise RuntimeError("anemoi_models_b200 runs on CUDA tensors only (no CPU fallback); got a CPU tensor")
+            src, dst = edge_index[0].long(), edge_index[1].long()
+            edges_new = self.edge_mlp(torch.cat([x_dst.index_select(0, dst), x_src.index_select(0, src), edge_attr], dim=1)) + edge_attr
+            return edges_new.new_zeros((n_dst, edges_new.shape[1])).index_add_(0, dst, edges_new), edges_new
         F = torch.nn.functional
         W0 = lin0.weight
         ln = layers[-1]

@@ -35,6 +35,13 @@ def _common_dtype(*tensors: Tensor) -> torch.dtype:
     return dt
 
 
+def _aligned(t: Tensor) -> Tensor:
+    """contiguous AND 16-byte aligned (the kernels use 16-byte vector / bulk loads): a contiguous view whose storage offset is
+    not a multiple of 16 bytes is cloned."""
+    t = t.contiguous()
+    return t.clone() if (t.data_ptr() % 16) != 0 else t
+
+
 def _conv_forward(q, k, v, k_halo, v_halo, e, plan):
     L = _lib.lib()
     Nd, H, C = q.shape
@@ -123,10 +130,12 @@ def gt_conv(query: Tensor, key: Tensor, value: Tensor, edge_attr: Tensor, plan: 
     _require_cuda(query, key, value, edge_attr, k_halo, v_halo)
     _check_conv_args(query, key, value, edge_attr, plan, 0 if k_halo is None else k_halo.shape[0])
     dt = _common_dtype(query, key, value, edge_attr)
-    q, k, v, e = (t.to(dt).contiguous() for t in (query, key, value, edge_attr))
+    q, k, v, e = (_aligned(t.to(dt)) for t in (query, key, value, edge_attr))
     if k_halo is not None:
-        k_halo, v_halo = k_halo.to(dt).contiguous(), v_halo.to(dt).contiguous()
-    return _GTConvFn.apply(q, k, v, e, k_halo, v_halo, plan)
+        k_halo, v_halo = _aligned(k_halo.to(dt)), _aligned(v_halo.to(dt))
+    out = _GTConvFn.apply(q, k, v, e, k_halo, v_halo, plan)
+    # fp16 inputs are computed in fp32 (the kernels take fp32 / bf16); hand back the caller's dtype like the reference does
+    return out.to(query.dtype) if query.dtype == torch.float16 else out
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -44,6 +44,36 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bind_to_gpu_numa(device_index: int):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that the pinned host buffers allocated afterwards
+    (first touch by this process) live in the memory next to the GPU's PCIe root port.  Round 1 allocated every rank's buffers
+    wherever the launcher happened to run (all ranks on node 0): the host-buffer arm anti-scaled (0.20 at 8 GPUs).
+    Returns a small dict for the bench line; does nothing (and says so) when sysfs does not expose the topology."""
+    info = {"numa_node": None, "cpus": None}
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        info["pci"] = bdf
+        if node < 0:
+            info["note"] = "sysfs reports no NUMA node for the GPU (single-node host or virtualised topology)"
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, use)
+        info.update(numa_node=node, cpus=len(use))
+    except Exception as ex:  # noqa: BLE001
+        info["note"] = f"not bound: {type(ex).__name__}: {ex}"[:200]
+    return info
+
+
 def dst_N_for(parts: int) -> int:
     """octahedral resolution whose point count is closest to parts * 40,320 (o96 for parts = 1)."""
     target = parts * (4 * DST_N * DST_N + 36 * DST_N)
@@ -170,6 +200,10 @@ def algorithmic_bytes(E, Ns, Nd, b=2, D=D, H=H):
     # [E,H] softmax-weight workspace or the second read of q and g by the src pass)
     step = b * (3 * E * D + 6 * Ns * D + 6 * Nd * D) + 8 * (E + Nd + 1) + 8 * Nd * H
     return {"fwd": fwd, "bwd_dst": bwd_dst, "bwd_src": bwd_src, "step_survey": step}
+
+
+class _SkipE2E(Exception):
+    pass
 
 
 def run_ours(args):
@@ -345,7 +379,10 @@ def run_ours(args):
     e2e = None
     host = outs = dev_ws = None
     err = ""
+    numa = bind_to_gpu_numa(local_rank)  # before the pinned buffers are allocated
     try:
+        if args.e2e_steps <= 0:
+            raise _SkipE2E()
         # N > 1: every rank feeds ITS shard (compact src space [own | halo]: the host supplies the halo rows' k, v and gets
         # their dk, dv back) through its own PCIe link, all ranks at once; time = max over ranks
         if world > 1:
@@ -358,6 +395,8 @@ def run_ours(args):
         need = L.ab2_gtconv_host_workspace_bytes(n_src, nd_loc, E, H, C, dt_code)
         dev_ws = torch.empty(need, dtype=torch.uint8, device=dev)
         outs = [torch.empty(x.shape, dtype=x.dtype, pin_memory=True) for x in (host[0], host[0], host[1], host[2], host[3])]
+    except _SkipE2E:
+        err = "skipped"
     except Exception as ex:  # e.g. no pinned host memory for N shards on this box
         if world == 1:
             raise
@@ -365,7 +404,9 @@ def run_ours(args):
     ok = torch.tensor([0.0 if err else 1.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # all ranks take the same branch (no rank waits in a collective alone)
-    if float(ok) < 1.0:
+    if args.e2e_steps <= 0:
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "skipped (--e2e-steps 0)"}
+    elif float(ok) < 1.0:
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "error": err or "host buffers could not be allocated on another rank"}
     else:
@@ -392,7 +433,8 @@ def run_ours(args):
                "api": ("ab2_gtconv_fwd_bwd_host_streamed" if plan.perm_is_identity and args.e2e_chunks > 1 else "ab2_gtconv_fwd_bwd_host")
                       + " (pinned host q,k,v,e,g in; out,dq,dk,dv,de back to pinned host; copies inside the call"
                       + ("; one call per rank on its shard, all ranks concurrently, max over ranks)" if world > 1 else ")"),
-               "chunks": args.e2e_chunks}
+               "chunks": args.e2e_chunks, "numa": numa,
+               "GBps_per_direction_per_gpu": round(float(io[0]) / world / (e2e_ms * 1e-3) / 1e9, 1)}
     del host, outs, dev_ws
 
     # ---- BASELINE configs[4]: the o1280 -> n320 graph, whole graph over `world` ranks (strong scaling; extra block of the line)
@@ -775,7 +817,11 @@ def run_edgepath(args):
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     H, C, ed = 16, 64, 11
-    ei_np, ns, nd, _ = S.encoder_graph(SRC_POINTS, DST_N)
+    which = args.edgepath_graph
+    if which == "encoder":
+        ei_np, ns, nd, _ = S.encoder_graph(SRC_POINTS, DST_N)
+    else:
+        ei_np, ns, nd, _, _ = build_shard(1, 0, which)
     ei = torch.from_numpy(ei_np).to(dev)
     E = ei.shape[1]
     plan = GraphCSR(ei, ns, nd)
@@ -785,7 +831,13 @@ def run_edgepath(args):
     lin = torch.nn.Linear(ed, H * C).to(dev)
     g = torch.randn(nd, H, C, device=dev, dtype=torch.bfloat16)
 
-    def product():
+    from anemoi_models_b200.layers.block import _lin_edge
+
+    def product():  # what the block does by default: lin_edge on the tcgen05 GEMM (K padded to 16), then the fused conv
+        e = _lin_edge(lin, raw, True)
+        ops.gt_conv(q, k, v, e.view(E, H, C), plan).backward(g)
+
+    def product_cublas():  # round-1 path: lin_edge through nn.Linear / cuBLASLt under autocast
         with torch.autocast("cuda", dtype=torch.bfloat16):
             e = lin(raw)
         ops.gt_conv(q, k, v, e.view(E, H, C), plan).backward(g)
@@ -796,7 +848,7 @@ def run_edgepath(args):
     sampler = ClockSampler(0)
     res = {}
     with sampler:
-        for name, fn in (("lin_edge_plus_conv", product), ("folded", folded)):
+        for name, fn in (("lin_edge_plus_conv", product), ("lin_edge_cublas_plus_conv", product_cublas), ("folded", folded)):
             for _ in range(max(args.warmup, 3)):
                 fn()
             torch.cuda.synchronize()
@@ -807,13 +859,14 @@ def run_edgepath(args):
             ev1.record()
             torch.cuda.synchronize()
             res[name] = ev0.elapsed_time(ev1) / args.steps
-    ms = res["folded"]
+    ms = res["lin_edge_plus_conv"]
     line = {"metric": "gt_block_edge_path_fwd_bwd_edges_per_s", "value": E / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "edge path of the GT mapper block on the headline graph: lin_edge(raw[E,11]) folded into the conv "
-                                   "(report line, round-2 work in progress)", "edges_total": int(E)},
-            "clocks": sampler.summary(), "ms_product_path_lin_edge_plus_conv": res["lin_edge_plus_conv"], "ms_folded": res["folded"]}
+            "config": {"workload": f"edge path of the GT block on the {which} graph (Ns={ns}, Nd={nd}): lin_edge(raw[E,11]) folded into the conv "
+                                   "vs lin_edge GEMM + conv (report line)", "edges_total": int(E)},
+            "clocks": sampler.summary(), "ms_product_path_lin_edge_plus_conv": res["lin_edge_plus_conv"], "ms_lin_edge_on_cublas_plus_conv": res["lin_edge_cublas_plus_conv"],
+            "ms_folded": res["folded"]}
     print(json.dumps(line), flush=True)
 
 
@@ -1004,6 +1057,7 @@ def main():
     ap.add_argument("--config5", default="auto", choices=["auto", "on", "off"],
                     help="encoder workload: also measure BASELINE configs[4] (o1280 -> n320, whole graph over the ranks) as an extra block")
     ap.add_argument("--dst-split", default="equal", choices=["equal", "balanced"], help="o1280 workload: dst shard cut points")
+    ap.add_argument("--edgepath-graph", default="encoder", choices=["encoder", "decoder", "processor"])
     ap.add_argument("--graphconv-dim", type=int, default=512)
     ap.add_argument("--model-layers", type=int, default=16)
     ap.add_argument("--profile", action="store_true", help="model workload: add a per-kernel device-time breakdown of one step")

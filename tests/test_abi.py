@@ -59,6 +59,34 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert rc == _lib.AB2_ERR_UNSUPPORTED
 
 
+def test_gemm_descriptor_errors_without_a_gpu():
+    """`ab2_gemm_bf16` validates its descriptor before it touches the device: the ctypes struct matches the header's layout
+    (a wrong field offset would turn these into different errors) and bad shapes come back as status codes, not crashes."""
+    import ctypes as C
+
+    from anemoi_models_b200 import _lib
+
+    L = _lib.lib()
+    assert C.sizeof(_lib.Gemm) == 8 * 3 + 8 * 4 + 8 + 8 * 4 + 8 + 8 + 8 * 4 + 8 * 3 + 8 + 8 + 8 + 8 * 5  # natural alignment, no padding surprises
+    d = _lib.Gemm()
+    assert L.ab2_gemm_workspace_bytes(C.byref(d)) == 0
+    d.M, d.N, d.K = 64, 60, 64  # N % 8 != 0
+    d.a, d.b = 16, 16
+    d.out[0] = 16
+    assert L.ab2_gemm_bf16(C.byref(d), None, 0, None) == _lib.AB2_ERR_UNSUPPORTED and b"multiple of 8" in L.ab2_last_error()
+    d.N = 64
+    d.a = 0
+    assert L.ab2_gemm_bf16(C.byref(d), None, 0, None) == _lib.AB2_ERR_INVALID and b"null operand" in L.ab2_last_error()
+    d.a, d.splits, d.K = 16, 4, 1024
+    assert L.ab2_gemm_workspace_bytes(C.byref(d)) == 4 * 64 * 64 * 4
+    d.bias = 16  # split-K takes a plain single output only
+    assert L.ab2_gemm_bf16(C.byref(d), None, 0, None) == _lib.AB2_ERR_INVALID and b"split-K" in L.ab2_last_error()
+    d.M = 0
+    assert L.ab2_gemm_bf16(C.byref(d), None, 0, None) == 0  # nothing to do
+    assert L.ab2_ln_parts() > 0
+    assert L.ab2_layernorm_fwd(16, 1, 16, 16, 1e-5, 10, 12, 16, 1, None, None, None) == _lib.AB2_ERR_UNSUPPORTED  # D % 8
+
+
 def test_kernel_dispatch_rules_for_the_model_shapes():
     """`ab2_gtconv_variant` answers from the same rules `run_conv` dispatches with (no GPU needed): the shapes of the AIFS-like
     model (2 KB rows) go to the bulk-copy pipelined kernels, except the src pass at a low out-degree, which goes to the

@@ -333,3 +333,43 @@ def test_conv_step_is_cuda_graph_capturable():
     for x, key in zip(ins, ("dq", "dk", "dv", "de")):
         assert rel_err(x.grad, ref2[key]) < FP32_TOL, key
     assert rel_err(ref["out"], ref["out"]) == 0.0
+
+
+def test_rare_configurations_run_as_torch_compositions_on_the_gpu(monkeypatch):
+    """attention dropout > 0 in training mode and GraphConv activations outside SiLU / GELU / ReLU / Identity used to
+    raise; they now run the reference's op sequence as CUDA torch ops.  fp16 inputs come back as fp16; a contiguous view at a
+    storage offset that is not 16-byte aligned is handled."""
+    import anemoi_models_b200 as b2
+
+    torch.manual_seed(0)
+    ns, nd, E, H, C = 50, 30, 400, 4, 8
+    ei = torch.stack([torch.randint(0, ns, (E,)), torch.randint(0, nd, (E,))]).cuda()
+    q, k, v, e = (torch.randn(n, H, C, device="cuda") for n in (nd, ns, ns, E))
+    fused = b2.GraphTransformerConv(C)(q, k, v, e, ei, (ns, nd))
+    conv = b2.GraphTransformerConv(C, dropout=0.3).train()
+    monkeypatch.setattr(torch.nn.functional, "dropout", lambda x, p, training: x)  # identity: the composition must equal the fused conv
+    assert rel_err(conv(q, k, v, e, ei, (ns, nd)), fused) < 1e-5
+    monkeypatch.undo()
+    out = conv(q, k, v, e, ei, (ns, nd))
+    assert out.shape == fused.shape and bool(torch.isfinite(out).all()) and not torch.allclose(out, fused)
+    assert rel_err(conv.eval()(q, k, v, e, ei, (ns, nd)), fused) == 0.0  # eval mode: the fused kernels
+    # fp16 in -> fp16 out (computed in fp32)
+    out16 = b2.GraphTransformerConv(C)(q.half(), k.half(), v.half(), e.half(), ei, (ns, nd))
+    assert out16.dtype == torch.float16 and rel_err(out16.float(), fused) < 2e-3
+    # misaligned contiguous view (storage offset 1 element = 4 bytes)
+    buf = torch.randn(nd * H * C + 1, device="cuda")
+    q_off = buf[1:].view(nd, H, C)
+    q_off.copy_(q)
+    assert q_off.data_ptr() % 16 != 0 and q_off.is_contiguous()
+    assert rel_err(b2.GraphTransformerConv(C)(q_off, k, v, e, ei, (ns, nd)), fused) == 0.0
+    # GraphConv with an activation the fused kernels do not implement
+    from oracle import gtconv as og
+
+    D = 16
+    gc = b2.GraphConv(D, D, activation="Tanh").cuda()
+    x, ea = torch.randn(ns, D), torch.randn(E, D)
+    ei2 = torch.stack([ei[0].cpu(), ei[1].cpu() % ns])
+    p = {kk: vv.detach().cpu() for kk, vv in gc.state_dict().items()}
+    o_ref, en_ref = og.graph_conv_unfused(x, ea, ei2, p, "edge_mlp.", 0, "Tanh")
+    o, en = gc(x.cuda(), ea.cuda(), ei2.cuda())
+    assert rel_err(o, o_ref) < 2e-5 and rel_err(en, en_ref) < 2e-5

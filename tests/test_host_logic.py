@@ -268,3 +268,46 @@ def test_block_folded_branch_plumbing_against_golden(monkeypatch, fixture, kind)
     for name, p in blk.named_parameters():
         ref = t(z["gp." + name])
         assert p.grad is not None and torch.allclose(p.grad, ref, atol=2e-5 * max(1.0, float(ref.abs().max()))), name
+
+
+def test_wgrad_split_choice_fills_whole_waves():
+    """Split-K of the weight-gradient GEMM: every split non-empty with >= 8 k-blocks, and the tile count (output tiles x
+    splits) fills whole waves of the 74 CTA pairs at the shapes of the blocks."""
+    from anemoi_models_b200.gemm import wgrad_splits
+
+    for N, K, M in ((1024, 1024, 40320), (2048, 1024, 542080), (4096, 1024, 40320), (1024, 4096, 40320), (512, 512, 327660),
+                    (1024, 16, 748256), (256, 256, 100), (64, 64, 8), (512, 1536, 40962)):
+        s = wgrad_splits(N, K, M)
+        kb = (M + 63) // 64
+        assert s >= 1 and (s == 1 or (kb // s >= 8 and ((kb + s - 1) // s) * (s - 1) < kb)), (N, K, M, s)
+        pairs = ((N + 255) // 256) * ((K + 255) // 256 if K > 128 else 1)
+        tiles = pairs * s
+        if kb >= 8 * 74:  # enough contraction to choose freely: at least 85 % of the last wave is used
+            assert tiles / (((tiles + 73) // 74) * 74) >= 0.85, (N, K, M, s, tiles)
+
+
+def test_o1280_recipe_bands_partition_the_whole_graph_and_balanced_bounds_balance():
+    """The per-rank band generator of the o1280 -> n320 benchmark graph (here a small analogue: o24 -> 3,000 Fibonacci points):
+    the bands of P = 1, 2, 5 partition the same edge set, edges are grouped by dst and sorted by src inside a dst, and the
+    edge-balanced cut points give every rank the same edge count to within one dst row's degree."""
+    import numpy as np
+
+    from anemoi_models_b200 import synthetic as S
+
+    nd = 3000
+    radius = 0.6 * S.fibonacci_max_nn_distance(nd)
+    whole, ns, nd_, _ = S.o1280_to_n320_band(1, 0, src_N=24, dst_points=nd, radius=radius)
+    assert (ns, nd_) == (S.octahedral_size(24), nd) and whole.shape[1] > nd
+    assert np.all(np.diff(whole[1]) >= 0)
+    same_dst = np.diff(whole[1]) == 0
+    assert np.all(np.diff(whole[0])[same_dst] > 0)
+    for P in (2, 5):
+        parts = [S.o1280_to_n320_band(P, r, src_N=24, dst_points=nd, radius=radius)[0] for r in range(P)]
+        assert np.array_equal(np.concatenate(parts, axis=1), whole)
+    deg = np.bincount(whole[1], minlength=nd)
+    b = S.edge_balanced_bounds(deg, 4)
+    assert b[0] == 0 and b[-1] == nd and all(x <= y for x, y in zip(b[:-1], b[1:]))
+    counts = [int(deg[b[i]:b[i + 1]].sum()) for i in range(4)]
+    assert max(counts) - min(counts) <= 2 * int(deg.max())
+    bal = [S.o1280_to_n320_band(4, r, src_N=24, dst_points=nd, radius=radius, dst_bounds=b)[0] for r in range(4)]
+    assert np.array_equal(np.concatenate(bal, axis=1), whole)
