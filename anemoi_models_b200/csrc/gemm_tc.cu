@@ -783,9 +783,10 @@ extern "C" int ab2_gemm_bf16(const ab2_gemm* d, void* workspace, size_t workspac
     else if (d->a_mn && d->b_mn) rc = tc::launch<BNV, true, true, CGV, EWV>(ta, tb, a, st);    \
     else rc = tc::launch<BNV, true, false, CGV, EWV>(ta, tb, a, st);                           \
   } while (0)
-  // epilogue warps: 16 when the epilogue does per-element work beyond a bias (activation, activation derivative, gathers,
-  // residual), 8 (one more pipeline stage) for the plain ones; AB2_GEMM_EW overrides for A/B runs
-  int EW = (e.act != 3 || e.dact_pre || e.gather[0] || e.gather[1] || e.residual || e.row_scale) ? 16 : 8;
+  // epilogue warps: 16 when the epilogue does special-function work or gathers per element (activation, activation derivative,
+  // row tables), 8 (and one more pipeline stage) for bias / residual epilogues -- measured both ways on every block shape
+  // (profiles/r02/gemm_probe_r02h_ew8.jsonl vs _ew16.jsonl); AB2_GEMM_EW overrides for A/B runs
+  int EW = (e.act != 3 || e.dact_pre || e.gather[0] || e.gather[1]) ? 16 : 8;
   if (const char* ew = getenv("AB2_GEMM_EW")) EW = atoi(ew) == 16 ? 16 : 8;
   if (CG == 1) {  // single-CTA tiles: A/B experiments only
     if (BN == 256) AB2_GEMM_DISPATCH(256, 1, 8); else AB2_GEMM_DISPATCH(128, 1, 8);

@@ -248,7 +248,7 @@ class _LinearFn(torch.autograd.Function):
         if need[3]:
             db = colsum(g2).to(bdt)
         if need[4]:
-            dres = g_in.to(rdt).view(rshape)
+            dres = g_in.to(rdt).reshape(rshape)
         return dx, dpre, dw, db, dres, None, None
 
 

