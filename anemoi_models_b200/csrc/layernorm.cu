@@ -113,26 +113,28 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_fwd_kernel(const TX* 
 }
 
 // backward: TG = dtype of the incoming gradient, TX = dtype of x and of dx.  partial: [gridDim.x][2][D] fp32.
-// One warp per row.  gamma and the dgamma / dbeta accumulators live in SHARED memory (a private [2][D] slice per warp, each lane
-// touches only its own columns): with them in registers the kernel needed 207 registers, i.e. 8 rows in flight per SM, and ran
-// at ~3 TB/s (latency-bound: load -> two warp reductions -> store per row); now ~90 registers and 24 rows in flight.
+// (A variant with gamma and the dgamma / dbeta accumulators in shared memory -- 96 instead of 207 registers, 20 instead of 8 rows
+// in flight per SM -- was measured SLOWER on the model step: 12.9 vs 9.7 ms over its 38 calls, profiles/r02/bench_model_r02k.json.)
 template <typename TG, typename TX, int VPL>
-__global__ void __launch_bounds__(kLnWarps * 32, 5) layernorm_bwd_kernel(const TG* __restrict__ g, const TX* __restrict__ x,
+__global__ void __launch_bounds__(kLnWarps * 32) layernorm_bwd_kernel(const TG* __restrict__ g, const TX* __restrict__ x,
                                                                      const float* __restrict__ gamma, const float* __restrict__ mean,
                                                                      const float* __restrict__ rstd, long long M, int D,
                                                                      const TX* __restrict__ add, TX* __restrict__ dx,
                                                                      float* __restrict__ partial) {
-  extern __shared__ float red[];  // [D] gamma | [kLnWarps][2][D] accumulators
+  extern __shared__ float red[];  // [kLnWarps][2][D]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int ngroups = D >> 3;
-  float* sg = red;
-  float* acc = red + D + (size_t)w * 2 * D;
-  for (int c = threadIdx.x; c < D; c += blockDim.x) sg[c] = gamma[c];
-  for (int c = lane; c < 2 * D; c += 32) acc[c] = 0.f;
-  __syncthreads();
   // fixed slice of rows per CTA, rows of a slice dealt round-robin to its warps: the summation order is a function of (M, grid)
   const long long per = (M + gridDim.x - 1) / gridDim.x;
   const long long r0 = (long long)blockIdx.x * per, r1 = min(r0 + per, M);
+  float gm[VPL][8], dg[VPL][8], db[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int gidx = lane + 32 * i;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) dg[i][u] = db[i][u] = 0.f;
+    if (gidx < ngroups) load_row_vec<float>(gamma + gidx * 8, gm[i]);
+  }
   for (long long row = r0 + w; row < r1; row += kLnWarps) {
     const float mu = mean[row], rs = rstd[row];
     float gv[VPL][8], xh[VPL][8];
@@ -143,32 +145,15 @@ __global__ void __launch_bounds__(kLnWarps * 32, 5) layernorm_bwd_kernel(const T
       if (gidx < ngroups) {
         load_row_vec<TG>(g + row * D + gidx * 8, gv[i]);
         load_row_vec<TX>(x + row * D + gidx * 8, xh[i]);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int gidx = lane + 32 * i;
-      if (gidx < ngroups) {
-        float4* a_g = reinterpret_cast<float4*>(acc + gidx * 8);
-        float4* a_b = reinterpret_cast<float4*>(acc + D + gidx * 8);
-        const float4 gm0 = *reinterpret_cast<const float4*>(sg + gidx * 8), gm1 = *reinterpret_cast<const float4*>(sg + gidx * 8 + 4);
-        const float gm[8] = {gm0.x, gm0.y, gm0.z, gm0.w, gm1.x, gm1.y, gm1.z, gm1.w};
-        float4 dg0 = a_g[0], dg1 = a_g[1], db0 = a_b[0], db1 = a_b[1];
-        float dgv[8] = {dg0.x, dg0.y, dg0.z, dg0.w, dg1.x, dg1.y, dg1.z, dg1.w};
-        float dbv[8] = {db0.x, db0.y, db0.z, db0.w, db1.x, db1.y, db1.z, db1.w};
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           xh[i][u] = (xh[i][u] - mu) * rs;
-          dgv[u] += gv[i][u] * xh[i][u];
-          dbv[u] += gv[i][u];
-          gv[i][u] *= gm[u];
+          dg[i][u] += gv[i][u] * xh[i][u];
+          db[i][u] += gv[i][u];
+          gv[i][u] *= gm[i][u];
           s1 += gv[i][u];
           s2 += gv[i][u] * xh[i][u];
         }
-        a_g[0] = make_float4(dgv[0], dgv[1], dgv[2], dgv[3]);
-        a_g[1] = make_float4(dgv[4], dgv[5], dgv[6], dgv[7]);
-        a_b[0] = make_float4(dbv[0], dbv[1], dbv[2], dbv[3]);
-        a_b[1] = make_float4(dbv[4], dbv[5], dbv[6], dbv[7]);
       }
     }
     s1 = warp_sum(s1) / (float)D;
@@ -190,12 +175,23 @@ __global__ void __launch_bounds__(kLnWarps * 32, 5) layernorm_bwd_kernel(const T
       }
     }
   }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int gidx = lane + 32 * i;
+    if (gidx < ngroups) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        red[(w * 2 + 0) * D + gidx * 8 + u] = dg[i][u];
+        red[(w * 2 + 1) * D + gidx * 8 + u] = db[i][u];
+      }
+    }
+  }
   __syncthreads();
   for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
-    float a = 0.f;
+    float acc = 0.f;
 #pragma unroll
-    for (int ww = 0; ww < kLnWarps; ++ww) a += red[D + (size_t)ww * 2 * D + c];
-    partial[(size_t)blockIdx.x * 2 * D + c] = a;
+    for (int ww = 0; ww < kLnWarps; ++ww) acc += red[ww * 2 * D + c];
+    partial[(size_t)blockIdx.x * 2 * D + c] = acc;
   }
 }
 
@@ -269,7 +265,7 @@ template <typename TG, typename TX>
 static int ln_bwd_dispatch(const void* g, const void* x, const float* gamma, const float* mean, const float* rstd, long long M, int D,
                            const void* add, void* dx, float* partial, cudaStream_t st) {
   const int vpl = (D / 8 + 31) / 32;
-  const size_t smem = ((size_t)kLnWarps * 2 + 1) * D * sizeof(float);
+  const size_t smem = (size_t)kLnWarps * 2 * D * sizeof(float);
 #define AB2_LN_BWD(V)                                                                                                       \
   layernorm_bwd_kernel<TG, TX, V><<<kLnParts, kLnWarps * 32, smem, st>>>((const TG*)g, (const TX*)x, gamma, mean, rstd, M, D, \
                                                                          (const TX*)add, (TX*)dx, partial)
