@@ -452,6 +452,29 @@ def run_ours(args):
         except Exception as ex:  # noqa: BLE001 -- the headline line must still be printed
             config5 = {"error": f"{type(ex).__name__}: {ex}"[:400]}
 
+    # ---- BASELINE configs[3]: step time of the AIFS-like n320/o96 model on this repo's blocks (the second half of the metric)
+    model_step = None
+    if args.workload == "encoder" and world == 1 and not args.no_model_step:
+        try:
+            import copy
+
+            margs = copy.copy(args)
+            margs.steps, margs.warmup, margs.profile = 5, 3, False
+            ml = run_model(margs, emit=False)
+            model_step = {"ms_per_step": ml["ms_per_step"], "workload": ml["config"]["workload"], "clocks": ml["clocks"],
+                          "peak_mem_GB": ml["peak_mem_GB"], "loss": ml["config"]["loss"]}
+            if os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "anemoi", "models")):
+                try:  # the same model from the unmodified reference blocks, on the same GPU
+                    margs.steps = 2
+                    rl = run_model(margs, emit=False, impl="reference")
+                    model_step["reference_blocks_same_gpu"] = {"ms_per_step": rl["ms_per_step"], "peak_mem_GB": rl["peak_mem_GB"],
+                                                               "loss": rl["config"]["loss"]}
+                except Exception as ex:  # noqa: BLE001
+                    model_step["reference_blocks_same_gpu"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+                    torch.cuda.empty_cache()
+        except Exception as ex:  # noqa: BLE001 -- the headline line must still be printed
+            model_step = {"error": f"{type(ex).__name__}: {ex}"[:400]}
+
     # ---- CPU baseline: the reference's op sequence (oracle port) on this box's host cores, bounded sample
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "encoder":
@@ -481,6 +504,7 @@ def run_ours(args):
             "cpu_baseline": cpu_baseline,
             "parity": parity,
             "config5_o1280_to_n320": config5,
+            "model_step_n320_o96": model_step,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -871,7 +895,7 @@ def run_edgepath(args):
     print(json.dumps(line), flush=True)
 
 
-def run_model(args):
+def run_model(args, emit=True, impl="ours"):
     """Report line (not the headline): AIFS-like n320/o96 encoder-processor-decoder training step (BASELINE configs[3]) built
     from this repo's drop-in blocks the way the reference's mappers/processor wire them (mapper.py:245-272,
     processor.py:317-343): node embeddings, trainable edge features (3 geometric + 8 trainable columns), GT mapper block
@@ -883,6 +907,17 @@ def run_model(args):
     import anemoi_models_b200 as b2
     from anemoi_models_b200 import synthetic as S
     from anemoi_models_b200.graph import get_csr
+
+    if impl == "reference":
+        # comparator: the SAME model wired from the UNMODIFIED reference blocks (baseline/_ref, PyG op sequence through the shim as
+        # torch ops on the GPU, nn.Linear / nn.LayerNorm on cuBLASLt / ATen) -- the like-for-like "reference on the same GPU"
+        ref = os.path.join(ROOT, "baseline", "_ref")
+        for p_ in (os.path.join(ROOT, "oracle", "pyg_shim"), ref):
+            if p_ not in sys.path:
+                sys.path.insert(0, p_)
+        from anemoi.models.layers import block as blocks_mod
+    else:
+        blocks_mod = b2
 
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
@@ -896,8 +931,9 @@ def run_model(args):
               "proc": (S.knn_edges(hidden_xyz, hidden_xyz, 8, exclude_self=True), Nh, Nh),
               "dec": (S.knn_edges(hidden_xyz, data_xyz, 3), Nh, Ndata)}
     ei = {k_: torch.from_numpy(g_[0]).to(dev) for k_, g_ in graphs.items()}
-    for k_, g_ in graphs.items():
-        get_csr(ei[k_], g_[1], g_[2])  # one-off plan build, outside the step like the reference's constant edge buffers
+    if impl != "reference":
+        for k_, g_ in graphs.items():
+            get_csr(ei[k_], g_[1], g_[2])  # one-off plan build, outside the step like the reference's constant edge buffers
 
     class Model(torch.nn.Module):
         def __init__(self):
@@ -908,10 +944,10 @@ def run_model(args):
             self.emb_data_dec = nn.Linear(nvar + 4, hid)
             self.edge_geo = nn.ParameterDict({k_: nn.Parameter(torch.rand(ei[k_].shape[1], 3), requires_grad=False) for k_ in ei})
             self.edge_train = nn.ParameterDict({k_: nn.Parameter(torch.randn(ei[k_].shape[1], 8) * 0.1) for k_ in ei})
-            self.enc = b2.GraphTransformerMapperBlock(hid, 4 * hid, hid, edge_dim=11, num_heads=heads)
-            self.proc = nn.ModuleList([b2.GraphTransformerProcessorBlock(hid, 4 * hid, hid, edge_dim=11, num_heads=heads)
+            self.enc = blocks_mod.GraphTransformerMapperBlock(hid, 4 * hid, hid, edge_dim=11, num_heads=heads)
+            self.proc = nn.ModuleList([blocks_mod.GraphTransformerProcessorBlock(hid, 4 * hid, hid, edge_dim=11, num_heads=heads)
                                        for _ in range(layers)])
-            self.dec = b2.GraphTransformerMapperBlock(hid, 4 * hid, hid, edge_dim=11, num_heads=heads)
+            self.dec = blocks_mod.GraphTransformerMapperBlock(hid, 4 * hid, hid, edge_dim=11, num_heads=heads)
             self.extract = nn.Sequential(nn.LayerNorm(hid), nn.Linear(hid, nvar))
 
         def edge_attr(self, k_):
@@ -984,7 +1020,7 @@ def run_model(args):
         breakdown.insert(0, {"kernel": "ALL ab2:: kernels (this repo)", "ms": round(mine / 1e3, 3), "share": round(mine / max(total, 1), 4)})
     nparams = sum(p.numel() for p in model.parameters() if p.requires_grad)
     etot = sum(ei[k_].shape[1] * (layers if k_ == "proc" else 1) for k_ in ei)
-    line = {"metric": "aifs_like_n320_o96_train_step_ms", "value": ms, "unit": "ms/step", "n_gpus": 1, "steps": n, "warmup": 3,
+    line = {"metric": "aifs_like_n320_o96_train_step_ms", "impl": impl, "value": ms, "unit": "ms/step", "n_gpus": 1, "steps": n, "warmup": 3,
             "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"AIFS-like enc-proc-dec step: GT mapper n320->o96 (E={ei['enc'].shape[1]}), {layers} GT processor layers on "
                                    f"o96 8-NN (E={ei['proc'].shape[1]}) in {chunks} checkpointed chunks, GT mapper o96->n320 3-NN "
@@ -993,7 +1029,11 @@ def run_model(args):
                        "conv_edges_per_step": int(etot), "loss": float(loss.detach())},
             "clocks": sampler.summary(), "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2**30, 1),
             "kernel_breakdown": breakdown}
-    print(json.dumps(line), flush=True)
+    if emit:
+        print(json.dumps(line), flush=True)
+    del model, opt
+    torch.cuda.empty_cache()
+    return line
 
 
 def run_o1280(args):
@@ -1054,6 +1094,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--src-split", default="aligned", choices=["aligned", "equal"],
                     help="multi-GPU: src row ownership aligned to the dst shards (default) or the reference's equal-count tensor_split")
+    ap.add_argument("--no-model-step", action="store_true", help="encoder workload at 1 GPU: skip the AIFS-like model step block")
     ap.add_argument("--no-parity-check", action="store_true", help="multi-GPU: skip the sharded-vs-single-rank comparison made before timing")
     ap.add_argument("--config5", default="auto", choices=["auto", "on", "off"],
                     help="encoder workload: also measure BASELINE configs[4] (o1280 -> n320, whole graph over the ranks) as an extra block")
@@ -1061,6 +1102,8 @@ def main():
     ap.add_argument("--edgepath-graph", default="encoder", choices=["encoder", "decoder", "processor"])
     ap.add_argument("--graphconv-dim", type=int, default=512)
     ap.add_argument("--model-layers", type=int, default=16)
+    ap.add_argument("--model-impl", default="ours", choices=["ours", "reference"],
+                    help="model workload: this repo's blocks, or the unmodified reference blocks from baseline/_ref on the same GPU")
     ap.add_argument("--profile", action="store_true", help="model workload: add a per-kernel device-time breakdown of one step")
     ap.add_argument("--workload", default="encoder", choices=["encoder", "decoder", "processor", "graphconv", "model", "edgepath", "o1280", "config1-enc", "config1-proc", "config1-dec"],
                     help="encoder = BASELINE configs[1] (the headline); the others are extra report lines")
@@ -1070,7 +1113,7 @@ def main():
     elif args.workload == "graphconv":
         run_graphconv(args)
     elif args.workload == "model":
-        run_model(args)
+        run_model(args, impl=args.model_impl)
     elif args.workload == "edgepath":
         run_edgepath(args)
     elif args.workload == "o1280":
