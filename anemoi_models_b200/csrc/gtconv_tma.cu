@@ -688,7 +688,14 @@ static bool launch_bwd_src_tma_t(const ConvArgs& a) {
   const size_t smem = SrcRing::kBytes + 128;
   if (!AB2_ENSURE_DYN_SMEM(kern, smem)) return false;
   const int nrows = a.src_hi - a.src_lo;
-  const int ctas = std::max(1, std::min(nrows, num_sms() * kCtasPerSmSrc));
+  // CTAs = concurrent streams of src rows.  ncu (profiles/r02/ncu_conv_decoder_r02n.md): at out-degree 40 the q / g rows of a
+  // dst are fetched from DRAM once per edge (L2 hit rate 6 %): between two consecutive src rows of one CTA the other 739 CTAs
+  // move ~95 MB through L2.  AB2_SRC_CTAS_PER_SM trades parallelism for that reuse distance (experiments).
+  static const int per_sm = [] {
+    const char* s = getenv("AB2_SRC_CTAS_PER_SM");
+    return s ? std::max(1, std::min(atoi(s), kCtasPerSmSrc)) : kCtasPerSmSrc;
+  }();
+  const int ctas = std::max(1, std::min(nrows, num_sms() * per_sm));
   const int rows_per_cta = (nrows + ctas - 1) / ctas;
   const int grid = (nrows + rows_per_cta - 1) / rows_per_cta;
   kern<<<grid, kTmaThreads, smem, a.st>>>(a, rows_per_cta);

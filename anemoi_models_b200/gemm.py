@@ -115,23 +115,44 @@ def colsum(a: Tensor) -> Tensor:
     return out
 
 
+# the two kernel calls are module-level functions so that the CPU tests can check the autograd glue against a torch emulation
+def _ln_fwd_kernel(x2: Tensor, gamma: Tensor, beta: Tensor, eps: float, out_dtype: torch.dtype):
+    L = _lib.lib()
+    M, D = x2.shape
+    y = torch.empty((M, D), dtype=out_dtype, device=x2.device)
+    mean = torch.empty(M, dtype=torch.float32, device=x2.device)
+    rstd = torch.empty(M, dtype=torch.float32, device=x2.device)
+    with torch.cuda.device(x2.device):
+        _lib.check(L.ab2_layernorm_fwd(x2.data_ptr(), _lib.dtype_code(x2.dtype), gamma.data_ptr(), beta.data_ptr(), eps, M, D,
+                                       y.data_ptr(), _lib.dtype_code(out_dtype), mean.data_ptr(), rstd.data_ptr(),
+                                       _lib.current_stream(x2.device)))
+    return y, mean, rstd
+
+
+def _ln_bwd_kernel(g2: Tensor, x2: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor):
+    L = _lib.lib()
+    M, D = x2.shape
+    dx = torch.empty_like(x2)
+    parts = L.ab2_ln_parts()
+    partial = torch.empty((parts + 1) * 2 * D, dtype=torch.float32, device=x2.device)
+    dgamma = torch.empty(D, dtype=torch.float32, device=x2.device)
+    dbeta = torch.empty(D, dtype=torch.float32, device=x2.device)
+    with torch.cuda.device(x2.device):
+        _lib.check(L.ab2_layernorm_bwd(g2.data_ptr(), _lib.dtype_code(g2.dtype), x2.data_ptr(), _lib.dtype_code(x2.dtype),
+                                       gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), M, D, 0, dx.data_ptr(),
+                                       partial.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _lib.current_stream(x2.device)))
+    return dx, dgamma, dbeta
+
+
 class _LayerNormFn(torch.autograd.Function):
     """nn.LayerNorm over the last dim, output directly in the dtype the next GEMM consumes (reference block.py:487-489, 611,
     349: LayerNorm in fp32 under autocast + the cast in front of each nn.Linear)."""
 
     @staticmethod
     def forward(ctx, x: Tensor, weight: Tensor, bias: Tensor, eps: float, out_dtype: torch.dtype) -> Tensor:
-        L = _lib.lib()
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
-        M, D = x2.shape
         gamma, beta = _f32(weight), _f32(bias)
-        y = torch.empty((M, D), dtype=out_dtype, device=x.device)
-        mean = torch.empty(M, dtype=torch.float32, device=x.device)
-        rstd = torch.empty(M, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
-            _lib.check(L.ab2_layernorm_fwd(x2.data_ptr(), _lib.dtype_code(x2.dtype), gamma.data_ptr(), beta.data_ptr(), float(eps), M, D,
-                                           y.data_ptr(), _lib.dtype_code(out_dtype), mean.data_ptr(), rstd.data_ptr(),
-                                           _lib.current_stream(x.device)))
+        y, mean, rstd = _ln_fwd_kernel(x2, gamma, beta, float(eps), out_dtype)
         ctx.save_for_backward(x2, gamma, mean, rstd)
         ctx.shape, ctx.pdt = tuple(x.shape), (weight.dtype, bias.dtype)
         return y.view(ctx.shape)
@@ -139,20 +160,11 @@ class _LayerNormFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g: Tensor):
         x2, gamma, mean, rstd = ctx.saved_tensors
-        L = _lib.lib()
         M, D = x2.shape
         g2 = g.reshape(M, D).contiguous()
         if g2.dtype not in (torch.float32, torch.bfloat16):
             g2 = g2.float()
-        dx = torch.empty_like(x2)
-        parts = L.ab2_ln_parts()
-        partial = torch.empty((parts + 1) * 2 * D, dtype=torch.float32, device=x2.device)
-        dgamma = torch.empty(D, dtype=torch.float32, device=x2.device)
-        dbeta = torch.empty(D, dtype=torch.float32, device=x2.device)
-        with torch.cuda.device(x2.device):
-            _lib.check(L.ab2_layernorm_bwd(g2.data_ptr(), _lib.dtype_code(g2.dtype), x2.data_ptr(), _lib.dtype_code(x2.dtype),
-                                           gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), M, D, 0, dx.data_ptr(),
-                                           partial.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _lib.current_stream(x2.device)))
+        dx, dgamma, dbeta = _ln_bwd_kernel(g2, x2, gamma, mean, rstd)
         return dx.view(ctx.shape), dgamma.to(ctx.pdt[0]), dbeta.to(ctx.pdt[1]), None, None
 
 
@@ -267,6 +279,19 @@ def act_linear(pre: Tensor, h: Tensor, lin: torch.nn.Linear, act: int, residual:
     return _LinearFn.apply(h, pre, lin.weight, lin.bias, residual, act, act_out)
 
 
+def _segment_sums_kernel(g2: Tensor, plan, want_dst: bool, want_src: bool):
+    """(sum of g over the edges into every dst, sum over the edges out of every src), bf16 [E, N] in original edge order"""
+    L = _lib.lib()
+    E, N = g2.shape
+    dpi = torch.empty((plan.num_dst, N), dtype=torch.bfloat16, device=g2.device) if want_dst else None
+    dpj = torch.empty((plan.num_src, N), dtype=torch.bfloat16, device=g2.device) if want_src else None
+    with torch.cuda.device(g2.device):
+        _lib.check(L.ab2_edge_segment_sums(g2.data_ptr(), plan.rowptr.data_ptr(), plan.perm.data_ptr(), plan.colptr.data_ptr(),
+                                           plan.cpos.data_ptr(), E, plan.num_src, plan.num_dst, N, _lib.AB2_BF16, _p(dpi), _p(dpj),
+                                           _lib.current_stream(g2.device)))
+    return dpi, dpj
+
+
 class _EdgeFirstLayerFn(torch.autograd.Function):
     """First layer of GraphConv's edge MLP on the split weight (reference conv.py:69, mlp.py:74):
     pre[t] = e[t] We^T + pi[dst_t] + pj[src_t], h = act(pre) -- ONE GEMM over the edges whose epilogue gathers the two node-side
@@ -303,13 +328,7 @@ class _EdgeFirstLayerFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         de = gemm(g2, w, E, K, N, b_mn=True).to(ctx.dts[0]) if need[0] else None
         dw = gemm(g2, e2, N, K, E, a_mn=True, b_mn=True, out_dtype=torch.float32, splits=wgrad_splits(N, K, E)).to(ctx.dts[3]) if need[3] else None
-        dpi = torch.empty((plan.num_dst, N), dtype=torch.bfloat16, device=g.device) if need[1] else None
-        dpj = torch.empty((plan.num_src, N), dtype=torch.bfloat16, device=g.device) if need[2] else None
-        if need[1] or need[2]:
-            with torch.cuda.device(g.device):
-                _lib.check(L.ab2_edge_segment_sums(g2.data_ptr(), plan.rowptr.data_ptr(), plan.perm.data_ptr(), plan.colptr.data_ptr(),
-                                                   plan.cpos.data_ptr(), E, plan.num_src, plan.num_dst, N, _lib.AB2_BF16, _p(dpi), _p(dpj),
-                                                   _lib.current_stream(g.device)))
+        dpi, dpj = _segment_sums_kernel(g2, plan, need[1], need[2]) if (need[1] or need[2]) else (None, None)
         return (de, None if dpi is None else dpi.to(ctx.dts[1]), None if dpj is None else dpj.to(ctx.dts[2]), dw, None, None)
 
 

@@ -311,3 +311,123 @@ def test_o1280_recipe_bands_partition_the_whole_graph_and_balanced_bounds_balanc
     assert max(counts) - min(counts) <= 2 * int(deg.max())
     bal = [S.o1280_to_n320_band(4, r, src_N=24, dst_points=nd, radius=radius, dst_bounds=b)[0] for r in range(4)]
     assert np.array_equal(np.concatenate(bal, axis=1), whole)
+
+
+def _emulated_gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, out=None, seg_cols=0, out_dtype=torch.bfloat16,
+                   bias=None, row_scale=None, row_shift=None, col_vec=None, act=3, pre_out=None, dact_pre=None, residual=None,
+                   splits=1, gather=None):
+    """torch restatement of what `ab2_gemm_bf16` computes (include/anemoi_b200.h), operand layouts and epilogue order included"""
+    F = torch.nn.functional
+    fn = {0: F.silu, 1: F.gelu, 2: F.relu}
+    A = (a.float().t() if a_mn else a.float())[:M, :K]
+    B = (b.float().t() if b_mn else b.float())[:N, :K]
+    acc = A @ B.t()
+    if row_scale is not None:
+        acc = row_scale[:, None] * acc + row_shift[:, None] * col_vec[None, :]
+    if bias is not None:
+        acc = acc + bias
+    if gather is not None:
+        (ta, ia), (tb, ib) = gather
+        acc = acc + ta.float()[ia] + tb.float()[ib]
+    if dact_pre is not None:
+        x = dact_pre.float().requires_grad_(True)
+        with torch.enable_grad():
+            (grad,) = torch.autograd.grad(fn[act](x).sum(), x)
+        acc = acc * grad
+    elif act != 3:
+        if pre_out is not None:
+            pre_out.copy_(acc.to(torch.bfloat16))
+            acc = pre_out.float()
+        acc = fn[act](acc)
+    if residual is not None:
+        acc = acc + residual.float()
+    res = acc.to(out_dtype)
+    if out is not None:
+        for i, o in enumerate(out):
+            o.copy_(res[:, i * seg_cols:(i + 1) * seg_cols])
+        return out
+    return res
+
+
+def test_tensor_core_autograd_glue_against_torch_on_the_cpu(monkeypatch):
+    """The autograd functions of gemm.py (which operand goes where in forward, dgrad and wgrad; which tensors are kept; how the
+    activation derivative, the bias gradient and the GraphConv node-table gradients are assembled) with the three device entry
+    points replaced by torch restatements: outputs and every gradient against plain fp32 autograd on bf16-rounded parameters."""
+    from anemoi_models_b200 import gemm as G
+
+    F = torch.nn.functional
+    monkeypatch.setattr(G, "gemm", _emulated_gemm)
+    monkeypatch.setattr(G, "colsum", lambda a_: a_.float().sum(0))
+
+    def ln_fwd(x2, gamma, beta, eps, out_dtype):
+        mean, var = x2.float().mean(1), x2.float().var(1, unbiased=False)
+        rstd = (var + eps).rsqrt()
+        return (((x2.float() - mean[:, None]) * rstd[:, None]) * gamma + beta).to(out_dtype), mean, rstd
+
+    def ln_bwd(g2, x2, gamma, mean, rstd):
+        xh = (x2.float() - mean[:, None]) * rstd[:, None]
+        gg = g2.float() * gamma
+        dx = rstd[:, None] * (gg - gg.mean(1, keepdim=True) - xh * (gg * xh).mean(1, keepdim=True))
+        return dx.to(x2.dtype), (g2.float() * xh).sum(0), g2.float().sum(0)
+
+    def seg(g2, plan, want_dst, want_src):
+        ei = plan.edge_index
+        dpi = torch.zeros(plan.num_dst, g2.shape[1]).index_add_(0, ei[1], g2.float()).bfloat16() if want_dst else None
+        dpj = torch.zeros(plan.num_src, g2.shape[1]).index_add_(0, ei[0], g2.float()).bfloat16() if want_src else None
+        return dpi, dpj
+
+    monkeypatch.setattr(G, "_ln_fwd_kernel", ln_fwd)
+    monkeypatch.setattr(G, "_ln_bwd_kernel", ln_bwd)
+    monkeypatch.setattr(G, "_segment_sums_kernel", seg)
+    torch.manual_seed(0)
+    M, D, Hd = 60, 16, 32
+    ln, l1, l2 = torch.nn.LayerNorm(D), torch.nn.Linear(D, Hd), torch.nn.Linear(Hd, D)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.normal_()
+    x, g = torch.randn(M, D), torch.randn(M, D)
+
+    def close(a_, b_, what):
+        err = float((a_.float() - b_.float()).abs().max() / max(1.0, float(b_.float().abs().max())))
+        assert err < 2e-2, (what, err)
+
+    # LayerNorm -> Linear + GELU (epilogue) -> Linear + residual: the node MLP of the GT blocks
+    for name, fn in (("GELU", F.gelu), ("SiLU", F.silu)):
+        act = G.ACT_CODES[name]
+        for m in (ln, l1, l2):
+            m.zero_grad()
+        x1 = x.clone().requires_grad_(True)
+        pre, h = G.linear(G.layer_norm(x1, ln), l1, act_out=act)
+        y = G.act_linear(pre, h, l2, act, residual=x1)
+        y.backward(g)
+        got = [y, x1.grad, ln.weight.grad.clone(), ln.bias.grad.clone(), l1.weight.grad.clone(), l1.bias.grad.clone(),
+               l2.weight.grad.clone(), l2.bias.grad.clone()]
+        for m in (ln, l1, l2):
+            m.zero_grad()
+        xr = x.clone().requires_grad_(True)
+        yr = l2(fn(l1(ln(xr)))) + xr
+        yr.backward(g)
+        ref = [yr, xr.grad, ln.weight.grad, ln.bias.grad, l1.weight.grad, l1.bias.grad, l2.weight.grad, l2.bias.grad]
+        for i, (a_, b_) in enumerate(zip(got, ref)):
+            close(a_, b_, (name, i))
+    # GraphConv first layer on the split weight: pre = e We^T + pi[dst] + pj[src]
+    ns, nd, E = 9, 7, 40
+    ei = torch.stack([torch.randint(0, ns, (E,)), torch.randint(0, nd, (E,))])
+
+    class Plan:
+        edge_index, num_src, num_dst = ei, ns, nd
+
+    W = torch.randn(Hd, 3 * D, requires_grad=True)
+    e, xs, xd = (torch.randn(n, D, requires_grad=True) for n in (E, ns, nd))
+    pi, pj = F.linear(xd, W[:, :D]), F.linear(xs, W[:, D:2 * D])
+    pre, h = G.edge_first_layer(e, pi, pj, W[:, 2 * D:], Plan, G.ACT_CODES["SiLU"])
+    out = G.act_linear(pre, h, l2, G.ACT_CODES["SiLU"])
+    ge = torch.randn(E, D)
+    out.backward(ge)
+    got = [out, e.grad.clone(), xs.grad.clone(), xd.grad.clone(), W.grad.clone()]
+    for t_ in (e, xs, xd, W):
+        t_.grad = None
+    ref_out = l2(F.silu(F.linear(torch.cat([xd[ei[1]], xs[ei[0]], e], 1), W)))
+    ref_out.backward(ge)
+    for i, (a_, b_) in enumerate(zip(got, [ref_out, e.grad, xs.grad, xd.grad, W.grad])):
+        close(a_, b_, ("edge_first_layer", i))
