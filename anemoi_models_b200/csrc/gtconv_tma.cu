@@ -691,10 +691,13 @@ static bool launch_bwd_src_tma_t(const ConvArgs& a) {
   // CTAs = concurrent streams of src rows.  ncu (profiles/r02/ncu_conv_decoder_r02n.md): at out-degree 40 the q / g rows of a
   // dst are fetched from DRAM once per edge (L2 hit rate 6 %): between two consecutive src rows of one CTA the other 739 CTAs
   // move ~95 MB through L2.  AB2_SRC_CTAS_PER_SM trades parallelism for that reuse distance (experiments).
-  static const int per_sm = [] {
+  // Measured (profiles/r02/SUMMARY.md): decoder (out-degree 40) 1.04 / 0.93 / 1.16 / 2.05 ms at 5 / 3 / 2 / 1 CTAs per SM,
+  // processor (out-degree 8) 0.137 / 0.169 / 0.221 / 0.379 ms -> 3 per SM at a mean out-degree >= 20, else 5.
+  static const int forced = [] {
     const char* s = getenv("AB2_SRC_CTAS_PER_SM");
-    return s ? std::max(1, std::min(atoi(s), kCtasPerSmSrc)) : kCtasPerSmSrc;
+    return s ? std::max(1, std::min(atoi(s), kCtasPerSmSrc)) : 0;
   }();
+  const int per_sm = forced ? forced : ((long long)a.E >= 20LL * std::max(a.Ns, 1) ? 3 : kCtasPerSmSrc);
   const int ctas = std::max(1, std::min(nrows, num_sms() * per_sm));
   const int rows_per_cta = (nrows + ctas - 1) / ctas;
   const int grid = (nrows + rows_per_cta - 1) / rows_per_cta;

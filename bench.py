@@ -462,13 +462,17 @@ def run_ours(args):
             margs.steps, margs.warmup, margs.profile = 5, 3, False
             ml = run_model(margs, emit=False)
             model_step = {"ms_per_step": ml["ms_per_step"], "workload": ml["config"]["workload"], "clocks": ml["clocks"],
-                          "peak_mem_GB": ml["peak_mem_GB"], "loss": ml["config"]["loss"]}
+                          "peak_mem_GB": ml["peak_mem_GB"], "loss": ml["config"]["loss"],
+                          "optimizer_steps_before_loss": ml["config"]["optimizer_steps_before_loss"]}
             if os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "anemoi", "models")):
                 try:  # the same model from the unmodified reference blocks, on the same GPU
                     margs.steps = 2
                     rl = run_model(margs, emit=False, impl="reference")
                     model_step["reference_blocks_same_gpu"] = {"ms_per_step": rl["ms_per_step"], "peak_mem_GB": rl["peak_mem_GB"],
-                                                               "loss": rl["config"]["loss"]}
+                                                               "loss": rl["config"]["loss"],
+                                                               "optimizer_steps_before_loss": rl["config"]["optimizer_steps_before_loss"],
+                                                               "what": "the same model wired from the unmodified reference blocks (baseline/_ref, PyG op "
+                                                                       "sequence as torch ops, nn.Linear / nn.LayerNorm), same GPU, same autocast"}
                 except Exception as ex:  # noqa: BLE001
                     model_step["reference_blocks_same_gpu"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
                     torch.cuda.empty_cache()
@@ -921,6 +925,7 @@ def run_model(args, emit=True, impl="ours"):
 
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
+    torch.cuda.reset_peak_memory_stats(dev)
     torch.manual_seed(0)
     hid, heads, layers, chunks, nvar = D, H, args.model_layers, 8, 100
     hidden_xyz, _ = S.octahedral_grid(DST_N)
@@ -1026,7 +1031,7 @@ def run_model(args, emit=True, impl="ours"):
                                    f"o96 8-NN (E={ei['proc'].shape[1]}) in {chunks} checkpointed chunks, GT mapper o96->n320 3-NN "
                                    f"(E={ei['dec'].shape[1]}); hidden {hid}, {heads} heads, MLP x4, bf16 autocast, fwd+bwd (with "
                                    f"checkpoint recompute) + fused AdamW; {nparams / 1e6:.0f} M parameters (report line)",
-                       "conv_edges_per_step": int(etot), "loss": float(loss.detach())},
+                       "conv_edges_per_step": int(etot), "loss": float(loss.detach()), "optimizer_steps_before_loss": 3 + n},
             "clocks": sampler.summary(), "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2**30, 1),
             "kernel_breakdown": breakdown}
     if emit:
