@@ -537,7 +537,7 @@ struct SrcRing {
 
 template <typename T, int LPH>
 __global__ void __launch_bounds__(kTmaThreads, kCtasPerSmSrc)
-gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) {
+gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta, int interleave) {
   extern __shared__ __align__(128) char smem_raw[];
   constexpr int VEC = Vec<T>::N;
   constexpr size_t D = kRowBytes / sizeof(T);
@@ -546,8 +546,12 @@ gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) 
   // largely the same q / g rows, and that reuse is within the CTA's own stream of stages.  (Two other layouts were measured
   // and dropped -- profiles/r01/ab_r01x, r01y: stages that mix edges of several rows, 0.206 vs 0.139 ms at out-degree 8,
   // and blocks of rows dealt round-robin, 0.175 ms / at out-degree 40 1.41 vs 1.04 ms.)
-  const int r0 = (int)min((long long)a.src_lo + (long long)blockIdx.x * rows_per_cta, (long long)a.src_hi);
-  const int r1 = (int)min((long long)r0 + rows_per_cta, (long long)a.src_hi);
+  // interleave != 0 (high out-degree, see the launcher): CTA c takes the rows src_lo + c, + gridDim.x, + 2 gridDim.x, ...: the rows
+  // in flight across the GPU are then ONE window of gridDim.x consecutive src rows, the q / g rows of a dst are wanted by its
+  // (neighbouring) src rows at about the same time and are served by L2 instead of being fetched from DRAM once per edge.
+  const int r0 = interleave ? (int)min((long long)a.src_lo + (long long)blockIdx.x, (long long)a.src_hi)
+                            : (int)min((long long)a.src_lo + (long long)blockIdx.x * rows_per_cta, (long long)a.src_hi);
+  const int r1 = interleave ? a.src_hi : (int)min((long long)r0 + rows_per_cta, (long long)a.src_hi);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(ring.full(s), 1);
@@ -567,6 +571,77 @@ gtconv_bwd_src_tma_kernel(const __grid_constant__ ConvArgs a, int rows_per_cta) 
     const uint32_t edge_w = (uint32_t)a.H * 8u;                 // bytes of (a, ds) per edge
     int s = 0;
     uint32_t phase = 0;
+    if (interleave) {
+      const int stride = (int)gridDim.x;
+      const int cnt = (r1 - r0 + stride - 1) / stride;  // rows of this CTA
+      auto batch = [&](int b, int e) { return b + lane < e ? cedge[b + lane].x : 0; };
+      // lane l keeps the CSC range of the CTA's row number (row_base + l); refreshed every 31 rows so that the NEXT row's range
+      // is always at hand (its index batches are requested one row ahead)
+      int row_base = 0, plo = 0, phi = 0;
+      auto load_ptrs = [&](int ibase) {
+        const long long jj = min((long long)r0 + (long long)(ibase + lane) * stride, (long long)a.src_hi - 1);
+        plo = a.colptr[jj];
+        phi = a.colptr[jj + 1];
+      };
+      load_ptrs(0);
+      int beg = __shfl_sync(0xffffffffu, plo, 0), end = __shfl_sync(0xffffffffu, phi, 0);
+      int i0 = batch(beg, end), i1 = batch(beg + 32, end);
+      for (int it = 0; it < cnt; ++it) {
+        const int j = r0 + it * stride;
+        if (it + 1 - row_base >= 32) {
+          row_base = it;
+          load_ptrs(it);
+        }
+        beg = __shfl_sync(0xffffffffu, plo, it - row_base);
+        end = __shfl_sync(0xffffffffu, phi, it - row_base);
+        int n0 = 0, n1 = 0;
+        if (it + 1 < cnt) {
+          const int nb = __shfl_sync(0xffffffffu, plo, it + 1 - row_base), ne = __shfl_sync(0xffffffffu, phi, it + 1 - row_base);
+          n0 = batch(nb, ne);
+          n1 = batch(nb + 32, ne);
+        }
+        int pb = beg, p = beg;
+        do {  // at least one stage per row, so that edge-less rows get their zeros written
+          const int n = min(kU, end - p);
+          if (p >= pb + 32) {
+            i0 = i1;
+            pb += 32;
+            i1 = batch(pb + 32, end);
+          }
+          mbar_wait(ring.empty(s), phase ^ 1u);
+          const int pp = p + (lane < kU ? lane : 0) - pb;
+          const int ia = __shfl_sync(0xffffffffu, i0, pp & 31), ib = __shfl_sync(0xffffffffu, i1, pp & 31);
+          const int i = pp < 32 ? ia : ib;
+          if (lane == 0) {
+            StageMeta* m = ring.meta(s);
+            m->row = j;
+            m->n = n;
+            m->first = p == beg;
+            m->last = p + n >= end;
+            mbar_arrive_expect_tx(ring.full(s), (uint32_t)n * (2u * kRowBytes + edge_w));
+          }
+          __syncwarp();
+          if (lane < n) {
+            bulk_g2s(ring.q(s, lane), qb + (size_t)i * D, kRowBytes, ring.full(s));
+            bulk_g2s(ring.g(s, lane), gb + (size_t)i * D, kRowBytes, ring.full(s));
+          }
+          if (lane == kU && n > 0) bulk_g2s(ring.w(s), a.ads + (size_t)p * a.H, (uint32_t)n * edge_w, ring.full(s));
+          p += n;
+          if (++s == kStages) {
+            s = 0;
+            phase ^= 1u;
+          }
+        } while (p < end);
+        i0 = n0;
+        i1 = n1;
+      }
+      mbar_wait(ring.empty(s), phase ^ 1u);
+      if (lane == 0) {
+        ring.meta(s)->row = -1;
+        mbar_arrive_expect_tx(ring.full(s), 0);
+      }
+      return;
+    }
     int pb = a.colptr[r0];
     const int pend = a.colptr[r1];
     auto load_batch = [&](int base) { return base + lane < pend ? cedge[base + lane].x : 0; };
@@ -697,11 +772,18 @@ static bool launch_bwd_src_tma_t(const ConvArgs& a) {
     const char* s = getenv("AB2_SRC_CTAS_PER_SM");
     return s ? std::max(1, std::min(atoi(s), kCtasPerSmSrc)) : 0;
   }();
-  const int per_sm = forced ? forced : ((long long)a.E >= 20LL * std::max(a.Ns, 1) ? 3 : kCtasPerSmSrc);
+  // AB2_SRC_INTERLEAVE = 1 / 0 forces / forbids the interleaved row assignment (default: at a mean out-degree >= 20)
+  static const int force_il = [] {
+    const char* s = getenv("AB2_SRC_INTERLEAVE");
+    return s ? (atoi(s) != 0 ? 1 : 0) : -1;
+  }();
+  const bool high_degree = (long long)a.E >= 20LL * std::max(a.Ns, 1);
+  const int interleave = force_il >= 0 ? force_il : (high_degree ? 1 : 0);
+  const int per_sm = forced ? forced : ((high_degree && !interleave) ? 3 : kCtasPerSmSrc);
   const int ctas = std::max(1, std::min(nrows, num_sms() * per_sm));
   const int rows_per_cta = (nrows + ctas - 1) / ctas;
-  const int grid = (nrows + rows_per_cta - 1) / rows_per_cta;
-  kern<<<grid, kTmaThreads, smem, a.st>>>(a, rows_per_cta);
+  const int grid = interleave ? ctas : (nrows + rows_per_cta - 1) / rows_per_cta;
+  kern<<<grid, kTmaThreads, smem, a.st>>>(a, rows_per_cta, interleave);
   return true;
 }
 

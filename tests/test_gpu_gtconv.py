@@ -373,3 +373,38 @@ def test_rare_configurations_run_as_torch_compositions_on_the_gpu(monkeypatch):
     o_ref, en_ref = og.graph_conv_unfused(x, ea, ei2, p, "edge_mlp.", 0, "Tanh")
     o, en = gc(x.cuda(), ea.cuda(), ei2.cuda())
     assert rel_err(o, o_ref) < 2e-5 and rel_err(en, en_ref) < 2e-5
+
+
+def test_high_out_degree_src_pass_interleaved_rows_bf16():
+    """Decoder-like graph (3 src per dst, mean out-degree 40 -> the pipelined src pass deals the src rows to the CTAs interleaved,
+    csrc/gtconv_tma.cu) with 2 KB rows: edge-less src rows, one src row with > 64 outgoing edges (index batches reloaded on
+    demand) and more rows than one pointer batch per CTA would cover, against the fp32 op sequence on bf16-rounded inputs."""
+    import anemoi_models_b200 as b2
+    from anemoi_models_b200 import _lib
+
+    gen = torch.Generator().manual_seed(5)
+    ns, nd, H, C = 151, 2011, 16, 64
+    base = (torch.arange(nd) * (ns - 9) // nd)
+    src = torch.stack([base, base + 1, base + 2 + torch.randint(0, 6, (nd,), generator=gen)], 1).clamp_(max=ns - 1).view(-1)
+    dst = torch.arange(nd).repeat_interleave(3)
+    keep = (src != 40) & (src != 41)                      # two src rows without any edge
+    src, dst = src[keep], dst[keep]
+    extra_dst = torch.randperm(nd, generator=gen)[:90]    # src row 7 gets 90 more edges (> 64: two index batches are not enough)
+    src, dst = torch.cat([src, torch.full((90,), 7)]), torch.cat([dst, extra_dst])
+    perm = torch.randperm(src.numel(), generator=gen)
+    ei = torch.stack([src, dst])[:, perm].contiguous()
+    E = ei.shape[1]
+    assert E >= 20 * ns
+    name = _lib.lib().ab2_gtconv_variant(2, 1, ns, nd, E, H, C).decode()
+    assert "src_tma" in name, name
+    q, k, v, e, g = (torch.randn(n, H, C, generator=gen).bfloat16() for n in (nd, ns, ns, E, nd))
+    ref_in = [t_.float().requires_grad_(True) for t_ in (q, k, v, e)]
+    ref = og.gt_conv_unfused(*ref_in, ei, (ns, nd))
+    ref.backward(g.float())
+    ins = [t_.cuda().requires_grad_(True) for t_ in (q, k, v, e)]
+    out = b2.GraphTransformerConv(C)(*ins, ei.cuda(), (ns, nd))
+    out.backward(g.cuda())
+    assert rel_err(out.float(), ref) < 2e-2
+    for nm, a_, b_ in zip("qkve", ins, ref_in):
+        assert rel_err(a_.grad.float(), b_.grad) < 2e-2, nm
+    assert float(ins[1].grad[40:42].abs().max()) == 0.0 and float(ins[2].grad[40:42].abs().max()) == 0.0
