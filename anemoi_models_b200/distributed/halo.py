@@ -258,7 +258,9 @@ def select_sharded_edges(edge_attr_shard: Tensor, shapes_edge, edge_ids: Tensor,
     blocks (reference processor.py:335-341): with `plan` given the gather + select (and, in backward, the reduce-scatter) runs
     once per forward and the result is shared by the blocks that follow (keyed by tensor identity and version; autograd sums
     their gradients into the one gather)."""
-    if plan is None:
+    if plan is None or (edge_attr_shard.requires_grad and edge_attr_shard.is_leaf):
+        # a leaf that requires grad (a Parameter handed in directly) is the same object in every training step: a result cached
+        # from the previous step would hang off that step's (freed) autograd graph
         return _SelectShardedEdges.apply(edge_attr_shard, shapes_edge, edge_ids, group)
     from ..graph import tensor_version
 
