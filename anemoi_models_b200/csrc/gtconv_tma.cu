@@ -772,13 +772,15 @@ static bool launch_bwd_src_tma_t(const ConvArgs& a) {
     const char* s = getenv("AB2_SRC_CTAS_PER_SM");
     return s ? std::max(1, std::min(atoi(s), kCtasPerSmSrc)) : 0;
   }();
-  // AB2_SRC_INTERLEAVE = 1 / 0 forces / forbids the interleaved row assignment (default: at a mean out-degree >= 20)
+  // AB2_SRC_INTERLEAVE = 1 / 0 forces / forbids the interleaved row assignment (default: at a mean out-degree >= 8)
   static const int force_il = [] {
     const char* s = getenv("AB2_SRC_INTERLEAVE");
     return s ? (atoi(s) != 0 ? 1 : 0) : -1;
   }();
   const bool high_degree = (long long)a.E >= 20LL * std::max(a.Ns, 1);
-  const int interleave = force_il >= 0 ? force_il : (high_degree ? 1 : 0);
+  // interleaved rows from a mean out-degree of 8: decoder (40) 1.04 -> 0.60 ms, processor (8) 0.137 -> 0.131 ms (r02t)
+  const bool il_degree = (long long)a.E >= 8LL * std::max(a.Ns, 1);
+  const int interleave = force_il >= 0 ? force_il : (il_degree ? 1 : 0);
   const int per_sm = forced ? forced : ((high_degree && !interleave) ? 3 : kCtasPerSmSrc);
   const int ctas = std::max(1, std::min(nrows, num_sms() * per_sm));
   const int rows_per_cta = (nrows + ctas - 1) / ctas;

@@ -91,17 +91,22 @@ def encoder_graph(src_points: int, dst_N: int, cutoff: float = 0.6):
     return ei, src_points, len(dst_xyz), radius
 
 
-def encoder_graph_band(src_points: int, dst_N: int, parts: int, part: int, cutoff: float = 0.6):
-    """Edges (GLOBAL node ids) whose dst lies in shard `part` of `tensor_split(arange(Nd), parts)` -- what one rank
-    of a dst-sharded run owns.  Only the src points of the matching latitude band are generated."""
+def encoder_graph_band(src_points: int, dst_N: int, parts: int, part: int, cutoff: float = 0.6, bounds=None):
+    """Edges (GLOBAL node ids) whose dst lies in shard `part` -- what one rank of a dst-sharded run owns.  The shards are
+    `tensor_split(arange(Nd), parts)` (the reference's shapes) unless `bounds` (parts+1 dst cut points) is given.  Only the
+    src points of the matching latitude band are generated."""
     from .distributed.shapes import tensor_split_sizes
 
     dst_xyz, _ = octahedral_grid(dst_N)
     nd = len(dst_xyz)
     radius = cutoff * max_nn_distance(dst_xyz)
-    sizes = tensor_split_sizes(nd, parts)
-    lo = sum(sizes[:part])
-    hi = lo + sizes[part]
+    if bounds is None:
+        sizes = tensor_split_sizes(nd, parts)
+        lo = sum(sizes[:part])
+        hi = lo + sizes[part]
+    else:
+        assert len(bounds) == parts + 1 and bounds[0] == 0 and bounds[-1] == nd
+        lo, hi = int(bounds[part]), int(bounds[part + 1])
     band = dst_xyz[lo:hi]
     # Fibonacci index range covering the band's z range plus the cut-off radius
     zmax, zmin = band[:, 2].max() + radius, band[:, 2].min() - radius
@@ -147,6 +152,30 @@ def o1280_to_n320_band(parts: int, part: int, src_N: int = 1280, dst_points: int
     src_xyz, first = octahedral_grid(src_N, r_lo, r_hi)
     ei = cutoff_edges(src_xyz, band, radius, src_offset=first, dst_offset=lo)
     return ei, ns, dst_points, radius
+
+
+def encoder_work_balanced_bounds(src_points: int, dst_N: int, parts: int, cutoff: float = 0.6, w_edge: float = 3.0,
+                                 w_src: float = 6.0, w_dst: float = 6.0):
+    """parts+1 dst cut points of the `fibonacci(src_points) -> o<dst_N>` cut-off graph that give every rank the same WORK when
+    the src rows follow the dst shards in latitude (`aligned_src_bounds`): work = rows moved through HBM by one forward +
+    backward = w_edge * edges + w_src * src rows + w_dst * dst rows (3 E D + 6 Ns D + 6 Nd D elements).
+
+    Closed form, no graph needed: the Fibonacci points are uniform in z, so the src rows under latitude row i of the octahedral
+    grid are src_points * dz_i / 2; a fixed cut-off radius r (chord) covers a cap of area pi r^2, so every dst row has
+    ~src_points r^2 / 4 edges.  Equal-COUNT dst shards (`tensor_split`) of an octahedral grid are not equal-area -- the grid is
+    denser towards the poles -- which leaves the equatorial rank of 8 with 1.13x the src rows of the single-GPU workload."""
+    lat, npts = octahedral_rows(dst_N)
+    dst_xyz, _ = octahedral_grid(dst_N)
+    radius = cutoff * max_nn_distance(dst_xyz)
+    z = np.sin(lat)
+    zedge = np.concatenate([[1.0], 0.5 * (z[:-1] + z[1:]), [-1.0]])
+    src_under_row = src_points * (zedge[:-1] - zedge[1:]) / 2.0
+    deg = src_points * radius * radius / 4.0
+    row_cost = (w_edge * deg + w_dst) * npts + w_src * src_under_row
+    per_point = np.repeat(row_cost / npts, npts)
+    csum = np.concatenate([[0.0], np.cumsum(per_point)])
+    cuts = [int(np.searchsorted(csum, csum[-1] * r / parts, side="left")) for r in range(1, parts)]
+    return [0] + cuts + [int(npts.sum())]
 
 
 def edge_balanced_bounds(in_degree: np.ndarray, parts: int):

@@ -158,14 +158,20 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # workload
 # ----------------------------------------------------------------------------------------------------------------
-def build_shard(parts: int, part: int, workload: str = "encoder"):
+def build_shard(parts: int, part: int, workload: str = "encoder", weak_split: str = "equal"):
     """edge_index (GLOBAL ids) of the edges into shard `part`, plus global sizes and shard bounds."""
     from anemoi_models_b200 import synthetic as S
     from anemoi_models_b200.distributed.shapes import tensor_split_sizes
 
     ns = parts * SRC_POINTS
     if workload == "encoder":
-        ei, ns, nd, radius = S.encoder_graph_band(ns, dst_N_for(parts), parts, part)
+        bounds = None
+        if parts > 1 and weak_split == "work":  # equal WORK per rank (what weak scaling means), not equal dst-row counts
+            bounds = S.encoder_work_balanced_bounds(ns, dst_N_for(parts), parts)
+        ei, ns, nd, radius = S.encoder_graph_band(ns, dst_N_for(parts), parts, part, bounds=bounds)
+        if bounds is not None:
+            sb = np.concatenate([[0], np.cumsum(tensor_split_sizes(ns, parts))]).tolist()
+            return ei, ns, nd, sb, [int(b) for b in bounds]
     else:
         assert parts == 1, "decoder / processor workloads are single-GPU report lines"
         if workload.startswith("config1"):  # BASELINE configs[0]: o96 data grid, o48 hidden grid
@@ -232,7 +238,7 @@ def run_ours(args):
     H, C = (16, 16) if cfg1 else (16, 64)
     D = H * C
     dt_code, esz = (0, 4) if cfg1 else (1, 2)
-    ei_np, Ns_g, Nd_g, sb, db = build_shard(world, rank, args.workload)
+    ei_np, Ns_g, Nd_g, sb, db = build_shard(world, rank, args.workload, args.weak_split)
     ei_glob = torch.from_numpy(ei_np).to(dev)
     E = ei_glob.shape[1]
     torch.manual_seed(1234 + rank)
@@ -311,14 +317,24 @@ def run_ours(args):
                 print(f"[trace rank {r}] " + "  ".join(f"{lab}={t}" for lab, t in p_), file=sys.stderr, flush=True)
     tmax = torch.tensor([ms], device=dev, dtype=torch.float64)
     etot = torch.tensor([float(E)], device=dev, dtype=torch.float64)
-    shard_stats = torch.tensor([float(ns_loc), float(hplan.n_halo if hplan is not None else 0), float(E)], device=dev, dtype=torch.float64)
-    shard_max = shard_stats.clone()
+    shard_stats = torch.tensor([float(ns_loc), float(hplan.n_halo if hplan is not None else 0), float(E), float(nd_loc)],
+                               device=dev, dtype=torch.float64)
+    shard_max, shard_min = shard_stats.clone(), shard_stats.clone()
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(etot, op=dist.ReduceOp.SUM)
         dist.all_reduce(shard_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(shard_min, op=dist.ReduceOp.MIN)
     ms_per_step = float(tmax) / args.steps
     value = float(etot) / (ms_per_step * 1e-3)
+
+    # ---- the same step on the reference's equal-count dst shards (`tensor_split`), for the record
+    other_split = None
+    if world > 1 and args.workload == "encoder" and args.weak_split == "work":
+        try:
+            other_split = sharded_step_other_split(args, world, rank, dev, group, "equal", H, C, bf)
+        except Exception as ex:  # noqa: BLE001 -- the headline line must still be printed
+            other_split = {"error": f"{type(ex).__name__}: {ex}"[:300]}
 
     # ---- per-kernel durations (CUDA events on the launching stream, rank 0's shard) -> roofline of the dominant kernel
     st = torch.cuda.current_stream(dev).cuda_stream
@@ -491,7 +507,12 @@ def run_ours(args):
             "dtype": "f32" if cfg1 else "bf16", "data": "synthetic",
             "config": {"workload": workload_name(world, args.workload), "edges_total": int(float(etot)), "edges_rank0": int(E),
                        "src_rows_rank0": int(n_src), "halo_rows_rank0": int(hplan.n_halo) if hplan is not None else 0, "dst_rows_rank0": int(nd_loc), "hidden": D, "heads": H,
-                       "src_split": (args.src_split if world > 1 else "n/a"), "own_src_rows_max_rank": int(shard_max[0]),
+                       "src_split": (args.src_split if world > 1 else "n/a"),
+                       "dst_split": ("n/a" if world == 1 else
+                                     "equal work per rank (3 E + 6 Ns + 6 Nd rows of D elements; synthetic.encoder_work_balanced_bounds)"
+                                     if args.weak_split == "work" else "equal dst-row counts (tensor_split, the reference's shapes)"),
+                       "dst_rows_min_max_rank": [int(shard_min[3]), int(shard_max[3])],
+                       "own_src_rows_max_rank": int(shard_max[0]),
                        "halo_rows_max_rank": int(shard_max[1]), "edges_max_rank": int(shard_max[2]),
                        "l2": ("inputs (>5 GB per step) exceed the 126 MB L2; no flush between steps" if not cfg1 else
                               "config-1 working set is L2-sized: steady-state (warm L2) numbers, no flush"),
@@ -507,6 +528,7 @@ def run_ours(args):
             "kernels": kern,
             "cpu_baseline": cpu_baseline,
             "parity": parity,
+            "equal_count_dst_split": other_split,
             "config5_o1280_to_n320": config5,
             "model_step_n320_o96": model_step,
         }
@@ -519,6 +541,56 @@ def run_ours(args):
 # ----------------------------------------------------------------------------------------------------------------
 # multi-GPU: driver-visible parity of the sharded step, and BASELINE configs[4] (o1280 -> n320, strong scaling)
 # ----------------------------------------------------------------------------------------------------------------
+def sharded_step_other_split(args, world, rank, dev, group, weak_split, H, C, bf):
+    """The weak-scaling step of the headline on the OTHER dst split (sub-block of the line): same graph, same timing rules."""
+    import torch.distributed as dist
+
+    from anemoi_models_b200 import ops
+    from anemoi_models_b200.distributed.halo import aligned_src_bounds, build_local_halo_plan
+    from anemoi_models_b200.graph import GraphCSR
+
+    ei_np, Ns_g, Nd_g, sb, db = build_shard(world, rank, args.workload, weak_split)
+    ei_glob = torch.from_numpy(ei_np).to(dev)
+    E = ei_glob.shape[1]
+    if args.src_split == "aligned":
+        sb = aligned_src_bounds(ei_glob, Ns_g, group)
+    nd_loc, ns_loc = db[rank + 1] - db[rank], sb[rank + 1] - sb[rank]
+    torch.manual_seed(4321 + rank)
+    q, g = (torch.randn(nd_loc, H, C, device=dev, dtype=bf) for _ in range(2))
+    e = torch.randn(E, H, C, device=dev, dtype=bf)
+    k, v = (torch.randn(ns_loc, H, C, device=dev, dtype=bf) for _ in range(2))
+    hplan = build_local_halo_plan(ei_glob, sb, db, group)
+    plan = GraphCSR(hplan.local_edge_index, hplan.n_src, nd_loc)
+
+    def step():
+        qq, ee = q.detach().requires_grad_(True), e.detach().requires_grad_(True)
+        kk, vv = k.detach().requires_grad_(True), v.detach().requires_grad_(True)
+        ops.gt_conv_sharded(qq, kk, vv, ee, plan, hplan, group).backward(g)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    stats = torch.tensor([float(E), float(ns_loc), float(nd_loc)], device=dev, dtype=torch.float64)
+    smax, ssum = stats.clone(), stats.clone()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(smax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(ssum, op=dist.ReduceOp.SUM)
+    ms = float(t) / args.steps
+    return {"dst_split": "equal dst-row counts (tensor_split, the reference's shapes)" if weak_split == "equal" else weak_split,
+            "ms_per_step": round(ms, 4), "value": float(ssum[0]) / (ms * 1e-3), "unit": UNIT, "edges_max_rank": int(smax[0]),
+            "own_src_rows_max_rank": int(smax[1]), "own_src_rows_mean": int(float(ssum[1]) / world), "dst_rows_max_rank": int(smax[2])}
+
+
+
 def _err_pair(a, b):
     """(max|a-b| / max(1, max|b|), ||a-b||_2 / ||b||_2) in fp64 on the device, chunked over rows (a, b may be 10+ GB)."""
     mx, num, den, bmax = 0.0, 0.0, 0.0, 0.0
@@ -1104,6 +1176,10 @@ def main():
     ap.add_argument("--config5", default="auto", choices=["auto", "on", "off"],
                     help="encoder workload: also measure BASELINE configs[4] (o1280 -> n320, whole graph over the ranks) as an extra block")
     ap.add_argument("--dst-split", default="equal", choices=["equal", "balanced"], help="o1280 workload: dst shard cut points")
+    ap.add_argument("--weak-split", default="work", choices=["work", "equal"],
+                    help="headline at --gpus > 1: dst cut points that give every rank the single-GPU workload's work (default), or the "
+                         "reference's equal-count tensor_split (whose equatorial rank has 1.13x the src rows at 8 ranks); the other "
+                         "one is measured too and reported as a sub-block")
     ap.add_argument("--edgepath-graph", default="encoder", choices=["encoder", "decoder", "processor"])
     ap.add_argument("--graphconv-dim", type=int, default=512)
     ap.add_argument("--model-layers", type=int, default=16)

@@ -313,6 +313,30 @@ def test_o1280_recipe_bands_partition_the_whole_graph_and_balanced_bounds_balanc
     assert np.array_equal(np.concatenate(bal, axis=1), whole)
 
 
+def test_encoder_work_balanced_bounds_even_out_the_weak_scaling_shards():
+    """The weak-scaling headline shards the `fibonacci -> oN` encoder graph by dst rows.  Equal-count dst shards of an octahedral
+    grid are not equal-area, so the equatorial rank holds more src rows than the single-GPU workload; the closed-form
+    work-balanced cut points (no graph needed) bring the busiest rank's work (3 E + 6 Ns + 6 Nd rows) to within 3 % of the
+    mean, and the bands they define still partition the whole edge set."""
+    import numpy as np
+
+    from anemoi_models_b200 import synthetic as S
+
+    P, N, ns = 8, 40, 8 * 20000
+    whole = S.encoder_graph_band(ns, N, 1, 0)[0]
+    b = S.encoder_work_balanced_bounds(ns, N, P)
+    assert b[0] == 0 and b[-1] == S.octahedral_size(N) and all(x < y for x, y in zip(b[:-1], b[1:]))
+
+    def work(bounds):
+        bands = [S.encoder_graph_band(ns, N, P, r, bounds=bounds)[0] for r in range(P)]
+        assert np.array_equal(np.concatenate(bands, axis=1), whole)
+        w = np.array([3.0 * e.shape[1] + 6.0 * (e[0].max() - e[0].min() + 1) + 6.0 * (e[1].max() - e[1].min() + 1) for e in bands])
+        return float(w.max() / w.mean())
+
+    equal, balanced = work(None), work(b)
+    assert equal > 1.05 and balanced < 1.03 and balanced < equal, (equal, balanced)
+
+
 def _emulated_gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, out=None, seg_cols=0, out_dtype=torch.bfloat16,
                    bias=None, row_scale=None, row_shift=None, col_vec=None, act=3, pre_out=None, dact_pre=None, residual=None,
                    splits=1, gather=None):
