@@ -25,7 +25,7 @@ class Gemm(C.Structure):
                 ("bias", _vp), ("row_scale", _vp), ("row_shift", _vp), ("col_vec", _vp), ("pre_out", _vp), ("dact_pre", _vp),
                 ("residual", _vp), ("ld_res", _i64), ("res_f32", C.c_int32), ("act", C.c_int32), ("splits", C.c_int32),
                 ("reserved", C.c_int32), ("gather_a", _vp), ("gather_a_idx", _vp), ("gather_b", _vp), ("gather_b_idx", _vp),
-                ("ld_gather", _i64)]
+                ("ld_gather", _i64), ("a_seg", _vp * 3), ("a_seg_len", _i64)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/anemoi_b200.h (tests/test_abi.py checks it)

@@ -12,6 +12,6 @@ long long* launch_counter() {
 }
 }  // namespace ab2
 
-extern "C" int ab2_version(void) { return 100; /* 0.1.0 */ }
+extern "C" int ab2_version(void) { return 101; /* 0.1.1: ab2_gemm gained a_seg / a_seg_len */ }
 extern "C" const char* ab2_last_error(void) { return ab2::last_error_buf(); }
 extern "C" long long ab2_launch_count(void) { return __atomic_load_n(ab2::launch_counter(), __ATOMIC_RELAXED); }

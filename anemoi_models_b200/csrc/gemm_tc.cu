@@ -33,6 +33,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <climits>
 #include <mutex>
 
 #include "common.cuh"
@@ -88,7 +89,14 @@ struct Args {
   int tiles_m, tiles_n, splits, kb_per_split, kb_total;
   long long split_stride;  // elements between the fp32 partials of two splits (split-K only)
   int k_lbo, k_sbo, mn_lbo, mn_sbo;  // descriptor byte offsets (fixed by the tile layout; overridable for bring-up probes only)
+  int a_seg_len;  // A given as up to 4 tensors, cut every a_seg_len elements along K (K-major A) or along M (MN-major A)
   Epi epi;
+};
+
+// A may be SEGMENTED: [dq | dk | dv | dself] of the fused q/k/v/self projection arrive from autograd as separate tensors; the
+// producer picks the tensor map by k-block (dgrad, K-major A) or by tile row (wgrad, MN-major A) instead of a concatenation pass
+struct AMaps {
+  CUtensorMap m[4];
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
@@ -223,42 +231,94 @@ __device__ __forceinline__ float tanh_approx(float x) {  // one MUFU.TANH (|rel 
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// erf with |error| < 5e-7 (Abramowitz & Stegun 7.1.26): one reciprocal, one exp2 and 7 FMAs / multiplies, branch-free -- libdevice's
-// erff (and __frcp_rn's refinement + slow path) cost 27 instructions and three branches per element in the first version
-__device__ __forceinline__ float erf_fast(float x) {
-  const float ax = fabsf(x);
-  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float r = fmaf(-p * t, fast_exp2(ax * (ax * -kLog2e)), 1.f);
-  return copysignf(r, x);
+// ---- epilogue math on PAIRS of fp32 values: sm_100 has packed FFMA2 / FMUL2 / FADD2 (two fp32 lanes per instruction), and the
+// epilogue of the activation shapes is issue-bound (ncu, profiles/r02/ncu_gemm_perf_mlp1_r02n.md: 900 warp instructions per
+// 32 x 32 chunk at 55 % issue-slot use while the tensor pipe idles 46 % of the time) -- so every polynomial step below is one
+// instruction for two elements; only the special-function ops (MUFU) and min / max / sign stay per element.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
 }
-// sigmoid through the tanh unit: ONE special-function op per element (exp2 + reciprocal would be two, and at K = 512 the SFU
-// pipe (16 lanes per SM and clock) would then need as long as the MMAs of the tile)
-__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
-template <int ACT>
-__device__ __forceinline__ float act_fn(float x) {
-  if constexpr (ACT == 0) return x * sigmoid_fast(x);
-  else if constexpr (ACT == 1) {
-    const float h = 0.5f * x;
-    return fmaf(h, erf_fast(x * 0.70710678118654752f), h);
-  } else if constexpr (ACT == 2) return fmaxf(x, 0.f);
-  else return x;
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 bc2(float c) { return pk2(c, c); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
 }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ void add_pair(float& a, float& b, float c0, float c1) { upk2(add2(pk2(a, b), pk2(c0, c1)), a, b); }
+
+// u(x) = -0.5 erfc(|x| / sqrt 2) for two values, and e = exp(-x^2 / 2): Abramowitz & Stegun 7.1.26 (|error| of erfc < 1.5e-7) with
+// the -0.5 folded into the coefficients; one MUFU.RCP and one MUFU.EX2 per element, everything else packed.  libdevice's erff (and
+// __frcp_rn's refinement + slow path) cost 27 instructions and three branches per element in the first version of this kernel.
+__device__ __forceinline__ void half_erfc_pair(f32x2 x, f32x2 ax, f32x2& u, f32x2& e) {
+  float d0, d1, s0, s1;
+  upk2(fma2(ax, bc2(0.3275911f * 0.70710678118654752f), bc2(1.f)), d0, d1);
+  const f32x2 t = pk2(rcp_approx(d0), rcp_approx(d1));
+  f32x2 p = fma2(bc2(-0.5f * 1.061405429f), t, bc2(0.5f * 1.453152027f));
+  p = fma2(p, t, bc2(-0.5f * 1.421413741f));
+  p = fma2(p, t, bc2(0.5f * 0.284496736f));
+  p = fma2(p, t, bc2(-0.5f * 0.254829592f));
+  const f32x2 y = mul2(x, bc2(0.84932180028801907f));  // sqrt(0.5 log2 e): exp(-x^2 / 2) = 2^(-y^2)
+  upk2(mul2(y, y), s0, s1);
+  e = pk2(fast_exp2(-s0), fast_exp2(-s1));
+  u = mul2(mul2(p, t), e);
+}
+// act(x) for two values.  GELU (erf form, nn.GELU()): x Phi(x) = max(x, 0) - |x| * 0.5 erfc(|x| / sqrt 2)  -- no sign select, no
+// 1 + erf cancellation.  SiLU: x * sigmoid(x) with the sigmoid through ONE MUFU.TANH (exp2 + reciprocal would be two, and at
+// K = 512 the SFU pipe -- 16 lanes per SM and clock -- would then need as long as the MMAs of the tile).
 template <int ACT>
-__device__ __forceinline__ float act_grad(float x) {
+__device__ __forceinline__ void act_pair(float& x0, float& x1) {
   if constexpr (ACT == 0) {
-    const float s = sigmoid_fast(x);
-    return s * fmaf(x, 1.f - s, 1.f);
+    const f32x2 x = pk2(x0, x1);
+    float h0, h1;
+    upk2(mul2(x, bc2(0.5f)), h0, h1);
+    const f32x2 sg = fma2(pk2(tanh_approx(h0), tanh_approx(h1)), bc2(0.5f), bc2(0.5f));
+    upk2(mul2(x, sg), x0, x1);
   } else if constexpr (ACT == 1) {
-    const float cdf = fmaf(0.5f, erf_fast(x * 0.70710678118654752f), 0.5f);
-    return fmaf(x * 0.3989422804014327f, fast_exp2(x * (x * (-0.5f * kLog2e))), cdf);
+    const f32x2 x = pk2(x0, x1), ax = pk2(fabsf(x0), fabsf(x1));
+    f32x2 u, e;
+    half_erfc_pair(x, ax, u, e);
+    upk2(fma2(ax, u, pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), x0, x1);
   } else if constexpr (ACT == 2) {
-    return x > 0.f ? 1.f : 0.f;
-  } else {
-    return 1.f;
+    x0 = fmaxf(x0, 0.f);
+    x1 = fmaxf(x1, 0.f);
+  }
+}
+// (f0, f1) *= act'(x0, x1)
+template <int ACT>
+__device__ __forceinline__ void act_grad_mul_pair(float& f0, float& f1, float x0, float x1) {
+  if constexpr (ACT == 0) {  // s (1 + x (1 - s))
+    const f32x2 x = pk2(x0, x1);
+    float h0, h1;
+    upk2(mul2(x, bc2(0.5f)), h0, h1);
+    const f32x2 sg = fma2(pk2(tanh_approx(h0), tanh_approx(h1)), bc2(0.5f), bc2(0.5f));
+    const f32x2 gr = mul2(sg, fma2(x, fma2(sg, bc2(-1.f), bc2(1.f)), bc2(1.f)));
+    upk2(mul2(pk2(f0, f1), gr), f0, f1);
+  } else if constexpr (ACT == 1) {  // Phi(x) + x phi(x);  Phi = 0.5 + copysign(0.5 + u, x),  phi = e / sqrt(2 pi)
+    const f32x2 x = pk2(x0, x1), ax = pk2(fabsf(x0), fabsf(x1));
+    f32x2 u, e;
+    half_erfc_pair(x, ax, u, e);
+    float c0, c1;
+    upk2(add2(u, bc2(0.5f)), c0, c1);
+    const f32x2 cdf = add2(pk2(copysignf(c0, x0), copysignf(c1, x1)), bc2(0.5f));
+    const f32x2 gr = fma2(mul2(x, bc2(0.3989422804014327f)), e, cdf);
+    upk2(mul2(pk2(f0, f1), gr), f0, f1);
+  } else if constexpr (ACT == 2) {
+    f0 = x0 > 0.f ? f0 : 0.f;
+    f1 = x1 > 0.f ? f1 : 0.f;
   }
 }
 // the activation code is a runtime argument: dispatch ONCE per 32-value chunk (warp-uniform), never per element -- a per-element
@@ -267,7 +327,7 @@ __device__ __forceinline__ float act_grad(float x) {
 template <int ACT>
 __device__ __forceinline__ void act_chunk(float (&f)[32]) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) f[j] = act_fn<ACT>(f[j]);
+  for (int j = 0; j < 32; j += 2) act_pair<ACT>(f[j], f[j + 1]);
 }
 __device__ __forceinline__ void act_chunk_rt(float (&f)[32], int act) {
   if (act == 0) act_chunk<0>(f);
@@ -277,7 +337,7 @@ __device__ __forceinline__ void act_chunk_rt(float (&f)[32], int act) {
 template <int ACT>
 __device__ __forceinline__ void act_grad_mul8(float (&f)[32], int j, const float (&p)[8]) {
 #pragma unroll
-  for (int u = 0; u < 8; ++u) f[j + u] *= act_grad<ACT>(p[u]);
+  for (int u = 0; u < 8; u += 2) act_grad_mul_pair<ACT>(f[j + u], f[j + u + 1], p[u], p[u + 1]);
 }
 
 // ---- the kernel --------------------------------------------------------------------------------------------------
@@ -289,11 +349,15 @@ __device__ __forceinline__ void store_chunk_packed(uint32_t patch, int lane, con
   for (int j = 0; j < 4; ++j) sts16(patch + lane * kPatchStride + j * 16, make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
   __syncwarp();
   const int c16 = lane & 3, rsub = lane >> 2;
+  __nv_bfloat16* dst = out + (size_t)(row0 + rsub) * ld + c16 * 8;  // one 64-bit address per chunk, + 8 rows per store
+  const size_t step = (size_t)8 * ld;
+  const bool col_ok = c16 * 8 < cols_left;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = i * 8 + rsub;
     const uint4 v = lds16(patch + r * kPatchStride + c16 * 16);
-    if (r < rows_left && c16 * 8 < cols_left) stg16(out + (size_t)(row0 + r) * ld + c16 * 8, v);
+    if (r < rows_left && col_ok) stg16(dst, v);
+    dst += step;
   }
   __syncwarp();
 }
@@ -303,7 +367,7 @@ __device__ __forceinline__ void pack_chunk(const float (&f)[32], uint32_t (&pk)[
 }
 
 template <int BN, bool A_MN, bool B_MN, int CG, int EW>
-__global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_constant__ AMaps tmAs,
                                                              const __grid_constant__ CUtensorMap tmB, const Args g) {
   using C = Cfg<BN, CG, EW>;
   constexpr int S = C::kStages;
@@ -352,14 +416,18 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int num_tiles = g.tiles_m * g.tiles_n * g.splits;
+  // work item t -> (split, output tile): the tiles of ONE K range are consecutive, so the CTA pairs in flight at any time read
+  // the same rows of both operands (split-K wgrad streams both from DRAM; with the splits of one tile consecutive instead, the
+  // pairs in flight covered ~5 tiles x 16 K ranges and every operand slab came from DRAM once per tile that uses it)
+  const int tiles_mn = g.tiles_m * g.tiles_n;
+  const int num_tiles = tiles_mn * g.splits;
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t c = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        const int split = t % g.splits, r = t / g.splits;
+        const int split = t / tiles_mn, r = t % tiles_mn;
         const int n0 = (r % g.tiles_n) * BN + (int)cta * C::kBRows, m0 = (r / g.tiles_n) * TM + (int)cta * BM;
         const int kb0 = split * g.kb_per_split, kb1 = min(kb0 + g.kb_per_split, g.kb_total);
         for (int kb = kb0; kb < kb1; ++kb, ++c) {
@@ -371,10 +439,12 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
             if constexpr (CG == 2) tma_load_2d_cg2(dst, m, fb, c0, c1); else tma_load_2d(dst, m, fb, c0, c1);
           };
           if constexpr (!A_MN) {
-            load(sA(s), &tmA, kb * BK, m0);
+            const int ka = kb * BK, seg = ka / g.a_seg_len;  // a_seg_len is a multiple of BK (or INT_MAX: one tensor)
+            load(sA(s), &tmAs.m[seg], ka - seg * g.a_seg_len, m0);
           } else {
+            const int seg = m0 / g.a_seg_len, ma = m0 - seg * g.a_seg_len;  // a_seg_len is a multiple of the tile rows
 #pragma unroll
-            for (int i = 0; i < BM / 64; ++i) load(sA(s) + i * kBoxBytes, &tmA, m0 + 64 * i, kb * BK);
+            for (int i = 0; i < BM / 64; ++i) load(sA(s) + i * kBoxBytes, &tmAs.m[seg], ma + 64 * i, kb * BK);
           }
           if constexpr (!B_MN) {
             load(sB(s), &tmB, kb * BK, n0);
@@ -403,7 +473,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
       constexpr uint32_t kBStep = B_MN ? (UMMA_K * 128) : (UMMA_K * 2);
       uint32_t c = 0, it = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
-        const int split = t % g.splits;
+        const int split = t / tiles_mn;
         const int kb0 = split * g.kb_per_split, kb1 = min(kb0 + g.kb_per_split, g.kb_total);
         const uint32_t a = it & 1u;
         mbar_wait(tempty(a), ((it >> 1) & 1u) ^ 1u);  // the epilogue (of both CTAs) has drained this accumulator stage
@@ -443,7 +513,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
     const uint32_t patch = patches + e * kPatchBytes;
     uint32_t it = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
-      const int split = t % g.splits, r = t / g.splits;
+      const int split = t / tiles_mn, r = t % tiles_mn;
       const int n0 = (r % g.tiles_n) * BN, m0 = (r / g.tiles_n) * TM + (int)cta * BM;
       const uint32_t a = it & 1u;
       mbar_wait(tfull(a), (it >> 1) & 1u);
@@ -496,10 +566,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
           for (int j = 0; j < 32; j += 4) {
             if (j < cols_left) {
               const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
-              f[j] += b.x;
-              f[j + 1] += b.y;
-              f[j + 2] += b.z;
-              f[j + 3] += b.w;
+              add_pair(f[j], f[j + 1], b.x, b.y);
+              add_pair(f[j + 2], f[j + 3], b.z, b.w);
             }
           }
         }
@@ -513,7 +581,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
                 float p[8];
                 unpack<__nv_bfloat16>(ldg16_keep(gp + j), p);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) f[j + u] += p[u];
+                for (int u = 0; u < 8; u += 2) add_pair(f[j + u], f[j + u + 1], p[u], p[u + 1]);
               }
             }
           }
@@ -555,8 +623,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
               if (j < cols_left) {
                 float p[4];
                 unpack<float>(ldg16_keep(rp + j), p);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) f[j + u] += p[u];
+                add_pair(f[j], f[j + 1], p[0], p[1]);
+                add_pair(f[j + 2], f[j + 3], p[2], p[3]);
               }
             }
           } else {
@@ -567,7 +635,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
                 float p[8];
                 unpack<__nv_bfloat16>(ldg16_keep(rp + j), p);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) f[j + u] += p[u];
+                for (int u = 0; u < 8; u += 2) add_pair(f[j + u], f[j + u + 1], p[u], p[u + 1]);
               }
             }
           }
@@ -660,7 +728,7 @@ static int make_map(CUtensorMap* m, const void* ptr, long long inner, long long 
 }
 
 template <int BN, bool A_MN, bool B_MN, int CG, int EW>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Args& a, cudaStream_t st) {
+static int launch(const AMaps& ta, const CUtensorMap& tb, const Args& a, cudaStream_t st) {
   using C = Cfg<BN, CG, EW>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CG, EW>;
   if (!AB2_ENSURE_DYN_SMEM(kern, C::kSmemBytes)) return fail(AB2_ERR_CUDA, "gemm_tc_kernel: cannot reserve %d B of shared memory", C::kSmemBytes);
@@ -767,12 +835,30 @@ extern "C" int ab2_gemm_bf16(const ab2_gemm* d, void* workspace, size_t workspac
     e.out_f32 = 1;
     a.split_stride = M * N;
   }
-  CUtensorMap ta, tb;
+  tc::AMaps ta;
+  CUtensorMap tb;
   int rc;
   // K-major operand: memory [rows][K] -> inner = K, outer = rows, box 64 x (rows this CTA stages).  MN-major: memory [K][rows]
   // -> inner = rows, outer = K, 64 x 64 boxes.
-  rc = d->a_mn ? tc::make_map(&ta, d->a, M, K, d->lda, 64) : tc::make_map(&ta, d->a, K, M, d->lda, tc::BM);
-  if (rc) return rc;
+  a.a_seg_len = INT_MAX;
+  int nsegA = 1;
+  const void* aptr[4] = {d->a, d->a_seg[0], d->a_seg[1], d->a_seg[2]};
+  if (d->a_seg_len > 0) {
+    const long long extent = d->a_mn ? M : K;  // the segmented dimension: K of a K-major A, M of an MN-major A
+    const long long unit = d->a_mn ? (long long)tc::BM * CG : tc::BK;
+    nsegA = (int)((extent + d->a_seg_len - 1) / d->a_seg_len);
+    if (d->a_seg_len % unit != 0 || extent % d->a_seg_len != 0 || nsegA > 4 || d->a_seg_len >= INT_MAX)
+      return fail(AB2_ERR_INVALID, "ab2_gemm_bf16: a_seg_len must be a multiple of %lld that divides %lld into at most 4 segments", unit, extent);
+    for (int i = 1; i < nsegA; ++i)
+      if (aptr[i] == nullptr) return fail(AB2_ERR_INVALID, "ab2_gemm_bf16: A segment %d is null", i);
+    a.a_seg_len = (int)d->a_seg_len;
+  }
+  for (int i = 0; i < 4; ++i) {
+    const void* p = i < nsegA ? aptr[i] : d->a;  // unused slots hold a valid map
+    const long long segM = (d->a_mn && nsegA > 1) ? d->a_seg_len : M, segK = (!d->a_mn && nsegA > 1) ? d->a_seg_len : K;
+    rc = d->a_mn ? tc::make_map(&ta.m[i], p, segM, K, d->lda, 64) : tc::make_map(&ta.m[i], p, segK, M, d->lda, tc::BM);
+    if (rc) return rc;
+  }
   rc = d->b_mn ? tc::make_map(&tb, d->b, N, K, d->ldb, 64) : tc::make_map(&tb, d->b, K, N, d->ldb, BN / CG);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;

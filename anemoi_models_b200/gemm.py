@@ -27,7 +27,8 @@ def gemm(a: Tensor, b: Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_
          ldb: Optional[int] = None, out: Optional[Sequence[Tensor]] = None, seg_cols: int = 0, out_dtype: torch.dtype = torch.bfloat16,
          bias: Optional[Tensor] = None, row_scale: Optional[Tensor] = None, row_shift: Optional[Tensor] = None,
          col_vec: Optional[Tensor] = None, act: int = ACT_NONE, pre_out: Optional[Tensor] = None, dact_pre: Optional[Tensor] = None,
-         residual: Optional[Tensor] = None, splits: int = 1, gather=None):
+         residual: Optional[Tensor] = None, splits: int = 1, gather=None, a_segs: Optional[Sequence[Tensor]] = None,
+         a_seg_len: int = 0):
     """D[M,N] = epilogue(A . B^T) on the tensor cores; see include/anemoi_b200.h (`ab2_gemm`).  a: [M,K] (or [K,M] when a_mn),
     b: [N,K] (or [K,N] when b_mn), bf16, last dim contiguous.  Returns the output tensor (or the list `out` when given)."""
     if not (a.is_cuda and b.is_cuda):
@@ -65,6 +66,12 @@ def gemm(a: Tensor, b: Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_
             raise TypeError("gemm residual must be fp32 or bf16, contiguous in its last dimension")
         d.residual, d.ld_res, d.res_f32 = residual.data_ptr(), residual.stride(0), int(residual.dtype == torch.float32)
     d.splits = splits
+    if a_segs:  # A = [a | a_segs...] along K (K-major) or along M (MN-major), each piece a_seg_len wide, never concatenated
+        for i, t_ in enumerate(a_segs):
+            if t_.dtype != torch.bfloat16 or t_.stride(-1) != 1 or t_.stride(0) != d.lda or t_.shape != a.shape:
+                raise TypeError("gemm A segments must be bf16 tensors of one shape and row stride")
+            d.a_seg[i] = t_.data_ptr()
+        d.a_seg_len = a_seg_len
     if gather is not None:  # ((table_a [Na, N] bf16, idx_a int64 [M]), (table_b, idx_b)): acc += table[idx[m], n], before the activation
         (ta, ia), (tb, ib) = gather
         for t_, i_ in ((ta, ia), (tb, ib)):
@@ -129,7 +136,8 @@ def _ln_fwd_kernel(x2: Tensor, gamma: Tensor, beta: Tensor, eps: float, out_dtyp
     return y, mean, rstd
 
 
-def _ln_bwd_kernel(g2: Tensor, x2: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor):
+def _ln_bwd_kernel(g2: Tensor, x2: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, add: Optional[Tensor] = None):
+    """dx = LN-backward(g) (+ add, the gradient that reached x through a residual branch: one pass instead of an add kernel)"""
     L = _lib.lib()
     M, D = x2.shape
     dx = torch.empty_like(x2)
@@ -139,7 +147,7 @@ def _ln_bwd_kernel(g2: Tensor, x2: Tensor, gamma: Tensor, mean: Tensor, rstd: Te
     dbeta = torch.empty(D, dtype=torch.float32, device=x2.device)
     with torch.cuda.device(x2.device):
         _lib.check(L.ab2_layernorm_bwd(g2.data_ptr(), _lib.dtype_code(g2.dtype), x2.data_ptr(), _lib.dtype_code(x2.dtype),
-                                       gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), M, D, 0, dx.data_ptr(),
+                                       gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), M, D, _p(add), dx.data_ptr(),
                                        partial.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _lib.current_stream(x2.device)))
     return dx, dgamma, dbeta
 
@@ -149,23 +157,33 @@ class _LayerNormFn(torch.autograd.Function):
     349: LayerNorm in fp32 under autocast + the cast in front of each nn.Linear)."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, weight: Tensor, bias: Tensor, eps: float, out_dtype: torch.dtype) -> Tensor:
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Tensor, eps: float, out_dtype: torch.dtype, fork: bool = False):
+        ctx.set_materialize_grads(False)
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
         gamma, beta = _f32(weight), _f32(bias)
         y, mean, rstd = _ln_fwd_kernel(x2, gamma, beta, float(eps), out_dtype)
         ctx.save_for_backward(x2, gamma, mean, rstd)
         ctx.shape, ctx.pdt = tuple(x.shape), (weight.dtype, bias.dtype)
+        if fork:  # (LN(x), x): the skip connection leaves through this node too, so both gradients meet in ONE backward kernel
+            return y.view(ctx.shape), x.view_as(x)
         return y.view(ctx.shape)
 
     @staticmethod
-    def backward(ctx, g: Tensor):
+    def backward(ctx, g: Optional[Tensor], g_skip: Optional[Tensor] = None):
         x2, gamma, mean, rstd = ctx.saved_tensors
         M, D = x2.shape
+        if g is None:  # only the skip branch reached the loss
+            return g_skip, None, None, None, None, None
         g2 = g.reshape(M, D).contiguous()
         if g2.dtype not in (torch.float32, torch.bfloat16):
             g2 = g2.float()
-        dx, dgamma, dbeta = _ln_bwd_kernel(g2, x2, gamma, mean, rstd)
-        return dx.view(ctx.shape), dgamma.to(ctx.pdt[0]), dbeta.to(ctx.pdt[1]), None, None
+        add = None
+        if g_skip is not None:
+            add = g_skip.reshape(M, D)
+            if add.dtype != x2.dtype or not add.is_contiguous():
+                add = add.to(x2.dtype).contiguous()
+        dx, dgamma, dbeta = _ln_bwd_kernel(g2, x2, gamma, mean, rstd, add)
+        return dx.view(ctx.shape), dgamma.to(ctx.pdt[0]), dbeta.to(ctx.pdt[1]), None, None, None
 
 
 def layer_norm(x: Tensor, ln: torch.nn.LayerNorm, out_dtype: torch.dtype = torch.bfloat16) -> Tensor:
@@ -173,6 +191,14 @@ def layer_norm(x: Tensor, ln: torch.nn.LayerNorm, out_dtype: torch.dtype = torch
     if x.dtype not in (torch.float32, torch.bfloat16):
         x = x.float()
     return _LayerNormFn.apply(x, ln.weight, ln.bias, ln.eps, out_dtype)
+
+
+def layer_norm_fork(x: Tensor, ln: torch.nn.LayerNorm, out_dtype: torch.dtype = torch.bfloat16):
+    """(`ln(x)`, x) for the pre-norm residual pattern `f(ln(x)) + x` (reference block.py:487-537, 611-633): take the skip
+    connection from the second result and its gradient is added inside the LayerNorm backward kernel."""
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    return _LayerNormFn.apply(x, ln.weight, ln.bias, ln.eps, out_dtype, True)
 
 
 def wgrad_splits(N: int, K: int, M: int, slots: int = 74) -> int:
@@ -262,6 +288,65 @@ class _LinearFn(torch.autograd.Function):
         if need[4]:
             dres = g_in.to(rdt).reshape(rshape)
         return dx, dpre, dw, db, dres, None, None
+
+
+class _MultiLinearFn(torch.autograd.Function):
+    """y_i = x W_i^T + b_i for 2-4 Linear layers of ONE shape reading the same x -- the block's q | k | v | self projections
+    (reference block.py:491-499, 613-620).  Forward: one GEMM over the stacked weights, each y_i written to its own tensor
+    (column segments of the epilogue).  Backward: one dgrad whose A operand is [dy_1 | ... | dy_n] read where autograd left the
+    pieces (segmented tensor maps, no concatenation, no add kernels between four partial dx), one split-K wgrad over the same
+    segmented operand, column sums for the biases."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, n: int, *wb):
+        weights, biases = wb[:n], wb[n:]
+        shape = tuple(x.shape)
+        x2 = x.reshape(-1, shape[-1])
+        if x2.dtype != torch.bfloat16 or x2.stride(-1) != 1 or (x2.stride(0) % 8) != 0 or (x2.data_ptr() % 16) != 0:
+            x2 = x2.to(torch.bfloat16).contiguous()
+        M, K = x2.shape
+        N = weights[0].shape[0]
+        wcat = torch.cat([w.detach().to(torch.bfloat16) for w in weights], dim=0)
+        bcat = None if biases[0] is None else torch.cat([b.detach().float() for b in biases])
+        outs = [torch.empty((M, N), dtype=torch.bfloat16, device=x.device) for _ in range(n)]
+        gemm(x2, wcat, M, n * N, K, out=outs, seg_cols=N, bias=bcat)
+        ctx.save_for_backward(x2, wcat)
+        ctx.meta = (shape, n, N, [w.dtype for w in weights], [None if b is None else b.dtype for b in biases])
+        return tuple(o.view(shape[:-1] + (N,)) for o in outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        x2, wcat = ctx.saved_tensors
+        shape, n, N, wdts, bdts = ctx.meta
+        M, K = x2.shape
+        need = ctx.needs_input_grad
+        g2 = []
+        for g in gs:  # materialised by autograd (zeros for an unused output)
+            g_ = g.reshape(M, N)
+            if g_.dtype != torch.bfloat16 or not g_.is_contiguous() or (g_.data_ptr() % 16) != 0:
+                g_ = g_.to(torch.bfloat16).contiguous()
+            g2.append(g_)
+        dx = None
+        if need[0]:  # dx = [dy_1 | ... | dy_n] Wcat : A segmented along the contraction (n * N), B = Wcat stored [n * N, K] (MN-major)
+            dx = gemm(g2[0], wcat, M, K, n * N, b_mn=True, a_segs=g2[1:], a_seg_len=N).view(shape)
+        dws = [None] * n
+        if any(need[2:2 + n]):  # dWcat [n * N, K] = [dy_1 | ... | dy_n]^T x : A MN-major, segmented along its rows
+            dwcat = gemm(g2[0], x2, n * N, K, M, a_mn=True, b_mn=True, out_dtype=torch.float32, splits=wgrad_splits(n * N, K, M),
+                         a_segs=g2[1:], a_seg_len=N)
+            dws = [dwcat[i * N:(i + 1) * N].to(wdts[i]) if need[2 + i] else None for i in range(n)]
+        dbs = [colsum(g2[i]).to(bdts[i]) if (bdts[i] is not None and need[2 + n + i]) else None for i in range(n)]
+        return (dx, None, *dws, *dbs)
+
+
+def linear_multi(x: Tensor, lins: Sequence[torch.nn.Linear]):
+    """[lin(x) for lin in lins] for 2-4 Linear layers of one shape (out_features a multiple of 256): one forward GEMM, one
+    dgrad, one wgrad (`_MultiLinearFn`); other shapes fall back to one GEMM per layer."""
+    n = len(lins)
+    N, K = lins[0].weight.shape
+    same = all(tuple(l.weight.shape) == (N, K) and (l.bias is None) == (lins[0].bias is None) for l in lins)
+    if not (2 <= n <= 4 and same and N % 256 == 0):
+        return [linear(x, l) for l in lins]
+    return list(_MultiLinearFn.apply(x, n, *[l.weight for l in lins], *[l.bias for l in lins]))
 
 
 def linear(x: Tensor, lin: torch.nn.Linear, residual: Optional[Tensor] = None, act_out: int = ACT_NONE):

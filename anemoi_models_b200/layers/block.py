@@ -205,6 +205,14 @@ class GraphTransformerBaseBlock(BaseBlock, ABC):
     def _ln(self, ln: nn.LayerNorm, x: Tensor, tc: bool) -> Tensor:
         return tcg.layer_norm(x, ln) if tc else _autocast_once(ln(x))
 
+    def _ln_fork(self, ln: nn.LayerNorm, x: Tensor, tc: bool) -> Tuple[Tensor, Tensor]:
+        """(ln(x), x as the skip connection): on the tensor-core path the skip gradient is added inside the LayerNorm backward"""
+        return tcg.layer_norm_fork(x, ln) if tc else (_autocast_once(ln(x)), x)
+
+    def _lin_multi(self, lins, x: Tensor, tc: bool):
+        """[lin(x) for lin in lins]: one GEMM forward, one dgrad, one wgrad on the tensor-core path (gemm.linear_multi)"""
+        return tcg.linear_multi(x, lins) if tc else [lin(x) for lin in lins]
+
     def _lin(self, lin: nn.Linear, x: Tensor, tc: bool, residual: Optional[Tensor] = None) -> Tensor:
         if tc:
             return tcg.linear(x, lin, residual=residual)
@@ -216,8 +224,9 @@ class GraphTransformerBaseBlock(BaseBlock, ABC):
         if not tc:
             return mlp(x) + x
         act = tcg.ACT_CODES[type(mlp[2]).__name__]
-        pre, h = tcg.linear(tcg.layer_norm(x, mlp[0]), mlp[1], act_out=act)
-        return tcg.act_linear(pre, h, mlp[3], act, residual=x)
+        xn, x_skip = tcg.layer_norm_fork(x, mlp[0])
+        pre, h = tcg.linear(xn, mlp[1], act_out=act)
+        return tcg.act_linear(pre, h, mlp[3], act, residual=x_skip)
 
     # -- API compatibility (reference block.py:366-414).  forward() does not use the head all-to-all with a group (it shards
     #    by dst rows and exchanges a halo, see _attend); on one rank these are pure reshapes.
@@ -299,13 +308,11 @@ class GraphTransformerMapperBlock(GraphTransformerBaseBlock):
 
     def forward(self, x: Tuple[Tensor, Tensor], edge_attr: Tensor, edge_index: Tensor, shapes: tuple, batch_size: int,
                 model_comm_group=None, size: Optional[Tuple[int, int]] = None):
-        x_skip = x
         tc = self._tc(x[0])
-        x = (self._ln(self.layer_norm1, x[0], tc), self._ln(self.layer_norm2, x[1], tc))
-        x_r = self._lin(self.lin_self, x[1], tc)
-        query = self._lin(self.lin_query, x[1], tc)
-        key = self._lin(self.lin_key, x[0], tc)
-        value = self._lin(self.lin_value, x[0], tc)
+        (x_src, skip_src), (x_dst, skip_dst) = self._ln_fork(self.layer_norm1, x[0], tc), self._ln_fork(self.layer_norm2, x[1], tc)
+        x_skip = (skip_src, skip_dst)
+        query, x_r = self._lin_multi((self.lin_query, self.lin_self), x_dst, tc)
+        key, value = self._lin_multi((self.lin_key, self.lin_value), x_src, tc)
 
         if model_comm_group is not None:
             assert (model_comm_group.size() == 1 or batch_size == 1), \
@@ -324,13 +331,9 @@ class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
 
     def forward(self, x: Tensor, edge_attr: Tensor, edge_index: Tensor, shapes: tuple, batch_size: int,
                 model_comm_group=None, size: Optional[Tuple[int, int]] = None):
-        x_skip = x
         tc = self._tc(x)
-        x = self._ln(self.layer_norm1, x, tc)
-        x_r = self._lin(self.lin_self, x, tc)
-        query = self._lin(self.lin_query, x, tc)
-        key = self._lin(self.lin_key, x, tc)
-        value = self._lin(self.lin_value, x, tc)
+        x, x_skip = self._ln_fork(self.layer_norm1, x, tc)
+        query, key, value, x_r = self._lin_multi((self.lin_query, self.lin_key, self.lin_value, self.lin_self), x, tc)
 
         if model_comm_group is not None:
             assert (model_comm_group.size() == 1 or batch_size == 1), \

@@ -480,6 +480,13 @@ def run_ours(args):
             model_step = {"ms_per_step": ml["ms_per_step"], "workload": ml["config"]["workload"], "clocks": ml["clocks"],
                           "peak_mem_GB": ml["peak_mem_GB"], "loss": ml["config"]["loss"],
                           "optimizer_steps_before_loss": ml["config"]["optimizer_steps_before_loss"]}
+            try:  # the same step with every activation kept in HBM instead of recomputed (180 GB: no need to checkpoint)
+                nl = run_model(margs, emit=False, recompute=False)
+                model_step["without_activation_checkpointing"] = {"ms_per_step": nl["ms_per_step"], "peak_mem_GB": nl["peak_mem_GB"],
+                                                                  "loss": nl["config"]["loss"]}
+            except Exception as ex:  # noqa: BLE001
+                model_step["without_activation_checkpointing"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+                torch.cuda.empty_cache()
             if os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "anemoi", "models")):
                 try:  # the same model from the unmodified reference blocks, on the same GPU
                     margs.steps = 2
@@ -971,18 +978,25 @@ def run_edgepath(args):
     print(json.dumps(line), flush=True)
 
 
-def run_model(args, emit=True, impl="ours"):
+def run_model(args, emit=True, impl="ours", recompute=None):
     """Report line (not the headline): AIFS-like n320/o96 encoder-processor-decoder training step (BASELINE configs[3]) built
     from this repo's drop-in blocks the way the reference's mappers/processor wire them (mapper.py:245-272,
     processor.py:317-343): node embeddings, trainable edge features (3 geometric + 8 trainable columns), GT mapper block
     n320->o96, 16 GT processor blocks on o96 (8-NN) in 8 checkpointed chunks, GT mapper block o96->n320 (3-NN), output
     extractor; bf16 autocast, fwd + bwd + fused AdamW step, activation checkpointing per mapper / chunk as in
     models/encoder_processor_decoder.py:159-166 and processor.py:73-77."""
-    from torch.utils.checkpoint import checkpoint
+    from torch.utils.checkpoint import checkpoint as _checkpoint
 
     import anemoi_models_b200 as b2
     from anemoi_models_b200 import synthetic as S
     from anemoi_models_b200.graph import get_csr
+
+    # --model-recompute off: the same step WITHOUT activation checkpointing (numerically the same training step; the reference
+    # checkpoints unconditionally because the model was sized for 40-80 GB GPUs -- at 180 GB the activations of this model fit)
+    recompute = (args.model_recompute != "off") if recompute is None else recompute
+
+    def checkpoint(fn, *a, use_reentrant=False):
+        return _checkpoint(fn, *a, use_reentrant=use_reentrant) if recompute else fn(*a)
 
     if impl == "reference":
         # comparator: the SAME model wired from the UNMODIFIED reference blocks (baseline/_ref, PyG op sequence through the shim as
@@ -1101,8 +1115,10 @@ def run_model(args, emit=True, impl="ours"):
             "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"AIFS-like enc-proc-dec step: GT mapper n320->o96 (E={ei['enc'].shape[1]}), {layers} GT processor layers on "
                                    f"o96 8-NN (E={ei['proc'].shape[1]}) in {chunks} checkpointed chunks, GT mapper o96->n320 3-NN "
-                                   f"(E={ei['dec'].shape[1]}); hidden {hid}, {heads} heads, MLP x4, bf16 autocast, fwd+bwd (with "
-                                   f"checkpoint recompute) + fused AdamW; {nparams / 1e6:.0f} M parameters (report line)",
+                                   f"(E={ei['dec'].shape[1]}); hidden {hid}, {heads} heads, MLP x4, bf16 autocast, fwd+bwd ("
+                                   + ("with checkpoint recompute" if recompute else "NO activation checkpointing: every activation kept")
+                                   + f") + fused AdamW; {nparams / 1e6:.0f} M parameters (report line)",
+                       "activation_checkpointing": bool(recompute),
                        "conv_edges_per_step": int(etot), "loss": float(loss.detach()), "optimizer_steps_before_loss": 3 + n},
             "clocks": sampler.summary(), "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2**30, 1),
             "kernel_breakdown": breakdown}
@@ -1185,6 +1201,9 @@ def main():
     ap.add_argument("--model-layers", type=int, default=16)
     ap.add_argument("--model-impl", default="ours", choices=["ours", "reference"],
                     help="model workload: this repo's blocks, or the unmodified reference blocks from baseline/_ref on the same GPU")
+    ap.add_argument("--model-recompute", default="on", choices=["on", "off"],
+                    help="model workload: activation checkpointing per mapper / processor chunk as the reference wires it (on), or every "
+                         "activation kept in HBM (off)")
     ap.add_argument("--profile", action="store_true", help="model workload: add a per-kernel device-time breakdown of one step")
     ap.add_argument("--workload", default="encoder", choices=["encoder", "decoder", "processor", "graphconv", "model", "edgepath", "o1280", "config1-enc", "config1-proc", "config1-dec"],
                     help="encoder = BASELINE configs[1] (the headline); the others are extra report lines")

@@ -277,6 +277,7 @@ int ab2_gtconv_fwd_bwd_host_streamed(const void* q_host, const void* k_host, con
  * act: 0 SiLU, 1 GELU(erf), 2 ReLU, 3 identity.  Requirements: N % 8 == 0, lda / ldb multiples of 8, 16-byte aligned pointers,
  * seg_cols % 32 == 0 (0 = one output).  splits > 1 (split-K): plain single fp32/bf16 output, fp32 partials in `workspace`
  * (ab2_gemm_workspace_bytes), summed in a fixed order by a second kernel -- deterministic.
+ * ab2_version() >= 101: the descriptor ends with a_seg / a_seg_len (segmented A operand).
  * ------------------------------------------------------------------------------------------------- */
 typedef struct ab2_gemm {
   int64_t M, N, K;
@@ -303,6 +304,12 @@ typedef struct ab2_gemm {
   const void* gather_b;
   const int64_t* gather_b_idx;
   int64_t ld_gather;
+  /* A given as up to 4 tensors of equal shape and row stride lda (a, a_seg[0..2]), cut every a_seg_len elements along K
+   * (K-major A: the fused q|k|v|self dgrad reads dq, dk, dv, dself where autograd left them) or along M (MN-major A: the
+   * fused wgrad).  a_seg_len = 0: A is the single tensor `a`.  a_seg_len must be a multiple of 64 (K-major) / 256 (MN-major)
+   * and divide the segmented extent into at most 4 pieces. */
+  const void* a_seg[3];
+  int64_t a_seg_len;
 } ab2_gemm;
 size_t ab2_gemm_workspace_bytes(const ab2_gemm* d);
 int ab2_gemm_bf16(const ab2_gemm* d, void* workspace, size_t workspace_bytes, void* stream);

@@ -38,7 +38,7 @@ def test_ctypes_signatures_cover_the_header():
 
     assert sorted(_lib.SIGNATURES) == declared_symbols()
     L = _lib.lib()
-    assert L.ab2_version() >= 100
+    assert L.ab2_version() >= 101
     # host-only helpers are callable without a GPU
     assert L.ab2_gtconv_bwd_workspace_bytes(1000, 16) == 1000 * 16 * 8
     assert L.ab2_csr_workspace_bytes(10, 100, 50) > 0
@@ -67,7 +67,7 @@ def test_gemm_descriptor_errors_without_a_gpu():
     from anemoi_models_b200 import _lib
 
     L = _lib.lib()
-    assert C.sizeof(_lib.Gemm) == 8 * 3 + 8 * 4 + 8 + 8 * 4 + 8 + 8 + 8 * 4 + 8 * 3 + 8 + 8 + 8 + 8 * 5  # natural alignment, no padding surprises
+    assert C.sizeof(_lib.Gemm) == 8 * 3 + 8 * 4 + 8 + 8 * 4 + 8 + 8 + 8 * 4 + 8 * 3 + 8 + 8 + 8 + 8 * 5 + 8 * 3 + 8  # natural alignment, no padding surprises
     d = _lib.Gemm()
     assert L.ab2_gemm_workspace_bytes(C.byref(d)) == 0
     d.M, d.N, d.K = 64, 60, 64  # N % 8 != 0
@@ -81,6 +81,11 @@ def test_gemm_descriptor_errors_without_a_gpu():
     assert L.ab2_gemm_workspace_bytes(C.byref(d)) == 4 * 64 * 64 * 4
     d.bias = 16  # split-K takes a plain single output only
     assert L.ab2_gemm_bf16(C.byref(d), None, 0, None) == _lib.AB2_ERR_INVALID and b"split-K" in L.ab2_last_error()
+    d.bias, d.splits = 0, 1
+    d.a_seg_len = 40  # segmented A: K-major pieces must be whole 64-element k-blocks, and every piece needs its tensor
+    assert L.ab2_gemm_bf16(C.byref(d), None, 0, None) == _lib.AB2_ERR_INVALID and b"a_seg_len" in L.ab2_last_error()
+    d.a_seg_len = 512
+    assert L.ab2_gemm_bf16(C.byref(d), None, 0, None) == _lib.AB2_ERR_INVALID and b"segment 1 is null" in L.ab2_last_error()
     d.M = 0
     assert L.ab2_gemm_bf16(C.byref(d), None, 0, None) == 0  # nothing to do
     assert L.ab2_ln_parts() > 0

@@ -87,6 +87,75 @@ def test_gemm_epilogues():
     assert rel_err(torch.cat(outs, 1), acc + bias) < 1e-2
 
 
+@pytest.mark.parametrize("nseg", [2, 3, 4])
+def test_segmented_a_operand_matches_the_concatenated_one(nseg):
+    """A given as 2-4 separate tensors (the q | k | v | self gradients where autograd left them): K-major segments along the
+    contraction (fused dgrad) and MN-major segments along the output rows (fused split-K wgrad) give the same result, bit for
+    bit, as the same GEMM on the concatenated operand."""
+    from anemoi_models_b200 import gemm as G
+
+    torch.manual_seed(nseg)
+    M, Nw, Kin = 1000, 256, 200  # rows, width of one layer, input width
+    dys = [torch.randn(M, Nw, device=DEV).bfloat16() for _ in range(nseg)]
+    w = torch.randn(nseg * Nw, Kin, device=DEV).bfloat16()
+    x = torch.randn(M, Kin, device=DEV).bfloat16()
+    cat = torch.cat(dys, dim=1)
+    dx_seg = G.gemm(dys[0], w, M, Kin, nseg * Nw, b_mn=True, a_segs=dys[1:], a_seg_len=Nw)
+    dx_cat = G.gemm(cat, w, M, Kin, nseg * Nw, b_mn=True)
+    assert torch.equal(dx_seg, dx_cat)
+    assert rel_err(dx_seg, cat.float() @ w.float()) < 1e-2
+    for splits in (1, 3):
+        dw_seg = G.gemm(dys[0], x, nseg * Nw, Kin, M, a_mn=True, b_mn=True, out_dtype=torch.float32, splits=splits, a_segs=dys[1:],
+                        a_seg_len=Nw)
+        dw_cat = G.gemm(cat, x, nseg * Nw, Kin, M, a_mn=True, b_mn=True, out_dtype=torch.float32, splits=splits)
+        assert torch.equal(dw_seg, dw_cat)
+        assert rel_err(dw_seg, cat.float().t() @ x.float()) < 1e-4
+    with pytest.raises(ValueError):  # segment width must be a multiple of 64 (K-major)
+        G.gemm(dys[0][:, :40].contiguous(), w, M, Kin, 80, b_mn=True, a_segs=[dys[1][:, :40].contiguous()], a_seg_len=40)
+    with pytest.raises(ValueError):  # MN-major segments must be whole 256-row tiles
+        G.gemm(dys[0][:, :128].contiguous(), x, 256, Kin, M, a_mn=True, b_mn=True, a_segs=[dys[1][:, :128].contiguous()], a_seg_len=128)
+
+
+def test_linear_multi_and_layernorm_fork_autograd():
+    """The GT block's attention input: (LayerNorm(x), skip) fork and q | k | v | self as one GEMM forward / one dgrad / one
+    wgrad, against the same layers run one by one through torch fp32 on bf16-rounded parameters."""
+    from anemoi_models_b200 import gemm as G
+
+    torch.manual_seed(0)
+    M, D = 777, 256
+    ln = torch.nn.LayerNorm(D).to(DEV)
+    lins = [torch.nn.Linear(D, D).to(DEV) for _ in range(4)]
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.normal_()
+    x = torch.randn(M, D, device=DEV)
+    gs = [torch.randn(M, D, device=DEV).bfloat16() for _ in range(4)] + [torch.randn(M, D, device=DEV)]
+    mods = [ln] + lins
+    for m in mods:
+        m.zero_grad()
+    x1 = x.clone().requires_grad_(True)
+    xn, skip = G.layer_norm_fork(x1, ln)
+    ys = G.linear_multi(xn, lins)
+    torch.autograd.backward(list(ys) + [skip], gs)
+    got = list(ys) + [x1.grad] + [p.grad.clone() for m in mods for p in m.parameters()]
+    for m in mods:
+        m.zero_grad()
+    xr = x.clone().requires_grad_(True)
+    xnr = ln(xr)
+    yr = [l(xnr) for l in lins]  # plain fp32 modules: the bf16 rounding of LN(x) and of the weights is inside the tolerance
+    torch.autograd.backward(yr + [xr], [g.float() for g in gs])
+    ref = yr + [xr.grad] + [p.grad for m in mods for p in m.parameters()]
+    for i, (a, b) in enumerate(zip(got, ref)):
+        assert rel_err(a, b) < 2e-2 and rel_l2(a, b) < 2e-2, (i, rel_err(a, b), rel_l2(a, b))
+    # a second call gives bit-identical gradients (fixed-order split-K partial sums, no atomics)
+    for m in mods:
+        m.zero_grad()
+    x2 = x.clone().requires_grad_(True)
+    xn2, skip2 = G.layer_norm_fork(x2, ln)
+    torch.autograd.backward(list(G.linear_multi(xn2, lins)) + [skip2], gs)
+    assert torch.equal(x2.grad, got[4]) and torch.equal(lins[2].weight.grad, got[5 + 2 + 2 * 2])
+
+
 def test_gemm_argument_errors():
     from anemoi_models_b200 import gemm as G
 

@@ -339,10 +339,13 @@ def test_encoder_work_balanced_bounds_even_out_the_weak_scaling_shards():
 
 def _emulated_gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, out=None, seg_cols=0, out_dtype=torch.bfloat16,
                    bias=None, row_scale=None, row_shift=None, col_vec=None, act=3, pre_out=None, dact_pre=None, residual=None,
-                   splits=1, gather=None):
+                   splits=1, gather=None, a_segs=None, a_seg_len=0):
     """torch restatement of what `ab2_gemm_bf16` computes (include/anemoi_b200.h), operand layouts and epilogue order included"""
     F = torch.nn.functional
     fn = {0: F.silu, 1: F.gelu, 2: F.relu}
+    if a_segs:  # segmented A: pieces of a_seg_len along K (K-major) or along M (MN-major) -- the inner dimension either way
+        assert all(t.shape == a.shape and t.shape[1] == a_seg_len for t in a_segs)
+        a = torch.cat([a, *a_segs], dim=1)
     A = (a.float().t() if a_mn else a.float())[:M, :K]
     B = (b.float().t() if b_mn else b.float())[:N, :K]
     acc = A @ B.t()
@@ -388,10 +391,13 @@ def test_tensor_core_autograd_glue_against_torch_on_the_cpu(monkeypatch):
         rstd = (var + eps).rsqrt()
         return (((x2.float() - mean[:, None]) * rstd[:, None]) * gamma + beta).to(out_dtype), mean, rstd
 
-    def ln_bwd(g2, x2, gamma, mean, rstd):
+    def ln_bwd(g2, x2, gamma, mean, rstd, add=None):
         xh = (x2.float() - mean[:, None]) * rstd[:, None]
         gg = g2.float() * gamma
         dx = rstd[:, None] * (gg - gg.mean(1, keepdim=True) - xh * (gg * xh).mean(1, keepdim=True))
+        if add is not None:
+            assert add.dtype == x2.dtype and add.shape == x2.shape
+            dx = dx + add.float()
         return dx.to(x2.dtype), (g2.float() * xh).sum(0), g2.float().sum(0)
 
     def seg(g2, plan, want_dst, want_src):
@@ -434,6 +440,33 @@ def test_tensor_core_autograd_glue_against_torch_on_the_cpu(monkeypatch):
         ref = [yr, xr.grad, ln.weight.grad, ln.bias.grad, l1.weight.grad, l1.bias.grad, l2.weight.grad, l2.bias.grad]
         for i, (a_, b_) in enumerate(zip(got, ref)):
             close(a_, b_, (name, i))
+    # the GT block's pre-norm attention input: (LN(x), skip) fork + q | k | v | self as ONE segmented GEMM each way
+    Dm = 256  # linear_multi fuses layers whose width is a multiple of 256
+    lnm = torch.nn.LayerNorm(Dm)
+    lins = [torch.nn.Linear(Dm, Dm) for _ in range(4)]
+    xm, gm = torch.randn(M, Dm), [torch.randn(M, Dm) for _ in range(5)]
+
+    def run(fused):
+        for m in [lnm] + lins:
+            m.zero_grad()
+        xi = xm.clone().requires_grad_(True)
+        if fused:
+            xn, skip = G.layer_norm_fork(xi, lnm)
+            ys = G.linear_multi(xn, lins)
+            assert len(ys) == 4 and G._MultiLinearFn.__name__ in type(ys[0].grad_fn).__name__
+        else:
+            xn, skip = lnm(xi), xi
+            ys = [l(xn) for l in lins]
+        torch.autograd.backward(list(ys) + [skip], gm)
+        return list(ys) + [xi.grad] + [p.grad.clone() for m in [lnm] + lins for p in m.parameters()]
+
+    for i, (a_, b_) in enumerate(zip(run(True), run(False))):
+        close(a_, b_, ("linear_multi", i))
+    two = G.linear_multi(G.layer_norm(xm, lnm), lins[:2])  # the mapper's pairs (k | v on src, q | self on dst)
+    close(two[1], lins[1](lnm(xm)), "linear_multi pair")
+    odd = [torch.nn.Linear(D, Hd) for _ in range(2)]  # widths the segmented kernel does not take: one GEMM per layer
+    assert all("_LinearFn" in type(y.grad_fn).__name__ for y in G.linear_multi(x, odd))
+
     # GraphConv first layer on the split weight: pre = e We^T + pi[dst] + pj[src]
     ns, nd, E = 9, 7, 40
     ei = torch.stack([torch.randint(0, ns, (E,)), torch.randint(0, nd, (E,))])
