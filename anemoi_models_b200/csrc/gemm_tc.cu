@@ -142,6 +142,21 @@ __device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap*
                "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
                : "memory");
 }
+// one lane of the (converged) warp; the warp keeps walking the loops together, so loop counters, addresses and descriptors stay
+// warp-uniform (uniform registers) -- with the loops inside `if (lane == 0)` ptxas treated every tcgen05 / TMA operand as
+// divergent and wrapped each instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall: ~120 issue slots per k-block on
+// the MMA warp, as long as the four MMAs of the k-block take (ncu source view, profiles/r02/SUMMARY.md)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -423,8 +438,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
   const int num_tiles = tiles_mn * g.splits;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+    // ===== TMA producer (whole warp walks the loop, one elected lane issues) =====
+    {
       uint32_t c = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         const int split = t / tiles_mn, r = t % tiles_mn;
@@ -435,6 +450,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
           mbar_wait(empty(s), ((c / S) & 1u) ^ 1u);
           uint32_t fb = full(s);
           if constexpr (CG == 2) fb = mapa(fb, 0);
+          if (!elect_one()) continue;
           auto load = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1) {
             if constexpr (CG == 2) tma_load_2d_cg2(dst, m, fb, c0, c1); else tma_load_2d(dst, m, fb, c0, c1);
           };
@@ -464,13 +480,20 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread of the leader CTA) =====
-    if (lane == 0 && cta == 0) {
+    // ===== MMA issuer: warp 1 of the leader CTA walks the loops converged, one elected lane issues =====
+    if (cta == 0) {
       // instruction descriptor: D fp32, A / B bf16, operand majors, N >> 3 at bit 17, M >> 4 at bit 24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-      constexpr uint32_t kAStep = A_MN ? (UMMA_K * 128) : (UMMA_K * 2);  // bytes per UMMA_K along the contraction
-      constexpr uint32_t kBStep = B_MN ? (UMMA_K * 128) : (UMMA_K * 2);
+      constexpr uint32_t kAStep = (A_MN ? (UMMA_K * 128) : (UMMA_K * 2)) >> 4;  // descriptor address units per UMMA_K
+      constexpr uint32_t kBStep = (B_MN ? (UMMA_K * 128) : (UMMA_K * 2)) >> 4;
+      // shared-memory descriptors: only the 14-bit start-address field (low word) changes with stage and k step, and it cannot
+      // carry out of its field (shared memory ends below 256 KB), so the per-MMA work is one 32-bit add per operand
+      const uint64_t da0 = A_MN ? smem_desc(sA(0), g.mn_lbo, g.mn_sbo) : smem_desc(sA(0), g.k_lbo, g.k_sbo);
+      const uint64_t db0 = B_MN ? smem_desc(sB(0), g.mn_lbo, g.mn_sbo) : smem_desc(sB(0), g.k_lbo, g.k_sbo);
+      const uint32_t da_hi = (uint32_t)(da0 >> 32), db_hi = (uint32_t)(db0 >> 32);
+      const uint32_t da_lo0 = (uint32_t)da0, db_lo0 = (uint32_t)db0;
+      auto desc64 = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
       uint32_t c = 0, it = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
         const int split = t / tiles_mn;
@@ -480,21 +503,25 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * BN;
         for (int kb = kb0; kb < kb1; ++kb, ++c) {
-          const int s = c % S;
+          const uint32_t s = c % S;
           mbar_wait(full(s), (c / S) & 1u);
           tc_fence_after();
-          const uint64_t da = A_MN ? smem_desc(sA(s), g.mn_lbo, g.mn_sbo) : smem_desc(sA(s), g.k_lbo, g.k_sbo);
-          const uint64_t db = B_MN ? smem_desc(sB(s), g.mn_lbo, g.mn_sbo) : smem_desc(sB(s), g.k_lbo, g.k_sbo);
+          if (elect_one()) {
+            const uint32_t soff = (s * (uint32_t)C::kStageBytes) >> 4;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t dak = da + (uint64_t)((k * kAStep) >> 4), dbk = db + (uint64_t)((k * kBStep) >> 4);
-            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-            if constexpr (CG == 2) tc_mma_cg2(d_tmem, dak, dbk, idesc, acc); else tc_mma(d_tmem, dak, dbk, idesc, acc);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t dak = desc64(da_hi, da_lo0 + soff + k * kAStep), dbk = desc64(db_hi, db_lo0 + soff + k * kBStep);
+              const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+              if constexpr (CG == 2) tc_mma_cg2(d_tmem, dak, dbk, idesc, acc); else tc_mma(d_tmem, dak, dbk, idesc, acc);
+            }
+            // stage reusable (in both CTAs) once these MMAs have read it
+            if constexpr (CG == 2) tc_commit_cg2(empty(s)); else tc_commit(empty(s));
+            if (kb == kb1 - 1) {  // accumulator complete
+              if constexpr (CG == 2) tc_commit_cg2(tfull(a)); else tc_commit(tfull(a));
+            }
           }
-          // stage reusable (in both CTAs) once these MMAs have read it
-          if constexpr (CG == 2) tc_commit_cg2(empty(s)); else tc_commit(empty(s));
+          __syncwarp();
         }
-        if constexpr (CG == 2) tc_commit_cg2(tfull(a)); else tc_commit(tfull(a));  // accumulator complete
       }
       if constexpr (CG == 2) {
         // the peer's epilogue arrives on THIS CTA's tmem_empty barriers: see its last arrivals in before leaving
