@@ -9,6 +9,9 @@
 // Backward: dx = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat)); dgamma / dbeta are column sums accumulated in
 // registers per CTA over a fixed slice of the rows, written as partials and reduced by a second kernel in a fixed order
 // (deterministic, no atomics).
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace ab2 {
@@ -195,6 +198,96 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_bwd_kernel(const TG* 
   }
 }
 
+// backward, second layout (the default): thread t of the CTA owns COLUMNS [8 t, 8 t + 8) for every row of the CTA's slice, so the
+// dgamma / dbeta accumulators are 16 registers (not 64 per warp-row lane), ~7 CTAs of D / 8 threads are resident per SM, and a
+// thread has the loads of R rows (g, x and the residual-branch gradient) in flight before it needs any of them.  The row sums
+// s1, s2 cross the CTA's warps through a double-buffered shared-memory slot: one __syncthreads per R rows.
+// Measured on the AIFS-like step (38 calls, 23 GB): warp-per-row kernel above 14.9 ms (1.5 TB/s); see profiles/r02/SUMMARY.md.
+template <typename TG, typename TX, int R>
+__global__ void __launch_bounds__(256) layernorm_bwd_cols_kernel(const TG* __restrict__ g, const TX* __restrict__ x,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                                 const float* __restrict__ rstd, long long M, int D,
+                                                                 const TX* __restrict__ add, TX* __restrict__ dx,
+                                                                 float* __restrict__ partial) {
+  __shared__ __align__(16) float red[2][R][2][8];  // [buffer][row][s1 | s2][warp]
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int col = tid * 8;
+  const bool active = col < D;  // blockDim = D / 8 rounded up to whole warps
+  const float inv_d = 1.f / (float)D;
+  const long long per = (M + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * per, r1 = min(r0 + per, M);
+  float gm[8], dg[8], db[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) gm[u] = dg[u] = db[u] = 0.f;
+  if (active) load_row_vec<float>(gamma + col, gm);
+  for (int i = tid; i < 2 * R * 2 * 8; i += blockDim.x) (&red[0][0][0][0])[i] = 0.f;  // slots of warps that do not exist stay zero
+  __syncthreads();
+  int buf = 0;
+  for (long long row = r0; row < r1; row += R, buf ^= 1) {
+    float gv[R][8], xh[R][8], av[R][8], rs[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {  // all loads of the R rows first
+      const long long rr = row + r;
+      const bool ok = active && rr < r1;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) gv[r][u] = xh[r][u] = av[r][u] = 0.f;
+      rs[r] = 0.f;
+      if (ok) {
+        load_row_vec<TG>(g + rr * D + col, gv[r]);
+        load_row_vec<TX>(x + rr * D + col, xh[r]);
+        if (add != nullptr) load_row_vec<TX>(add + rr * D + col, av[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long rr = row + r;
+      float s1 = 0.f, s2 = 0.f;
+      if (active && rr < r1) {
+        const float mu = mean[rr];
+        rs[r] = rstd[rr];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          xh[r][u] = (xh[r][u] - mu) * rs[r];
+          dg[u] += gv[r][u] * xh[r][u];
+          db[u] += gv[r][u];
+          gv[r][u] *= gm[u];
+          s1 += gv[r][u];
+          s2 += gv[r][u] * xh[r][u];
+        }
+      }
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane == 0) {
+        red[buf][r][0][w] = s1;
+        red[buf][r][1][w] = s2;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long rr = row + r;
+      const float4 a0 = *reinterpret_cast<const float4*>(&red[buf][r][0][0]), a1 = *reinterpret_cast<const float4*>(&red[buf][r][0][4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&red[buf][r][1][0]), b1 = *reinterpret_cast<const float4*>(&red[buf][r][1][4]);
+      const float s1 = (((a0.x + a0.y) + (a0.z + a0.w)) + ((a1.x + a1.y) + (a1.z + a1.w))) * inv_d;
+      const float s2 = (((b0.x + b0.y) + (b0.z + b0.w)) + ((b1.x + b1.y) + (b1.z + b1.w))) * inv_d;
+      if (active && rr < r1) {
+        float o[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) o[u] = rs[r] * (gv[r][u] - s1 - xh[r][u] * s2) + av[r][u];
+        store_row_vec<TX>(dx + rr * D + col, o);
+      }
+    }
+  }
+  if (active) {
+    float* p0 = partial + (size_t)blockIdx.x * 2 * D + col;
+    float lo[4] = {dg[0], dg[1], dg[2], dg[3]}, hi[4] = {dg[4], dg[5], dg[6], dg[7]};
+    *reinterpret_cast<float4*>(p0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<float4*>(p0 + 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<float4*>(p0 + D) = make_float4(db[0], db[1], db[2], db[3]);
+    *reinterpret_cast<float4*>(p0 + D + 4) = make_float4(db[4], db[5], db[6], db[7]);
+  }
+}
+
 // out[c] = sum_p partial[p][c], c < n, in a fixed order: block = 32 columns x 32 part-lanes; lane y sums the parts p = y, y + 32, ...
 // (coalesced 128-byte reads), then the 32 lane sums of a column are added in lane order
 __global__ void __launch_bounds__(1024) partial_reduce_kernel(const float* __restrict__ partial, int parts, int n, float* __restrict__ out) {
@@ -264,6 +357,18 @@ static int ln_fwd_dispatch(const void* x, const float* gamma, const float* beta,
 template <typename TG, typename TX>
 static int ln_bwd_dispatch(const void* g, const void* x, const float* gamma, const float* mean, const float* rstd, long long M, int D,
                            const void* add, void* dx, float* partial, cudaStream_t st) {
+  // AB2_LN_BWD=rows keeps the warp-per-row kernel (A/B runs); the column-owner kernel takes D <= 2048
+  static const bool by_rows = [] {
+    const char* e = getenv("AB2_LN_BWD");
+    return e != nullptr && strcmp(e, "rows") == 0;
+  }();
+  if (!by_rows && D <= 2048) {
+    const int threads = ((D / 8 + 31) / 32) * 32;
+    layernorm_bwd_cols_kernel<TG, TX, 2><<<kLnParts, threads, 0, st>>>((const TG*)g, (const TX*)x, gamma, mean, rstd, M, D,
+                                                                        (const TX*)add, (TX*)dx, partial);
+    AB2_LAUNCH_OK("layernorm_bwd_cols_kernel");
+    return AB2_OK;
+  }
   const int vpl = (D / 8 + 31) / 32;
   const size_t smem = (size_t)kLnWarps * 2 * D * sizeof(float);
 #define AB2_LN_BWD(V)                                                                                                       \

@@ -34,6 +34,9 @@ PERF = {
     "perf_kv": (542080, 2048, 1024, 0, 0, 1, "bias,seg"),
     "perf_q": (40320, 2048, 1024, 0, 0, 1, "bias,seg"),
     "perf_proj": (40320, 1024, 1024, 0, 0, 1, "bias,res"),
+    "perf_proj_bias": (40320, 1024, 1024, 0, 0, 1, "bias"),
+    "perf_proj_plain": (40320, 1024, 1024, 0, 0, 1, ""),
+    "perf_proj_res32": (40320, 1024, 1024, 0, 0, 1, "bias,res32"),
     "perf_mlp1": (40320, 4096, 1024, 0, 0, 1, "bias,gelu,pre"),
     "perf_mlp2": (40320, 1024, 4096, 0, 0, 1, "bias,res"),
     "perf_dgrad": (542080, 1024, 2048, 0, 1, 1, ""),

@@ -169,7 +169,7 @@ def test_gemm_argument_errors():
 
 
 @pytest.mark.parametrize("xd,yd", [(torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16), (torch.float32, torch.float32)])
-@pytest.mark.parametrize("M,D", [(1000, 1024), (77, 256), (5, 8), (300, 520)])
+@pytest.mark.parametrize("M,D", [(1000, 1024), (77, 256), (5, 8), (300, 520), (123, 2048), (2500, 1024)])
 def test_layernorm_forward_backward(M, D, xd, yd):
     from anemoi_models_b200 import gemm as G
 
@@ -198,6 +198,31 @@ def test_layernorm_forward_backward(M, D, xd, yd):
     x2 = x.detach().clone().requires_grad_(True)
     G.layer_norm(x2, ln, out_dtype=yd).backward(g.to(yd))
     assert torch.equal(x2.grad, x1.grad)
+
+
+def test_layernorm_backward_warp_per_row_variant_in_a_subprocess():
+    """AB2_LN_BWD=rows keeps the first backward kernel (one warp per row, accumulators for all of D in registers) for A/B
+    runs; the switch is read once per process, so the kept kernel is checked in a child process."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import torch, torch.nn.functional as F\n"
+        "from anemoi_models_b200 import gemm as G\n"
+        "torch.manual_seed(0)\n"
+        "x = torch.randn(777, 1024, device='cuda'); g = torch.randn(777, 1024, device='cuda')\n"
+        "ln = torch.nn.LayerNorm(1024).to('cuda')\n"
+        "xr = x.clone().requires_grad_(True); F.layer_norm(xr, (1024,), ln.weight, ln.bias, ln.eps).backward(g)\n"
+        "rw = ln.weight.grad.clone(); ln.zero_grad()\n"
+        "x1 = x.clone().requires_grad_(True); G.layer_norm(x1, ln, out_dtype=torch.float32).backward(g)\n"
+        "e1 = float((x1.grad - xr.grad).abs().max() / xr.grad.abs().max()); e2 = float((ln.weight.grad - rw).abs().max() / rw.abs().max())\n"
+        "assert e1 < 1e-5 and e2 < 1e-5, (e1, e2)\n"
+        "print('ok')\n")
+    env = dict(os.environ, AB2_LN_BWD="rows")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env, cwd=root)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-800:]
 
 
 def test_colsum():
