@@ -376,6 +376,27 @@ __device__ __forceinline__ void store_chunk_packed(uint32_t patch, int lane, con
   }
   __syncwarp();
 }
+// global memory -> one ROW per lane, for the per-element inputs of the epilogue (residual, saved pre-activation, gathered node
+// rows): 32 rows x 64 bytes, row r at `row_ptr` of lane r (0 = no such row).  With every lane loading ITS row, one load
+// instruction touched 32 different 128-byte lines for 16 bytes each and the uncoalesced requests, not the latency, set the cost
+// (projection shape: +30 us for a bf16 residual, +67 us for an fp32 one, profiles/r02/gemm_probe_proj_r02y.jsonl); here each
+// instruction reads 8 rows x 64 contiguous bytes and the rows are handed out through the warp's shared-memory patch.
+__device__ __forceinline__ void load_chunk_rows(uint32_t patch, int lane, const void* row_ptr, int bytes_left, uint4 (&out)[4]) {
+  const int c16 = lane & 3, rsub = lane >> 2;
+  const unsigned long long mine = reinterpret_cast<unsigned long long>(row_ptr);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + rsub;
+    const unsigned long long p = __shfl_sync(0xffffffffu, mine, r);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (p != 0ull && c16 * 16 < bytes_left) v = ldg16_keep(reinterpret_cast<const char*>(p) + c16 * 16);
+    sts16(patch + r * kPatchStride + c16 * 16, v);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) out[j] = lds16(patch + lane * kPatchStride + j * 16);
+  __syncwarp();
+}
 __device__ __forceinline__ void pack_chunk(const float (&f)[32], uint32_t (&pk)[16]) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
@@ -600,32 +621,29 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          if (ep.gather[i] != nullptr && row_ok) {
-            const __nv_bfloat16* gp = ep.gather[i] + grow[i] * ep.ld_gather + col0;
+          if (ep.gather[i] != nullptr) {  // warp-uniform
+            uint4 rows[4];
+            load_chunk_rows(patch, lane, row_ok ? ep.gather[i] + grow[i] * ep.ld_gather + col0 : nullptr, cols_left * 2, rows);
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              if (j < cols_left) {
-                float p[8];
-                unpack<__nv_bfloat16>(ldg16_keep(gp + j), p);
+              float p[8];
+              unpack<__nv_bfloat16>(rows[j / 8], p);  // zeros beyond the matrix
 #pragma unroll
-                for (int u = 0; u < 8; u += 2) add_pair(f[j + u], f[j + u + 1], p[u], p[u + 1]);
-              }
+              for (int u = 0; u < 8; u += 2) add_pair(f[j + u], f[j + u + 1], p[u], p[u + 1]);
             }
           }
         }
         if (ep.dact_pre != nullptr) {
-          if (row_ok) {
-            const __nv_bfloat16* pp = reinterpret_cast<const __nv_bfloat16*>(ep.dact_pre) + (size_t)row * g.N + col0;
+          uint4 rows[4];
+          load_chunk_rows(patch, lane, row_ok ? reinterpret_cast<const __nv_bfloat16*>(ep.dact_pre) + (size_t)row * g.N + col0 : nullptr,
+                          cols_left * 2, rows);
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (j < cols_left) {
-                float p[8];
-                unpack<__nv_bfloat16>(ldg16_keep(pp + j), p);
-                if (ep.act == 0) act_grad_mul8<0>(f, j, p);
-                else if (ep.act == 1) act_grad_mul8<1>(f, j, p);
-                else if (ep.act == 2) act_grad_mul8<2>(f, j, p);
-              }
-            }
+          for (int j = 0; j < 32; j += 8) {
+            float p[8];
+            unpack<__nv_bfloat16>(rows[j / 8], p);
+            if (ep.act == 0) act_grad_mul8<0>(f, j, p);
+            else if (ep.act == 1) act_grad_mul8<1>(f, j, p);
+            else if (ep.act == 2) act_grad_mul8<2>(f, j, p);
           }
         } else if (ep.act != 3) {
           if (ep.pre_out != nullptr) {
@@ -642,28 +660,32 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
           }
           act_chunk_rt(f, ep.act);
         }
-        if (ep.residual != nullptr && row_ok) {
-          if (ep.res_f32) {
+        if (ep.residual != nullptr) {
+          if (ep.res_f32) {  // 32 fp32 columns = two 64-byte halves
             const float* rp = reinterpret_cast<const float*>(ep.residual) + (size_t)row * ep.ld_res + col0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (j < cols_left) {
+            for (int h = 0; h < 2; ++h) {
+              uint4 rows[4];
+              load_chunk_rows(patch, lane, row_ok ? rp + 16 * h : nullptr, (cols_left - 16 * h) * 4, rows);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
                 float p[4];
-                unpack<float>(ldg16_keep(rp + j), p);
-                add_pair(f[j], f[j + 1], p[0], p[1]);
-                add_pair(f[j + 2], f[j + 3], p[2], p[3]);
+                unpack<float>(rows[j], p);
+                add_pair(f[16 * h + 4 * j], f[16 * h + 4 * j + 1], p[0], p[1]);
+                add_pair(f[16 * h + 4 * j + 2], f[16 * h + 4 * j + 3], p[2], p[3]);
               }
             }
           } else {
-            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (size_t)row * ep.ld_res + col0;
+            uint4 rows[4];
+            load_chunk_rows(patch, lane,
+                            row_ok ? reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (size_t)row * ep.ld_res + col0 : nullptr,
+                            cols_left * 2, rows);
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              if (j < cols_left) {
-                float p[8];
-                unpack<__nv_bfloat16>(ldg16_keep(rp + j), p);
+              float p[8];
+              unpack<__nv_bfloat16>(rows[j / 8], p);
 #pragma unroll
-                for (int u = 0; u < 8; u += 2) add_pair(f[j + u], f[j + u + 1], p[u], p[u + 1]);
-              }
+              for (int u = 0; u < 8; u += 2) add_pair(f[j + u], f[j + u + 1], p[u], p[u + 1]);
             }
           }
         }

@@ -9,6 +9,7 @@
 // Backward: dx = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat)); dgamma / dbeta are column sums accumulated in
 // registers per CTA over a fixed slice of the rows, written as partials and reduced by a second kernel in a fixed order
 // (deterministic, no atomics).
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -356,7 +357,8 @@ static int ln_fwd_dispatch(const void* x, const float* gamma, const float* beta,
 
 template <typename TG, typename TX>
 static int ln_bwd_dispatch(const void* g, const void* x, const float* gamma, const float* mean, const float* rstd, long long M, int D,
-                           const void* add, void* dx, float* partial, cudaStream_t st) {
+                           const void* add, void* dx, float* partial, int* parts_used, cudaStream_t st) {
+  *parts_used = kLnParts;
   // AB2_LN_BWD=rows keeps the warp-per-row kernel (A/B runs); the column-owner kernel takes D <= 2048
   static const bool by_rows = [] {
     const char* e = getenv("AB2_LN_BWD");
@@ -364,8 +366,12 @@ static int ln_bwd_dispatch(const void* g, const void* x, const float* gamma, con
   }();
   if (!by_rows && D <= 2048) {
     const int threads = ((D / 8 + 31) / 32) * 32;
-    layernorm_bwd_cols_kernel<TG, TX, 2><<<kLnParts, threads, 0, st>>>((const TG*)g, (const TX*)x, gamma, mean, rstd, M, D,
-                                                                        (const TX*)add, (TX*)dx, partial);
+    // one wave: as many CTAs as are resident at once (888 CTAs at 5 per SM ran as 740 + a tail of 148), at most kLnParts
+    int per_sm = 0;
+    AB2_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layernorm_bwd_cols_kernel<TG, TX, 2>, threads, 0));
+    *parts_used = std::max(1, std::min(kLnParts, num_sms() * std::max(per_sm, 1)));
+    layernorm_bwd_cols_kernel<TG, TX, 2><<<*parts_used, threads, 0, st>>>((const TG*)g, (const TX*)x, gamma, mean, rstd, M, D,
+                                                                           (const TX*)add, (TX*)dx, partial);
     AB2_LAUNCH_OK("layernorm_bwd_cols_kernel");
     return AB2_OK;
   }
@@ -410,15 +416,15 @@ extern "C" int ab2_layernorm_bwd(const void* g, int g_dtype, const void* x, int 
       dgamma == nullptr || dbeta == nullptr)
     return fail(AB2_ERR_INVALID, "layernorm backward: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc;
-  if (g_dtype == AB2_BF16 && x_dtype == AB2_BF16) rc = ln_bwd_dispatch<__nv_bfloat16, __nv_bfloat16>(g, x, gamma, mean, rstd, M, D, add, dx, partial, st);
-  else if (g_dtype == AB2_BF16 && x_dtype == AB2_F32) rc = ln_bwd_dispatch<__nv_bfloat16, float>(g, x, gamma, mean, rstd, M, D, add, dx, partial, st);
-  else if (g_dtype == AB2_F32 && x_dtype == AB2_F32) rc = ln_bwd_dispatch<float, float>(g, x, gamma, mean, rstd, M, D, add, dx, partial, st);
-  else if (g_dtype == AB2_F32 && x_dtype == AB2_BF16) rc = ln_bwd_dispatch<float, __nv_bfloat16>(g, x, gamma, mean, rstd, M, D, add, dx, partial, st);
+  int rc, parts = kLnParts;
+  if (g_dtype == AB2_BF16 && x_dtype == AB2_BF16) rc = ln_bwd_dispatch<__nv_bfloat16, __nv_bfloat16>(g, x, gamma, mean, rstd, M, D, add, dx, partial, &parts, st);
+  else if (g_dtype == AB2_BF16 && x_dtype == AB2_F32) rc = ln_bwd_dispatch<__nv_bfloat16, float>(g, x, gamma, mean, rstd, M, D, add, dx, partial, &parts, st);
+  else if (g_dtype == AB2_F32 && x_dtype == AB2_F32) rc = ln_bwd_dispatch<float, float>(g, x, gamma, mean, rstd, M, D, add, dx, partial, &parts, st);
+  else if (g_dtype == AB2_F32 && x_dtype == AB2_BF16) rc = ln_bwd_dispatch<float, __nv_bfloat16>(g, x, gamma, mean, rstd, M, D, add, dx, partial, &parts, st);
   else return fail(AB2_ERR_INVALID, "layernorm backward: bad dtype");
   if (rc) return rc;
   // partial is [kLnParts][2][D]: dgamma = columns [0, D), dbeta = [D, 2D) of the reduced row
-  partial_reduce_kernel<<<(2 * D + 31) / 32, dim3(32, 32), 0, st>>>(partial, kLnParts, 2 * D, partial + (size_t)kLnParts * 2 * D);
+  partial_reduce_kernel<<<(2 * D + 31) / 32, dim3(32, 32), 0, st>>>(partial, parts, 2 * D, partial + (size_t)kLnParts * 2 * D);
   AB2_LAUNCH_OK("partial_reduce_kernel");
   AB2_CUDA_OK(cudaMemcpyAsync(dgamma, partial + (size_t)kLnParts * 2 * D, D * sizeof(float), cudaMemcpyDeviceToDevice, st));
   AB2_CUDA_OK(cudaMemcpyAsync(dbeta, partial + (size_t)kLnParts * 2 * D + D, D * sizeof(float), cudaMemcpyDeviceToDevice, st));
