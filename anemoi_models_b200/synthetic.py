@@ -154,16 +154,21 @@ def o1280_to_n320_band(parts: int, part: int, src_N: int = 1280, dst_points: int
     return ei, ns, dst_points, radius
 
 
-def encoder_work_balanced_bounds(src_points: int, dst_N: int, parts: int, cutoff: float = 0.6, w_edge: float = 3.0,
-                                 w_src: float = 6.0, w_dst: float = 6.0):
+def encoder_work_balanced_bounds(src_points: int, dst_N: int, parts: int, cutoff: float = 0.6, w_edge: float = 1.7,
+                                 w_src: float = 1.0, w_dst: float = 0.0):
     """parts+1 dst cut points of the `fibonacci(src_points) -> o<dst_N>` cut-off graph that give every rank the same WORK when
-    the src rows follow the dst shards in latitude (`aligned_src_bounds`): work = rows moved through HBM by one forward +
-    backward = w_edge * edges + w_src * src rows + w_dst * dst rows (3 E D + 6 Ns D + 6 Nd D elements).
+    the src rows follow the dst shards in latitude (`aligned_src_bounds`): work = w_edge * edges + w_src * src rows
+    (+ w_dst * dst rows).  The default weights are MEASURED: per-rank kernel times of a 4-GPU run (AB2_TRACE, profiles/r02/
+    trace_r02ab_n4.txt) fit 2.08 ns per edge + 1.21 ns per src row -- an edge costs 1.7 src rows, not the 0.5 its share of the
+    HBM bytes suggests (the k / v rows of an edge come through L2 once per edge); cut points from the byte weights (3 : 6 : 6)
+    were measured SLOWER than equal-count shards.
 
     Closed form, no graph needed: the Fibonacci points are uniform in z, so the src rows under latitude row i of the octahedral
     grid are src_points * dz_i / 2; a fixed cut-off radius r (chord) covers a cap of area pi r^2, so every dst row has
     ~src_points r^2 / 4 edges.  Equal-COUNT dst shards (`tensor_split`) of an octahedral grid are not equal-area -- the grid is
-    denser towards the poles -- which leaves the equatorial rank of 8 with 1.13x the src rows of the single-GPU workload."""
+    denser (per area) towards the equator -- which leaves the polar ranks of 8 with 1.13x the src rows of the single-GPU
+    workload.  Cut points are snapped to whole latitude rows (a cut inside a row makes both neighbours need the src rows
+    around it)."""
     lat, npts = octahedral_rows(dst_N)
     dst_xyz, _ = octahedral_grid(dst_N)
     radius = cutoff * max_nn_distance(dst_xyz)
@@ -172,9 +177,13 @@ def encoder_work_balanced_bounds(src_points: int, dst_N: int, parts: int, cutoff
     src_under_row = src_points * (zedge[:-1] - zedge[1:]) / 2.0
     deg = src_points * radius * radius / 4.0
     row_cost = (w_edge * deg + w_dst) * npts + w_src * src_under_row
-    per_point = np.repeat(row_cost / npts, npts)
-    csum = np.concatenate([[0.0], np.cumsum(per_point)])
-    cuts = [int(np.searchsorted(csum, csum[-1] * r / parts, side="left")) for r in range(1, parts)]
+    csum = np.concatenate([[0.0], np.cumsum(row_cost)])  # cost above each row boundary
+    first = np.concatenate([[0], np.cumsum(npts)])       # dst index of each row boundary
+    cuts = []
+    for r in range(1, parts):
+        i = int(np.argmin(np.abs(csum - csum[-1] * r / parts)))
+        i = min(max(i, len(cuts) + 1), len(npts) - (parts - r))  # strictly increasing, room for the ranks after it
+        cuts.append(int(first[i]))
     return [0] + cuts + [int(npts.sum())]
 
 

@@ -516,7 +516,7 @@ def run_ours(args):
                        "src_rows_rank0": int(n_src), "halo_rows_rank0": int(hplan.n_halo) if hplan is not None else 0, "dst_rows_rank0": int(nd_loc), "hidden": D, "heads": H,
                        "src_split": (args.src_split if world > 1 else "n/a"),
                        "dst_split": ("n/a" if world == 1 else
-                                     "equal work per rank (3 E + 6 Ns + 6 Nd rows of D elements; synthetic.encoder_work_balanced_bounds)"
+                                     "equal work per rank (measured weights: 1.7 x edges + src rows; synthetic.encoder_work_balanced_bounds)"
                                      if args.weak_split == "work" else "equal dst-row counts (tensor_split, the reference's shapes)"),
                        "dst_rows_min_max_rank": [int(shard_min[3]), int(shard_max[3])],
                        "own_src_rows_max_rank": int(shard_max[0]),
@@ -909,7 +909,7 @@ def run_graphconv(args):
             "config": {"workload": f"GraphConvProcessorBlock layer, multi-scale icosahedral mesh r6 (N={N}, E={E}), D={Dg}, bf16 fwd+bwd (report line)"},
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": round(tfs, 1), "peak": tpeak, "unit": "TFLOP/s", "frac": round(tfs / tpeak, 4),
-                         "traffic": None, "note": "executed GEMM FLOPs (split first layer) of the whole block over the block time; GEMMs run on cuBLASLt"},
+                         "traffic": None, "note": "executed GEMM FLOPs (split first layer) of the whole block over the block time; GEMMs run on the tcgen05 kernel (csrc/gemm_tc.cu)"},
             "kernel_breakdown": breakdown}
     print(json.dumps(line), flush=True)
 
@@ -1194,7 +1194,7 @@ def main():
     ap.add_argument("--dst-split", default="equal", choices=["equal", "balanced"], help="o1280 workload: dst shard cut points")
     ap.add_argument("--weak-split", default="work", choices=["work", "equal"],
                     help="headline at --gpus > 1: dst cut points that give every rank the single-GPU workload's work (default), or the "
-                         "reference's equal-count tensor_split (whose equatorial rank has 1.13x the src rows at 8 ranks); the other "
+                         "reference's equal-count tensor_split (whose polar ranks have 1.13x the src rows at 8 ranks); the other "
                          "one is measured too and reported as a sub-block")
     ap.add_argument("--edgepath-graph", default="encoder", choices=["encoder", "decoder", "processor"])
     ap.add_argument("--graphconv-dim", type=int, default=512)

@@ -14,3 +14,7 @@ if [ "${NCCL_BARRIER:-0}" == "1" ]; then
 AB2_BARRIER=nccl timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus $N --steps 20 --warmup 5 --config5 off --no-parity-check > $OUT/bench_n${N}_ncclbarrier.json 2> $OUT/bench_n${N}_ncclbarrier.err
 tail -c 600 $OUT/bench_n${N}_ncclbarrier.json
 fi
+if [ "${TRACE:-0}" == "1" ]; then
+AB2_TRACE=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29535 bench.py --gpus $N --steps 10 --warmup 5 --config5 off --no-parity-check --e2e-steps 0 > $OUT/bench_n${N}_trace.json 2> $OUT/bench_n${N}_trace.err
+grep "trace rank" $OUT/bench_n${N}_trace.err | cut -c1-400
+fi
