@@ -72,6 +72,8 @@ SIGNATURES = {
     "ab2_layernorm_bwd": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ab2_colsum": (_i32, [_vp, _i32, _i64, _i32, _i64, _vp, _vp, _vp]),
     "ab2_edge_segment_sums": (_i32, [_vp] * 5 + [_i64] * 3 + [_i32, _i32, _vp, _vp, _vp]),
+    "ab2_pad_cast_rows": (_i32, [_vp, _i32, _i64, _i32, _i64, _vp, _i32, _vp]),
+    "ab2_unpad_cast_rows": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _i64, _vp]),
     "ab2_gtconv_host_workspace_bytes": (_sz, [_i64] * 3 + [_i32] * 3),
     "ab2_gtconv_fwd_bwd_host_streamed": (_i32, [_vp] * 5 + [_i32] + [_vp] * 6 + [_i64] * 3 + [_i32] * 2 + [_vp] * 5 + [_vp, _i32, _vp, _sz, _vp]),
     "ab2_gtconv_fwd_bwd_host": (_i32, [_vp] * 5 + [_i32] + [_vp] * 6 + [_i64] * 3 + [_i32] * 2 + [_vp] * 5 + [_vp, _sz, _vp]),

@@ -389,9 +389,67 @@ static int ln_bwd_dispatch(const void* g, const void* x, const float* gamma, con
   return AB2_OK;
 }
 
+// Rows of k raw features (the reference's edge_dim = 11: 3 geometric + 8 trainable columns, fp32) -> bf16 rows of kp >= k columns,
+// zero-padded: what the `lin_edge` GEMM reads (16-byte aligned rows).  F.pad + .to(bfloat16) ran as two strided elementwise
+// kernels at ~90 GB/s (5.4 ms of the AIFS-like step for 36 calls).  One thread per (row, 8-column group).
+template <typename TI>
+__global__ void pad_cast_rows_kernel(const TI* __restrict__ x, long long rows, int k, long long ld, __nv_bfloat16* __restrict__ out, int kp) {
+  const int groups = kp >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long row = i / groups;
+  const int c0 = (int)(i - row * groups) * 8;
+  if (row >= rows) return;
+  float f[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) f[u] = (c0 + u < k) ? to_f(x[row * ld + c0 + u]) : 0.f;
+  stg16(out + row * kp + c0, pack<__nv_bfloat16>(f));
+}
+// backward of the above: the first k columns of bf16 [rows, kp] -> [rows, k] in the dtype of the raw features
+template <typename TO>
+__global__ void unpad_cast_rows_kernel(const __nv_bfloat16* __restrict__ g, long long rows, int kp, TO* __restrict__ out, int k, long long ld) {
+  const int groups = kp >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long row = i / groups;
+  const int c0 = (int)(i - row * groups) * 8;
+  if (row >= rows || c0 >= k) return;
+  float f[8];
+  unpack<__nv_bfloat16>(ldg16(g + row * kp + c0), f);
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    if (c0 + u < k) out[row * ld + c0 + u] = from_f<TO>(f[u]);
+}
+
 }  // namespace ab2
 
 using namespace ab2;
+
+extern "C" int ab2_pad_cast_rows(const void* x, int x_dtype, int64_t rows, int k, int64_t ld, void* out, int kp, void* stream) {
+  if (rows < 0 || k <= 0 || kp < k || kp % 8 != 0 || ld < k) return fail(AB2_ERR_INVALID, "pad_cast_rows: need 0 < k <= kp, kp %% 8 == 0, ld >= k");
+  if (rows == 0) return AB2_OK;
+  if (x == nullptr || out == nullptr) return fail(AB2_ERR_INVALID, "pad_cast_rows: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)rows * (kp / 8);
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (x_dtype == AB2_F32) pad_cast_rows_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, rows, k, ld, (__nv_bfloat16*)out, kp);
+  else if (x_dtype == AB2_BF16) pad_cast_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, rows, k, ld, (__nv_bfloat16*)out, kp);
+  else return fail(AB2_ERR_INVALID, "pad_cast_rows: bad dtype");
+  AB2_LAUNCH_OK("pad_cast_rows_kernel");
+  return AB2_OK;
+}
+
+extern "C" int ab2_unpad_cast_rows(const void* g, int64_t rows, int kp, void* out, int out_dtype, int k, int64_t ld, void* stream) {
+  if (rows < 0 || k <= 0 || kp < k || kp % 8 != 0 || ld < k) return fail(AB2_ERR_INVALID, "unpad_cast_rows: need 0 < k <= kp, kp %% 8 == 0, ld >= k");
+  if (rows == 0) return AB2_OK;
+  if (g == nullptr || out == nullptr) return fail(AB2_ERR_INVALID, "unpad_cast_rows: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)rows * (kp / 8);
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (out_dtype == AB2_F32) unpad_cast_rows_kernel<float><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)g, rows, kp, (float*)out, k, ld);
+  else if (out_dtype == AB2_BF16) unpad_cast_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)g, rows, kp, (__nv_bfloat16*)out, k, ld);
+  else return fail(AB2_ERR_INVALID, "unpad_cast_rows: bad dtype");
+  AB2_LAUNCH_OK("unpad_cast_rows_kernel");
+  return AB2_OK;
+}
 
 extern "C" int ab2_ln_parts(void) { return kLnParts; }
 

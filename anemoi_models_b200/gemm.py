@@ -109,6 +109,12 @@ def _f32(t: Optional[Tensor]) -> Optional[Tensor]:
     return None if t is None else t.detach().float().contiguous()
 
 
+def _bf16_weight(w: Tensor) -> Tensor:
+    """bf16 operand copy of a weight.  (Caching it per parameter `_version` would save the re-cast in the checkpoint recompute,
+    ~1.5 ms of the AIFS-like step, but a weight updated through `.data` does not bump the version: not worth a stale weight.)"""
+    return w.detach().to(torch.bfloat16).contiguous()
+
+
 def colsum(a: Tensor) -> Tensor:
     """fp32 column sums of a [M, N] matrix (bias gradients), deterministic two-stage reduction."""
     L = _lib.lib()
@@ -236,7 +242,7 @@ class _LinearFn(torch.autograd.Function):
             x2 = x2.to(torch.bfloat16).contiguous()
         M, K = x2.shape
         N = weight.shape[0]
-        w = weight.detach().to(torch.bfloat16).contiguous()
+        w = _bf16_weight(weight)
         b = _f32(bias)
         res2 = None
         if residual is not None:
@@ -306,7 +312,7 @@ class _MultiLinearFn(torch.autograd.Function):
             x2 = x2.to(torch.bfloat16).contiguous()
         M, K = x2.shape
         N = weights[0].shape[0]
-        wcat = torch.cat([w.detach().to(torch.bfloat16) for w in weights], dim=0)
+        wcat = torch.cat([_bf16_weight(w) for w in weights], dim=0)
         bcat = None if biases[0] is None else torch.cat([b.detach().float() for b in biases])
         outs = [torch.empty((M, N), dtype=torch.bfloat16, device=x.device) for _ in range(n)]
         gemm(x2, wcat, M, n * N, K, out=outs, seg_cols=N, bias=bcat)
@@ -336,6 +342,42 @@ class _MultiLinearFn(torch.autograd.Function):
             dws = [dwcat[i * N:(i + 1) * N].to(wdts[i]) if need[2 + i] else None for i in range(n)]
         dbs = [colsum(g2[i]).to(bdts[i]) if (bdts[i] is not None and need[2 + n + i]) else None for i in range(n)]
         return (dx, None, *dws, *dbs)
+
+
+class _PadCastFn(torch.autograd.Function):
+    """[rows, k] raw features (fp32 / bf16) -> bf16 [rows, kp] zero-padded rows for the `lin_edge` GEMM, one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, kp: int) -> Tensor:
+        rows, k = x.shape
+        if x.stride(-1) != 1 or x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float().contiguous()
+        out = torch.empty((rows, kp), dtype=torch.bfloat16, device=x.device)
+        L = _lib.lib()
+        with torch.cuda.device(x.device):
+            _lib.check(L.ab2_pad_cast_rows(x.data_ptr(), _lib.dtype_code(x.dtype), rows, k, x.stride(0), out.data_ptr(), kp,
+                                           _lib.current_stream(x.device)))
+        ctx.meta = (rows, k, kp, x.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        rows, k, kp, dt = ctx.meta
+        g2 = g if (g.dtype == torch.bfloat16 and g.is_contiguous()) else g.to(torch.bfloat16).contiguous()
+        dx = torch.empty((rows, k), dtype=dt, device=g.device)
+        L = _lib.lib()
+        with torch.cuda.device(g.device):
+            _lib.check(L.ab2_unpad_cast_rows(g2.data_ptr(), rows, kp, dx.data_ptr(), _lib.dtype_code(dt), k, k,
+                                             _lib.current_stream(g.device)))
+        return dx, None
+
+
+def pad_cast(x: Tensor, multiple: int = 16) -> Tensor:
+    """bf16 copy of the rows of `x` [rows, k], zero-padded to a multiple of `multiple` columns (differentiable)."""
+    kp = ((x.shape[-1] + multiple - 1) // multiple) * multiple
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    return _PadCastFn.apply(x, kp)
 
 
 def linear_multi(x: Tensor, lins: Sequence[torch.nn.Linear]):

@@ -68,7 +68,7 @@ def _lin_edge(lin: nn.Linear, edge_attr: Tensor, tc: bool) -> Tensor:
         return _linear_padded_k(lin, edge_attr)
     F = torch.nn.functional
     pad = (-edge_attr.shape[-1]) % 16
-    x = F.pad(edge_attr, (0, pad)) if pad else edge_attr
+    x = tcg.pad_cast(edge_attr, 16) if (pad or edge_attr.dtype != torch.bfloat16) else edge_attr  # one kernel: pad + bf16
     w = F.pad(lin.weight, (0, pad)) if pad else lin.weight
     return tcg.linear_wb(x, w, lin.bias)
 

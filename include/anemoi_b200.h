@@ -331,6 +331,11 @@ int ab2_layernorm_bwd(const void* g, int g_dtype, const void* x, int x_dtype, co
                       const float* rstd, int64_t M, int D, const void* add, void* dx, float* partial, float* dgamma, float* dbeta,
                       void* stream);
 int ab2_colsum(const void* a, int dtype, int64_t M, int N, int64_t ld, float* partial, float* out, void* stream);
+/* Raw edge features in front of `lin_edge` (layers/block.py:497, 618; edge_dim = 11 in the reference configs): x [rows, k] (fp32 or
+ * bf16, row stride ld) -> out bf16 [rows, kp], kp >= k a multiple of 8, zero-padded -- the K-major A operand of ab2_gemm_bf16
+ * (replaces F.pad + the autocast cast).  ab2_unpad_cast_rows is its backward: g bf16 [rows, kp] -> out [rows, k] (row stride ld). */
+int ab2_pad_cast_rows(const void* x, int x_dtype, int64_t rows, int k, int64_t ld, void* out, int kp, void* stream);
+int ab2_unpad_cast_rows(const void* g, int64_t rows, int kp, void* out, int out_dtype, int k, int64_t ld, void* stream);
 /* dpi[i] = sum of g[t] over the edges t into dst i (CSR order), dpj[j] = sum over the edges out of src j (CSC order); g [E,D] in
  * original edge order.  The node-side gradients of GraphConv's split first layer (conv.py:69) when g = d(pre-activation) already
  * came out of a GEMM epilogue.  Either output may be NULL.  Deterministic. */

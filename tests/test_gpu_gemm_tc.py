@@ -225,6 +225,25 @@ def test_layernorm_backward_warp_per_row_variant_in_a_subprocess():
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-800:]
 
 
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,k", [(1000, 11), (7, 3), (513, 16), (100, 24)])
+def test_pad_cast_rows_and_its_backward(rows, k, dt):
+    """Raw edge features -> zero-padded bf16 rows for the lin_edge GEMM (one kernel each way) against F.pad + cast, exact."""
+    from anemoi_models_b200 import gemm as G
+
+    torch.manual_seed(rows + k)
+    x = torch.randn(rows, k, device=DEV).to(dt).requires_grad_(True)
+    y = G.pad_cast(x, 16)
+    kp = ((k + 15) // 16) * 16
+    assert y.shape == (rows, kp) and y.dtype == torch.bfloat16
+    assert torch.equal(y, F.pad(x.detach(), (0, kp - k)).bfloat16())
+    g = torch.randn(rows, kp, device=DEV).bfloat16()
+    y.backward(g)
+    assert x.grad.dtype == dt and torch.equal(x.grad, g[:, :k].to(dt))
+    xs = torch.randn(rows, k + 5, device=DEV).to(dt)[:, :k]  # a row stride that is not k
+    assert torch.equal(G.pad_cast(xs, 16), F.pad(xs, (0, kp - k)).bfloat16())
+
+
 def test_colsum():
     from anemoi_models_b200 import gemm as G
 
