@@ -248,7 +248,8 @@ def test_colsum():
     from anemoi_models_b200 import gemm as G
 
     gen = torch.Generator().manual_seed(9)
-    for M, N, dt in ((5000, 2048, torch.bfloat16), (3, 8, torch.float32), (1234, 520, torch.bfloat16)):
+    for M, N, dt in ((5000, 2048, torch.bfloat16), (3, 8, torch.float32), (1234, 520, torch.bfloat16), (40321, 1024, torch.bfloat16),
+                     (9000, 4096, torch.bfloat16), (777, 256, torch.float32)):
         a = torch.randn(M, N, generator=gen).to(DEV).to(dt)
         assert rel_err(G.colsum(a), a.float().sum(0)) < 1e-5
         assert torch.equal(G.colsum(a), G.colsum(a))
