@@ -15,16 +15,17 @@
 // cuBLAS, profiles/r02/gemm_probe_r02a.jsonl):
 //   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B boxes) of the A / B k-blocks into a shared-memory ring,
 //               completion counted in bytes on the stage's `full` mbarrier (CG = 2: both CTAs' copies signal the LEADER's);
-//   warp 1      MMA issuer (leader CTA): ONE thread issues tcgen05.mma.kind::f16 (128*CG x BN x 16 per instruction) on the
-//               staged tiles; tcgen05.commit releases the stage (`empty`, multicast to both CTAs) and, after the last k-block,
+//   warp 1      MMA issuer (leader CTA): the warp walks its loops converged, ONE elected lane issues tcgen05.mma.kind::f16
+//               (128*CG x BN x 16 per instruction) on the staged tiles; tcgen05.commit releases the stage (`empty`, multicast to both CTAs) and, after the last k-block,
 //               publishes the accumulator (`tmem_full`).  The warp also owns the TMEM allocation (512 columns = two
 //               accumulator stages of BN <= 256);
 //   warps 2..9  epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) of the finished accumulator while the MMA warp
 //               already works on the next tile in the other TMEM stage; bias / LayerNorm-fold / activation (+ pre-activation
-//               side output) / activation-derivative / residual; bf16 results are transposed through a per-warp shared-memory
-//               patch so that global stores are row-contiguous 64 B runs (a thread owns a ROW of the accumulator: storing
-//               straight from registers writes 32 rows x 16 B per instruction, half a sector each -- measured 2-4x slower on
-//               epilogue-bound shapes); outputs optionally split by column segments (q | self, k | v land in separate tensors).
+//               side output) / activation-derivative / residual; a thread owns a ROW of the accumulator, so bf16 results go
+//               through per-warp shared-memory patch buffers (TMA SWIZZLE_64B layout) and leave as TMA stores of 32 x 32
+//               boxes (storing straight from registers writes 32 rows x 16 B per instruction, half a sector each -- measured
+//               2-4x slower on epilogue-bound shapes); outputs optionally split by column segments (q | self, k | v land in
+//               separate tensors).
 // Operands may be K-major (contraction contiguous in memory: x [M,K], W [N,K]) or MN-major (contraction strided: W as the
 // B operand of dgrad, dY^T and x as the operands of wgrad), selected per operand in the instruction descriptor; no transposes
 // are materialised.  wgrad splits the (long) contraction over CTAs into fp32 partials that a second kernel sums in a fixed
@@ -33,6 +34,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <climits>
 #include <mutex>
 
@@ -46,8 +48,12 @@ constexpr int BK = 64;      // 64 bf16 = 128 B = one SWIZZLE_128B atom along the
 constexpr int UMMA_K = 16;  // contraction per tcgen05.mma for 16-bit operands
 constexpr int kBoxBytes = 64 * 64 * 2;  // one 64 x 64 bf16 box (MN-major operands are loaded box by box)
 
-constexpr int kPatchStride = 80;                      // bytes per row of an epilogue patch: 64 B of bf16 + 16 B pad (bank spread)
-constexpr int kPatchBytes = 32 * kPatchStride;        // 32 rows x 32 bf16 columns per epilogue warp
+// Epilogue patches: per epilogue warp TWO buffers of 32 rows x 64 bytes (32 bf16 columns), dense, 16-byte chunks XOR-swizzled
+// with the row (the TMA SWIZZLE_64B pattern: chunk ^= (row >> 1) & 3) -- conflict-free both for "lane = row" accesses and for
+// "8 rows x 4 chunks" accesses, and the layout a TMA store reads.  Two buffers so that the store of one chunk (or of the
+// pre-activation) is still being read by the TMA engine while the warp fills the other.
+constexpr int kPatchBuf = 32 * 64;
+constexpr int kPatchBytes = 2 * kPatchBuf;
 
 // EW = number of epilogue warps (8 or 16: two or four per scheduler -- the epilogue is a latency chain of TMEM load, gathers and
 // the shared-memory transpose, so the epilogue-heavy shapes want four; the price is one pipeline stage of shared memory)
@@ -97,6 +103,11 @@ struct Args {
 // producer picks the tensor map by k-block (dgrad, K-major A) or by tile row (wgrad, MN-major A) instead of a concatenation pass
 struct AMaps {
   CUtensorMap m[4];
+};
+// bf16 results leave through TMA stores (box = 32 columns x 32 rows, SWIZZLE_64B): one map per output segment + the pre-activation
+struct OMaps {
+  CUtensorMap out[4];
+  CUtensorMap pre;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
@@ -356,45 +367,57 @@ __device__ __forceinline__ void act_grad_mul8(float (&f)[32], int j, const float
 }
 
 // ---- the kernel --------------------------------------------------------------------------------------------------
-// bf16 chunk of 32 rows x 32 columns held one ROW per lane (pk[j] = columns 2j, 2j+1 of row `lane`, packed bf16x2) -> global
-// memory, through the warp's shared-memory patch so that each store instruction writes 8 rows x 64 contiguous bytes.
-__device__ __forceinline__ void store_chunk_packed(uint32_t patch, int lane, const uint32_t (&pk)[16], __nv_bfloat16* out, long long ld,
-                                                   int row0, int rows_left, int cols_left) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) sts16(patch + lane * kPatchStride + j * 16, make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
-  __syncwarp();
-  const int c16 = lane & 3, rsub = lane >> 2;
-  __nv_bfloat16* dst = out + (size_t)(row0 + rsub) * ld + c16 * 8;  // one 64-bit address per chunk, + 8 rows per store
-  const size_t step = (size_t)8 * ld;
-  const bool col_ok = c16 * 8 < cols_left;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = i * 8 + rsub;
-    const uint4 v = lds16(patch + r * kPatchStride + c16 * 16);
-    if (r < rows_left && col_ok) stg16(dst, v);
-    dst += step;
+// swizzled address of 16-byte chunk `c` of row `r` in a patch buffer
+__device__ __forceinline__ uint32_t patch_addr(uint32_t buf, int r, int c) { return buf + r * 64 + ((c ^ ((r >> 1) & 3)) << 4); }
+
+// One warp's patch buffers.  A buffer may be refilled only after the TMA store that read it has finished reading: lane 0 issues
+// every store of the warp (bulk groups are per thread) and keeps at most one group pending while the other buffer is filled.
+struct Patch {
+  uint32_t base;
+  uint32_t cur;  // 0 or kPatchBuf
+  __device__ __forceinline__ uint32_t acquire(int lane) {  // the buffer to fill next (warp-uniform call)
+    cur ^= (uint32_t)kPatchBuf;
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncwarp();
+    return base + cur;
   }
+};
+
+// bf16 chunk of 32 rows x 32 columns held one ROW per lane (pk[j] = columns 2j, 2j+1 of row `lane`, packed bf16x2) -> global
+// memory: the lanes write their rows into a patch buffer, ONE lane hands the buffer to the TMA engine (which clips rows / columns
+// beyond the matrix).  No shared-memory read-back, no store instructions, no address arithmetic in the warp: the epilogue of the
+// activation shapes had the LSU data pipe 70 % busy (ncu, profiles/r02/ncu_gemm_perf_mlp1_r02w.md).
+__device__ __forceinline__ void store_chunk_tma(Patch& p, int lane, const uint32_t (&pk)[16], const CUtensorMap* map, int col, int row0) {
+  const uint32_t b = p.acquire(lane);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sts16(patch_addr(b, lane, j), make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
   __syncwarp();
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(col), "r"(row0), "r"(b)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
 }
 // global memory -> one ROW per lane, for the per-element inputs of the epilogue (residual, saved pre-activation, gathered node
 // rows): 32 rows x 64 bytes, row r at `row_ptr` of lane r (0 = no such row).  With every lane loading ITS row, one load
-// instruction touched 32 different 128-byte lines for 16 bytes each and the uncoalesced requests, not the latency, set the cost
-// (projection shape: +30 us for a bf16 residual, +67 us for an fp32 one, profiles/r02/gemm_probe_proj_r02y.jsonl); here each
-// instruction reads 8 rows x 64 contiguous bytes and the rows are handed out through the warp's shared-memory patch.
-__device__ __forceinline__ void load_chunk_rows(uint32_t patch, int lane, const void* row_ptr, int bytes_left, uint4 (&out)[4]) {
+// instruction touched 32 different 128-byte lines for 16 bytes each; here each instruction reads 8 rows x 64 contiguous bytes
+// and the rows are handed out through a patch buffer.
+__device__ __forceinline__ void load_chunk_rows(Patch& p, int lane, const void* row_ptr, int bytes_left, uint4 (&out)[4]) {
+  const uint32_t b = p.acquire(lane);
   const int c16 = lane & 3, rsub = lane >> 2;
   const unsigned long long mine = reinterpret_cast<unsigned long long>(row_ptr);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = i * 8 + rsub;
-    const unsigned long long p = __shfl_sync(0xffffffffu, mine, r);
+    const unsigned long long q = __shfl_sync(0xffffffffu, mine, r);
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (p != 0ull && c16 * 16 < bytes_left) v = ldg16_keep(reinterpret_cast<const char*>(p) + c16 * 16);
-    sts16(patch + r * kPatchStride + c16 * 16, v);
+    if (q != 0ull && c16 * 16 < bytes_left) v = ldg16_keep(reinterpret_cast<const char*>(q) + c16 * 16);
+    sts16(patch_addr(b, r, c16), v);
   }
   __syncwarp();
 #pragma unroll
-  for (int j = 0; j < 4; ++j) out[j] = lds16(patch + lane * kPatchStride + j * 16);
+  for (int j = 0; j < 4; ++j) out[j] = lds16(patch_addr(b, lane, j));
   __syncwarp();
 }
 __device__ __forceinline__ void pack_chunk(const float (&f)[32], uint32_t (&pk)[16]) {
@@ -404,7 +427,8 @@ __device__ __forceinline__ void pack_chunk(const float (&f)[32], uint32_t (&pk)[
 
 template <int BN, bool A_MN, bool B_MN, int CG, int EW>
 __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_constant__ AMaps tmAs,
-                                                             const __grid_constant__ CUtensorMap tmB, const Args g) {
+                                                             const __grid_constant__ CUtensorMap tmB,
+                                                             const __grid_constant__ OMaps tmO, const Args g) {
   using C = Cfg<BN, CG, EW>;
   constexpr int S = C::kStages;
   constexpr int TM = BM * CG;  // rows of the tile the CTA pair (or the single CTA) accumulates
@@ -558,7 +582,9 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
     const int half = e >> 2;    // EW / 4 warps per lane quadrant: each takes an equal share of the BN columns
     constexpr int kChunks = BN / 32 / (EW / 4);
     const Epi& ep = g.epi;
-    const uint32_t patch = patches + e * kPatchBytes;
+    Patch patch;
+    patch.base = patches + e * kPatchBytes;
+    patch.cur = 0;
     uint32_t it = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
       const int split = t / tiles_mn, r = t % tiles_mn;
@@ -651,7 +677,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
             // differentiates exactly the function forward applied
             uint32_t pk[16];
             pack_chunk(f, pk);
-            store_chunk_packed(patch, lane, pk, reinterpret_cast<__nv_bfloat16*>(ep.pre_out) + col0, g.N, row0, rows_left, cols_left);
+            store_chunk_tma(patch, lane, pk, &tmO.pre, col0, row0);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {  // bf16 -> fp32 is a shift / a mask
               f[2 * j] = __uint_as_float(pk[j] << 16);
@@ -705,12 +731,13 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
         } else {
           uint32_t pk[16];
           pack_chunk(f, pk);
-          store_chunk_packed(patch, lane, pk, reinterpret_cast<__nv_bfloat16*>(ep.out[seg]) + cs, ep.ld_out, row0, rows_left, cols_left);
+          store_chunk_tma(patch, lane, pk, &tmO.out[seg], cs, row0);
         }
       }
     }
   }
 
+  if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's TMA stores are complete
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
@@ -776,8 +803,24 @@ static int make_map(CUtensorMap* m, const void* ptr, long long inner, long long 
   return AB2_OK;
 }
 
+// output map: bf16 [outer rows][inner columns], row stride ld elements; box = 32 columns x 32 rows, SWIZZLE_64B (TMA stores)
+static int make_out_map(CUtensorMap* m, const void* ptr, long long inner, long long outer, long long ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return fail(AB2_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (ld * 2) % 16 != 0)
+    return fail(AB2_ERR_INVALID, "gemm bf16 output must be 16-byte aligned with a row stride that is a multiple of 8 elements");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(AB2_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed with CUresult %d", (int)r);
+  return AB2_OK;
+}
+
 template <int BN, bool A_MN, bool B_MN, int CG, int EW>
-static int launch(const AMaps& ta, const CUtensorMap& tb, const Args& a, cudaStream_t st) {
+static int launch(const AMaps& ta, const CUtensorMap& tb, const OMaps& to, const Args& a, cudaStream_t st) {
   using C = Cfg<BN, CG, EW>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CG, EW>;
   if (!AB2_ENSURE_DYN_SMEM(kern, C::kSmemBytes)) return fail(AB2_ERR_CUDA, "gemm_tc_kernel: cannot reserve %d B of shared memory", C::kSmemBytes);
@@ -799,7 +842,7 @@ static int launch(const AMaps& ta, const CUtensorMap& tb, const Args& a, cudaStr
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  AB2_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, a));
+  AB2_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, a));
   AB2_LAUNCH_OK("gemm_tc_kernel");
   return AB2_OK;
 }
@@ -910,13 +953,26 @@ extern "C" int ab2_gemm_bf16(const ab2_gemm* d, void* workspace, size_t workspac
   }
   rc = d->b_mn ? tc::make_map(&tb, d->b, N, K, d->ldb, 64) : tc::make_map(&tb, d->b, K, N, d->ldb, BN / CG);
   if (rc) return rc;
+  tc::OMaps to;
+  memset(&to, 0, sizeof(to));
+  if (!e.out_f32) {  // bf16 results leave through TMA stores; fp32 ones (split-K partials, fp32 outputs) are stored directly
+    for (int i = 0; i < nseg; ++i) {
+      const long long width = std::min<long long>(e.seg_cols, N - (long long)i * e.seg_cols);
+      rc = tc::make_out_map(&to.out[i], e.out[i], width, M, e.ld_out);
+      if (rc) return rc;
+    }
+  }
+  if (e.pre_out != nullptr) {
+    rc = tc::make_out_map(&to.pre, e.pre_out, N, M, N);
+    if (rc) return rc;
+  }
   cudaStream_t st = (cudaStream_t)stream;
 #define AB2_GEMM_DISPATCH(BNV, CGV, EWV)                                                       \
   do {                                                                                         \
-    if (!d->a_mn && !d->b_mn) rc = tc::launch<BNV, false, false, CGV, EWV>(ta, tb, a, st);     \
-    else if (!d->a_mn && d->b_mn) rc = tc::launch<BNV, false, true, CGV, EWV>(ta, tb, a, st);  \
-    else if (d->a_mn && d->b_mn) rc = tc::launch<BNV, true, true, CGV, EWV>(ta, tb, a, st);    \
-    else rc = tc::launch<BNV, true, false, CGV, EWV>(ta, tb, a, st);                           \
+    if (!d->a_mn && !d->b_mn) rc = tc::launch<BNV, false, false, CGV, EWV>(ta, tb, to, a, st);     \
+    else if (!d->a_mn && d->b_mn) rc = tc::launch<BNV, false, true, CGV, EWV>(ta, tb, to, a, st);  \
+    else if (d->a_mn && d->b_mn) rc = tc::launch<BNV, true, true, CGV, EWV>(ta, tb, to, a, st);    \
+    else rc = tc::launch<BNV, true, false, CGV, EWV>(ta, tb, to, a, st);                           \
   } while (0)
   // epilogue warps: 16 when the epilogue does special-function work or gathers per element (activation, activation derivative,
   // row tables), 8 (and one more pipeline stage) for bias / residual epilogues -- measured both ways on every block shape
