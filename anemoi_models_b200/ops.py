@@ -302,12 +302,18 @@ def trace_summary():
     return out
 
 
+# AB2_BOUNDARY_STREAM=0: the boundary rows run on the main stream after / before the interior rows (round-2 first version).
+# Default: they run on the exchange's side stream, next to the interior kernels -- the boundary launches are small (0.02-0.075 ms
+# each at 8 GPUs, a few hundred dst rows: they cannot fill the GPU on their own) and sat on the critical path of every rank.
+_BOUNDARY_STREAM = _os.environ.get("AB2_BOUNDARY_STREAM", "1") != "0"
+
+
 class _GTConvShardedOverlapFn(torch.autograd.Function):
     """dst-row-sharded conv with the NVLink peer-memory exchange hidden behind the interior rows.
-    forward : side stream pushes k / v halo rows | main stream runs the forward on the interior dst rows, then (halo landed) the
-              boundary rows;
-    backward: dst pass on the boundary rows and src pass on the halo rows first, their gradients leave on the side stream
-              while the interior dst pass and the src pass of the own rows run, then the peers' contributions are added."""
+    forward : side stream pushes k / v halo rows and, once the peers' rows have landed, runs the forward on the boundary dst rows |
+              main stream runs the forward on the interior dst rows;
+    backward: side stream runs the dst pass on the boundary rows and the src pass on the halo rows and sends their gradients |
+              main stream runs the interior dst pass and the src pass of the own rows; then the peers' contributions are added."""
 
     @staticmethod
     def forward(ctx, q, k, v, e, plan: GraphCSR, hplan, group, px):
@@ -320,11 +326,20 @@ class _GTConvShardedOverlapFn(torch.autograd.Function):
             k_halo, v_halo, landed = px.forward_async(k, v)
             _fwd_rows(q, k, v, k_halo, v_halo, e, plan, out, lse2, *rng["interior"])
             _mark("fwd:interior", q.device)
-            torch.cuda.current_stream(q.device).wait_event(landed)
-            _mark("fwd:wait_halo", q.device)
-            for blk in rng["boundary"]:
-                _fwd_rows(q, k, v, k_halo, v_halo, e, plan, out, lse2, *blk)
-            _mark("fwd:boundary", q.device)
+            if _BOUNDARY_STREAM:
+                with torch.cuda.stream(px.stream):  # behind the push and the wait for the peers' rows, in stream order
+                    for blk in rng["boundary"]:
+                        _fwd_rows(q, k, v, k_halo, v_halo, e, plan, out, lse2, *blk)
+                    bdone = torch.cuda.Event()
+                    bdone.record(px.stream)
+                torch.cuda.current_stream(q.device).wait_event(bdone)
+                _mark("fwd:wait_boundary", q.device)
+            else:
+                torch.cuda.current_stream(q.device).wait_event(landed)
+                _mark("fwd:wait_halo", q.device)
+                for blk in rng["boundary"]:
+                    _fwd_rows(q, k, v, k_halo, v_halo, e, plan, out, lse2, *blk)
+                _mark("fwd:boundary", q.device)
         ctx.save_for_backward(q, k, v, e, out, lse2, k_halo, v_halo)
         ctx.plan, ctx.hplan, ctx.group, ctx.px = plan, hplan, group, px
         return out
@@ -345,13 +360,29 @@ class _GTConvShardedOverlapFn(torch.autograd.Function):
         rng = px.ranges(plan)
         with torch.cuda.device(q.device):
             _mark("bwd:start", q.device)
-            for blk in rng["boundary"]:
-                _bwd_dst_rows(q, k, v, k_halo, v_halo, e, plan, out, lse2, g, dq, de, ws, *blk)
-            _bwd_src_rows(q, g, plan, n_own, Ns, ws, dk, dv, dkh, dvh, n_own, Ns)  # halo rows: only boundary edges touch them
-            _mark("bwd:boundary+halo_src", q.device)
-            parity, pushed = px.backward_async(dkh, dvh)
-            _bwd_dst_rows(q, k, v, k_halo, v_halo, e, plan, out, lse2, g, dq, de, ws, *rng["interior"])
-            _mark("bwd:interior_dst", q.device)
+            main = torch.cuda.current_stream(q.device)
+            if _BOUNDARY_STREAM:
+                ready = torch.cuda.Event()
+                ready.record(main)
+                with torch.cuda.stream(px.stream):
+                    px.stream.wait_event(ready)
+                    for blk in rng["boundary"]:
+                        _bwd_dst_rows(q, k, v, k_halo, v_halo, e, plan, out, lse2, g, dq, de, ws, *blk)
+                    bdst = torch.cuda.Event()  # the own-row src pass reads the softmax-weight workspace of the boundary edges too
+                    bdst.record(px.stream)
+                    _bwd_src_rows(q, g, plan, n_own, Ns, ws, dk, dv, dkh, dvh, n_own, Ns)  # halo rows: only boundary edges touch them
+                    parity, pushed = px.backward_async(dkh, dvh)
+                _bwd_dst_rows(q, k, v, k_halo, v_halo, e, plan, out, lse2, g, dq, de, ws, *rng["interior"])
+                _mark("bwd:interior_dst", q.device)
+                main.wait_event(bdst)
+            else:
+                for blk in rng["boundary"]:
+                    _bwd_dst_rows(q, k, v, k_halo, v_halo, e, plan, out, lse2, g, dq, de, ws, *blk)
+                _bwd_src_rows(q, g, plan, n_own, Ns, ws, dk, dv, dkh, dvh, n_own, Ns)  # halo rows: only boundary edges touch them
+                _mark("bwd:boundary+halo_src", q.device)
+                parity, pushed = px.backward_async(dkh, dvh)
+                _bwd_dst_rows(q, k, v, k_halo, v_halo, e, plan, out, lse2, g, dq, de, ws, *rng["interior"])
+                _mark("bwd:interior_dst", q.device)
             _bwd_src_rows(q, g, plan, n_own, Ns, ws, dk, dv, dkh, dvh, 0, n_own)
             _mark("bwd:own_src", q.device)
             torch.cuda.current_stream(q.device).wait_event(pushed)
