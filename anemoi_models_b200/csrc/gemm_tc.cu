@@ -945,12 +945,12 @@ extern "C" int ab2_gemm_bf16(const ab2_gemm* d, void* workspace, size_t workspac
       if (aptr[i] == nullptr) return fail(AB2_ERR_INVALID, "ab2_gemm_bf16: A segment %d is null", i);
     a.a_seg_len = (int)d->a_seg_len;
   }
-  for (int i = 0; i < 4; ++i) {
-    const void* p = i < nsegA ? aptr[i] : d->a;  // unused slots hold a valid map
+  for (int i = 0; i < nsegA; ++i) {
     const long long segM = (d->a_mn && nsegA > 1) ? d->a_seg_len : M, segK = (!d->a_mn && nsegA > 1) ? d->a_seg_len : K;
-    rc = d->a_mn ? tc::make_map(&ta.m[i], p, segM, K, d->lda, 64) : tc::make_map(&ta.m[i], p, segK, M, d->lda, tc::BM);
+    rc = d->a_mn ? tc::make_map(&ta.m[i], aptr[i], segM, K, d->lda, 64) : tc::make_map(&ta.m[i], aptr[i], segK, M, d->lda, tc::BM);
     if (rc) return rc;
   }
+  for (int i = nsegA; i < 4; ++i) ta.m[i] = ta.m[0];  // unused slots hold a valid map (no second encode: ~1 us of host time each)
   rc = d->b_mn ? tc::make_map(&tb, d->b, N, K, d->ldb, 64) : tc::make_map(&tb, d->b, K, N, d->ldb, BN / CG);
   if (rc) return rc;
   tc::OMaps to;
