@@ -857,6 +857,17 @@ extern "C" size_t ab2_gemm_workspace_bytes(const ab2_gemm* d) {
   return (size_t)d->splits * (size_t)d->M * (size_t)d->N * sizeof(float);
 }
 
+// cuTensorMapEncodeTiled is a DRIVER API call and needs a context current on the calling thread.  A thread that has only ever been
+// handed device 0 by PyTorch (an autograd worker whose first operation is one of these GEMMs) has made no runtime call yet, so
+// nothing has bound the primary context: the encode then fails with CUDA_ERROR_INVALID_CONTEXT (201).  One runtime call binds it.
+static void ensure_context_on_this_thread() {
+  static thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(nullptr);
+    bound = true;
+  }
+}
+
 extern "C" int ab2_gemm_bf16(const ab2_gemm* d, void* workspace, size_t workspace_bytes, void* stream) {
   if (d == nullptr) return fail(AB2_ERR_INVALID, "ab2_gemm_bf16: null descriptor");
   const long long M = d->M, N = d->N, K = d->K;
@@ -927,6 +938,7 @@ extern "C" int ab2_gemm_bf16(const ab2_gemm* d, void* workspace, size_t workspac
     e.out_f32 = 1;
     a.split_stride = M * N;
   }
+  ensure_context_on_this_thread();
   tc::AMaps ta;
   CUtensorMap tb;
   int rc;

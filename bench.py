@@ -894,6 +894,33 @@ def run_graphconv(args):
         total = sum(r.device_time_total for r in rows)
         breakdown = [{"kernel": r.key[:100], "ms": round(r.device_time_total / 1e3, 3), "calls": r.count,
                       "share": round(r.device_time_total / max(total, 1), 4)} for r in rows[:20]]
+    # the same forward + backward captured ONCE into a CUDA graph and replayed (~100 launches of 10-300 us: the eager step is partly
+    # bound by the host issuing them); every kernel of this library launches on the capturing stream, nothing synchronises
+    graphed = None
+    if args.cuda_graph:
+        try:
+            xs, es = x.detach().clone().requires_grad_(True), e.detach().clone().requires_grad_(True)
+            nodes_e, edges_e = blk(xs, es, ei, shapes)  # eager result on the static inputs, for the comparison below
+            nodes_e, edges_e = nodes_e.detach().clone(), edges_e.detach().clone()
+            for p_ in blk.parameters():
+                p_.grad = None
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                nodes_g, edges_g = blk(xs, es, ei, shapes)
+                torch.autograd.backward([nodes_g, edges_g], [gx, ge])
+            for _ in range(3):
+                cg.replay()
+            torch.cuda.synchronize()
+            same = bool(torch.equal(nodes_g, nodes_e) and torch.equal(edges_g, edges_e))
+            ev0.record()
+            for _ in range(args.steps):
+                cg.replay()
+            ev1.record()
+            torch.cuda.synchronize()
+            graphed = {"ms_per_step": ev0.elapsed_time(ev1) / args.steps, "outputs_bit_identical_to_eager": same,
+                       "what": "torch.cuda.CUDAGraph capture of the block's forward + backward, replayed"}
+        except Exception as ex:  # noqa: BLE001 -- report line only
+            graphed = {"error": f"{type(ex).__name__}: {ex}"[:300]}
     # executed GEMM FLOPs with the split first layer: edge GEMMs pe, W1, W2 (3 x 2*E*D^2), node GEMMs pi, pj (2 x 2*N*D^2),
     # node MLP 2*N*(2D*D + D*D + D*D); backward = 2x forward
     flops_fwd = 6 * E * Dg * Dg + 4 * N * Dg * Dg + 8 * N * Dg * Dg
@@ -910,6 +937,7 @@ def run_graphconv(args):
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": round(tfs, 1), "peak": tpeak, "unit": "TFLOP/s", "frac": round(tfs / tpeak, 4),
                          "traffic": None, "note": "executed GEMM FLOPs (split first layer) of the whole block over the block time; GEMMs run on the tcgen05 kernel (csrc/gemm_tc.cu)"},
+            "cuda_graph": graphed,
             "kernel_breakdown": breakdown}
     print(json.dumps(line), flush=True)
 
@@ -1204,6 +1232,8 @@ def main():
     ap.add_argument("--model-recompute", default="on", choices=["on", "off"],
                     help="model workload: activation checkpointing per mapper / processor chunk as the reference wires it (on), or every "
                          "activation kept in HBM (off)")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="graphconv workload: also capture the block's forward + backward into a CUDA graph and time its replay")
     ap.add_argument("--profile", action="store_true", help="model workload: add a per-kernel device-time breakdown of one step")
     ap.add_argument("--workload", default="encoder", choices=["encoder", "decoder", "processor", "graphconv", "model", "edgepath", "o1280", "config1-enc", "config1-proc", "config1-dec"],
                     help="encoder = BASELINE configs[1] (the headline); the others are extra report lines")
