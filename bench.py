@@ -1023,8 +1023,11 @@ def run_model(args, emit=True, impl="ours", recompute=None):
     # checkpoints unconditionally because the model was sized for 40-80 GB GPUs -- at 180 GB the activations of this model fit)
     recompute = (args.model_recompute != "off") if recompute is None else recompute
 
+    use_graph = bool(getattr(args, "cuda_graph", False)) and impl != "reference"
+
     def checkpoint(fn, *a, use_reentrant=False):
-        return _checkpoint(fn, *a, use_reentrant=use_reentrant) if recompute else fn(*a)
+        # (no dropout anywhere: the RNG state need not be stashed -- reading it is not allowed while a CUDA graph is captured)
+        return _checkpoint(fn, *a, use_reentrant=use_reentrant, preserve_rng_state=not use_graph) if recompute else fn(*a)
 
     if impl == "reference":
         # comparator: the SAME model wired from the UNMODIFIED reference blocks (baseline/_ref, PyG op sequence through the shim as
@@ -1097,7 +1100,7 @@ def run_model(args, emit=True, impl="ours", recompute=None):
             return checkpoint(run_dec, x, x_data, use_reentrant=False)
 
     model = Model().to(dev)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True, capturable=use_graph)
     x_data = torch.randn(Ndata, nvar + 4, device=dev)
     x_hidden = torch.randn(Nh, 4, device=dev)
     target = torch.randn(Ndata, nvar, device=dev)
@@ -1124,8 +1127,35 @@ def run_model(args, emit=True, impl="ours", recompute=None):
         ev1.record()
         torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / n
+    graphed = None
+    if use_graph:  # the whole training step (forward, checkpoint recompute, backward, fused AdamW) captured once and replayed
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            loss = None
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                loss_g = step()
+            for _ in range(2):
+                cg.replay()
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(n):
+                cg.replay()
+            ev1.record()
+            torch.cuda.synchronize()
+            graphed = {"ms_per_step": ev0.elapsed_time(ev1) / n, "loss": float(loss_g.detach()),
+                       "what": "torch.cuda.CUDAGraph capture of the whole training step, replayed"}
+            loss = loss_g
+        except Exception as ex:  # noqa: BLE001 -- report line only
+            graphed = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+            loss = torch.zeros(())
     breakdown = None
-    if args.profile:
+    if args.profile and graphed is None:
         from torch.profiler import ProfilerActivity, profile
 
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
@@ -1149,7 +1179,7 @@ def run_model(args, emit=True, impl="ours", recompute=None):
                        "activation_checkpointing": bool(recompute),
                        "conv_edges_per_step": int(etot), "loss": float(loss.detach()), "optimizer_steps_before_loss": 3 + n},
             "clocks": sampler.summary(), "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2**30, 1),
-            "kernel_breakdown": breakdown}
+            "cuda_graph": graphed, "kernel_breakdown": breakdown}
     if emit:
         print(json.dumps(line), flush=True)
     del model, opt
@@ -1233,7 +1263,7 @@ def main():
                     help="model workload: activation checkpointing per mapper / processor chunk as the reference wires it (on), or every "
                          "activation kept in HBM (off)")
     ap.add_argument("--cuda-graph", action="store_true",
-                    help="graphconv workload: also capture the block's forward + backward into a CUDA graph and time its replay")
+                    help="graphconv / model workloads: also capture the step into a CUDA graph and time its replay")
     ap.add_argument("--profile", action="store_true", help="model workload: add a per-kernel device-time breakdown of one step")
     ap.add_argument("--workload", default="encoder", choices=["encoder", "decoder", "processor", "graphconv", "model", "edgepath", "o1280", "config1-enc", "config1-proc", "config1-dec"],
                     help="encoder = BASELINE configs[1] (the headline); the others are extra report lines")
