@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
         }
         const int col0 = n0 + cc;
         if (row0 >= g.M || col0 >= g.N) continue;  // warp-uniform
-        const int cols_left = g.N - col0, rows_left = g.M - row0;
+        const int cols_left = g.N - col0;
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
